@@ -1,0 +1,83 @@
+"""Synthetic read generators, shared by tests/ and bench.py.
+
+numpy variant: small, CPU, deterministic -- used by parity tests (same bytes go to oracle and GPU).
+torch variant: large, generated directly in HBM -- used by bench.py (inputs resident when timing starts).
+"""
+import numpy as np
+
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def genome_codes(length, seed):
+    return np.random.default_rng(seed).integers(0, 4, length, dtype=np.uint8)
+
+
+def reads_numpy(n_reads, read_len=150, genome_len=100_000, seed=1, err=0.001, lowq=0.0005, n_rate=0.0, genome=None,
+                var_len=False):
+    """Returns (bases u8[n*L], quals u8[...], off u64[n+1]).  Phred+33: 'I' everywhere, '+' at substitution errors,
+    '#' (Q2 < minQuality) at a `lowq` fraction of bases, 'N' at an `n_rate` fraction."""
+    rng = np.random.default_rng(seed + 77)
+    g = genome if genome is not None else genome_codes(genome_len, seed)
+    G = len(g)
+    lens = np.full(n_reads, read_len, dtype=np.int64)
+    if var_len:
+        lens = rng.integers(max(1, read_len // 4), read_len + 1, n_reads)
+    off = np.zeros(n_reads + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    total = int(off[-1])
+    starts = rng.integers(0, G - read_len, n_reads)
+    strand = rng.integers(0, 2, n_reads)
+    codes = np.empty(total, dtype=np.uint8)
+    for i in range(n_reads):
+        L = int(lens[i])
+        seg = g[starts[i]: starts[i] + L]
+        if strand[i]:
+            seg = (3 - seg)[::-1]
+        codes[int(off[i]): int(off[i]) + L] = seg
+    quals = np.full(total, ord("I"), dtype=np.uint8)
+    e = rng.random(total) < err
+    codes[e] = (codes[e] + rng.integers(1, 4, int(e.sum()), dtype=np.uint8)) & 3
+    quals[e] = ord("+")
+    lq = rng.random(total) < lowq
+    quals[lq] = ord("#")
+    bases = ACGT[codes]
+    if n_rate > 0:
+        nn = rng.random(total) < n_rate
+        bases = bases.copy()
+        bases[nn] = ord("N")
+    return np.ascontiguousarray(bases), quals, off
+
+
+def reads_torch(n_reads, read_len=150, genome_len=250_000_000, seed=0x4B6D6572, err=0.001, lowq=0.0005, device="cuda",
+                chunk=4_000_000):
+    """Config C2/C3-shaped reads generated in HBM.  Returns (bases u8[n*L], quals u8[n*L], off int64[n+1]) on `device`."""
+    import torch
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    g = torch.randint(0, 4, (genome_len,), dtype=torch.uint8, device=device, generator=gen)
+    bases = torch.empty(n_reads * read_len, dtype=torch.uint8, device=device)
+    quals = torch.empty(n_reads * read_len, dtype=torch.uint8, device=device)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    ar = torch.arange(read_len, device=device, dtype=torch.int64)
+    for c0 in range(0, n_reads, chunk):
+        n = min(chunk, n_reads - c0)
+        starts = torch.randint(0, genome_len - read_len, (n,), device=device, generator=gen, dtype=torch.int64)
+        strand = torch.randint(0, 2, (n, 1), device=device, generator=gen, dtype=torch.int64).bool()
+        idx_f = starts[:, None] + ar[None, :]
+        idx_r = starts[:, None] + (read_len - 1 - ar)[None, :]
+        codes = torch.where(strand, 3 - g[idx_r], g[idx_f])
+        del idx_f, idx_r
+        r = torch.rand((n, read_len), device=device, generator=gen)
+        e = r < err
+        shift = torch.randint(1, 4, (n, read_len), device=device, generator=gen, dtype=torch.uint8)
+        codes = torch.where(e, (codes + shift) & 3, codes)
+        q = torch.full((n, read_len), ord("I"), dtype=torch.uint8, device=device)
+        q[e] = ord("+")
+        q[(r >= err) & (r < err + lowq)] = ord("#")
+        bases[c0 * read_len: (c0 + n) * read_len] = lut[codes.long()].reshape(-1)
+        quals[c0 * read_len: (c0 + n) * read_len] = q.reshape(-1)
+        del codes, r, e, shift, q
+    off = torch.arange(n_reads + 1, device=device, dtype=torch.int64) * read_len
+    del g
+    return bases, quals, off

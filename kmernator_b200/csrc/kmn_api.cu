@@ -1,0 +1,803 @@
+// kmn_api.cu -- host side of the C ABI declared in include/kmernator_b200.h.
+// Owns the device memory plan (count table, partitioned staging, input staging), launches the kernels of
+// kmn_kernels.cuh on one stream, and runs the NCCL exchange of the owner-sharded build.
+#include "../../include/kmernator_b200.h"
+#include "kmn_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#ifdef KMN_WITH_NCCL
+#include <nccl.h>
+#endif
+
+using namespace kmn;
+
+static thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct kmn_ctx {
+    kmn_opts o;
+    int W = 1, kb = 0, pad = 0;
+    bool hasx = false, ext = false, weights = false;
+    int RW = 1;
+    int device = 0, n_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_in_free[2] = {nullptr, nullptr};
+    std::string err;
+    uint64_t launches = 0;
+
+    // table
+    TableView table{};
+    uint64_t n_slots = 0;
+    size_t slot_bytes = 0;
+    // staging
+    StageView stage{};
+    uint64_t stage_keys = 0;          // total record capacity targeted before a drain
+    uint64_t staged_upper = 0;        // upper bound of records currently staged
+    u64 *chunk_start = nullptr, *next_item = nullptr;
+    Counters *ctr = nullptr;
+    double *ptab = nullptr;
+    u64 *scratch = nullptr;           // small device scalars
+    // phase-1 launch geometry
+    int parse_tpb = 512;
+    uint32_t bin_cap = 0, flush_thresh = 0;
+    size_t parse_smem = 0;
+    // input staging (host inputs)
+    DevBuf in_bases, in_quals, in_off, in_disc;
+    // lookup pass scratch
+    DevBuf vals, first_nx, out_off, out_len, out_score, out_trim, lk_keys, lk_out;
+    uint32_t purged_depth = 0;
+    bool finished = false;
+    // multi-GPU
+    int rank = 0, nranks = 1;
+    u64 *send_recs = nullptr, *send_cursor = nullptr, *recv_recs = nullptr, *all_counts = nullptr;
+    uint64_t send_cap = 0, recv_cap = 0;
+#ifdef KMN_WITH_NCCL
+    ncclComm_t comm = nullptr;
+#endif
+};
+
+static int fail(kmn_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(ctx, call)                                                                                        \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? KMN_ERR_NOMEM : KMN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                         \
+    } while (0)
+
+static int ensure(kmn_ctx *c, DevBuf &b, size_t bytes)
+{
+    if (b.cap >= bytes && b.p) return 0;
+    if (b.p) { CK(c, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    CK(c, cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+
+static bool is_device_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// dispatch on (W, HASX, EXT, DIST)
+#define KMN_DISPATCH_W(c, ...)                                         \
+    switch ((c)->W) {                                                  \
+    case 1: { constexpr int W_ = 1; __VA_ARGS__; } break;              \
+    case 2: { constexpr int W_ = 2; __VA_ARGS__; } break;              \
+    case 3: { constexpr int W_ = 3; __VA_ARGS__; } break;              \
+    case 4: { constexpr int W_ = 4; __VA_ARGS__; } break;              \
+    default: return fail(c, KMN_ERR_INVALID, "unsupported key width"); \
+    }
+#define KMN_DISPATCH_X(c, ...)                                   \
+    if ((c)->hasx) { constexpr bool X_ = true; __VA_ARGS__; }    \
+    else { constexpr bool X_ = false; __VA_ARGS__; }
+
+const char *kmn_version(void) { return "kmernator_b200 0.1 (sm_100a)"; }
+
+void kmn_default_opts(kmn_opts *o)
+{
+    memset(o, 0, sizeof *o);
+    o->struct_size = sizeof *o;
+    o->kmer_size = 31;
+    o->fastq_start_char = 33;
+    o->min_quality_score = 3;       // src/Options.h:329
+    o->min_kmer_quality = 0.10f;    // src/KmerSpectrum.h:92
+    o->min_depth = 2;               // src/KmerSpectrum.h:92
+    o->hash_kind = KMN_HASH_LOOKUP3_HASHLITTLE2;
+    o->value_kind = KMN_VALUE_DIR;
+    o->slice_bytes = 32u << 20;
+}
+
+const char *kmn_last_error(const kmn_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+void *kmn_stream(kmn_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t kmn_launch_count(const kmn_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int plan_and_alloc(kmn_ctx *c)
+{
+    const kmn_opts &o = c->o;
+    c->W = (int)((o.kmer_size + 31) / 32);
+    c->kb = (int)((o.kmer_size + 3) / 4);
+    c->pad = 64 * c->W - 2 * (int)o.kmer_size;
+    c->ext = (o.value_kind & KMN_VALUE_DIR_EXT) != 0;
+    c->weights = (o.value_kind & KMN_VALUE_WEIGHTS) != 0;
+    c->hasx = c->ext || c->weights || (o.kmer_size % 32 == 0);
+    c->RW = c->W + (c->hasx ? 1 : 0);
+    c->slot_bytes = 8 * (size_t)(c->W + 1);
+
+    size_t free_b = 0, total_b = 0;
+    CK(c, cudaMemGetInfo(&free_b, &total_b));
+
+    // table capacity: explicit, or the reference's own sizing guess (weak = est/estimatedDepth(20), singleton =
+    // est*estimatedErrorRate(0.35), src/KmerSpectrum.h:414-421) at load factor 0.5, bounded by 40% of free memory
+    uint64_t slots = o.table_slots;
+    const size_t per_slot = c->slot_bytes + (c->weights ? 4 : 0) + (c->ext ? 48 : 0);
+    if (!slots) {
+        double est = (double)(o.est_raw_kmers ? o.est_raw_kmers : (1ull << 20));
+        double distinct = est / 20.0 + est * 0.35;
+        slots = (uint64_t)(distinct / 0.5) + 1024;
+        uint64_t lim = (uint64_t)(0.40 * (double)free_b / (double)per_slot);
+        if (slots > lim) slots = lim;
+    }
+    if (slots < 1024) slots = 1024;
+
+    // partitions: slice_bytes each so that one slice stays L2-resident during phase 2; the number of partitions
+    // is bounded by the shared memory the phase-1 bins need (>= 16 records per bin)
+    int dev_smem = 0;
+    CK(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    const size_t smem_avail = (size_t)dev_smem - 256 * sizeof(double) - 1024;
+    const uint32_t slice = o.slice_bytes ? o.slice_bytes : (32u << 20);
+    uint64_t part_slots = std::max<uint64_t>(slice / c->slot_bytes, 256);
+    uint64_t n_parts = (slots + part_slots - 1) / part_slots;
+    const uint64_t p_max = smem_avail / (16 * (size_t)c->RW * 8 + 4);
+    if (n_parts > p_max) n_parts = p_max;
+    if (n_parts < 1) n_parts = 1;
+    part_slots = (slots + n_parts - 1) / n_parts;
+    if (part_slots >= (1ull << 32)) return fail(c, KMN_ERR_INVALID, "partition too large (%llu slots)", (unsigned long long)part_slots);
+    slots = part_slots * n_parts;
+    c->n_slots = slots;
+    c->table.part_slots = part_slots;
+    c->table.n_parts = (u32)n_parts;
+
+    c->parse_tpb = c->RW == 1 ? 512 : (c->RW == 2 ? 256 : 128);
+    uint64_t cap = (smem_avail - 4 * n_parts) / (n_parts * (size_t)c->RW * 8);
+    if (cap > 8192) cap = 8192;
+    c->bin_cap = (uint32_t)cap;
+    c->flush_thresh = std::max<uint32_t>(1, c->bin_cap / 2);
+    c->parse_smem = 256 * sizeof(double) + (size_t)n_parts * c->bin_cap * c->RW * 8 + 4 * n_parts;
+
+    CK(c, cudaMalloc(&c->table.slots, slots * c->slot_bytes));
+    if (c->weights) CK(c, cudaMalloc((void **)&c->table.wsum, slots * 4));
+    if (c->ext) CK(c, cudaMalloc((void **)&c->table.ext, slots * 48));
+
+    // staging capacity
+    CK(c, cudaMemGetInfo(&free_b, &total_b));
+    uint64_t sk = o.stage_keys;
+    if (!sk) {
+        sk = o.est_raw_kmers ? o.est_raw_kmers : (1ull << 22);
+        uint64_t lim = (uint64_t)(0.35 * (double)free_b / (double)(c->RW * 8));
+        if (sk > lim) sk = lim;
+    }
+    if (sk < (1ull << 16)) sk = 1ull << 16;
+    c->stage_keys = sk;
+    c->stage.part_cap = sk / n_parts + sk / n_parts / 8 + 4096;
+    CK(c, cudaMalloc((void **)&c->stage.recs, (size_t)n_parts * c->stage.part_cap * c->RW * 8));
+    CK(c, cudaMalloc((void **)&c->stage.cursor, n_parts * 8));
+    CK(c, cudaMalloc((void **)&c->chunk_start, (n_parts + 1) * 8));
+    CK(c, cudaMalloc((void **)&c->next_item, 8));
+    CK(c, cudaMalloc((void **)&c->ctr, sizeof(Counters)));
+    CK(c, cudaMalloc((void **)&c->scratch, 64));
+    CK(c, cudaMalloc((void **)&c->ptab, 256 * sizeof(double)));
+
+    // Read::qualityToProbability, computed on the host with the same libm the reference uses (src/Sequence.cpp:522-540)
+    double p[256];
+    for (int i = 0; i < 256; i++) p[i] = 0.0;
+    const int start = (int)o.fastq_start_char;
+    for (int i = start + (int)o.min_quality_score; i < 103 && i < 256; i++) p[i] = 1.0 - pow(10.0, (start - i) / 10.0);
+    for (int i = 103; i < 256; i++) p[i] = 1.0;
+    if (o.ignore_quality) for (int i = 0; i < 256; i++) p[i] = 1.0;
+    CK(c, cudaMemcpy(c->ptab, p, sizeof p, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int kmn_reset(kmn_ctx *c)
+{
+    if (!c) return KMN_ERR_INVALID;
+    CK(c, cudaMemsetAsync(c->table.slots, 0, c->n_slots * c->slot_bytes, c->stream));
+    if (c->table.wsum) CK(c, cudaMemsetAsync(c->table.wsum, 0, c->n_slots * 4, c->stream));
+    if (c->table.ext) CK(c, cudaMemsetAsync(c->table.ext, 0, c->n_slots * 48, c->stream));
+    CK(c, cudaMemsetAsync(c->stage.cursor, 0, (size_t)c->table.n_parts * 8, c->stream));
+    CK(c, cudaMemsetAsync(c->ctr, 0, sizeof(Counters), c->stream));
+    if (c->send_cursor) CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)c->nranks * 8, c->stream));
+    c->staged_upper = 0;
+    c->purged_depth = 0;
+    c->finished = false;
+    return 0;
+}
+
+template <int W, bool X>
+static int set_smem_attrs(kmn_ctx *c)
+{
+    size_t s = c->parse_smem;
+    CK(c, cudaFuncSetAttribute(k_count_parse<W, X, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s));
+    CK(c, cudaFuncSetAttribute(k_count_parse<W, X, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s));
+    if (X) {
+        CK(c, cudaFuncSetAttribute(k_count_parse<W, X, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s));
+        CK(c, cudaFuncSetAttribute(k_count_parse<W, X, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s));
+    }
+    CK(c, cudaFuncSetAttribute(k_route_records<W, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s));
+    return 0;
+}
+
+int kmn_create(kmn_ctx **out, const kmn_opts *opts)
+{
+    if (!out || !opts) return fail(nullptr, KMN_ERR_INVALID, "null argument");
+    if (opts->struct_size != sizeof(kmn_opts)) return fail(nullptr, KMN_ERR_INVALID, "kmn_opts size mismatch (%u vs %zu)", opts->struct_size, sizeof(kmn_opts));
+    if (opts->kmer_size < 1 || opts->kmer_size > 128) return fail(nullptr, KMN_ERR_INVALID, "kmer_size %u out of range 1..128", opts->kmer_size);
+    if (opts->fastq_start_char != 33 && opts->fastq_start_char != 64) return fail(nullptr, KMN_ERR_INVALID, "fastq_start_char must be 33 or 64");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(nullptr, KMN_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e)); }
+    if ((int)opts->device >= ndev) return fail(nullptr, KMN_ERR_INVALID, "device %u not present (%d devices)", opts->device, ndev);
+    kmn_ctx *c = new kmn_ctx();
+    c->o = *opts;
+    c->device = (int)opts->device;
+    int rc = 0;
+    do {
+        if (cudaSetDevice(c->device) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "cudaSetDevice failed"); break; }
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "cudaGetDeviceProperties failed"); break; }
+        c->n_sms = prop.multiProcessorCount;
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "stream create failed"); break; }
+        rc = plan_and_alloc(c);
+        if (rc) break;
+        {
+            kmn_ctx *cc = c;
+            auto body = [&]() -> int { KMN_DISPATCH_W(cc, KMN_DISPATCH_X(cc, { int r_ = set_smem_attrs<W_, X_>(cc); if (r_) return r_; })); return 0; };
+            rc = body();
+            if (rc) break;
+        }
+        rc = kmn_reset(c);
+        if (rc) break;
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = fail(c, KMN_ERR_CUDA, "sync failed"); break; }
+    } while (0);
+    if (rc) {
+        if (!c->err.empty()) g_create_error = c->err;
+        kmn_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+void kmn_destroy(kmn_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+#ifdef KMN_WITH_NCCL
+    if (c->comm) ncclCommDestroy(c->comm);
+#endif
+    void *ptrs[] = {c->table.slots, c->table.wsum, c->table.ext, c->stage.recs, c->stage.cursor, c->chunk_start, c->next_item,
+                    c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts,
+                    c->in_bases.p, c->in_quals.p, c->in_off.p, c->in_disc.p, c->vals.p, c->first_nx.p, c->out_off.p,
+                    c->out_len.p, c->out_score.p, c->out_trim.p, c->lk_keys.p, c->lk_out.p};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// phase 2: drain the staging regions into the table
+// ---------------------------------------------------------------------------------------------------------
+static int drain(kmn_ctx *c)
+{
+    if (c->staged_upper == 0) return 0;
+    k_build_worklist<<<1, 1024, 0, c->stream>>>(c->stage.cursor, c->stage.part_cap, c->table.n_parts, c->chunk_start, c->next_item);
+    c->launches++;
+    const int grid = c->n_sms * 8;
+    KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
+        k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, c->stream>>>(c->table, c->stage, c->chunk_start, c->next_item, c->ctr);
+    }));
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemsetAsync(c->stage.cursor, 0, (size_t)c->table.n_parts * 8, c->stream));
+    c->staged_upper = 0;
+    return 0;
+}
+
+static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, const uint8_t *quals, const u64 *off,
+                            const uint8_t *disc, uint64_t n_reads, uint64_t total_bytes)
+{
+    memset(&a, 0, sizeof a);
+    a.bases = bases; a.quals = quals; a.read_off = off; a.discarded = disc;
+    a.n_reads = n_reads; a.total_bytes = total_bytes; a.ptab = c->ptab;
+    a.k = c->o.kmer_size; a.kb = (u32)c->kb; a.pad = c->pad;
+    a.min_weight = c->o.min_kmer_quality; a.start_char = c->o.fastq_start_char;
+    a.bin_cap = c->bin_cap; a.flush_thresh = c->flush_thresh;
+    a.nranks = (u32)c->nranks; a.rank = (u32)c->rank;
+    a.use_lookup8 = c->o.hash_kind == KMN_HASH_LOOKUP8_HASH2;
+    a.table = c->table; a.stage = c->stage; a.ctr = c->ctr;
+    a.send_recs = c->send_recs; a.send_cursor = c->send_cursor; a.send_cap = c->send_cap;
+}
+
+static int launch_parse(kmn_ctx *c, const ParseArgs &a)
+{
+    const int grid = c->n_sms;
+    const bool dist = c->nranks > 1;
+    KMN_DISPATCH_W(c, {
+        if (!c->hasx) {
+            if (dist) k_count_parse<W_, false, false, true><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
+            else k_count_parse<W_, false, false, false><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
+        } else if (c->ext) {
+            if (dist) k_count_parse<W_, true, true, true><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
+            else k_count_parse<W_, true, true, false><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
+        } else {
+            if (dist) k_count_parse<W_, true, false, true><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
+            else k_count_parse<W_, true, false, false><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
+        }
+    });
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// multi-GPU exchange: the k-mer shuffle of _buildKmerSpectrumMPI (src/DistributedFunctions.h:340-458) /
+// MPIAllToAllMessageBuffer::sendReceive (src/MPIBuffer.h:588-600,872-892) as an NCCL all-to-all of 8*RW-byte
+// records, preceded by an all-gather of the per-destination counts.
+// ---------------------------------------------------------------------------------------------------------
+static int exchange(kmn_ctx *c)
+{
+#ifdef KMN_WITH_NCCL
+    if (c->nranks <= 1) return 0;
+    const int R = c->nranks;
+    ncclResult_t nr = ncclAllGather(c->send_cursor, c->all_counts, (size_t)R, ncclUint64, c->comm, c->stream);
+    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclAllGather failed: %s", ncclGetErrorString(nr));
+    std::vector<u64> counts((size_t)R * R);
+    CK(c, cudaMemcpyAsync(counts.data(), c->all_counts, counts.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    // counts[src*R + dst]
+    u64 recv_total = 0;
+    for (int s = 0; s < R; ++s) {
+        if (counts[(size_t)s * R + (s == c->rank ? 0 : 0)] > 0) {}
+        if (s != c->rank) recv_total += counts[(size_t)s * R + c->rank];
+        for (int d = 0; d < R; ++d)
+            if (s == c->rank && counts[(size_t)s * R + d] > c->send_cap)
+                return fail(c, KMN_ERR_COMM, "send region overflow: %llu records for rank %d (capacity %llu); use smaller batches",
+                            (unsigned long long)counts[(size_t)s * R + d], d, (unsigned long long)c->send_cap);
+    }
+    if (recv_total > c->recv_cap) return fail(c, KMN_ERR_COMM, "receive region overflow: %llu > %llu", (unsigned long long)recv_total, (unsigned long long)c->recv_cap);
+    ncclGroupStart();
+    u64 roff = 0;
+    for (int p = 0; p < R; ++p) {
+        if (p == c->rank) continue;
+        u64 ns = counts[(size_t)c->rank * R + p], nrv = counts[(size_t)p * R + c->rank];
+        if (ns) ncclSend(c->send_recs + (size_t)p * c->send_cap * c->RW, ns * c->RW, ncclUint64, p, c->comm, c->stream);
+        if (nrv) ncclRecv(c->recv_recs + roff * c->RW, nrv * c->RW, ncclUint64, p, c->comm, c->stream);
+        roff += nrv;
+    }
+    nr = ncclGroupEnd();
+    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "nccl all-to-all failed: %s", ncclGetErrorString(nr));
+    CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)R * 8, c->stream));
+    if (recv_total) {
+        if (c->staged_upper + recv_total > c->stage_keys) { int r = drain(c); if (r) return r; }
+        RouteArgs ra;
+        ra.recs = c->recv_recs; ra.n_recs = recv_total; ra.bin_cap = c->bin_cap; ra.flush_thresh = c->flush_thresh;
+        ra.table = c->table; ra.stage = c->stage; ra.ctr = c->ctr;
+        KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
+            k_route_records<W_, X_><<<c->n_sms, c->parse_tpb, c->parse_smem, c->stream>>>(ra);
+        }));
+        c->launches++;
+        CK(c, cudaGetLastError());
+        c->staged_upper += recv_total;
+    }
+    return 0;
+#else
+    (void)c;
+    return 0;
+#endif
+}
+
+int kmn_comm_unique_id(void *id128)
+{
+#ifdef KMN_WITH_NCCL
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    if (ncclGetUniqueId(&id) != ncclSuccess) return KMN_ERR_COMM;
+    memcpy(id128, &id, 128);
+    return 0;
+#else
+    (void)id128;
+    return KMN_ERR_COMM;
+#endif
+}
+
+int kmn_comm_init(kmn_ctx *c, int rank, int nranks, const void *id128)
+{
+    if (!c) return KMN_ERR_INVALID;
+#ifdef KMN_WITH_NCCL
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, KMN_ERR_INVALID, "bad rank %d / %d", rank, nranks);
+    if (c->staged_upper) return fail(c, KMN_ERR_STATE, "kmn_comm_init after counting started");
+    c->rank = rank; c->nranks = nranks;
+    if (nranks == 1) return 0;
+    CK(c, cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclResult_t nr = ncclCommInitRank(&c->comm, nranks, id, rank);
+    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclCommInitRank failed: %s", ncclGetErrorString(nr));
+    // send/recv regions: a batch is bounded by stage_keys/2 records, 1/nranks of which go to each peer on average
+    c->send_cap = c->stage_keys / 2 / (uint64_t)nranks * 3 / 2 + 65536;
+    c->recv_cap = c->send_cap * (uint64_t)(nranks - 1);
+    CK(c, cudaMalloc((void **)&c->send_recs, (size_t)nranks * c->send_cap * c->RW * 8));
+    CK(c, cudaMalloc((void **)&c->recv_recs, (size_t)c->recv_cap * c->RW * 8));
+    CK(c, cudaMalloc((void **)&c->send_cursor, (size_t)nranks * 8));
+    CK(c, cudaMalloc((void **)&c->all_counts, (size_t)nranks * nranks * 8));
+    CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)nranks * 8, c->stream));
+    return 0;
+#else
+    (void)rank; (void)nranks; (void)id128;
+    return fail(c, KMN_ERR_COMM, "library built without NCCL");
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// count pass
+// ---------------------------------------------------------------------------------------------------------
+struct BatchPtrs {
+    const uint8_t *bases, *quals, *disc;
+    const u64 *off;
+    uint64_t total_bytes;
+    std::vector<u64> host_off;     // filled only when splitting is needed or offsets were on the host
+    bool off_on_host;
+};
+
+static int stage_inputs(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, const uint64_t *read_off, uint64_t n_reads,
+                        const uint8_t *discarded, bool need_quals, BatchPtrs &bp)
+{
+    bp.off_on_host = !is_device_ptr(read_off);
+    u64 first = 0, last = 0;
+    if (bp.off_on_host) { first = read_off[0]; last = read_off[n_reads]; }
+    else {
+        CK(c, cudaMemcpyAsync(&first, read_off, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemcpyAsync(&last, read_off + n_reads, 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+    }
+    if (first != 0) return fail(c, KMN_ERR_INVALID, "read_off[0] must be 0");
+    bp.total_bytes = last;
+    if (bp.off_on_host) {
+        int r = ensure(c, c->in_off, (n_reads + 1) * 8); if (r) return r;
+        CK(c, cudaMemcpyAsync(c->in_off.p, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        bp.off = (const u64 *)c->in_off.p;
+    } else bp.off = reinterpret_cast<const u64 *>(read_off);
+    if (!is_device_ptr(bases)) {
+        int r = ensure(c, c->in_bases, last + 16); if (r) return r;
+        CK(c, cudaMemcpyAsync(c->in_bases.p, bases, last, cudaMemcpyHostToDevice, c->stream));
+        bp.bases = (const uint8_t *)c->in_bases.p;
+    } else bp.bases = bases;
+    bp.quals = nullptr;
+    if (need_quals) {
+        if (!quals) return fail(c, KMN_ERR_INVALID, "quals is required");
+        if (!is_device_ptr(quals)) {
+            int r = ensure(c, c->in_quals, last + 16); if (r) return r;
+            CK(c, cudaMemcpyAsync(c->in_quals.p, quals, last, cudaMemcpyHostToDevice, c->stream));
+            bp.quals = (const uint8_t *)c->in_quals.p;
+        } else bp.quals = quals;
+    }
+    bp.disc = nullptr;
+    if (discarded) {
+        if (!is_device_ptr(discarded)) {
+            int r = ensure(c, c->in_disc, n_reads + 16); if (r) return r;
+            CK(c, cudaMemcpyAsync(c->in_disc.p, discarded, n_reads, cudaMemcpyHostToDevice, c->stream));
+            bp.disc = (const uint8_t *)c->in_disc.p;
+        } else bp.disc = discarded;
+    }
+    return 0;
+}
+
+int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, const uint64_t *read_off, uint64_t n_reads,
+                    const uint8_t *discarded)
+{
+    if (!c) return KMN_ERR_INVALID;
+    if (n_reads && (!bases || !read_off)) return fail(c, KMN_ERR_INVALID, "null input");
+    CK(c, cudaSetDevice(c->device));
+    c->finished = false;
+    if (n_reads == 0) return c->nranks > 1 ? exchange(c) : 0;
+    BatchPtrs bp;
+    int r = stage_inputs(c, bases, quals, read_off, n_reads, discarded, true, bp);
+    if (r) return r;
+    // sub-batches are bounded so that staging (and, multi-GPU, the send regions) cannot overflow
+    const uint64_t limit = std::max<uint64_t>(c->stage_keys / 2, 1);
+    if (bp.total_bytes <= limit) {
+        if (c->staged_upper + bp.total_bytes > c->stage_keys) { r = drain(c); if (r) return r; }
+        ParseArgs a;
+        fill_parse_args(c, a, bp.bases, bp.quals, bp.off, bp.disc, n_reads, bp.total_bytes);
+        r = launch_parse(c, a); if (r) return r;
+        c->staged_upper += bp.total_bytes;
+        return exchange(c);
+    }
+    // split by reads; needs the offsets on the host
+    std::vector<u64> hoff;
+    const u64 *ho = nullptr;
+    if (bp.off_on_host) ho = reinterpret_cast<const u64 *>(read_off);
+    else {
+        hoff.resize(n_reads + 1);
+        CK(c, cudaMemcpyAsync(hoff.data(), read_off, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        ho = hoff.data();
+    }
+    uint64_t r0 = 0;
+    while (r0 < n_reads) {
+        uint64_t lo = r0 + 1, hi = n_reads;          // largest r1 with ho[r1]-ho[r0] <= limit (at least one read)
+        while (lo < hi) { uint64_t mid = (lo + hi + 1) / 2; if (ho[mid] - ho[r0] <= limit) lo = mid; else hi = mid - 1; }
+        uint64_t r1 = lo;
+        uint64_t nb = ho[r1] - ho[r0];
+        if (c->staged_upper + nb > c->stage_keys) { r = drain(c); if (r) return r; }
+        ParseArgs a;
+        fill_parse_args(c, a, bp.bases, bp.quals, bp.off + r0, bp.disc ? bp.disc + r0 : nullptr, r1 - r0, bp.total_bytes);
+        r = launch_parse(c, a); if (r) return r;
+        c->staged_upper += nb;
+        r = exchange(c); if (r) return r;
+        r0 = r1;
+    }
+    return 0;
+}
+
+static int launch_purge(kmn_ctx *c, uint32_t min_depth)
+{
+    CK(c, cudaMemsetAsync(c->scratch, 0, 8, c->stream));
+    KMN_DISPATCH_W(c, { k_purge<W_><<<c->n_sms * 8, 256, 0, c->stream>>>(c->table, c->n_slots, min_depth, c->scratch); });
+    c->launches++;
+    CK(c, cudaGetLastError());
+    if (min_depth > c->purged_depth) c->purged_depth = min_depth;
+    return 0;
+}
+
+int kmn_count_finish(kmn_ctx *c, int apply_purge)
+{
+    if (!c) return KMN_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    int r = drain(c);
+    if (r) return r;
+    Counters h;
+    CK(c, cudaMemcpyAsync(&h, c->ctr, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (h.table_full) return fail(c, KMN_ERR_TABLE_FULL, "count table overflow: %llu k-mer instances could not be inserted (capacity %llu slots); "
+                                  "raise table_slots / est_raw_kmers", (unsigned long long)h.table_full, (unsigned long long)c->n_slots);
+    // post-build purge: singletons dropped when minDepth>=2, count<minDepth dropped when minDepth>2
+    // (src/KmerSpectrum.h:1825,1805-1815; src/DistributedFunctions.h:559-569)
+    if (apply_purge && c->o.min_depth > 1) { r = launch_purge(c, c->o.min_depth); if (r) return r; }
+    c->finished = true;
+    return 0;
+}
+
+int kmn_purge_min_depth(kmn_ctx *c, uint32_t min_depth)
+{
+    if (!c) return KMN_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    int r = drain(c); if (r) return r;
+    if (min_depth > 1) { r = launch_purge(c, min_depth); if (r) return r; }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int kmn_get_stats(kmn_ctx *c, kmn_stats *out)
+{
+    if (!c || !out) return KMN_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    int r = drain(c); if (r) return r;
+    CK(c, cudaMemsetAsync(c->scratch, 0, 16, c->stream));
+    KMN_DISPATCH_W(c, { k_count_live<W_><<<c->n_sms * 8, 256, 0, c->stream>>>(c->table, c->n_slots, 1, c->scratch, c->scratch + 1); });
+    c->launches++;
+    Counters h; u64 ls[2];
+    CK(c, cudaMemcpyAsync(&h, c->ctr, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(ls, c->scratch, 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof *out);
+    out->raw_kmers = h.raw; out->raw_good_kmers = h.raw_good; out->unique_kmers = h.unique; out->singleton_kmers = ls[1];
+    out->discarded_kmers = h.raw - h.raw_good; out->table_slots = c->n_slots; out->table_partitions = c->table.n_parts;
+    out->direct_inserts = h.direct;
+    return 0;
+}
+
+int kmn_histogram(kmn_ctx *c, uint64_t *hist, double *wsum)
+{
+    if (!c || !hist) return KMN_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    int r = drain(c); if (r) return r;
+    DevBuf &hb = c->lk_out;
+    r = ensure(c, hb, 65536 * 16); if (r) return r;
+    u64 *dh = (u64 *)hb.p; double *dw = (double *)(dh + 65536);
+    CK(c, cudaMemsetAsync(dh, 0, 65536 * 16, c->stream));
+    KMN_DISPATCH_W(c, { k_histogram<W_><<<c->n_sms * 4, 256, 0, c->stream>>>(c->table, c->n_slots, dh, wsum ? dw : nullptr); });
+    c->launches++;
+    CK(c, cudaGetLastError());
+#ifdef KMN_WITH_NCCL
+    if (c->nranks > 1) {   // MPIHistogram::reduce (src/DistributedFunctions.h:495-535)
+        ncclGroupStart();
+        ncclAllReduce(dh, dh, 65536, ncclUint64, ncclSum, c->comm, c->stream);
+        ncclAllReduce(dw, dw, 65536, ncclDouble, ncclSum, c->comm, c->stream);
+        if (ncclGroupEnd() != ncclSuccess) return fail(c, KMN_ERR_COMM, "histogram all-reduce failed");
+    }
+#endif
+    CK(c, cudaMemcpyAsync(hist, dh, 65536 * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (wsum) CK(c, cudaMemcpyAsync(wsum, dw, 65536 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int kmn_lookup(kmn_ctx *c, const uint8_t *keys, uint64_t n, uint16_t *counts)
+{
+    if (!c || (n && (!keys || !counts))) return KMN_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    int r = drain(c); if (r) return r;
+    if (n == 0) return 0;
+    if (c->nranks > 1) return fail(c, KMN_ERR_INVALID, "kmn_lookup with a communicator is not implemented yet (keys must be looked up on their owner)");
+    const uint8_t *dk = keys;
+    if (!is_device_ptr(keys)) {
+        r = ensure(c, c->lk_keys, n * c->kb); if (r) return r;
+        CK(c, cudaMemcpyAsync(c->lk_keys.p, keys, n * c->kb, cudaMemcpyHostToDevice, c->stream));
+        dk = (const uint8_t *)c->lk_keys.p;
+    }
+    uint16_t *dout = counts;
+    bool out_host = !is_device_ptr(counts);
+    if (out_host) { r = ensure(c, c->lk_out, n * 2); if (r) return r; dout = (uint16_t *)c->lk_out.p; }
+    KMN_DISPATCH_W(c, { k_lookup_keys<W_><<<c->n_sms * 8, 256, 0, c->stream>>>(c->table, dk, n, (u32)c->kb, dout); });
+    c->launches++;
+    CK(c, cudaGetLastError());
+    if (out_host) CK(c, cudaMemcpyAsync(counts, dout, n * 2, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int kmn_trim_batch(kmn_ctx *c, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads, const uint8_t *discarded,
+                   uint32_t min_depth, int scoring, uint32_t *trim_off, uint32_t *trim_len, float *score, uint8_t *was_trimmed)
+{
+    if (!c) return KMN_ERR_INVALID;
+    if (n_reads == 0) return 0;
+    if (!bases || !read_off || !trim_off || !trim_len || !score || !was_trimmed) return fail(c, KMN_ERR_INVALID, "null argument");
+    if (scoring < 0 || scoring > 4) return fail(c, KMN_ERR_INVALID, "Invalid scoring type!");
+    if (c->nranks > 1) return fail(c, KMN_ERR_INVALID, "kmn_trim_batch with a communicator is not implemented yet");
+    CK(c, cudaSetDevice(c->device));
+    int r = drain(c); if (r) return r;
+    BatchPtrs bp;
+    r = stage_inputs(c, bases, nullptr, read_off, n_reads, discarded, false, bp);
+    if (r) return r;
+    r = ensure(c, c->vals, bp.total_bytes * 2 + 64); if (r) return r;
+    r = ensure(c, c->first_nx, n_reads * 4); if (r) return r;
+    ParseArgs a;
+    fill_parse_args(c, a, bp.bases, nullptr, bp.off, bp.disc, n_reads, bp.total_bytes);
+    const int grid = c->n_sms * 8;
+    KMN_DISPATCH_W(c, { k_lookup_vals<W_><<<grid, 256, 0, c->stream>>>(a, min_depth, (uint16_t *)c->vals.p, (u32 *)c->first_nx.p); });
+    c->launches++;
+    CK(c, cudaGetLastError());
+    TrimArgs t;
+    t.read_off = bp.off; t.discarded = bp.disc; t.vals = (const uint16_t *)c->vals.p; t.first_nx = (const u32 *)c->first_nx.p;
+    t.n_reads = n_reads; t.k = c->o.kmer_size; t.min_depth = min_depth; t.scoring = scoring;
+    const bool host_out = !is_device_ptr(trim_off);
+    if (host_out) {
+        r = ensure(c, c->out_off, n_reads * 4); if (r) return r;
+        r = ensure(c, c->out_len, n_reads * 4); if (r) return r;
+        r = ensure(c, c->out_score, n_reads * 4); if (r) return r;
+        r = ensure(c, c->out_trim, n_reads); if (r) return r;
+        t.trim_off = (u32 *)c->out_off.p; t.trim_len = (u32 *)c->out_len.p; t.score = (float *)c->out_score.p; t.was_trimmed = (uint8_t *)c->out_trim.p;
+    } else { t.trim_off = trim_off; t.trim_len = trim_len; t.score = score; t.was_trimmed = was_trimmed; }
+    k_trim_score<<<c->n_sms * 8, 256, 0, c->stream>>>(t);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    if (host_out) {
+        CK(c, cudaMemcpyAsync(trim_off, t.trim_off, n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemcpyAsync(trim_len, t.trim_len, n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemcpyAsync(score, t.score, n_reads * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaMemcpyAsync(was_trimmed, t.was_trimmed, n_reads, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int kmn_export(kmn_ctx *c, uint32_t min_count, uint8_t *keys, uint16_t *count, uint16_t *dir, float *wsum, uint32_t *ext,
+               uint64_t cap, uint64_t *n_out)
+{
+    if (!c || !n_out) return KMN_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    int r = drain(c); if (r) return r;
+    if (min_count < 1) min_count = 1;
+    CK(c, cudaMemsetAsync(c->scratch, 0, 16, c->stream));
+    KMN_DISPATCH_W(c, { k_count_live<W_><<<c->n_sms * 8, 256, 0, c->stream>>>(c->table, c->n_slots, min_count, c->scratch, c->scratch + 1); });
+    c->launches++;
+    u64 n_live = 0;
+    CK(c, cudaMemcpyAsync(&n_live, c->scratch, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    *n_out = n_live;
+    if (cap == 0 || n_live == 0) return 0;
+    if (cap < n_live) return fail(c, KMN_ERR_INVALID, "export capacity %llu < %llu entries", (unsigned long long)cap, (unsigned long long)n_live);
+    uint8_t *dk = nullptr; uint16_t *dc = nullptr, *dd = nullptr; float *dw = nullptr; u32 *de = nullptr;
+    if (keys) CK(c, cudaMalloc((void **)&dk, n_live * c->kb));
+    if (count) CK(c, cudaMalloc((void **)&dc, n_live * 2));
+    if (dir) CK(c, cudaMalloc((void **)&dd, n_live * 2));
+    if (wsum) CK(c, cudaMalloc((void **)&dw, n_live * 4));
+    if (ext) CK(c, cudaMalloc((void **)&de, n_live * 48));
+    CK(c, cudaMemsetAsync(c->scratch, 0, 8, c->stream));
+    KMN_DISPATCH_W(c, { k_export<W_><<<c->n_sms * 8, 256, 0, c->stream>>>(c->table, c->n_slots, min_count, (u32)c->kb, n_live, c->scratch, dk, dc, dd, dw, de); });
+    c->launches++;
+    CK(c, cudaGetLastError());
+    if (keys) CK(c, cudaMemcpyAsync(keys, dk, n_live * c->kb, cudaMemcpyDeviceToHost, c->stream));
+    if (count) CK(c, cudaMemcpyAsync(count, dc, n_live * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (dir) CK(c, cudaMemcpyAsync(dir, dd, n_live * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (wsum) CK(c, cudaMemcpyAsync(wsum, dw, n_live * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (ext) CK(c, cudaMemcpyAsync(ext, de, n_live * 48, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dk); cudaFree(dc); cudaFree(dd); cudaFree(dw); cudaFree(de);
+    return 0;
+}
+
+int kmn_debug_kmers(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, const uint64_t *read_off, uint64_t n_reads,
+                    uint8_t *keys, uint8_t *is_fwd, float *weight, uint64_t *hash, uint64_t *n_out)
+{
+    if (!c || !bases || !quals || !read_off || !n_out) return KMN_ERR_INVALID;
+    if (is_device_ptr(read_off)) return fail(c, KMN_ERR_INVALID, "kmn_debug_kmers needs host offsets");
+    CK(c, cudaSetDevice(c->device));
+    const uint32_t k = c->o.kmer_size;
+    std::vector<u64> koff(n_reads + 1, 0);
+    for (uint64_t r = 0; r < n_reads; ++r) {
+        u64 len = read_off[r + 1] - read_off[r];
+        koff[r + 1] = koff[r] + (len >= k ? len - k + 1 : 0);
+    }
+    const u64 nk = koff[n_reads];
+    *n_out = nk;
+    if (!keys || nk == 0) return 0;
+    BatchPtrs bp;
+    int r = stage_inputs(c, bases, quals, read_off, n_reads, nullptr, true, bp); if (r) return r;
+    u64 *dko; uint8_t *dk, *df; float *dw; u64 *dh;
+    CK(c, cudaMalloc((void **)&dko, (n_reads + 1) * 8));
+    CK(c, cudaMalloc((void **)&dk, nk * c->kb)); CK(c, cudaMalloc((void **)&df, nk));
+    CK(c, cudaMalloc((void **)&dw, nk * 4)); CK(c, cudaMalloc((void **)&dh, nk * 8));
+    CK(c, cudaMemcpyAsync(dko, koff.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    ParseArgs a;
+    fill_parse_args(c, a, bp.bases, bp.quals, bp.off, nullptr, n_reads, bp.total_bytes);
+    KMN_DISPATCH_W(c, { k_debug_kmers<W_><<<c->n_sms * 4, 128, 0, c->stream>>>(a, dko, dk, df, dw, dh); });
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(keys, dk, nk * c->kb, cudaMemcpyDeviceToHost, c->stream));
+    if (is_fwd) CK(c, cudaMemcpyAsync(is_fwd, df, nk, cudaMemcpyDeviceToHost, c->stream));
+    if (weight) CK(c, cudaMemcpyAsync(weight, dw, nk * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (hash) CK(c, cudaMemcpyAsync(hash, dh, nk * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dko); cudaFree(dk); cudaFree(df); cudaFree(dw); cudaFree(dh);
+    return 0;
+}
+
+int kmn_sync(kmn_ctx *c)
+{
+    if (!c) return KMN_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+

@@ -1,0 +1,826 @@
+// kmn_kernels.cuh -- sm_100a kernels of the k-mer spectrum path.
+//
+//   count pass  = k_count_parse  (phase 1: bases -> canonical k-mers -> weight test -> partitioned staging)
+//               + k_insert_staged (phase 2: per-partition inserts into an L2-resident table slice)
+//   lookup pass = k_lookup_vals + k_trim_score
+//   table scans = k_histogram, k_purge, k_export, k_count_singletons
+//
+// Why two phases: on B200 a 64-bit atomic to an HBM-resident table runs at ~20 G/s while the same
+// atomic to a <=64 MB (L2-resident) region runs at 60-190 G/s (profiles/r01_randacc_microbench.csv).
+// Phase 1 therefore scatters every k-mer into one of n_parts staging regions through shared-memory
+// write-combining bins, and phase 2 walks the regions in order so that only one table slice is hot.
+#pragma once
+#include "kmn_device.cuh"
+
+namespace kmn {
+
+static constexpr int PARSE_TPB = 512;      // threads per CTA in phase 1 (1 CTA per SM, bins own the shared memory)
+static constexpr int INSERT_TPB = 256;
+static constexpr int INSERT_UNROLL = 4;
+static constexpr int INSERT_CHUNK = INSERT_TPB * INSERT_UNROLL;
+
+struct ParseArgs {
+    const uint8_t *bases;
+    const uint8_t *quals;
+    const u64 *read_off;
+    const uint8_t *discarded;
+    u64 n_reads;
+    u64 total_bytes;       // bytes valid behind bases / quals
+    const double *ptab;    // 256 doubles: Read::qualityToProbability (host-computed, src/Sequence.cpp:522-540)
+    u32 k, kb;
+    int pad;               // 64*W - 2k
+    float min_weight;
+    u32 start_char;
+    u32 bin_cap;           // records per shared-memory bin
+    u32 flush_thresh;
+    u32 nranks, rank;
+    u32 use_lookup8;
+    TableView table;
+    StageView stage;
+    Counters *ctr;
+    // multi-GPU: records owned by other ranks are appended to per-destination send regions
+    u64 *send_recs;        // [nranks][send_cap][RW]
+    u64 *send_cursor;      // [nranks]
+    u64 send_cap;
+};
+
+// ------------------------------------------------------------------------------------------------
+// unaligned 8-byte fetch from a byte buffer through two aligned, bounds-guarded 8-byte loads
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 ld_nc64(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u64 load8(const uint8_t *buf, long long idx, long long total)
+{
+    // bytes buf[idx .. idx+8), zero where out of [0,total)
+    const unsigned long long base = (unsigned long long)buf;
+    long long a = (long long)(base + idx);
+    long long a0 = a & ~7ll;
+    int sh = (int)(a & 7) * 8;
+    long long lo_lim = (long long)(base & ~7ull);
+    long long hi_lim = (long long)((base + (unsigned long long)total + 7ull) & ~7ull);   // exclusive, aligned
+    u64 w0 = (a0 >= lo_lim && a0 < hi_lim) ? ld_nc64((const u64 *)a0) : 0ull;
+    if (sh == 0) return w0;
+    long long a1 = a0 + 8;
+    u64 w1 = (a1 >= lo_lim && a1 < hi_lim) ? ld_nc64((const u64 *)a1) : 0ull;
+    return (w0 >> sh) | (w1 << (64 - sh));
+}
+
+// ------------------------------------------------------------------------------------------------
+// record = W key words [+ 1 extra word].  Without the extra word the strand flag sits in bit 0 of the
+// last key word (free because k%32 != 0).  Extra word: bit0 strand, bits 8..15 extension byte,
+// bits 32..63 fp32 weight.
+// ------------------------------------------------------------------------------------------------
+template <int W, bool HASX>
+struct Rec {
+    static constexpr int RW = W + (HASX ? 1 : 0);
+    u64 w[RW];
+    __device__ __forceinline__ void pack(const u64 (&key)[W], bool fwd, float weight, u32 extbyte)
+    {
+#pragma unroll
+        for (int i = 0; i < W; ++i) w[i] = key[i];
+        if (HASX) w[W] = (u64)(fwd ? 1u : 0u) | ((u64)(extbyte & 0xffu) << 8) | ((u64)__float_as_uint(weight) << 32);
+        else w[W - 1] |= (fwd ? 1ull : 0ull);
+    }
+    __device__ __forceinline__ void unpack(u64 (&key)[W], bool &fwd, float &weight, u32 &extbyte) const
+    {
+#pragma unroll
+        for (int i = 0; i < W; ++i) key[i] = w[i];
+        if (HASX) { fwd = w[W] & 1ull; extbyte = (u32)(w[W] >> 8) & 0xffu; weight = __uint_as_float((u32)(w[W] >> 32)); }
+        else { fwd = key[W - 1] & 1ull; key[W - 1] &= ~1ull; weight = 0.f; extbyte = 0x3f; }
+    }
+};
+
+// extension byte: bits 0..2 left code, bits 3..5 right code; codes A,C,G,T,N,X = 0..5, 7 = not counted
+// (ExtensionTracking::trackExtension src/KmerTrackingData.h:195-201: counted iff qual>=20 or base is N/X)
+
+template <int W, bool HASX>
+__device__ __forceinline__ void insert_record(const TableView &t, const Rec<W, HASX> &rec, u64 &n_unique, u64 &n_full, u64 &n_probes)
+{
+    u64 key[W]; bool fwd; float weight; u32 eb;
+    rec.unpack(key, fwd, weight, eb);
+    u64 ph = place_hash<W>(key);
+    u32 part = part_of(ph, t.n_parts);
+    u64 slot; u32 probes = 0;
+    int r = table_insert<W>(t, part, home_slot(ph, t.part_slots), key, 1ull | ((u64)(fwd ? 1u : 0u) << 32), &slot, &probes);
+    if (r < 0) { n_full++; return; }
+    n_unique += (u64)r;
+    n_probes += probes;
+    if (HASX) {
+        if (t.wsum) atomicAdd(&t.wsum[slot], weight);
+        if (t.ext) {
+            u32 l = eb & 7u, rr = (eb >> 3) & 7u;
+            if (l < 6) atomicAdd(&t.ext[slot * 12 + l], 1u);
+            if (rr < 6) atomicAdd(&t.ext[slot * 12 + 6 + rr], 1u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory write-combining bins
+// ------------------------------------------------------------------------------------------------
+template <int RW>
+struct Bins {
+    u32 *cnt;      // [n_parts]
+    u64 *recs;     // [n_parts][cap][RW]
+    u32 n_parts, cap;
+};
+
+template <int W, bool HASX>
+__device__ __forceinline__ void bins_flush(const Bins<Rec<W, HASX>::RW> &b, const StageView &st, const TableView &tab, u32 thresh,
+                                           u64 &n_unique, u64 &n_full, u64 &n_direct, u64 &n_probes)
+{
+    constexpr int RW = Rec<W, HASX>::RW;
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (u32 g = warp; g * 32u < b.n_parts; g += nwarps) {
+        u32 bi = g * 32u + lane;
+        u32 c = bi < b.n_parts ? min(b.cnt[bi], b.cap) : 0u;
+        u32 mask = __ballot_sync(0xffffffffu, c >= thresh && c > 0);
+        while (mask) {
+            int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            u32 bb = g * 32u + (u32)src;
+            u32 cc = __shfl_sync(0xffffffffu, c, src);
+            u64 pos = 0;
+            if (lane == 0) pos = atomicAdd(&st.cursor[bb], (u64)cc);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            const u64 *srcw = b.recs + (size_t)bb * b.cap * RW;
+            u64 room = pos < st.part_cap ? st.part_cap - pos : 0;           // records that still fit
+            u32 fit = room < cc ? (u32)room : cc;
+            u64 *dst = st.recs + ((size_t)bb * st.part_cap + pos) * RW;
+            for (u32 i = lane; i < fit * RW; i += 32u) dst[i] = srcw[i];
+            for (u32 i = fit + lane; i < cc; i += 32u) {                    // staging region full: insert directly
+                Rec<W, HASX> rec;
+#pragma unroll
+                for (int q = 0; q < RW; ++q) rec.w[q] = srcw[(size_t)i * RW + q];
+                insert_record<W, HASX>(tab, rec, n_unique, n_full, n_probes);
+                n_direct++;
+            }
+            __syncwarp();
+            if (lane == 0) b.cnt[bb] = 0;
+        }
+    }
+}
+
+template <int W, bool HASX>
+__device__ __forceinline__ void bins_put(const Bins<Rec<W, HASX>::RW> &b, const TableView &tab, u32 part, const Rec<W, HASX> &rec,
+                                         u64 &n_unique, u64 &n_full, u64 &n_direct, u64 &n_probes)
+{
+    constexpr int RW = Rec<W, HASX>::RW;
+    u32 s = atomicAdd(&b.cnt[part], 1u);
+    if (s < b.cap) {
+        u64 *d = b.recs + ((size_t)part * b.cap + s) * RW;
+#pragma unroll
+        for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
+    } else {                                                                // bin overflow inside one step (rare)
+        insert_record<W, HASX>(tab, rec, n_unique, n_full, n_probes);
+        n_direct++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-read walker: rolls the canonical k-mer and the quality weight along one read, 8 bases per step.
+// a2 KmerArrayPair::build (src/Kmer.h:1323-1375), a3 KmerReadUtils::buildWeightedKmers
+// (src/KmerReadUtils.h:176-248): w re-seeded at i%1024==0 or w==0, otherwise w *= p[q_in]/p[q_out];
+// any markup inside the window zeroes w; stored weight is (float)w.
+// ------------------------------------------------------------------------------------------------
+template <int W>
+struct Walker {
+    Roll<W> roll;
+    double w;
+    u64 off;
+    u32 len, j;
+    int last_bad;      // last position holding a markup (non-ACGT), -1 none
+    int last_zero;     // last position whose quality has probability 0, -1 none
+    u32 first_nx;      // firstMarkupNorX: position+1 of the first N/X markup, 0 none
+    u32 prev_code, prev_q;
+
+    __device__ __forceinline__ void begin(u64 off_, u32 len_)
+    {
+        roll.reset(); w = 0.0; off = off_; len = len_; j = 0; last_bad = -1; last_zero = -1; first_nx = 0;
+        prev_code = 5; prev_q = 20;
+    }
+};
+
+// One step = up to 8 bases.  EMIT(i, key, fwd, weightf, good, extbyte) is called for every k-mer position i.
+template <int W, bool NEED_W, bool EXT, typename EMIT>
+__device__ __forceinline__ void walker_step(Walker<W> &s, const ParseArgs &a, const double *ptab, EMIT &&emit)
+{
+    const u32 k = a.k;
+    const long long total = (long long)a.total_bytes;
+    const u32 j0 = s.j;
+    u64 bw = load8(a.bases, (long long)s.off + j0, total);
+    u64 qin = 0, qout = 0, bnext = 0, qnext = 0;
+    if (NEED_W || EXT) {
+        qin = load8(a.quals, (long long)s.off + j0, total);
+        qout = load8(a.quals, (long long)s.off + (long long)j0 - (long long)k, total);
+    }
+    if (EXT) {
+        bnext = load8(a.bases, (long long)s.off + j0 + 8, total);
+        qnext = load8(a.quals, (long long)s.off + j0 + 8, total);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const u32 j = j0 + u;
+        if (j < s.len) {
+            u32 c = (u32)(bw >> (8 * u)) & 0xffu;
+            u32 code = base_code(c);
+            if (code >= 4) {
+                s.last_bad = (int)j;
+                if (code == 4 && s.first_nx == 0) s.first_nx = j + 1;
+                code = 0;                                      // markups are packed as A
+            }
+            u32 out_code = (u32)(s.roll.f[0] >> 62);          // base leaving the window (left neighbour of the new k-mer)
+            s.roll.push(code, a.pad);
+            u32 qi = 0, qo = 0;
+            if (NEED_W || EXT) { qi = (u32)(qin >> (8 * u)) & 0xffu; qo = (u32)(qout >> (8 * u)) & 0xffu; }
+            if (NEED_W) {
+                double pi = ptab[qi];
+                if (pi == 0.0) s.last_zero = (int)j;
+                if (j < k) {                                   // first window: w = p[q0]*p[q1]*... left to right
+                    s.w = (j == 0) ? pi : s.w * pi;
+                }
+            }
+            if (j + 1 >= k) {
+                const u32 i = j + 1 - k;
+                float wf = 1.0f;
+                if (NEED_W) {
+                    if (i > 0) {
+                        if ((i & 1023u) == 0u || s.w == 0.0) {
+                            if (s.last_zero >= (int)i) s.w = 0.0;          // a zero factor makes the product exactly 0
+                            else {
+                                double ww = 1.0;
+                                for (u32 q = 0; q < k; ++q) ww *= ptab[a.quals[s.off + i + q]];
+                                s.w = ww;
+                            }
+                        } else if (qi != qo) {
+                            double change = ptab[qi] / ptab[qo];
+                            s.w *= change;
+                        }
+                    }
+                    if (s.last_bad >= (int)i) s.w = 0.0;                   // markup inside [i, i+k)
+                    wf = (float)s.w;
+                }
+                bool fwd = s.roll.fwd_is_least();
+                u32 eb = 0x3f;
+                if (EXT) {
+                    // left = base i-1 (or X,20), right = base i+k (or X,20); N neighbours read as A   KmerReadUtils.h:224-236
+                    u32 lc = (i == 0) ? 5u : out_code, lq = (i == 0) ? 20u : (qo - a.start_char);
+                    u32 rc = 5u, rq = 20u;
+                    if (j + 1 < s.len) {
+                        u32 nb = (u < 7) ? ((u32)(bw >> (8 * (u + 1))) & 0xffu) : ((u32)bnext & 0xffu);
+                        u32 nq = (u < 7) ? ((u32)(qin >> (8 * (u + 1))) & 0xffu) : ((u32)qnext & 0xffu);
+                        u32 ncode = base_code(nb);
+                        rc = ncode >= 4 ? 0u : ncode;
+                        rq = nq - a.start_char;
+                    }
+                    if (!fwd) { u32 tl = lc, tq = lq; lc = rc < 4 ? 3u - rc : rc; lq = rq; rc = tl < 4 ? 3u - tl : tl; rq = tq; }
+                    u32 le = ((lq & 0xffu) >= 20u || lc >= 4) ? lc : 7u;
+                    u32 re = ((rq & 0xffu) >= 20u || rc >= 4) ? rc : 7u;
+                    eb = le | (re << 3);
+                }
+                emit(i, fwd ? s.roll.f : s.roll.r, fwd, wf, wf > a.min_weight, eb);
+            }
+        }
+    }
+    s.j = j0 + 8;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1+K2 (+K5 partition): phase 1 of the count pass.  One thread walks one read; k-mers that pass the weight
+// test are dropped into shared-memory bins keyed by table partition and flushed to the staging regions in
+// >=thresh-record coalesced bursts.  Multi-GPU: records owned by another rank (owner = lookup3 hash,
+// src/Kmer.h:2284-2295) go to that rank's send region instead.
+// ------------------------------------------------------------------------------------------------
+template <int W, bool HASX, bool EXT, bool DIST>
+__global__ void __launch_bounds__(PARSE_TPB, 1) k_count_parse(ParseArgs a)
+{
+    constexpr int RW = Rec<W, HASX>::RW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *ptab = reinterpret_cast<double *>(smem_raw);
+    u64 *bin_recs = reinterpret_cast<u64 *>(smem_raw + 256 * sizeof(double));
+    u32 *bin_cnt = reinterpret_cast<u32 *>(bin_recs + (size_t)a.table.n_parts * a.bin_cap * RW);
+    for (u32 i = threadIdx.x; i < 256; i += blockDim.x) ptab[i] = a.ptab[i];
+    for (u32 i = threadIdx.x; i < a.table.n_parts; i += blockDim.x) bin_cnt[i] = 0;
+    __syncthreads();
+    Bins<RW> bins{bin_cnt, bin_recs, a.table.n_parts, a.bin_cap};
+
+    u64 n_raw = 0, n_good = 0, n_unique = 0, n_full = 0, n_direct = 0, n_probes = 0;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = false;
+    Walker<W> st;
+    st.begin(0, 0);
+
+    auto emit = [&](u32 /*i*/, const u64 (&key)[W], bool fwd, float wf, bool good, u32 eb) {
+        n_raw++;
+        if (!good) return;
+        n_good++;
+        Rec<W, HASX> rec;
+        rec.pack(key, fwd, wf, eb);
+        if (DIST) {
+            u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
+            u32 own = owner_of(h, a.nranks);
+            if (own != a.rank) {
+                u64 pos = atomicAdd(&a.send_cursor[own], 1ull);
+                if (pos < a.send_cap) {
+                    u64 *d = a.send_recs + ((size_t)own * a.send_cap + pos) * RW;
+#pragma unroll
+                    for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
+                }
+                return;
+            }
+        }
+        u64 ph = place_hash<W>(key);
+        bins_put<W, HASX>(bins, a.table, part_of(ph, a.table.n_parts), rec, n_unique, n_full, n_direct, n_probes);
+    };
+
+    while (true) {
+        if (!active) {
+            while (r < a.n_reads) {
+                u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
+                u32 len = (u32)(o1 - o0);
+                bool disc = a.discarded && a.discarded[r];
+                if (!disc && len >= a.k) { st.begin(o0, len); active = true; break; }
+                r += stride;
+            }
+        }
+        if (active) {
+            walker_step<W, true, EXT>(st, a, ptab, emit);
+            if (st.j >= st.len) { active = false; r += stride; }
+        }
+        int more = __syncthreads_or(active || r < a.n_reads);
+        bins_flush<W, HASX>(bins, a.stage, a.table, a.flush_thresh, n_unique, n_full, n_direct, n_probes);
+        __syncthreads();
+        if (!more) break;
+    }
+    bins_flush<W, HASX>(bins, a.stage, a.table, 1u, n_unique, n_full, n_direct, n_probes);
+
+    // statistics: warp reduce, one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_raw += __shfl_xor_sync(0xffffffffu, n_raw, o);
+        n_good += __shfl_xor_sync(0xffffffffu, n_good, o);
+        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
+        n_direct += __shfl_xor_sync(0xffffffffu, n_direct, o);
+        n_probes += __shfl_xor_sync(0xffffffffu, n_probes, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_raw) atomicAdd(&a.ctr->raw, n_raw);
+        if (n_good) atomicAdd(&a.ctr->raw_good, n_good);
+        if (n_unique) atomicAdd(&a.ctr->unique, n_unique);
+        if (n_full) atomicAdd(&a.ctr->table_full, n_full);
+        if (n_direct) atomicAdd(&a.ctr->direct, n_direct);
+        if (n_probes) atomicAdd(&a.ctr->probe_steps, n_probes);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU: records received from other ranks are routed into the local staging regions through the
+// same shared-memory bins (the receiving half of MPIAllToAllMessageBuffer, src/MPIBuffer.h:412-1073).
+// ------------------------------------------------------------------------------------------------
+struct RouteArgs {
+    const u64 *recs; u64 n_recs;
+    u32 bin_cap, flush_thresh;
+    TableView table; StageView stage; Counters *ctr;
+};
+
+template <int W, bool HASX>
+__global__ void __launch_bounds__(PARSE_TPB, 1) k_route_records(RouteArgs a)
+{
+    constexpr int RW = Rec<W, HASX>::RW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *bin_recs = reinterpret_cast<u64 *>(smem_raw + 256 * sizeof(double));
+    u32 *bin_cnt = reinterpret_cast<u32 *>(bin_recs + (size_t)a.table.n_parts * a.bin_cap * RW);
+    for (u32 i = threadIdx.x; i < a.table.n_parts; i += blockDim.x) bin_cnt[i] = 0;
+    __syncthreads();
+    Bins<RW> bins{bin_cnt, bin_recs, a.table.n_parts, a.bin_cap};
+    u64 n_unique = 0, n_full = 0, n_direct = 0, n_probes = 0;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    // each round a thread routes up to 4 records, then the CTA flushes (keeps bins from overflowing)
+    for (u64 base = (u64)blockIdx.x * blockDim.x; ; base += stride * 4) {
+        int any = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            u64 idx = base + (u64)u * stride + threadIdx.x;
+            if (idx < a.n_recs) {
+                any = 1;
+                Rec<W, HASX> rec;
+#pragma unroll
+                for (int q = 0; q < RW; ++q) rec.w[q] = a.recs[idx * RW + q];
+                u64 key[W]; bool fwd; float wt; u32 eb;
+                rec.unpack(key, fwd, wt, eb);
+                u64 ph = place_hash<W>(key);
+                bins_put<W, HASX>(bins, a.table, part_of(ph, a.table.n_parts), rec, n_unique, n_full, n_direct, n_probes);
+            }
+        }
+        int more = __syncthreads_or(any);
+        bins_flush<W, HASX>(bins, a.stage, a.table, a.flush_thresh, n_unique, n_full, n_direct, n_probes);
+        __syncthreads();
+        if (!more) break;
+    }
+    bins_flush<W, HASX>(bins, a.stage, a.table, 1u, n_unique, n_full, n_direct, n_probes);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
+        n_direct += __shfl_xor_sync(0xffffffffu, n_direct, o);
+        n_probes += __shfl_xor_sync(0xffffffffu, n_probes, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_unique) atomicAdd(&a.ctr->unique, n_unique);
+        if (n_full) atomicAdd(&a.ctr->table_full, n_full);
+        if (n_direct) atomicAdd(&a.ctr->direct, n_direct);
+        if (n_probes) atomicAdd(&a.ctr->probe_steps, n_probes);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase 2 work list: chunk_start[p] = first chunk index of partition p (exclusive scan), single CTA
+// ------------------------------------------------------------------------------------------------
+__global__ void k_build_worklist(const u64 *cursor, u64 part_cap, u32 n_parts, u64 *chunk_start, u64 *next_item)
+{
+    __shared__ u64 carry;
+    if (threadIdx.x == 0) { carry = 0; *next_item = 0; }
+    __syncthreads();
+    for (u32 base = 0; base < n_parts; base += blockDim.x) {
+        u32 p = base + threadIdx.x;
+        u64 n = 0;
+        if (p < n_parts) { u64 c = cursor[p]; if (c > part_cap) c = part_cap; n = (c + INSERT_CHUNK - 1) / INSERT_CHUNK; }
+        // block-wide inclusive scan (simple: warp scan + shared partials)
+        __shared__ u64 wsum[32];
+        u64 v = n;
+        const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { u64 t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (u32)o) v += t; }
+        if (lane == 31) wsum[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            u64 t = lane < (blockDim.x >> 5) ? wsum[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { u64 q = __shfl_up_sync(0xffffffffu, t, o); if (lane >= (u32)o) t += q; }
+            wsum[lane] = t;
+        }
+        __syncthreads();
+        u64 incl = v + (warp ? wsum[warp - 1] : 0) + carry;
+        if (p < n_parts) chunk_start[p] = incl - n;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) chunk_start[n_parts] = carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: phase 2 of the count pass.  Persistent CTAs take (partition, chunk) items in partition order from an
+// atomic ticket, so at any time the whole GPU works on at most ~2 neighbouring partitions whose table
+// slices (slice_bytes each) stay L2-resident.  Per record: 16-B slot load, then CAS (new key) or RED (hit).
+// Replaces KmerSpectrum::append (src/KmerSpectrum.h:1578-1668) + KmerMapByKmerArrayPair insert/find
+// (src/Kmer.h:1491-1544,3095-3110) + TrackingData::track (src/KmerTrackingData.h:427-448,517-529).
+// ------------------------------------------------------------------------------------------------
+template <int W, bool HASX>
+__global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, StageView st, const u64 *chunk_start, u64 *next_item, Counters *ctr)
+{
+    constexpr int RW = Rec<W, HASX>::RW;
+    __shared__ u64 s_item;
+    u64 n_unique = 0, n_full = 0, n_probes = 0;
+    const u64 total_items = chunk_start[t.n_parts];
+    while (true) {
+        if (threadIdx.x == 0) s_item = atomicAdd(next_item, 1ull);
+        __syncthreads();
+        const u64 item = s_item;
+        __syncthreads();
+        if (item >= total_items) break;
+        // partition of this item: last p with chunk_start[p] <= item
+        u32 lo = 0, hi = t.n_parts;
+        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (chunk_start[mid] <= item) lo = mid; else hi = mid; }
+        const u32 part = lo;
+        u64 n = st.cursor[part]; if (n > st.part_cap) n = st.part_cap;
+        const u64 first = (item - chunk_start[part]) * INSERT_CHUNK;
+        const u64 *src = st.recs + ((size_t)part * st.part_cap + first) * RW;
+        const u64 cnt = n - first < (u64)INSERT_CHUNK ? n - first : (u64)INSERT_CHUNK;
+        Rec<W, HASX> rec[INSERT_UNROLL];
+        bool have[INSERT_UNROLL];
+#pragma unroll
+        for (int u = 0; u < INSERT_UNROLL; ++u) {
+            u64 idx = (u64)u * INSERT_TPB + threadIdx.x;
+            have[u] = idx < cnt;
+            if (have[u]) {
+#pragma unroll
+                for (int q = 0; q < RW; ++q) rec[u].w[q] = ld_nc64(src + idx * RW + q);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < INSERT_UNROLL; ++u) {
+            if (have[u]) {
+                u64 key[W]; bool fwd; float weight; u32 eb;
+                rec[u].unpack(key, fwd, weight, eb);
+                u64 ph = place_hash<W>(key);
+                u64 slot; u32 probes = 0;
+                int r = table_insert<W>(t, part, home_slot(ph, t.part_slots), key, 1ull | ((u64)(fwd ? 1u : 0u) << 32), &slot, &probes);
+                if (r < 0) { n_full++; continue; }
+                n_unique += (u64)r; n_probes += probes;
+                if (HASX) {
+                    if (t.wsum) atomicAdd(&t.wsum[slot], weight);
+                    if (t.ext) {
+                        u32 l = eb & 7u, rr = (eb >> 3) & 7u;
+                        if (l < 6) atomicAdd(&t.ext[slot * 12 + l], 1u);
+                        if (rr < 6) atomicAdd(&t.ext[slot * 12 + 6 + rr], 1u);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
+        n_probes += __shfl_xor_sync(0xffffffffu, n_probes, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_unique) atomicAdd(&ctr->unique, n_unique);
+        if (n_full) atomicAdd(&ctr->table_full, n_full);
+        if (n_probes) atomicAdd(&ctr->probe_steps, n_probes);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// table scans
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ bool slot_live(const Slot<W> &s)
+{
+    if (W == 1) return s.k[0] != 0 && (u32)s.val != 0;
+    return (s.val & VAL_READY) && (u32)s.val != 0;
+}
+__device__ __forceinline__ u32 clamp_count(u64 val) { u32 c = (u32)val; return c > MAX_COUNT ? MAX_COUNT : c; }
+__device__ __forceinline__ u32 clamp_dir(u64 val) { u32 d = (u32)(val >> 32) & 0x3fffffffu; return d > MAX_COUNT ? MAX_COUNT : d; }
+
+// weightedCount / directionBias as the reference reports them: a count-1 entry is a TrackingDataSingleton
+// (weight quantised to (u8)(w*254)+1, direction 0)   src/KmerTrackingData.h:641-661
+__device__ __forceinline__ float report_wsum(u32 count, float wsum)
+{
+    if (count == 1) { unsigned char q = (unsigned char)((double)wsum * 254.0); return (float)(((int)q + 1 - 1) / 254.0); }
+    return wsum;
+}
+
+// K6: exact count histogram, 65536 bins (a9: KmerSpectrum::Histogram::set src/KmerSpectrum.h:1036-1056;
+// the zoomed/log bins are a host-side fold).  Low counts go through shared memory.
+template <int W>
+__global__ void __launch_bounds__(256) k_histogram(TableView t, u64 n_slots, u64 *hist, double *whist)
+{
+    __shared__ u32 sh[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const Slot<W> *sl = reinterpret_cast<const Slot<W> *>(t.slots);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) {
+        Slot<W> s = sl[i];
+        if (!slot_live<W>(s)) continue;
+        u32 c = clamp_count(s.val);
+        if (c < 1024) atomicAdd(&sh[c], 1u); else atomicAdd(&hist[c], 1ull);
+        if (whist && t.wsum) atomicAdd(&whist[c], (double)report_wsum(c, t.wsum[i]));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], (u64)sh[i]);
+}
+
+// a8: purgeMinDepth (src/KmerSpectrum.h:1805-1815): entries with count < min_depth lose their value; the slot
+// keeps its key so probe chains stay intact (count 0 == absent everywhere).
+template <int W>
+__global__ void __launch_bounds__(256) k_purge(TableView t, u64 n_slots, u32 min_depth, u64 *n_purged)
+{
+    Slot<W> *sl = reinterpret_cast<Slot<W> *>(t.slots);
+    u64 mine = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) {
+        u64 v = sl[i].val;
+        u32 c = (u32)v;
+        if (c != 0 && c < min_depth) {
+            sl[i].val = v & VAL_READY;
+            if (t.wsum) t.wsum[i] = 0.f;
+            if (t.ext) for (int q = 0; q < 12; ++q) t.ext[i * 12 + q] = 0;
+            mine++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_purged, mine);
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) k_count_live(TableView t, u64 n_slots, u32 min_count, u64 *n_live, u64 *n_single)
+{
+    const Slot<W> *sl = reinterpret_cast<const Slot<W> *>(t.slots);
+    u64 live = 0, single = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) {
+        Slot<W> s = sl[i];
+        if (!slot_live<W>(s)) continue;
+        u32 c = clamp_count(s.val);
+        if (c >= min_count) live++;
+        if (c == 1) single++;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { live += __shfl_xor_sync(0xffffffffu, live, o); single += __shfl_xor_sync(0xffffffffu, single, o); }
+    if ((threadIdx.x & 31) == 0) { if (live) atomicAdd(n_live, live); if (single) atomicAdd(n_single, single); }
+}
+
+// export: compacts live entries (count >= min_count) into flat arrays; keys as reference bytes
+template <int W>
+__global__ void __launch_bounds__(256) k_export(TableView t, u64 n_slots, u32 min_count, u32 kb, u64 cap, u64 *cursor,
+                                                uint8_t *keys, uint16_t *count, uint16_t *dir, float *wsum, u32 *ext)
+{
+    const Slot<W> *sl = reinterpret_cast<const Slot<W> *>(t.slots);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) {
+        Slot<W> s = sl[i];
+        if (!slot_live<W>(s)) continue;
+        u32 c = clamp_count(s.val);
+        if (c < min_count) continue;
+        u64 o = atomicAdd(cursor, 1ull);
+        if (o >= cap) continue;
+        u64 key[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) key[q] = (W == 1) ? ~s.k[q] : s.k[q];
+        if (keys) for (u32 b = 0; b < kb; ++b) keys[o * kb + b] = (uint8_t)(key[b >> 3] >> (56 - 8 * (b & 7)));
+        if (count) count[o] = (uint16_t)c;
+        if (dir) dir[o] = (uint16_t)(c == 1 ? 0 : clamp_dir(s.val));
+        if (wsum) wsum[o] = t.wsum ? report_wsum(c, t.wsum[i]) : 0.f;
+        if (ext) for (int q = 0; q < 12; ++q) ext[o * 12 + q] = t.ext ? t.ext[i * 12 + q] : 0u;
+    }
+}
+
+// kmn_lookup: reference-format key bytes -> u16 count (0 = absent/purged)
+template <int W>
+__global__ void __launch_bounds__(256) k_lookup_keys(TableView t, const uint8_t *keys, u64 n, u32 kb, uint16_t *out)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 key[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) key[q] = 0;
+        for (u32 b = 0; b < kb; ++b) key[b >> 3] |= (u64)keys[i * kb + b] << (56 - 8 * (b & 7));
+        u64 ph = place_hash<W>(key);
+        u64 v = table_find<W>(t, part_of(ph, t.n_parts), home_slot(ph, t.part_slots), key, nullptr);
+        out[i] = (uint16_t)clamp_count(v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7a: lookup pass, part 1.  One thread walks one read (no weights), probes the table for every
+// canonical k-mer and writes value(kmer) = count if count >= min_depth else 0 (setKmerValues,
+// src/ReadSelector.h:1064-1076) to vals[off+i]; also records firstMarkupNorX per read.
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256) k_lookup_vals(ParseArgs a, u32 min_depth, uint16_t *vals, u32 *first_nx)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += stride) {
+        u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
+        u32 len = (u32)(o1 - o0);
+        bool disc = a.discarded && a.discarded[r];
+        Walker<W> st;
+        st.begin(o0, len);
+        if (!disc && len >= a.k) {
+            auto emit = [&](u32 i, const u64 (&key)[W], bool, float, bool, u32) {
+                u64 ph = place_hash<W>(key);
+                u64 v = table_find<W>(a.table, part_of(ph, a.table.n_parts), home_slot(ph, a.table.part_slots), key, nullptr);
+                u32 c = clamp_count(v);
+                vals[o0 + i] = (uint16_t)(c >= min_depth ? c : 0u);
+            };
+            while (st.j < st.len) walker_step<W, false, false>(st, a, nullptr, emit);
+        } else if (!disc) {
+            // reads shorter than k still need firstMarkupNorX
+            for (u32 j = 0; j < len; ++j) { u32 c = base_code(a.bases[o0 + j]); if (c == 4 && st.first_nx == 0) st.first_nx = j + 1; }
+        }
+        first_nx[r] = st.first_nx;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7b: lookup pass, part 2.  One warp per read: longest run of vals >= min_depth over [0,numKmers)
+// (first-longest wins), score of the run, ReadTrimType after setTrimHeaders.
+// ReadSelector::trimReadByMinimumKmerScore / scoreReadByScoringType / setTrimHeaders / _setNumKmers
+// (src/ReadSelector.h:948-1047,1092-1180).  KS_SUM never assigns the score (:1151-1162) -> 0.
+// ------------------------------------------------------------------------------------------------
+struct TrimArgs {
+    const u64 *read_off; const uint8_t *discarded; const uint16_t *vals; const u32 *first_nx;
+    u64 n_reads; u32 k, min_depth; int scoring;
+    u32 *trim_off, *trim_len; float *score; uint8_t *was_trimmed;
+};
+
+__global__ void __launch_bounds__(256) k_trim_score(TrimArgs a)
+{
+    __shared__ u32 hist[8][256];
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u64 wstride = (u64)gridDim.x * (blockDim.x >> 5);
+    for (u64 r = (u64)blockIdx.x * (blockDim.x >> 5) + warp; r < a.n_reads; r += wstride) {
+        if (a.discarded && a.discarded[r]) {          // never scored (src/ReadSelector.h:1196-1198): default ReadTrimType
+            if (lane == 0) { a.trim_off[r] = 0; a.trim_len[r] = 0; a.score[r] = 0.f; a.was_trimmed[r] = 0; }
+            continue;
+        }
+        const u64 o0 = a.read_off[r];
+        const u32 len = (u32)(a.read_off[r + 1] - o0);
+        u32 num = len >= a.k ? len - a.k + 1 : 0;
+        const u32 ml = a.first_nx[r];
+        if (ml != 0) { u32 capn = ml > a.k ? ml - a.k : 0; if (capn < num) num = capn; }
+        const uint16_t *v = a.vals + o0;
+        // longest run, first-longest wins; every lane runs the same scalar scan over ballot words
+        u32 best_off = 0, best_len = 0, cur_off = 0, cur_len = 0;
+        for (u32 base = 0; base < num; base += 32) {
+            u32 i = base + lane;
+            bool ok = i < num && v[i] >= a.min_depth;
+            u32 m = __ballot_sync(0xffffffffu, ok);
+            u32 nbits = num - base < 32u ? num - base : 32u;
+            u32 pos = 0;
+            while (pos < nbits) {
+                u32 rest = m >> pos;
+                if (rest & 1u) {                       // run of ones
+                    u32 ones = (~rest) ? (u32)__ffs(~rest) - 1u : 32u;
+                    if (ones > nbits - pos) ones = nbits - pos;
+                    if (cur_len == 0) cur_off = base + pos;
+                    cur_len += ones; pos += ones;
+                } else {                               // run of zeros ends the current run
+                    if (cur_len > best_len) { best_len = cur_len; best_off = cur_off; }
+                    cur_len = 0;
+                    u32 zeros = rest ? (u32)__ffs(rest) - 1u : 32u;
+                    if (zeros > nbits - pos) zeros = nbits - pos;
+                    pos += zeros;
+                }
+            }
+        }
+        if (cur_len > best_len) { best_len = cur_len; best_off = cur_off; }
+        const bool trimmed = best_len < num;
+        float sc = -1.f;
+        u32 out_off = best_off, out_len = 0;
+        if (best_len > 0) {
+            const uint16_t *b = v + best_off;
+            if (a.scoring == 3 || a.scoring == 2) {                 // MAX / MIN
+                u32 m = a.scoring == 3 ? 0u : 0xffffffffu;
+                for (u32 i = lane; i < best_len; i += 32) { u32 x = b[i]; m = a.scoring == 3 ? max(m, x) : min(m, x); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { u32 x = __shfl_xor_sync(0xffffffffu, m, o); m = a.scoring == 3 ? max(m, x) : min(m, x); }
+                sc = (float)m;
+            } else if (a.scoring == 4) {                            // AVG: double sum of integers is exact in any order
+                u64 s = 0;
+                for (u32 i = lane; i < best_len; i += 32) s += b[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                sc = (float)((double)s / (int)best_len);
+            } else if (a.scoring == 1) {                            // MEDIAN = sorted[len/2]: two-pass radix select
+                u32 *h = hist[warp];
+                u32 want = best_len / 2;                            // 0-based rank
+                for (u32 i = lane; i < 256; i += 32) h[i] = 0;
+                __syncwarp();
+                for (u32 i = lane; i < best_len; i += 32) atomicAdd(&h[b[i] >> 8], 1u);
+                __syncwarp();
+                u32 hi = 0, acc = 0;
+                for (u32 q = 0; q < 256; ++q) { u32 c = h[q]; if (acc + c > want) { hi = q; break; } acc += c; }
+                __syncwarp();
+                for (u32 i = lane; i < 256; i += 32) h[i] = 0;
+                __syncwarp();
+                for (u32 i = lane; i < best_len; i += 32) if ((u32)(b[i] >> 8) == hi) atomicAdd(&h[b[i] & 0xff], 1u);
+                __syncwarp();
+                u32 lo = 0;
+                for (u32 q = 0; q < 256; ++q) { u32 c = h[q]; if (acc + c > want) { lo = q; break; } acc += c; }
+                __syncwarp();
+                sc = (float)((hi << 8) | lo);
+            } else {
+                sc = 0.f;                                           // KS_SUM: score never assigned
+            }
+            out_len = best_len + a.k - 1;
+        } else {
+            out_off = 0; sc = -1.f;
+        }
+        if (lane == 0) { a.trim_off[r] = out_off; a.trim_len[r] = out_len; a.score[r] = sc; a.was_trimmed[r] = trimmed ? 1 : 0; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// debug / parity: per-k-mer records of a batch (steps 1-3 of the path)
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(128) k_debug_kmers(ParseArgs a, const u64 *kmer_off, uint8_t *keys, uint8_t *is_fwd, float *weight, u64 *hash)
+{
+    __shared__ double ptab[256];
+    for (u32 i = threadIdx.x; i < 256; i += blockDim.x) ptab[i] = a.ptab[i];
+    __syncthreads();
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += stride) {
+        u64 o0 = a.read_off[r];
+        u32 len = (u32)(a.read_off[r + 1] - o0);
+        if (len < a.k) continue;
+        const u64 ko = kmer_off[r];
+        Walker<W> st;
+        st.begin(o0, len);
+        auto emit = [&](u32 i, const u64 (&key)[W], bool fwd, float wf, bool, u32) {
+            for (u32 b = 0; b < a.kb; ++b) keys[(ko + i) * a.kb + b] = (uint8_t)(key[b >> 3] >> (56 - 8 * (b & 7)));
+            is_fwd[ko + i] = fwd ? 1 : 0;
+            weight[ko + i] = wf;
+            hash[ko + i] = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
+        };
+        while (st.j < st.len) walker_step<W, true, false>(st, a, ptab, emit);
+    }
+}
+
+}  // namespace kmn

@@ -529,7 +529,7 @@ uint64_t orc_spectrum_purge_min_depth(orc_spectrum *s, uint32_t min_depth)
     for (t = 0; t < s->nshards; t++) {
         orc_shard *sh = &s->sh[t];
         for (i = 0; i < sh->cap; i++) if (sh->used[i] && sh->count[i] && sh->count[i] < min_depth) {
-            if (sh->count[i] == 1) { s->purged_singletons++; s->singleton--; }
+            if (sh->count[i] == 1) s->singleton--;   /* purgedSingletons only grows in the periodic purge (:1790-1803), off by default */
             sh->count[i] = 0; sh->single_w[i] = 0; purged++;
         }
     }

@@ -1,0 +1,271 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit-exact on integer work.
+Run on the B200 box with `pytest -m gpu`."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from bench import synth
+from oracle import filter_oracle as F
+from tests.gpu_util import assert_tables_equal, oracle_table
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    import kmernator_b200 as K_
+    K_.capi.load()
+    return K_
+
+
+def _fixture_reads(golden_dir, start=33):
+    recs = F.parse_fastq(open(os.path.join(golden_dir, "1000.fastq")).read())
+    F.normalise_quals(recs, start=start)
+    return recs
+
+
+def _tricky_reads():
+    """N runs, lower case, '.', other IUPAC markups, low-quality tails, reads shorter than k, empty read."""
+    rng = np.random.default_rng(5)
+    seqs, quals = [], []
+    for i in range(400):
+        L = int(rng.integers(0, 260))
+        s = bytearray(synth.ACGT[rng.integers(0, 4, L)].tobytes())
+        q = bytearray(rng.integers(33 + 2, 33 + 42, L, dtype=np.uint8).tobytes())
+        for _ in range(int(rng.integers(0, 4))):
+            if L:
+                p = int(rng.integers(0, L))
+                s[p] = rng.choice(list(b"NnX.RYacgt"))
+        if L > 40 and i % 3 == 0:
+            q[L - 20:] = b"#" * 20
+        if L > 10 and i % 7 == 0:
+            q[3] = 33
+        seqs.append(bytes(s))
+        quals.append(bytes(q))
+    return seqs, quals
+
+
+@pytest.mark.parametrize("k", [1, 4, 15, 21, 31, 32, 33, 47, 48, 49, 63, 64, 65, 96, 97, 128])
+def test_kmers_weights_hash(K, k):
+    """steps (1)-(3): pack, canonical k-mers, fp32 weight, KmerHasher hash -- bit exact vs oracle"""
+    seqs, quals = _tricky_reads()
+    bases, q, off = oracle.concat_reads(seqs, quals)
+    ctx = K.Context(kmer_size=k, table_slots=4096)
+    keys, fw, wt, hs = ctx.debug_kmers(np.frombuffer(bases, np.uint8), q, off)
+    pos = 0
+    for s_, q_ in zip(seqs, quals):
+        ok, ofw, owt, _ = oracle.read_kmers(s_, q_, k, with_ext=False)
+        n = len(ok)
+        assert (keys[pos:pos + n] == ok).all()
+        assert (fw[pos:pos + n] == ofw).all()
+        assert (wt[pos:pos + n].view(np.uint32) == owt.view(np.uint32)).all()
+        for i in range(0, n, 7):
+            assert int(hs[pos + i]) == oracle.kmer_hash(ok[i].tobytes())
+        pos += n
+    assert pos == len(keys)
+    ctx.close()
+
+
+def test_kmers_lookup8_hash(K):
+    seqs, quals = _tricky_reads()
+    bases, q, off = oracle.concat_reads(seqs[:50], quals[:50])
+    for k in (21, 31, 63):
+        ctx = K.Context(kmer_size=k, table_slots=4096, hash_kind=K.capi.KMN_HASH_LOOKUP8)
+        keys, fw, wt, hs = ctx.debug_kmers(np.frombuffer(bases, np.uint8), q, off)
+        for i in range(0, len(keys), 5):
+            assert int(hs[i]) == oracle.kmer_hash_lookup8(keys[i].tobytes())
+        ctx.close()
+
+
+def test_long_read_reseed(K):
+    """weight re-seed every 1024 positions (KmerReadUtils.h:204) on a 5 kb read with varied qualities"""
+    rng = np.random.default_rng(11)
+    L = 5000
+    s = synth.ACGT[rng.integers(0, 4, L)].tobytes()
+    q = rng.integers(33 + 3, 33 + 41, L, dtype=np.uint8).tobytes()
+    bases, qq, off = oracle.concat_reads([s], [q])
+    ctx = K.Context(kmer_size=31, table_slots=1 << 14)
+    keys, fw, wt, hs = ctx.debug_kmers(np.frombuffer(bases, np.uint8), qq, off)
+    ok, ofw, owt, _ = oracle.read_kmers(s, q, 31, with_ext=False)
+    assert (keys == ok).all() and (wt.view(np.uint32) == owt.view(np.uint32)).all()
+    ctx.close()
+
+
+@pytest.mark.parametrize("k,start", [(31, 33), (31, 64), (21, 33), (63, 33), (32, 33)])
+def test_count_table_1000_fastq(K, golden_dir, k, start):
+    """config C1: k-mer -> count table of test/1000.fastq identical to the oracle (which reproduces the goldens)"""
+    recs = _fixture_reads(golden_dir, start)
+    bases, q, off, disc = F.to_buffers(recs)
+    ctx = K.Context(kmer_size=k, fastq_start_char=start, table_slots=1 << 18, value_kind=K.capi.KMN_VALUE_WEIGHTS)
+    ctx.count_batch(np.frombuffer(bases, np.uint8), q, off)
+    ctx.count_finish(apply_purge=False)
+    g = ctx.export()
+    o = oracle_table(bases, q, off, k, start=start).export()
+    assert_tables_equal(g, o, check_wsum=True)
+    st, ost = ctx.stats(), oracle_table(bases, q, off, k, start=start).stats()
+    assert st["raw_kmers"] == ost["raw"] and st["raw_good_kmers"] == ost["raw_good"]
+    assert st["unique_kmers"] == ost["unique"] and st["singleton_kmers"] == ost["singleton"]
+    ctx.close()
+
+
+def test_meraculous_golden(K, golden_dir):
+    """config C5b on the reference fixture: counts and extension counters equal phix.mercount.m21 / phix.mergraph.m21.D2"""
+    recs = _fixture_reads(golden_dir, 33)
+    bases, q, off, _ = F.to_buffers(recs)
+    ctx = K.Context(kmer_size=21, min_quality_score=2, min_kmer_quality=0.0, table_slots=1 << 18,
+                    value_kind=K.capi.KMN_VALUE_DIR_EXT)
+    ctx.count_batch(np.frombuffer(bases, np.uint8), q, off)
+    ctx.count_finish(apply_purge=False)
+    g = ctx.export(min_count=2)
+    idx = "ACGTNX"
+    counts, graph = set(), set()
+    for key, c, ext in zip(g["keys"], g["count"], g["ext"]):
+        km = "".join("ACGT"[(key[i >> 2] >> (6 - 2 * (i & 3))) & 3] for i in range(21))
+        rc = F.revcomp(km)
+        counts |= {"%s\t%d" % (km, c), "%s\t%d" % (rc, c)}
+        re = [0] * 12
+        for i, b in enumerate(idx):
+            j = idx.index(F.COMP[b])
+            re[j] = int(ext[6 + i])
+            re[6 + j] = int(ext[i])
+        graph |= {km + "\t" + " ".join(str(int(x)) for x in ext) + " 0", rc + "\t" + " ".join(map(str, re)) + " 0"}
+    assert counts == set(l.rstrip("\n") for l in open(os.path.join(golden_dir, "phix.mercount.m21")))
+    assert graph == set(l.rstrip("\n") for l in open(os.path.join(golden_dir, "phix.mergraph.m21.D2")))
+    ctx.close()
+
+
+@pytest.mark.parametrize("k,n_reads,kw", [
+    (31, 20000, dict()),
+    (31, 20000, dict(stage_keys=1 << 16, slice_bytes=1 << 16)),      # many drains, many partitions
+    (31, 6000, dict(stage_keys=1 << 16, slice_bytes=1 << 12)),       # partition count capped by shared memory
+    (63, 8000, dict(slice_bytes=1 << 18)),
+    (64, 4000, dict()),
+    (96, 3000, dict()),
+    (21, 8000, dict()),
+])
+def test_count_table_synthetic(K, k, n_reads, kw):
+    """config C2-shaped reads (scaled down): identical table, histogram and stats; multi-batch input"""
+    bases, q, off = synth.reads_numpy(n_reads, 150, 40000, seed=3, err=0.002, lowq=0.001, n_rate=0.0005)
+    ctx = K.Context(kmer_size=k, table_slots=1 << 22, **kw)
+    half = n_reads // 2
+    cut = int(off[half])
+    ctx.count_batch(bases[:cut], q[:cut], np.ascontiguousarray(off[:half + 1]))
+    ctx.count_batch(bases[cut:], q[cut:], np.ascontiguousarray(off[half:] - off[half]))
+    ctx.count_finish(apply_purge=False)
+    osp = oracle_table(bases, q, off, k, threads=4)
+    assert_tables_equal(ctx.export(), osp.export())
+    gh = ctx.histogram()
+    ov, oc, ow = osp.histogram(256)
+    exact = np.zeros(65536, np.uint64)
+    for c in np.unique(osp.export()["count"]):
+        exact[c] = (osp.export()["count"] == c).sum()
+    assert (gh == exact).all()
+    st, ost = ctx.stats(), osp.stats()
+    assert (st["raw_kmers"], st["raw_good_kmers"], st["unique_kmers"], st["singleton_kmers"]) == (ost["raw"], ost["raw_good"], ost["unique"], ost["singleton"])
+    # purge: singletons dropped at min_depth 2, count<3 dropped at 3
+    for md in (2, 3):
+        ctx.purge_min_depth(md)
+        osp.purge_min_depth(md)
+        assert_tables_equal(ctx.export(), osp.export())
+    ctx.close()
+
+
+def test_count_saturation(K):
+    """uint16 saturating count (KmerTrackingData.h:306): 70000 copies of one read -> every count == 65535"""
+    seq = b"ACGTTGCAAGGCTTAACCGGATATCGCGATTACGGATCCA"
+    n = 70000
+    bases, q, off = oracle.concat_reads([seq] * n)
+    ctx = K.Context(kmer_size=31, table_slots=1 << 12)
+    ctx.count_batch(np.frombuffer(bases, np.uint8), q, off)
+    ctx.count_finish(apply_purge=False)
+    g = ctx.export()
+    assert len(g["count"]) == 10 and (g["count"] == 65535).all()
+    st = ctx.stats()
+    assert st["raw_kmers"] == n * 10 and st["unique_kmers"] == 10
+    ctx.close()
+
+
+def test_table_full_is_an_error(K):
+    bases, q, off = synth.reads_numpy(3000, 150, 200000, seed=9)
+    ctx = K.Context(kmer_size=31, table_slots=1024)
+    ctx.count_batch(bases, q, off)
+    with pytest.raises(K.KmnError) as ei:
+        ctx.count_finish()
+    assert ei.value.code == -4
+    ctx.close()
+
+
+def test_lookup_api(K):
+    bases, q, off = synth.reads_numpy(3000, 150, 20000, seed=4)
+    ctx = K.Context(kmer_size=31, table_slots=1 << 20)
+    ctx.count_batch(bases, q, off)
+    ctx.count_finish(apply_purge=True)
+    osp = oracle_table(bases, q, off, 31)
+    osp.purge_min_depth(2)
+    e = osp.export()
+    got = ctx.lookup(e["keys"])
+    assert (got == e["count"]).all()
+    absent = np.random.default_rng(1).integers(0, 256, (100, 8), dtype=np.uint8)
+    absent[:, 7] &= 0xFC
+    exp = np.array([osp.lookup(k.tobytes()) for k in absent], dtype=np.uint16)
+    assert (ctx.lookup(absent) == exp).all()
+    ctx.close()
+
+
+@pytest.mark.parametrize("scoring", ["MAX", "MEDIAN", "MIN", "AVG", "SUM"])
+@pytest.mark.parametrize("k", [31, 63])
+def test_trim_scores(K, scoring, k):
+    """lookup pass: (trimOffset, trimLength, score, wasTrimmed) per read identical to the oracle"""
+    bases, q, off = synth.reads_numpy(6000, 150, 30000, seed=8, err=0.01, lowq=0.002, n_rate=0.002, var_len=True)
+    disc = (np.arange(6000) % 97 == 0).astype(np.uint8)
+    ctx = K.Context(kmer_size=k, table_slots=1 << 21)
+    ctx.count_batch(bases, q, off, discarded=disc)
+    ctx.count_finish(apply_purge=True)
+    osp = oracle_table(bases, q, off, k, disc=disc, threads=4)
+    osp.purge_min_depth(2)
+    for md in (2, 3):
+        g = ctx.trim_batch(bases, off, md, scoring, discarded=disc)
+        o = osp.trim_reads(bases, off, md, oracle.SCORING[scoring], disc, threads=4)
+        for a, b, name in zip(g, o, ("off", "len", "score", "was")):
+            assert (a == b).all(), name
+    ctx.close()
+
+
+FILTER_CASES = [
+    ("1000-Filtered-0.85.fastq", 0.85, 1, 64),
+    ("1000-Filtered-0.85.std.fastq", 0.85, 1, 33),
+    ("1000-Filtered-readlength.fastq", 1.0, 1, 64),
+    ("1000-Filtered-readlength-both.fastq", 1.0, 2, 64),
+    ("1000-Filtered.fastq", 25.0, 1, 64),
+]
+
+
+@pytest.mark.parametrize("fn,minlen,both,start", FILTER_CASES)
+def test_filter_goldens_gpu(K, golden_dir, fn, minlen, both, start):
+    """config C1: FilterReads on test/1000.fastq with the count and lookup passes on the GPU reproduces the
+    reference's golden output byte for byte (test/runFilterTests.sh:26,44-76)"""
+    recs = _fixture_reads(golden_dir, start)
+    F.artifact_quality_trim(recs, start, 3, minlen)
+    bases, q, off, disc = F.to_buffers(recs)
+    ctx = K.Context(kmer_size=31, fastq_start_char=start, table_slots=1 << 18)
+    ctx.count_batch(np.frombuffer(bases, np.uint8), q, off, discarded=disc)
+    ctx.count_finish(apply_purge=True)
+    toff, tlen, score, wast = ctx.trim_batch(np.frombuffer(bases, np.uint8), off, 2, "MEDIAN", discarded=disc)
+    res = []
+    for i, r in enumerate(recs):
+        if r["discarded"]:
+            res.append(dict(label="", passes=False, off=0, len=0))
+            continue
+        label = ("Trim:%d+%d" % (toff[i], tlen[i])) if wast[i] else ""
+        label += (" " if label else "") + "MedianScore:%d" % int(score[i] + np.float32(0.5))
+        res.append(dict(label=label, passes=bool(score[i] >= 2) and oracle.passes_length(tlen[i], len(r["seq"]), minlen),
+                        off=int(toff[i]), len=int(tlen[i])))
+    out = []
+    for i, j in F.identify_pairs(recs):
+        r1, r2 = res[i]["passes"], res[j]["passes"]
+        if (r1 and r2) if both >= 2 else (r1 or r2):
+            out += [F.format_fastq(recs[i], res[i], start), F.format_fastq(recs[j], res[j], start)]
+    assert "".join(out) == open(os.path.join(golden_dir, fn)).read()
+    ctx.close()
