@@ -218,6 +218,7 @@ class Context:
         n_reads = len(read_off) - 1
         n = C.c_uint64()
         self._ck(self._L.kmn_debug_kmers(self._h, _ptr(bases), _ptr(quals), read_off.ctypes.data, n_reads, None, None, None, None, C.byref(n)))
+        nn = n
         n = n.value
         keys = np.zeros((n, self.kb), np.uint8)
         fw = np.zeros(n, np.uint8)
@@ -225,7 +226,7 @@ class Context:
         hs = np.zeros(n, np.uint64)
         if n:
             self._ck(self._L.kmn_debug_kmers(self._h, _ptr(bases), _ptr(quals), read_off.ctypes.data, n_reads, keys.ctypes.data,
-                                             fw.ctypes.data, wt.ctypes.data, hs.ctypes.data, C.byref(n)))
+                                             fw.ctypes.data, wt.ctypes.data, hs.ctypes.data, C.byref(nn)))
         return keys, fw, wt, hs
 
     def sync(self):
