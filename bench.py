@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- k-mer insertions/sec (k=31, 150 bp reads) on N B200, vs the CPU restatement of FilterReads-P.
+
+Contract (one JSON line on rank 0):
+  value    = whole-job k-mer insertions/s of the count pass (kmn_reset + kmn_count_batch + kmn_count_finish incl. the
+             post-build min-depth purge) with the reads already resident in HBM, CUDA events on the library's stream,
+             max over ranks.
+  e2e      = same metric through the C ABI with HOST (pinned) buffers: H2D of every batch and a D2H read of the
+             spectrum counters inside the timed region.
+  roofline = dominant kernel (k_insert_staged): 64 algorithmic bytes per staged instance (32-B sector read + 32-B
+             write-back of a 16-B slot RMW) / its measured launch time vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline = the oracle port (reference binary is not buildable: no MPI/Boost) on a bounded sample, all host threads.
+
+`--impl reference` times only that CPU port (the one other place oracle/ may be executed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 31
+READ_LEN = 150
+KMERS_PER_READ = READ_LEN - K + 1
+ALGO_BYTES_PER_INSERT = 64.0      # table RMW: one 32-B sector in, one out
+ALGO_BYTES_PER_INSTANCE = 66.5    # + 2.5 B streamed input per instance (whole count pass)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU (config C2: 100M x 150 bp)")
+    ap.add_argument("--genome", type=int, default=250_000_000, help="genome length per GPU-worth of reads (60x coverage)")
+    ap.add_argument("--table-slots", type=int, default=0)
+    ap.add_argument("--stage-keys", type=int, default=0)
+    ap.add_argument("--slice-mb", type=int, default=32)
+    ap.add_argument("--e2e-reads", type=int, default=20_000_000)
+    ap.add_argument("--e2e-batch", type=int, default=2_000_000)
+    ap.add_argument("--cpu-reads", type=int, default=400_000)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.t = index, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_port_rate(bases_np, quals_np, off_np, threads, steps=1, warmup=0):
+    """oracle port of the count pass (serial/OpenMP T x T build), k-mer instances / s"""
+    import oracle
+    n_reads = len(off_np) - 1
+    inst = n_reads * KMERS_PER_READ
+    times = []
+    for it in range(warmup + steps):
+        s = oracle.OracleSpectrum(K, threads=threads, est_distinct=max(1 << 16, inst // 3))
+        t0 = time.perf_counter()
+        s.add_reads(bases_np.tobytes() if not isinstance(bases_np, bytes) else bases_np, quals_np, off_np)
+        s.purge_min_depth(2)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        del s
+    return inst / (sum(times) / len(times)), sum(times) / len(times)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference path on the box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from bench import synth
+    threads = os.cpu_count() or 1
+    n = args.cpu_reads
+    bases, quals, off = synth.reads_numpy(n, READ_LEN, max(10_000, int(n * READ_LEN / 60)), seed=0x5245)
+    rate, dt = cpu_port_rate(bases, quals, off, threads, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    sample = "%d synthetic 150bp reads (60x of a %d bp genome, same error/quality model) per step" % (n, max(10_000, int(n * READ_LEN / 60)))
+    line = {
+        "impl": "reference", "metric": "k-mer insertions/sec (k=31, 150bp reads)", "value": rate, "unit": "kmers/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "C2: k=31 count + min-depth-2 purge, synthetic 150bp reads (bounded CPU sample)", "reads_per_step": n},
+        "cpu_baseline": {"value": rate, "unit": "kmers/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "restated CPU baseline - reference binary not buildable here (no MPI/Boost)"},
+        "e2e": {"value": rate, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import kmernator_b200 as KM
+    from bench import synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic input, generated in HBM (config C2; multi-GPU: each rank holds a contiguous slice of the reads) ----
+    n_reads = args.reads
+    genome_len = args.genome * world
+    bases, quals, off = synth.reads_torch(n_reads, READ_LEN, genome_len, seed=0x4B6D6572, device=dev, read_seed=0x5245414453 + rank)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    off_u64 = off  # int64 bit pattern == uint64
+    inst_per_rank = n_reads * KMERS_PER_READ
+
+    # ---- table / staging plan ----
+    # distinct k-mers ~ genome (coverage 60x) + ~30 error k-mers per substitution: 0.7 G for C2 -> 1.4 G slots at load 0.5
+    est_distinct = int(genome_len / world * 1.02 + n_reads * READ_LEN * 0.001 * 31 * 1.05)
+    table_slots = args.table_slots or int(est_distinct / 0.5)
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    stage_keys = args.stage_keys
+    if not stage_keys:
+        budget = free_b - table_slots * 16 - (6 << 30)
+        if world > 1:
+            budget = int(budget * 0.55)
+        stage_keys = max(1 << 24, min(int(inst_per_rank * 1.02), int(budget / 8 / 1.13)))
+    ctx = KM.Context(kmer_size=K, est_raw_kmers=inst_per_rank, table_slots=table_slots, stage_keys=stage_keys,
+                     slice_bytes=args.slice_mb << 20, device=local_rank)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.from_numpy(KM.Context.comm_unique_id().copy())
+        uid = uid.to(dev)
+        dist.broadcast(uid, 0)
+        ctx.comm_init(rank, world, uid.cpu().numpy())
+    kstream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step_device():
+        ctx.reset()
+        ctx.count_batch(bases, quals, off_u64, n_reads=n_reads)
+        ctx.count_finish(apply_purge=True)
+
+    # ---- warm-up ----
+    for _ in range(args.warmup):
+        step_device()
+    ctx.sync()
+    ctx.profile_enable(True)
+    ctx.profile_read()
+    launches0 = ctx.launches
+
+    # ---- timed region: K steps, CUDA events on the library stream, barrier + sync on both sides ----
+    # inputs (30 GB) and table (>20 GB) are far larger than the 126 MB L2, and every step starts by clearing the table
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record(kstream)
+        for _ in range(args.steps):
+            step_device()
+        ev1.record(kstream)
+        ctx.sync()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    launches = ctx.launches - launches0
+    stats = ctx.stats()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = inst_per_rank * world / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (phase-2 insert) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    ins = prof.get("insert", {"ms": 0.0, "launches": 0, "units": 0})
+    par = prof.get("parse", {"ms": 0.0, "launches": 0, "units": 0})
+    good_per_step = stats["raw_good_kmers"]              # instances actually inserted in the last step
+    ins_ms_per_launch = ins["ms"] / max(1, ins["launches"])
+    ins_units_per_launch = good_per_step * args.steps / max(1, ins["launches"])
+    achieved = ALGO_BYTES_PER_INSERT * ins_units_per_launch / (ins_ms_per_launch * 1e-3) / 1e9 if ins["ms"] else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": "k_insert_staged", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_unit": ALGO_BYTES_PER_INSERT, "units_per_launch": ins_units_per_launch,
+        "ms_per_launch": ins_ms_per_launch, "launches": ins["launches"],
+        "share_of_step": ins["ms"] / ms if ms else None,
+        "parse_kernel": {"ms_per_step": par["ms"] / args.steps, "share_of_step": par["ms"] / ms if ms else None,
+                         "GBps_input": (2.0 * n_reads * READ_LEN * args.steps) / (par["ms"] * 1e-3) / 1e9 if par["ms"] else None},
+        "whole_pass": {"achieved": ALGO_BYTES_PER_INSTANCE * inst_per_rank / (ms_per_step * 1e-3) / 1e9,
+                       "frac": ALGO_BYTES_PER_INSTANCE * inst_per_rank / (ms_per_step * 1e-3) / 1e9 / peak},
+    }
+
+    # ---- e2e: host (pinned) buffers through the C ABI, H2D of every batch + D2H of the counters inside the timing ----
+    e2e = None
+    if not args.no_e2e:
+        n_e = min(args.e2e_reads, n_reads)
+        hb = torch.empty(n_e * READ_LEN, dtype=torch.uint8, pin_memory=True)
+        hq = torch.empty(n_e * READ_LEN, dtype=torch.uint8, pin_memory=True)
+        hb.copy_(bases[: n_e * READ_LEN])
+        hq.copy_(quals[: n_e * READ_LEN])
+        torch.cuda.synchronize()
+        hbn, hqn = hb.numpy(), hq.numpy()
+        bsz = args.e2e_batch
+        hoff = (np.arange(bsz + 1, dtype=np.uint64) * READ_LEN)
+
+        def step_e2e():
+            ctx.reset()
+            for r0 in range(0, n_e, bsz):
+                nb = min(bsz, n_e - r0)
+                ctx.count_batch(hbn[r0 * READ_LEN: (r0 + nb) * READ_LEN], hqn[r0 * READ_LEN: (r0 + nb) * READ_LEN], hoff[: nb + 1], n_reads=nb)
+            ctx.count_finish(apply_purge=True)
+            return ctx.stats()      # D2H read of the spectrum counters
+
+        for _ in range(min(2, args.warmup)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            st_e = step_e2e()
+        ctx.sync()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.steps
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dt = float(te.item())
+        e2e = {"value": n_e * KMERS_PER_READ * world / dt, "unit": "kmers/s", "h2d_bytes_per_step": 2 * n_e * READ_LEN + (n_e // bsz + 1) * (bsz + 1) * 8,
+               "d2h_bytes_per_step": 64 + 48, "reads_per_step": n_e, "batch_reads": bsz, "ms_per_step": dt * 1e3,
+               "raw_good_kmers": st_e["raw_good_kmers"]}
+        del hb, hq
+
+    # ---- CPU baseline on a bounded sample of the same workload (rank 0 only) ----
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        n_c = min(args.cpu_reads, n_reads)
+        cb = bases[: n_c * READ_LEN].cpu().numpy()
+        cq = quals[: n_c * READ_LEN].cpu().numpy()
+        co = (np.arange(n_c + 1, dtype=np.uint64) * READ_LEN)
+        threads = os.cpu_count() or 1
+        rate, dtc = cpu_port_rate(cb, cq, co, threads)
+        cpu = {"value": rate, "unit": "kmers/s", "cores": threads, "kind": "port",
+               "sample": "first %d reads of the same synthetic input (%.1f s of CPU work)" % (n_c, dtc),
+               "note": "restated CPU baseline - reference binary not buildable here (no MPI/Boost)"}
+
+    if rank == 0:
+        line = {
+            "metric": "k-mer insertions/sec (k=31, 150bp reads)", "value": value, "unit": "kmers/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "C2: k=31 count + min-depth-2 purge on %d synthetic 150bp reads per GPU (60x coverage, 0.1%% substitutions)" % n_reads,
+                       "reads_per_gpu": n_reads, "genome_bp": genome_len, "table_slots": stats["table_slots"],
+                       "table_partitions": stats["table_partitions"], "stage_keys": stage_keys, "slice_mb": args.slice_mb,
+                       "l2_policy": "inputs (30 GB) and table (>20 GB) exceed the 126 MB L2; table cleared every step",
+                       "parallelism": "owner-sharded x%d" % world if world > 1 else "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "stats": {k: int(v) for k, v in stats.items()},
+            "profile_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -49,13 +49,14 @@ def reads_numpy(n_reads, read_len=150, genome_len=100_000, seed=1, err=0.001, lo
 
 
 def reads_torch(n_reads, read_len=150, genome_len=250_000_000, seed=0x4B6D6572, err=0.001, lowq=0.0005, device="cuda",
-                chunk=4_000_000):
+                chunk=4_000_000, read_seed=0x5245414453):
     """Config C2/C3-shaped reads generated in HBM.  Returns (bases u8[n*L], quals u8[n*L], off int64[n+1]) on `device`."""
     import torch
 
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
     g = torch.randint(0, 4, (genome_len,), dtype=torch.uint8, device=device, generator=gen)
+    gen.manual_seed(read_seed)            # same genome on every rank, rank-specific reads
     bases = torch.empty(n_reads * read_len, dtype=torch.uint8, device=device)
     quals = torch.empty(n_reads * read_len, dtype=torch.uint8, device=device)
     lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)

@@ -137,8 +137,20 @@ int  kmn_export(kmn_ctx *ctx, uint32_t min_count, uint8_t *keys, uint16_t *count
 int  kmn_debug_kmers(kmn_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *read_off,
                      uint64_t n_reads, uint8_t *keys, uint8_t *is_fwd, float *weight, uint64_t *hash, uint64_t *n_out);
 
-/* timing of the device work issued since the last call (ms, CUDA events on the context's stream)            */
 int  kmn_sync(kmn_ctx *ctx);
+
+/* Per-kernel device timing (CUDA events on the context's stream around every launch of each kernel class).
+ * Off by default (events cost a few microseconds per launch).  kmn_profile_read synchronises, returns the sums
+ * accumulated since the last read and clears them.                                                             */
+enum { KMN_PROF_PARSE = 0, KMN_PROF_INSERT = 1, KMN_PROF_ROUTE = 2, KMN_PROF_LOOKUP = 3, KMN_PROF_TRIM = 4, KMN_PROF_SCAN = 5,
+       KMN_PROF_KINDS = 8 };
+typedef struct {
+    double   ms[KMN_PROF_KINDS];        /* summed device time per kernel class                                  */
+    uint64_t launches[KMN_PROF_KINDS];
+    uint64_t units[KMN_PROF_KINDS];     /* k-mer instances (parse: upper bound = bases; insert: staged records)  */
+} kmn_profile;
+int  kmn_profile_enable(kmn_ctx *ctx, int on);
+int  kmn_profile_read(kmn_ctx *ctx, kmn_profile *out);
 /* the cudaStream_t all kernels of this context are launched on (for CUDA-event timing by the caller)       */
 void *kmn_stream(kmn_ctx *ctx);
 /* number of kernels launched by this context so far                                                        */

@@ -16,7 +16,13 @@ EXPORTED = [
     "kmn_default_opts", "kmn_last_error", "kmn_version", "kmn_create", "kmn_destroy", "kmn_reset", "kmn_comm_unique_id",
     "kmn_comm_init", "kmn_count_batch", "kmn_count_finish", "kmn_get_stats", "kmn_purge_min_depth", "kmn_histogram",
     "kmn_lookup", "kmn_trim_batch", "kmn_export", "kmn_debug_kmers", "kmn_sync", "kmn_stream", "kmn_launch_count",
+    "kmn_profile_enable", "kmn_profile_read",
 ]
+PROF_KINDS = ["parse", "insert", "route", "lookup", "trim", "scan", "k6", "k7"]
+
+
+class KmnProfile(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_uint64 * 8), ("units", C.c_uint64 * 8)]
 
 
 class KmnOpts(C.Structure):
@@ -73,6 +79,8 @@ def load():
     L.kmn_export.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.kmn_debug_kmers.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
     L.kmn_sync.argtypes = [vp]
+    L.kmn_profile_enable.argtypes = [vp, C.c_int]
+    L.kmn_profile_read.argtypes = [vp, C.POINTER(KmnProfile)]
     L.kmn_stream.restype = vp
     L.kmn_stream.argtypes = [vp]
     L.kmn_launch_count.restype = C.c_uint64
@@ -228,6 +236,14 @@ class Context:
             self._ck(self._L.kmn_debug_kmers(self._h, _ptr(bases), _ptr(quals), read_off.ctypes.data, n_reads, keys.ctypes.data,
                                              fw.ctypes.data, wt.ctypes.data, hs.ctypes.data, C.byref(nn)))
         return keys, fw, wt, hs
+
+    def profile_enable(self, on=True):
+        self._ck(self._L.kmn_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        p = KmnProfile()
+        self._ck(self._L.kmn_profile_read(self._h, C.byref(p)))
+        return {k: dict(ms=p.ms[i], launches=p.launches[i], units=p.units[i]) for i, k in enumerate(PROF_KINDS) if p.launches[i]}
 
     def sync(self):
         self._ck(self._L.kmn_sync(self._h))

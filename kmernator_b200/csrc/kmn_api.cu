@@ -36,6 +36,11 @@ struct kmn_ctx {
     cudaEvent_t ev_in_free[2] = {nullptr, nullptr};
     std::string err;
     uint64_t launches = 0;
+    // optional per-kernel timing
+    bool prof_on = false;
+    struct ProfEv { cudaEvent_t a, b; int kind; uint64_t units; };
+    std::vector<ProfEv> prof_events;
+    kmn_profile prof_acc{};
 
     // table
     TableView table{};
@@ -86,6 +91,23 @@ static int fail(kmn_ctx *c, int code, const char *fmt, ...)
             return fail(ctx, e_ == cudaErrorMemoryAllocation ? KMN_ERR_NOMEM : KMN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
                         cudaGetErrorString(e_), __FILE__, __LINE__);                                         \
     } while (0)
+
+// RAII timer around one kernel launch (no-op unless profiling is enabled)
+struct ProfScope {
+    kmn_ctx *c; cudaEvent_t a = nullptr, b = nullptr; int kind; uint64_t units;
+    ProfScope(kmn_ctx *c_, int kind_, uint64_t units_) : c(c_), kind(kind_), units(units_)
+    {
+        if (!c->prof_on) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope()
+    {
+        if (!a) return;
+        cudaEventRecord(b, c->stream);
+        c->prof_events.push_back({a, b, kind, units});
+    }
+};
 
 static int ensure(kmn_ctx *c, DevBuf &b, size_t bytes)
 {
@@ -322,9 +344,12 @@ static int drain(kmn_ctx *c)
     k_build_worklist<<<1, 1024, 0, c->stream>>>(c->stage.cursor, c->stage.part_cap, c->table.n_parts, c->chunk_start, c->next_item);
     c->launches++;
     const int grid = c->n_sms * 8;
-    KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
-        k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, c->stream>>>(c->table, c->stage, c->chunk_start, c->next_item, c->ctr);
-    }));
+    {
+        ProfScope ps(c, KMN_PROF_INSERT, c->staged_upper);
+        KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
+            k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, c->stream>>>(c->table, c->stage, c->chunk_start, c->next_item, c->ctr);
+        }));
+    }
     c->launches++;
     CK(c, cudaGetLastError());
     CK(c, cudaMemsetAsync(c->stage.cursor, 0, (size_t)c->table.n_parts * 8, c->stream));
@@ -351,6 +376,7 @@ static int launch_parse(kmn_ctx *c, const ParseArgs &a)
 {
     const int grid = c->n_sms;
     const bool dist = c->nranks > 1;
+    ProfScope ps(c, KMN_PROF_PARSE, a.total_bytes);
     KMN_DISPATCH_W(c, {
         if (!c->hasx) {
             if (dist) k_count_parse<W_, false, false, true><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
@@ -411,9 +437,12 @@ static int exchange(kmn_ctx *c)
         RouteArgs ra;
         ra.recs = c->recv_recs; ra.n_recs = recv_total; ra.bin_cap = c->bin_cap; ra.flush_thresh = c->flush_thresh;
         ra.table = c->table; ra.stage = c->stage; ra.ctr = c->ctr;
-        KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
-            k_route_records<W_, X_><<<c->n_sms, c->parse_tpb, c->parse_smem, c->stream>>>(ra);
-        }));
+        {
+            ProfScope ps(c, KMN_PROF_ROUTE, recv_total);
+            KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
+                k_route_records<W_, X_><<<c->n_sms, c->parse_tpb, c->parse_smem, c->stream>>>(ra);
+            }));
+        }
         c->launches++;
         CK(c, cudaGetLastError());
         c->staged_upper += recv_total;
@@ -572,7 +601,10 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
 static int launch_purge(kmn_ctx *c, uint32_t min_depth)
 {
     CK(c, cudaMemsetAsync(c->scratch, 0, 8, c->stream));
-    KMN_DISPATCH_W(c, { k_purge<W_><<<c->n_sms * 8, 256, 0, c->stream>>>(c->table, c->n_slots, min_depth, c->scratch); });
+    {
+        ProfScope ps(c, KMN_PROF_SCAN, c->n_slots);
+        KMN_DISPATCH_W(c, { k_purge<W_><<<c->n_sms * 8, 256, 0, c->stream>>>(c->table, c->n_slots, min_depth, c->scratch); });
+    }
     c->launches++;
     CK(c, cudaGetLastError());
     if (min_depth > c->purged_depth) c->purged_depth = min_depth;
@@ -694,7 +726,10 @@ int kmn_trim_batch(kmn_ctx *c, const uint8_t *bases, const uint64_t *read_off, u
     ParseArgs a;
     fill_parse_args(c, a, bp.bases, nullptr, bp.off, bp.disc, n_reads, bp.total_bytes);
     const int grid = c->n_sms * 8;
-    KMN_DISPATCH_W(c, { k_lookup_vals<W_><<<grid, 256, 0, c->stream>>>(a, min_depth, (uint16_t *)c->vals.p, (u32 *)c->first_nx.p); });
+    {
+        ProfScope ps(c, KMN_PROF_LOOKUP, bp.total_bytes);
+        KMN_DISPATCH_W(c, { k_lookup_vals<W_><<<grid, 256, 0, c->stream>>>(a, min_depth, (uint16_t *)c->vals.p, (u32 *)c->first_nx.p); });
+    }
     c->launches++;
     CK(c, cudaGetLastError());
     TrimArgs t;
@@ -708,7 +743,10 @@ int kmn_trim_batch(kmn_ctx *c, const uint8_t *bases, const uint64_t *read_off, u
         r = ensure(c, c->out_trim, n_reads); if (r) return r;
         t.trim_off = (u32 *)c->out_off.p; t.trim_len = (u32 *)c->out_len.p; t.score = (float *)c->out_score.p; t.was_trimmed = (uint8_t *)c->out_trim.p;
     } else { t.trim_off = trim_off; t.trim_len = trim_len; t.score = score; t.was_trimmed = was_trimmed; }
-    k_trim_score<<<c->n_sms * 8, 256, 0, c->stream>>>(t);
+    {
+        ProfScope ps(c, KMN_PROF_TRIM, n_reads);
+        k_trim_score<<<c->n_sms * 8, 256, 0, c->stream>>>(t);
+    }
     c->launches++;
     CK(c, cudaGetLastError());
     if (host_out) {
@@ -790,6 +828,30 @@ int kmn_debug_kmers(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
     if (hash) CK(c, cudaMemcpyAsync(hash, dh, nk * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     cudaFree(dko); cudaFree(dk); cudaFree(df); cudaFree(dw); cudaFree(dh);
+    return 0;
+}
+
+int kmn_profile_enable(kmn_ctx *c, int on)
+{
+    if (!c) return KMN_ERR_INVALID;
+    c->prof_on = on != 0;
+    return 0;
+}
+
+int kmn_profile_read(kmn_ctx *c, kmn_profile *out)
+{
+    if (!c || !out) return KMN_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    for (auto &e : c->prof_events) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        c->prof_acc.ms[e.kind] += ms; c->prof_acc.launches[e.kind]++; c->prof_acc.units[e.kind] += e.units;
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    c->prof_events.clear();
+    *out = c->prof_acc;
+    memset(&c->prof_acc, 0, sizeof c->prof_acc);
     return 0;
 }
 
