@@ -357,6 +357,17 @@ static int drain(kmn_ctx *c)
     return 0;
 }
 
+static int count_positions(kmn_ctx *c, const u64 *off, const uint8_t *disc, uint64_t n_reads, uint64_t *out)
+{
+    CK(c, cudaMemsetAsync(c->scratch + 4, 0, 8, c->stream));
+    k_count_positions<<<c->n_sms * 4, 256, 0, c->stream>>>(off, disc, n_reads, c->o.kmer_size, c->scratch + 4);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out, c->scratch + 4, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, const uint8_t *quals, const u64 *off,
                             const uint8_t *disc, uint64_t n_reads, uint64_t total_bytes)
 {
@@ -376,7 +387,7 @@ static int launch_parse(kmn_ctx *c, const ParseArgs &a)
 {
     const int grid = c->n_sms;
     const bool dist = c->nranks > 1;
-    ProfScope ps(c, KMN_PROF_PARSE, a.total_bytes);
+    ProfScope ps(c, KMN_PROF_PARSE, a.n_reads);
     KMN_DISPATCH_W(c, {
         if (!c->hasx) {
             if (dist) k_count_parse<W_, false, false, true><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
@@ -561,39 +572,39 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
     BatchPtrs bp;
     int r = stage_inputs(c, bases, quals, read_off, n_reads, discarded, true, bp);
     if (r) return r;
-    // sub-batches are bounded so that staging (and, multi-GPU, the send regions) cannot overflow
-    const uint64_t limit = std::max<uint64_t>(c->stage_keys / 2, 1);
-    if (bp.total_bytes <= limit) {
-        if (c->staged_upper + bp.total_bytes > c->stage_keys) { r = drain(c); if (r) return r; }
+    // A launch may stage at most `limit` instances (staging capacity; multi-GPU: also bounds the send regions).
+    // The exact number of k-mer positions of a read range is computed on the device; ranges that do not fit are halved.
+    const uint64_t limit = std::max<uint64_t>(c->nranks > 1 ? c->stage_keys / 2 : c->stage_keys, 1);
+    struct Range { uint64_t r0, r1; };
+    std::vector<Range> todo;
+    todo.push_back({0, n_reads});
+    while (!todo.empty()) {
+        Range rg = todo.back();
+        todo.pop_back();
+        uint64_t npos = 0;
+        if (bp.off_on_host && (!discarded || !is_device_ptr(discarded))) {     // host offsets: no device round trip
+            const uint32_t k = c->o.kmer_size;
+            for (uint64_t q = rg.r0; q < rg.r1; ++q) {
+                uint64_t len = read_off[q + 1] - read_off[q];
+                if (len >= k && !(discarded && discarded[q])) npos += len - k + 1;
+            }
+        } else {
+            r = count_positions(c, bp.off + rg.r0, bp.disc ? bp.disc + rg.r0 : nullptr, rg.r1 - rg.r0, &npos);
+            if (r) return r;
+        }
+        if (npos > limit && rg.r1 - rg.r0 > 1) {
+            uint64_t mid = rg.r0 + (rg.r1 - rg.r0) / 2;
+            todo.push_back({mid, rg.r1});          // processed after the first half (stack order)
+            todo.push_back({rg.r0, mid});
+            continue;
+        }
+        if (npos == 0) continue;
+        if (c->staged_upper + npos > c->stage_keys) { r = drain(c); if (r) return r; }
         ParseArgs a;
-        fill_parse_args(c, a, bp.bases, bp.quals, bp.off, bp.disc, n_reads, bp.total_bytes);
+        fill_parse_args(c, a, bp.bases, bp.quals, bp.off + rg.r0, bp.disc ? bp.disc + rg.r0 : nullptr, rg.r1 - rg.r0, bp.total_bytes);
         r = launch_parse(c, a); if (r) return r;
-        c->staged_upper += bp.total_bytes;
-        return exchange(c);
-    }
-    // split by reads; needs the offsets on the host
-    std::vector<u64> hoff;
-    const u64 *ho = nullptr;
-    if (bp.off_on_host) ho = reinterpret_cast<const u64 *>(read_off);
-    else {
-        hoff.resize(n_reads + 1);
-        CK(c, cudaMemcpyAsync(hoff.data(), read_off, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-        CK(c, cudaStreamSynchronize(c->stream));
-        ho = hoff.data();
-    }
-    uint64_t r0 = 0;
-    while (r0 < n_reads) {
-        uint64_t lo = r0 + 1, hi = n_reads;          // largest r1 with ho[r1]-ho[r0] <= limit (at least one read)
-        while (lo < hi) { uint64_t mid = (lo + hi + 1) / 2; if (ho[mid] - ho[r0] <= limit) lo = mid; else hi = mid - 1; }
-        uint64_t r1 = lo;
-        uint64_t nb = ho[r1] - ho[r0];
-        if (c->staged_upper + nb > c->stage_keys) { r = drain(c); if (r) return r; }
-        ParseArgs a;
-        fill_parse_args(c, a, bp.bases, bp.quals, bp.off + r0, bp.disc ? bp.disc + r0 : nullptr, r1 - r0, bp.total_bytes);
-        r = launch_parse(c, a); if (r) return r;
-        c->staged_upper += nb;
+        c->staged_upper += npos;
         r = exchange(c); if (r) return r;
-        r0 = r1;
     }
     return 0;
 }

@@ -138,15 +138,17 @@ __device__ __forceinline__ void bins_flush(const Bins<Rec<W, HASX>::RW> &b, cons
     for (u32 g = warp; g * 32u < b.n_parts; g += nwarps) {
         u32 bi = g * 32u + lane;
         u32 c = bi < b.n_parts ? min(b.cnt[bi], b.cap) : 0u;
-        u32 mask = __ballot_sync(0xffffffffu, c >= thresh && c > 0);
+        const bool need = c >= thresh && c > 0;
+        // all reservations of this group of 32 bins are issued together: one atomic round trip per group, not per bin
+        u64 mypos = need ? atomicAdd(&st.cursor[bi], (u64)c) : 0ull;
+        if (need) b.cnt[bi] = 0;
+        u32 mask = __ballot_sync(0xffffffffu, need);
         while (mask) {
             int src = __ffs(mask) - 1;
             mask &= mask - 1;
             u32 bb = g * 32u + (u32)src;
             u32 cc = __shfl_sync(0xffffffffu, c, src);
-            u64 pos = 0;
-            if (lane == 0) pos = atomicAdd(&st.cursor[bb], (u64)cc);
-            pos = __shfl_sync(0xffffffffu, pos, 0);
+            u64 pos = __shfl_sync(0xffffffffu, mypos, src);
             const u64 *srcw = b.recs + (size_t)bb * b.cap * RW;
             u64 room = pos < st.part_cap ? st.part_cap - pos : 0;           // records that still fit
             u32 fit = room < cc ? (u32)room : cc;
@@ -159,8 +161,6 @@ __device__ __forceinline__ void bins_flush(const Bins<Rec<W, HASX>::RW> &b, cons
                 insert_record<W, HASX>(tab, rec, n_unique, n_full, n_probes);
                 n_direct++;
             }
-            __syncwarp();
-            if (lane == 0) b.cnt[bb] = 0;
         }
     }
 }
@@ -437,6 +437,19 @@ __global__ void __launch_bounds__(PARSE_TPB, 1) k_route_records(RouteArgs a)
         if (n_direct) atomicAdd(&a.ctr->direct, n_direct);
         if (n_probes) atomicAdd(&a.ctr->probe_steps, n_probes);
     }
+}
+
+// number of k-mer positions in reads [0,n): sum max(0, len-k+1) (discarded reads excluded)
+__global__ void __launch_bounds__(256) k_count_positions(const u64 *read_off, const uint8_t *discarded, u64 n_reads, u32 k, u64 *total)
+{
+    u64 mine = 0;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (u64)gridDim.x * blockDim.x) {
+        u64 len = read_off[r + 1] - read_off[r];
+        if (len >= k && !(discarded && discarded[r])) mine += len - k + 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total, mine);
 }
 
 // ------------------------------------------------------------------------------------------------
