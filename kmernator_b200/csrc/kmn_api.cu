@@ -56,7 +56,7 @@ struct kmn_ctx {
     u64 *scratch = nullptr;           // small device scalars
     // phase-1 launch geometry
     int parse_tpb = 512;
-    uint32_t bin_cap = 0, flush_thresh = 0;
+    uint32_t nb_log2 = 1, zero_below = 0;
     size_t parse_smem = 0;
     // input staging (host inputs)
     DevBuf in_bases, in_quals, in_off, in_disc;
@@ -197,7 +197,8 @@ static int plan_and_alloc(kmn_ctx *c)
     const uint32_t slice = o.slice_bytes ? o.slice_bytes : (32u << 20);
     uint64_t part_slots = std::max<uint64_t>(slice / c->slot_bytes, 256);
     uint64_t n_parts = (slots + part_slots - 1) / part_slots;
-    const uint64_t p_max = smem_avail / (16 * (size_t)c->RW * 8 + 4);
+    // shared memory per partition with the minimum ring (2 blocks x 8 records): 2*(64*RW+4)+4 bytes
+    const uint64_t p_max = smem_avail / (2 * (64 * (size_t)c->RW + 4) + 4);
     if (n_parts > p_max) n_parts = p_max;
     if (n_parts < 1) n_parts = 1;
     part_slots = (slots + n_parts - 1) / n_parts;
@@ -207,12 +208,11 @@ static int plan_and_alloc(kmn_ctx *c)
     c->table.part_slots = part_slots;
     c->table.n_parts = (u32)n_parts;
 
-    c->parse_tpb = c->RW == 1 ? 512 : (c->RW == 2 ? 256 : 128);
-    uint64_t cap = (smem_avail - 4 * n_parts) / (n_parts * (size_t)c->RW * 8);
-    if (cap > 8192) cap = 8192;
-    c->bin_cap = (uint32_t)cap;
-    c->flush_thresh = std::max<uint32_t>(1, c->bin_cap / 2);
-    c->parse_smem = 256 * sizeof(double) + (size_t)n_parts * c->bin_cap * c->RW * 8 + 4 * n_parts;
+    c->parse_tpb = 512;
+    uint32_t nbl = 1;                       // ring blocks per bin: largest power of two that fits, at most 64
+    while (nbl < 6 && (uint64_t)n_parts * ((2ull << nbl) * (64 * (size_t)c->RW + 4) + 4) <= smem_avail) nbl++;
+    c->nb_log2 = nbl;
+    c->parse_smem = 256 * sizeof(double) + (size_t)n_parts * ((1ull << nbl) * (64 * (size_t)c->RW + 4) + 4);
 
     CK(c, cudaMalloc(&c->table.slots, slots * c->slot_bytes));
     if (c->weights) CK(c, cudaMalloc((void **)&c->table.wsum, slots * 4));
@@ -244,6 +244,9 @@ static int plan_and_alloc(kmn_ctx *c)
     for (int i = start + (int)o.min_quality_score; i < 103 && i < 256; i++) p[i] = 1.0 - pow(10.0, (start - i) / 10.0);
     for (int i = 103; i < 256; i++) p[i] = 1.0;
     if (o.ignore_quality) for (int i = 0; i < 256; i++) p[i] = 1.0;
+    c->zero_below = 0;                      // p[q]==0 exactly for q < zero_below (and for no other q)
+    while (c->zero_below < 256 && p[c->zero_below] == 0.0) c->zero_below++;
+    for (int i = (int)c->zero_below; i < 256; i++) if (p[i] == 0.0) return fail(c, KMN_ERR_INVALID, "quality table not monotone");
     CK(c, cudaMemcpy(c->ptab, p, sizeof p, cudaMemcpyHostToDevice));
     return 0;
 }
@@ -376,7 +379,7 @@ static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, cons
     a.n_reads = n_reads; a.total_bytes = total_bytes; a.ptab = c->ptab;
     a.k = c->o.kmer_size; a.kb = (u32)c->kb; a.pad = c->pad;
     a.min_weight = c->o.min_kmer_quality; a.start_char = c->o.fastq_start_char;
-    a.bin_cap = c->bin_cap; a.flush_thresh = c->flush_thresh;
+    a.nb_log2 = c->nb_log2; a.zero_below = c->zero_below;
     a.nranks = (u32)c->nranks; a.rank = (u32)c->rank;
     a.use_lookup8 = c->o.hash_kind == KMN_HASH_LOOKUP8_HASH2;
     a.table = c->table; a.stage = c->stage; a.ctr = c->ctr;
@@ -446,7 +449,7 @@ static int exchange(kmn_ctx *c)
     if (recv_total) {
         if (c->staged_upper + recv_total > c->stage_keys) { int r = drain(c); if (r) return r; }
         RouteArgs ra;
-        ra.recs = c->recv_recs; ra.n_recs = recv_total; ra.bin_cap = c->bin_cap; ra.flush_thresh = c->flush_thresh;
+        ra.recs = c->recv_recs; ra.n_recs = recv_total; ra.nb_log2 = c->nb_log2; ra.pad = 0;
         ra.table = c->table; ra.stage = c->stage; ra.ctr = c->ctr;
         {
             ProfScope ps(c, KMN_PROF_ROUTE, recv_total);

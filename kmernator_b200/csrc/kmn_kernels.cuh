@@ -31,8 +31,8 @@ struct ParseArgs {
     int pad;               // 64*W - 2k
     float min_weight;
     u32 start_char;
-    u32 bin_cap;           // records per shared-memory bin
-    u32 flush_thresh;
+    u32 nb_log2;           // log2(ring blocks per shared-memory bin)
+    u32 zero_below;        // qualities below this value have probability 0
     u32 nranks, rank;
     u32 use_lookup8;
     TableView table;
@@ -120,65 +120,154 @@ __device__ __forceinline__ void insert_record(const TableView &t, const Rec<W, H
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory write-combining bins
+// shared-memory write-combining bins, lock free (no CTA barrier on the hot path).
+// Every table partition owns a ring of NB blocks x 8 records in shared memory.  A producer reserves a slot with one
+// shared atomicAdd, waits (rarely) until the ring block's previous incarnation has been flushed, writes its record and
+// commits.  Whoever commits the 8th record of a block flushes the whole block (64*RW contiguous bytes) to the
+// partition's staging region and bumps the block's generation.  state word: bits 0..7 commits, bits 8..31 generation.
 // ------------------------------------------------------------------------------------------------
+static constexpr u32 BIN_BLK = 8;
+
 template <int RW>
 struct Bins {
-    u32 *cnt;      // [n_parts]
-    u64 *recs;     // [n_parts][cap][RW]
-    u32 n_parts, cap;
+    u32 *res;      // [n_parts] slots reserved so far
+    u32 *state;    // [n_parts][nb]
+    u64 *ring;     // [n_parts][nb][8][RW]
+    u32 n_parts, nb_log2;
 };
 
+struct LocalCtr { u64 raw, good, unique, full, direct, probes; };
+
 template <int W, bool HASX>
-__device__ __forceinline__ void bins_flush(const Bins<Rec<W, HASX>::RW> &b, const StageView &st, const TableView &tab, u32 thresh,
-                                           u64 &n_unique, u64 &n_full, u64 &n_direct, u64 &n_probes)
+__device__ __forceinline__ void flush_block(const Bins<Rec<W, HASX>::RW> &b, const StageView &st, const TableView &tab, u32 bin, u32 rb,
+                                            u32 count, LocalCtr &lc)
 {
     constexpr int RW = Rec<W, HASX>::RW;
-    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (u32 g = warp; g * 32u < b.n_parts; g += nwarps) {
-        u32 bi = g * 32u + lane;
-        u32 c = bi < b.n_parts ? min(b.cnt[bi], b.cap) : 0u;
-        const bool need = c >= thresh && c > 0;
-        // all reservations of this group of 32 bins are issued together: one atomic round trip per group, not per bin
-        u64 mypos = need ? atomicAdd(&st.cursor[bi], (u64)c) : 0ull;
-        if (need) b.cnt[bi] = 0;
-        u32 mask = __ballot_sync(0xffffffffu, need);
-        while (mask) {
-            int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            u32 bb = g * 32u + (u32)src;
-            u32 cc = __shfl_sync(0xffffffffu, c, src);
-            u64 pos = __shfl_sync(0xffffffffu, mypos, src);
-            const u64 *srcw = b.recs + (size_t)bb * b.cap * RW;
-            u64 room = pos < st.part_cap ? st.part_cap - pos : 0;           // records that still fit
-            u32 fit = room < cc ? (u32)room : cc;
-            u64 *dst = st.recs + ((size_t)bb * st.part_cap + pos) * RW;
-            for (u32 i = lane; i < fit * RW; i += 32u) dst[i] = srcw[i];
-            for (u32 i = fit + lane; i < cc; i += 32u) {                    // staging region full: insert directly
-                Rec<W, HASX> rec;
+    const u64 pos = atomicAdd(&st.cursor[bin], (u64)count);
+    const u64 *src = b.ring + ((((size_t)bin << b.nb_log2) + rb) * BIN_BLK) * RW;
+    u64 *dst = st.recs + ((size_t)bin * st.part_cap + pos) * RW;
+    if (count == BIN_BLK && pos + BIN_BLK <= st.part_cap) {
 #pragma unroll
-                for (int q = 0; q < RW; ++q) rec.w[q] = srcw[(size_t)i * RW + q];
-                insert_record<W, HASX>(tab, rec, n_unique, n_full, n_probes);
-                n_direct++;
-            }
+        for (int i = 0; i < (int)BIN_BLK * RW; ++i) dst[i] = src[i];
+        return;
+    }
+    for (u32 i = 0; i < count; ++i) {
+        if (pos + i < st.part_cap) {
+#pragma unroll
+            for (int q = 0; q < RW; ++q) dst[(size_t)i * RW + q] = src[(size_t)i * RW + q];
+        } else {                                                            // staging region full: insert directly
+            Rec<W, HASX> rec;
+#pragma unroll
+            for (int q = 0; q < RW; ++q) rec.w[q] = src[(size_t)i * RW + q];
+            insert_record<W, HASX>(tab, rec, lc.unique, lc.full, lc.probes);
+            lc.direct++;
         }
     }
 }
 
 template <int W, bool HASX>
-__device__ __forceinline__ void bins_put(const Bins<Rec<W, HASX>::RW> &b, const TableView &tab, u32 part, const Rec<W, HASX> &rec,
-                                         u64 &n_unique, u64 &n_full, u64 &n_direct, u64 &n_probes)
+__device__ __forceinline__ void bins_put(const Bins<Rec<W, HASX>::RW> &b, const StageView &st, const TableView &tab, u32 bin,
+                                         const Rec<W, HASX> &rec, LocalCtr &lc)
 {
     constexpr int RW = Rec<W, HASX>::RW;
-    u32 s = atomicAdd(&b.cnt[part], 1u);
-    if (s < b.cap) {
-        u64 *d = b.recs + ((size_t)part * b.cap + s) * RW;
+    const u32 s = atomicAdd(&b.res[bin], 1u);
+    const u32 blk = s >> 3, rb = blk & ((1u << b.nb_log2) - 1u), inc = (blk >> b.nb_log2) & 0xffffffu;
+    volatile u32 *stp = &b.state[((size_t)bin << b.nb_log2) + rb];
+    while ((*stp >> 8) != inc) __nanosleep(20);                             // ring block still holds its previous incarnation
+    u64 *d = b.ring + (((((size_t)bin << b.nb_log2) + rb) * BIN_BLK) + (s & 7u)) * RW;
 #pragma unroll
-        for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
-    } else {                                                                // bin overflow inside one step (rare)
-        insert_record<W, HASX>(tab, rec, n_unique, n_full, n_probes);
-        n_direct++;
+    for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
+    __threadfence_block();
+    const u32 c = atomicAdd((u32 *)stp, 1u) & 0xffu;
+    if (c == BIN_BLK - 1) {                                                 // last committer flushes the block
+        __threadfence_block();
+        flush_block<W, HASX>(b, st, tab, bin, rb, BIN_BLK, lc);
+        __threadfence_block();
+        atomicAdd((u32 *)stp, 256u - BIN_BLK);                              // commits -> 0, generation + 1
     }
+}
+
+// after the last producer is done (CTA barrier): partial blocks
+template <int W, bool HASX>
+__device__ __forceinline__ void bins_drain(const Bins<Rec<W, HASX>::RW> &b, const StageView &st, const TableView &tab, LocalCtr &lc)
+{
+    for (u32 bin = threadIdx.x; bin < b.n_parts; bin += blockDim.x) {
+        const u32 n = b.res[bin], part = n & 7u;
+        if (part) flush_block<W, HASX>(b, st, tab, bin, (n >> 3) & ((1u << b.nb_log2) - 1u), part, lc);
+    }
+}
+
+template <int RW>
+__device__ __forceinline__ Bins<RW> bins_init(unsigned char *smem_after_ptab, u32 n_parts, u32 nb_log2)
+{
+    Bins<RW> b;
+    b.n_parts = n_parts; b.nb_log2 = nb_log2;
+    const size_t nblk = (size_t)n_parts << nb_log2;
+    b.ring = reinterpret_cast<u64 *>(smem_after_ptab);
+    b.state = reinterpret_cast<u32 *>(b.ring + nblk * BIN_BLK * RW);
+    b.res = b.state + nblk;
+    for (size_t i = threadIdx.x; i < nblk; i += blockDim.x) b.state[i] = 0;
+    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) b.res[i] = 0;
+    return b;
+}
+
+__device__ __forceinline__ void ctr_commit(Counters *ctr, LocalCtr lc)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lc.raw += __shfl_xor_sync(0xffffffffu, lc.raw, o);
+        lc.good += __shfl_xor_sync(0xffffffffu, lc.good, o);
+        lc.unique += __shfl_xor_sync(0xffffffffu, lc.unique, o);
+        lc.full += __shfl_xor_sync(0xffffffffu, lc.full, o);
+        lc.direct += __shfl_xor_sync(0xffffffffu, lc.direct, o);
+        lc.probes += __shfl_xor_sync(0xffffffffu, lc.probes, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (lc.raw) atomicAdd(&ctr->raw, lc.raw);
+        if (lc.good) atomicAdd(&ctr->raw_good, lc.good);
+        if (lc.unique) atomicAdd(&ctr->unique, lc.unique);
+        if (lc.full) atomicAdd(&ctr->table_full, lc.full);
+        if (lc.direct) atomicAdd(&ctr->direct, lc.direct);
+        if (lc.probes) atomicAdd(&ctr->probe_steps, lc.probes);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// byte stream over a (possibly unaligned) region of a global buffer, 8 bytes per step, with the aligned word
+// of the NEXT step requested one step ahead so its latency is hidden behind the current step's arithmetic.
+// ------------------------------------------------------------------------------------------------
+struct Stream {
+    const u64 *p;       // aligned word holding the current position
+    u64 w0, w1;         // words p[0], p[1]
+    u64 wn;             // p[2], in flight
+    int sh;
+    __device__ __forceinline__ static u64 guarded(const u64 *q, const uint8_t *buf, u64 total)
+    {
+        const unsigned long long base = (unsigned long long)buf;
+        const unsigned long long lo = base & ~7ull, hi = (base + total + 7ull) & ~7ull;
+        const unsigned long long a = (unsigned long long)q;
+        return (a >= lo && a < hi) ? ld_nc64(q) : 0ull;
+    }
+    __device__ __forceinline__ void init(const uint8_t *buf, long long idx, u64 total)
+    {
+        const unsigned long long a = (unsigned long long)buf + (unsigned long long)idx;
+        p = (const u64 *)(a & ~7ull);
+        sh = (int)(a & 7ull) * 8;
+        w0 = guarded(p, buf, total);
+        w1 = guarded(p + 1, buf, total);
+        wn = 0;
+    }
+    __device__ __forceinline__ void prefetch(const uint8_t *buf, u64 total) { wn = guarded(p + 2, buf, total); }
+    __device__ __forceinline__ u64 get() const { return sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0; }
+    __device__ __forceinline__ u64 peek() const { return sh ? (w1 >> sh) | (wn << (64 - sh)) : w1; }   // next 8 bytes
+    __device__ __forceinline__ void advance() { ++p; w0 = w1; w1 = wn; }
+};
+
+// SWAR helpers on 8 packed bytes
+__device__ __forceinline__ u64 bytes_eq(u64 x, u64 pat)          // 0x80 in every byte of x equal to the pattern byte
+{
+    const u64 t = x ^ pat, m = 0x7f7f7f7f7f7f7f7full;
+    return ~(((t & m) + m) | t | m);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -186,22 +275,36 @@ __device__ __forceinline__ void bins_put(const Bins<Rec<W, HASX>::RW> &b, const 
 // a2 KmerArrayPair::build (src/Kmer.h:1323-1375), a3 KmerReadUtils::buildWeightedKmers
 // (src/KmerReadUtils.h:176-248): w re-seeded at i%1024==0 or w==0, otherwise w *= p[q_in]/p[q_out];
 // any markup inside the window zeroes w; stored weight is (float)w.
+// The per-base body is branch-light: the weight is only touched when something can change it (first window,
+// incoming quality != outgoing quality -- x/x is exactly 1.0 --, re-seed boundary, w==0, markup in the window).
 // ------------------------------------------------------------------------------------------------
 template <int W>
 struct Walker {
     Roll<W> roll;
     double w;
+    float wf;          // (float)w of the last emitted k-mer
+    bool good;         // wf > min_weight
     u64 off;
     u32 len, j;
     int last_bad;      // last position holding a markup (non-ACGT), -1 none
     int last_zero;     // last position whose quality has probability 0, -1 none
     u32 first_nx;      // firstMarkupNorX: position+1 of the first N/X markup, 0 none
-    u32 prev_code, prev_q;
+    Stream sb, sqi, sqo;
 
-    __device__ __forceinline__ void begin(u64 off_, u32 len_)
+    __device__ __forceinline__ void clear()
     {
-        roll.reset(); w = 0.0; off = off_; len = len_; j = 0; last_bad = -1; last_zero = -1; first_nx = 0;
-        prev_code = 5; prev_q = 20;
+        roll.reset(); w = 0.0; wf = 0.f; good = false; off = 0; len = 0; j = 0; last_bad = -1; last_zero = -1; first_nx = 0;
+    }
+    template <bool NEED_Q>
+    __device__ __forceinline__ void begin(const ParseArgs &a, u64 off_, u32 len_)
+    {
+        clear();
+        off = off_; len = len_;
+        sb.init(a.bases, (long long)off_, a.total_bytes);
+        if (NEED_Q) {
+            sqi.init(a.quals, (long long)off_, a.total_bytes);
+            sqo.init(a.quals, (long long)off_ - (long long)a.k, a.total_bytes);
+        }
     }
 };
 
@@ -210,89 +313,100 @@ template <int W, bool NEED_W, bool EXT, typename EMIT>
 __device__ __forceinline__ void walker_step(Walker<W> &s, const ParseArgs &a, const double *ptab, EMIT &&emit)
 {
     const u32 k = a.k;
-    const long long total = (long long)a.total_bytes;
     const u32 j0 = s.j;
-    u64 bw = load8(a.bases, (long long)s.off + j0, total);
-    u64 qin = 0, qout = 0, bnext = 0, qnext = 0;
-    if (NEED_W || EXT) {
-        qin = load8(a.quals, (long long)s.off + j0, total);
-        qout = load8(a.quals, (long long)s.off + (long long)j0 - (long long)k, total);
-    }
-    if (EXT) {
-        bnext = load8(a.bases, (long long)s.off + j0 + 8, total);
-        qnext = load8(a.quals, (long long)s.off + j0 + 8, total);
-    }
+    constexpr bool NEED_Q = NEED_W || EXT;
+    s.sb.prefetch(a.bases, a.total_bytes);
+    if (NEED_Q) { s.sqi.prefetch(a.quals, a.total_bytes); s.sqo.prefetch(a.quals, a.total_bytes); }
+    const u64 bw = s.sb.get();
+    u64 qin = 0, qout = 0;
+    if (NEED_Q) { qin = s.sqi.get(); qout = s.sqo.get(); }
+
+    // base codes, SWAR: x=(c>>1)&3 -> A0 C1 G3 T2 ; code = x ^ (x>>1) -> A0 C1 G2 T3 ; markups -> 0 (packed as A)
+    const u64 up = bw & 0xDFDFDFDFDFDFDFDFull;
+    const u64 valid = bytes_eq(up, 0x4141414141414141ull) | bytes_eq(up, 0x4343434343434343ull) |
+                      bytes_eq(up, 0x4747474747474747ull) | bytes_eq(up, 0x5454545454545454ull);
+    u64 codes = (bw >> 1) & 0x0303030303030303ull;
+    codes ^= (codes >> 1) & 0x0101010101010101ull;
+    codes &= (valid >> 7) * 3ull;
+    const u64 qdiff = qin ^ qout;                                   // non-zero byte: incoming quality != outgoing quality
+    u64 bnext = 0, qnext = 0;
+    if (EXT) { bnext = s.sb.peek(); qnext = s.sqi.peek(); }
+
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         const u32 j = j0 + u;
         if (j < s.len) {
-            u32 c = (u32)(bw >> (8 * u)) & 0xffu;
-            u32 code = base_code(c);
-            if (code >= 4) {
+            if (!((valid >> (8 * u + 7)) & 1ull)) {                 // markup (rare)
+                const u32 c = (u32)(bw >> (8 * u)) & 0xffu;
                 s.last_bad = (int)j;
-                if (code == 4 && s.first_nx == 0) s.first_nx = j + 1;
-                code = 0;                                      // markups are packed as A
+                if ((c == 'N' || c == 'X' || c == '.') && s.first_nx == 0) s.first_nx = j + 1;
             }
-            u32 out_code = (u32)(s.roll.f[0] >> 62);          // base leaving the window (left neighbour of the new k-mer)
-            s.roll.push(code, a.pad);
-            u32 qi = 0, qo = 0;
-            if (NEED_W || EXT) { qi = (u32)(qin >> (8 * u)) & 0xffu; qo = (u32)(qout >> (8 * u)) & 0xffu; }
+            const u32 out_code = (u32)(s.roll.f[0] >> 62);          // base leaving the window (left neighbour of the new k-mer)
+            s.roll.push((u32)(codes >> (8 * u)) & 3u, a.pad);
+            const u32 i = j + 1 - k;                                // k-mer index (valid when j+1 >= k)
             if (NEED_W) {
-                double pi = ptab[qi];
-                if (pi == 0.0) s.last_zero = (int)j;
-                if (j < k) {                                   // first window: w = p[q0]*p[q1]*... left to right
-                    s.w = (j == 0) ? pi : s.w * pi;
+                const u32 qi = (u32)(qin >> (8 * u)) & 0xffu;
+                const bool first = j < k;
+                if (first || qi < a.zero_below) {                   // first window product / zero-probability bookkeeping
+                    const double pi = ptab[qi];
+                    if (pi == 0.0) s.last_zero = (int)j;
+                    if (first) s.w = (j == 0) ? pi : s.w * pi;      // w = p[q0]*p[q1]*... left to right
+                }
+                if (j + 1 >= k) {
+                    const bool touch = i == 0 || ((qdiff >> (8 * u)) & 0xffull) != 0 || (i & 1023u) == 0u || s.w == 0.0 || s.last_bad >= (int)i;
+                    if (touch) {
+                        if (i > 0) {
+                            if ((i & 1023u) == 0u || s.w == 0.0) {
+                                if (s.last_zero >= (int)i) s.w = 0.0;      // a zero factor makes the product exactly 0
+                                else {
+                                    double ww = 1.0;
+                                    for (u32 q = 0; q < k; ++q) ww *= ptab[a.quals[s.off + i + q]];
+                                    s.w = ww;
+                                }
+                            } else {
+                                const u32 qo = (u32)(qout >> (8 * u)) & 0xffu;
+                                if (qi != qo) { const double change = ptab[qi] / ptab[qo]; s.w *= change; }
+                            }
+                        }
+                        if (s.last_bad >= (int)i) s.w = 0.0;               // markup inside [i, i+k)
+                        s.wf = (float)s.w;
+                        s.good = s.wf > a.min_weight;
+                    }
                 }
             }
             if (j + 1 >= k) {
-                const u32 i = j + 1 - k;
-                float wf = 1.0f;
-                if (NEED_W) {
-                    if (i > 0) {
-                        if ((i & 1023u) == 0u || s.w == 0.0) {
-                            if (s.last_zero >= (int)i) s.w = 0.0;          // a zero factor makes the product exactly 0
-                            else {
-                                double ww = 1.0;
-                                for (u32 q = 0; q < k; ++q) ww *= ptab[a.quals[s.off + i + q]];
-                                s.w = ww;
-                            }
-                        } else if (qi != qo) {
-                            double change = ptab[qi] / ptab[qo];
-                            s.w *= change;
-                        }
-                    }
-                    if (s.last_bad >= (int)i) s.w = 0.0;                   // markup inside [i, i+k)
-                    wf = (float)s.w;
-                }
-                bool fwd = s.roll.fwd_is_least();
+                const bool fwd = s.roll.fwd_is_least();
                 u32 eb = 0x3f;
                 if (EXT) {
                     // left = base i-1 (or X,20), right = base i+k (or X,20); N neighbours read as A   KmerReadUtils.h:224-236
+                    const u32 qo = (u32)(qout >> (8 * u)) & 0xffu;
                     u32 lc = (i == 0) ? 5u : out_code, lq = (i == 0) ? 20u : (qo - a.start_char);
                     u32 rc = 5u, rq = 20u;
                     if (j + 1 < s.len) {
-                        u32 nb = (u < 7) ? ((u32)(bw >> (8 * (u + 1))) & 0xffu) : ((u32)bnext & 0xffu);
-                        u32 nq = (u < 7) ? ((u32)(qin >> (8 * (u + 1))) & 0xffu) : ((u32)qnext & 0xffu);
-                        u32 ncode = base_code(nb);
+                        const u32 nb = (u < 7) ? ((u32)(bw >> (8 * ((u + 1) & 7))) & 0xffu) : ((u32)bnext & 0xffu);
+                        const u32 nq = (u < 7) ? ((u32)(qin >> (8 * ((u + 1) & 7))) & 0xffu) : ((u32)qnext & 0xffu);
+                        const u32 ncode = base_code(nb);
                         rc = ncode >= 4 ? 0u : ncode;
                         rq = nq - a.start_char;
                     }
                     if (!fwd) { u32 tl = lc, tq = lq; lc = rc < 4 ? 3u - rc : rc; lq = rq; rc = tl < 4 ? 3u - tl : tl; rq = tq; }
-                    u32 le = ((lq & 0xffu) >= 20u || lc >= 4) ? lc : 7u;
-                    u32 re = ((rq & 0xffu) >= 20u || rc >= 4) ? rc : 7u;
+                    const u32 le = ((lq & 0xffu) >= 20u || lc >= 4) ? lc : 7u;
+                    const u32 re = ((rq & 0xffu) >= 20u || rc >= 4) ? rc : 7u;
                     eb = le | (re << 3);
                 }
-                emit(i, fwd ? s.roll.f : s.roll.r, fwd, wf, wf > a.min_weight, eb);
+                emit(i, fwd ? s.roll.f : s.roll.r, fwd, NEED_W ? s.wf : 1.0f, NEED_W ? s.good : true, eb);
             }
         }
     }
+    s.sb.advance();
+    if (NEED_Q) { s.sqi.advance(); s.sqo.advance(); }
     s.j = j0 + 8;
 }
 
 // ------------------------------------------------------------------------------------------------
 // K1+K2 (+K5 partition): phase 1 of the count pass.  One thread walks one read; k-mers that pass the weight
-// test are dropped into shared-memory bins keyed by table partition and flushed to the staging regions in
-// >=thresh-record coalesced bursts.  Multi-GPU: records owned by another rank (owner = lookup3 hash,
+// test are dropped into the lock-free shared-memory bins keyed by table partition and leave for the staging
+// regions in 8-record bursts.  Multi-GPU: records owned by another rank (owner = lookup3 hash,
 // src/Kmer.h:2284-2295) go to that rank's send region instead.
 // ------------------------------------------------------------------------------------------------
 template <int W, bool HASX, bool EXT, bool DIST>
@@ -301,24 +415,19 @@ __global__ void __launch_bounds__(PARSE_TPB, 1) k_count_parse(ParseArgs a)
     constexpr int RW = Rec<W, HASX>::RW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *ptab = reinterpret_cast<double *>(smem_raw);
-    u64 *bin_recs = reinterpret_cast<u64 *>(smem_raw + 256 * sizeof(double));
-    u32 *bin_cnt = reinterpret_cast<u32 *>(bin_recs + (size_t)a.table.n_parts * a.bin_cap * RW);
     for (u32 i = threadIdx.x; i < 256; i += blockDim.x) ptab[i] = a.ptab[i];
-    for (u32 i = threadIdx.x; i < a.table.n_parts; i += blockDim.x) bin_cnt[i] = 0;
+    Bins<RW> bins = bins_init<RW>(smem_raw + 256 * sizeof(double), a.table.n_parts, a.nb_log2);
     __syncthreads();
-    Bins<RW> bins{bin_cnt, bin_recs, a.table.n_parts, a.bin_cap};
 
-    u64 n_raw = 0, n_good = 0, n_unique = 0, n_full = 0, n_direct = 0, n_probes = 0;
+    LocalCtr lc{0, 0, 0, 0, 0, 0};
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = false;
     Walker<W> st;
-    st.begin(0, 0);
+    st.clear();
 
     auto emit = [&](u32 /*i*/, const u64 (&key)[W], bool fwd, float wf, bool good, u32 eb) {
-        n_raw++;
+        lc.raw++;
         if (!good) return;
-        n_good++;
+        lc.good++;
         Rec<W, HASX> rec;
         rec.pack(key, fwd, wf, eb);
         if (DIST) {
@@ -335,48 +444,19 @@ __global__ void __launch_bounds__(PARSE_TPB, 1) k_count_parse(ParseArgs a)
             }
         }
         u64 ph = place_hash<W>(key);
-        bins_put<W, HASX>(bins, a.table, part_of(ph, a.table.n_parts), rec, n_unique, n_full, n_direct, n_probes);
+        bins_put<W, HASX>(bins, a.stage, a.table, part_of(ph, a.table.n_parts), rec, lc);
     };
 
-    while (true) {
-        if (!active) {
-            while (r < a.n_reads) {
-                u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
-                u32 len = (u32)(o1 - o0);
-                bool disc = a.discarded && a.discarded[r];
-                if (!disc && len >= a.k) { st.begin(o0, len); active = true; break; }
-                r += stride;
-            }
-        }
-        if (active) {
-            walker_step<W, true, EXT>(st, a, ptab, emit);
-            if (st.j >= st.len) { active = false; r += stride; }
-        }
-        int more = __syncthreads_or(active || r < a.n_reads);
-        bins_flush<W, HASX>(bins, a.stage, a.table, a.flush_thresh, n_unique, n_full, n_direct, n_probes);
-        __syncthreads();
-        if (!more) break;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += stride) {
+        const u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
+        const u32 len = (u32)(o1 - o0);
+        if (len < a.k || (a.discarded && a.discarded[r])) continue;
+        st.template begin<true>(a, o0, len);
+        while (st.j < st.len) walker_step<W, true, EXT>(st, a, ptab, emit);
     }
-    bins_flush<W, HASX>(bins, a.stage, a.table, 1u, n_unique, n_full, n_direct, n_probes);
-
-    // statistics: warp reduce, one atomic per warp
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_raw += __shfl_xor_sync(0xffffffffu, n_raw, o);
-        n_good += __shfl_xor_sync(0xffffffffu, n_good, o);
-        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
-        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
-        n_direct += __shfl_xor_sync(0xffffffffu, n_direct, o);
-        n_probes += __shfl_xor_sync(0xffffffffu, n_probes, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (n_raw) atomicAdd(&a.ctr->raw, n_raw);
-        if (n_good) atomicAdd(&a.ctr->raw_good, n_good);
-        if (n_unique) atomicAdd(&a.ctr->unique, n_unique);
-        if (n_full) atomicAdd(&a.ctr->table_full, n_full);
-        if (n_direct) atomicAdd(&a.ctr->direct, n_direct);
-        if (n_probes) atomicAdd(&a.ctr->probe_steps, n_probes);
-    }
+    __syncthreads();
+    bins_drain<W, HASX>(bins, a.stage, a.table, lc);
+    ctr_commit(a.ctr, lc);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -385,7 +465,7 @@ __global__ void __launch_bounds__(PARSE_TPB, 1) k_count_parse(ParseArgs a)
 // ------------------------------------------------------------------------------------------------
 struct RouteArgs {
     const u64 *recs; u64 n_recs;
-    u32 bin_cap, flush_thresh;
+    u32 nb_log2, pad;
     TableView table; StageView stage; Counters *ctr;
 };
 
@@ -394,49 +474,22 @@ __global__ void __launch_bounds__(PARSE_TPB, 1) k_route_records(RouteArgs a)
 {
     constexpr int RW = Rec<W, HASX>::RW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *bin_recs = reinterpret_cast<u64 *>(smem_raw + 256 * sizeof(double));
-    u32 *bin_cnt = reinterpret_cast<u32 *>(bin_recs + (size_t)a.table.n_parts * a.bin_cap * RW);
-    for (u32 i = threadIdx.x; i < a.table.n_parts; i += blockDim.x) bin_cnt[i] = 0;
+    Bins<RW> bins = bins_init<RW>(smem_raw + 256 * sizeof(double), a.table.n_parts, a.nb_log2);
     __syncthreads();
-    Bins<RW> bins{bin_cnt, bin_recs, a.table.n_parts, a.bin_cap};
-    u64 n_unique = 0, n_full = 0, n_direct = 0, n_probes = 0;
+    LocalCtr lc{0, 0, 0, 0, 0, 0};
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    // each round a thread routes up to 4 records, then the CTA flushes (keeps bins from overflowing)
-    for (u64 base = (u64)blockIdx.x * blockDim.x; ; base += stride * 4) {
-        int any = 0;
+    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n_recs; idx += stride) {
+        Rec<W, HASX> rec;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            u64 idx = base + (u64)u * stride + threadIdx.x;
-            if (idx < a.n_recs) {
-                any = 1;
-                Rec<W, HASX> rec;
-#pragma unroll
-                for (int q = 0; q < RW; ++q) rec.w[q] = a.recs[idx * RW + q];
-                u64 key[W]; bool fwd; float wt; u32 eb;
-                rec.unpack(key, fwd, wt, eb);
-                u64 ph = place_hash<W>(key);
-                bins_put<W, HASX>(bins, a.table, part_of(ph, a.table.n_parts), rec, n_unique, n_full, n_direct, n_probes);
-            }
-        }
-        int more = __syncthreads_or(any);
-        bins_flush<W, HASX>(bins, a.stage, a.table, a.flush_thresh, n_unique, n_full, n_direct, n_probes);
-        __syncthreads();
-        if (!more) break;
+        for (int q = 0; q < RW; ++q) rec.w[q] = ld_nc64(a.recs + idx * RW + q);
+        u64 key[W]; bool fwd; float wt; u32 eb;
+        rec.unpack(key, fwd, wt, eb);
+        u64 ph = place_hash<W>(key);
+        bins_put<W, HASX>(bins, a.stage, a.table, part_of(ph, a.table.n_parts), rec, lc);
     }
-    bins_flush<W, HASX>(bins, a.stage, a.table, 1u, n_unique, n_full, n_direct, n_probes);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
-        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
-        n_direct += __shfl_xor_sync(0xffffffffu, n_direct, o);
-        n_probes += __shfl_xor_sync(0xffffffffu, n_probes, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (n_unique) atomicAdd(&a.ctr->unique, n_unique);
-        if (n_full) atomicAdd(&a.ctr->table_full, n_full);
-        if (n_direct) atomicAdd(&a.ctr->direct, n_direct);
-        if (n_probes) atomicAdd(&a.ctr->probe_steps, n_probes);
-    }
+    __syncthreads();
+    bins_drain<W, HASX>(bins, a.stage, a.table, lc);
+    ctr_commit(a.ctr, lc);
 }
 
 // number of k-mer positions in reads [0,n): sum max(0, len-k+1) (discarded reads excluded)
@@ -693,8 +746,9 @@ __global__ void __launch_bounds__(256) k_lookup_vals(ParseArgs a, u32 min_depth,
         u32 len = (u32)(o1 - o0);
         bool disc = a.discarded && a.discarded[r];
         Walker<W> st;
-        st.begin(o0, len);
+        st.clear();
         if (!disc && len >= a.k) {
+            st.template begin<false>(a, o0, len);
             auto emit = [&](u32 i, const u64 (&key)[W], bool, float, bool, u32) {
                 u64 ph = place_hash<W>(key);
                 u64 v = table_find<W>(a.table, part_of(ph, a.table.n_parts), home_slot(ph, a.table.part_slots), key, nullptr);
@@ -825,7 +879,7 @@ __global__ void __launch_bounds__(128) k_debug_kmers(ParseArgs a, const u64 *kme
         if (len < a.k) continue;
         const u64 ko = kmer_off[r];
         Walker<W> st;
-        st.begin(o0, len);
+        st.template begin<true>(a, o0, len);
         auto emit = [&](u32 i, const u64 (&key)[W], bool fwd, float wf, bool, u32) {
             for (u32 b = 0; b < a.kb; ++b) keys[(ko + i) * a.kb + b] = (uint8_t)(key[b >> 3] >> (56 - 8 * (b & 7)));
             is_fwd[ko + i] = fwd ? 1 : 0;
