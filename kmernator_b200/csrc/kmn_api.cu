@@ -62,6 +62,7 @@ struct kmn_ctx {
     DevBuf in_bases, in_quals, in_off, in_disc;
     // lookup pass scratch
     DevBuf vals, first_nx, out_off, out_len, out_score, out_trim, lk_keys, lk_out;
+    DevBuf lk_origin, lk_resp_in, lk_resp_out;   // multi-GPU lookup pass: request origins, answers in / out
     uint32_t purged_depth = 0;
     bool finished = false;
     // multi-GPU
@@ -332,6 +333,7 @@ void kmn_destroy(kmn_ctx *c)
     void *ptrs[] = {c->table.slots, c->table.wsum, c->table.ext, c->stage.recs, c->stage.cursor, c->chunk_start, c->next_item,
                     c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts,
                     c->in_bases.p, c->in_quals.p, c->in_off.p, c->in_disc.p, c->vals.p, c->first_nx.p, c->out_off.p,
+                    c->lk_origin.p, c->lk_resp_in.p, c->lk_resp_out.p,
                     c->out_len.p, c->out_score.p, c->out_trim.p, c->lk_keys.p, c->lk_out.p};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -722,16 +724,97 @@ int kmn_lookup(kmn_ctx *c, const uint8_t *keys, uint64_t n, uint16_t *counts)
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// multi-GPU lookup pass (DistributedReadSelector::scoreAndTrimReads, src/DistributedFunctions.h:903-1045): one round =
+// requests out (keys to their owner), answers back (u16 counts in request order).  Every rank takes part in every
+// round; a rank without work sends nothing.
+// ---------------------------------------------------------------------------------------------------------
+#ifdef KMN_WITH_NCCL
+static int allreduce_max_u64(kmn_ctx *c, u64 mine, u64 *out)
+{
+    CK(c, cudaMemcpyAsync(c->scratch + 6, &mine, 8, cudaMemcpyHostToDevice, c->stream));
+    ncclResult_t nr = ncclAllReduce(c->scratch + 6, c->scratch + 7, 1, ncclUint64, ncclMax, c->comm, c->stream);
+    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclAllReduce failed: %s", ncclGetErrorString(nr));
+    CK(c, cudaMemcpyAsync(out, c->scratch + 7, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// requests are in send_recs[dest][0..send_cursor[dest]) as W words per key, origins in lk_origin at the same positions
+static int lookup_exchange(kmn_ctx *c, uint32_t min_depth, uint16_t *vals)
+{
+    const int R = c->nranks, W = c->W;
+    ncclResult_t nr = ncclAllGather(c->send_cursor, c->all_counts, (size_t)R, ncclUint64, c->comm, c->stream);
+    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclAllGather failed: %s", ncclGetErrorString(nr));
+    std::vector<u64> counts((size_t)R * R);
+    CK(c, cudaMemcpyAsync(counts.data(), c->all_counts, counts.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    u64 recv_total = 0;
+    for (int p = 0; p < R; ++p) {
+        if (p == c->rank) continue;
+        if (counts[(size_t)c->rank * R + p] > c->send_cap) return fail(c, KMN_ERR_COMM, "lookup request region overflow");
+        recv_total += counts[(size_t)p * R + c->rank];
+    }
+    if (recv_total * W > c->recv_cap * (u64)c->RW) return fail(c, KMN_ERR_COMM, "lookup receive region overflow");
+    int r = ensure(c, c->lk_resp_out, recv_total * 2 + 16); if (r) return r;
+    ncclGroupStart();
+    u64 roff = 0;
+    for (int p = 0; p < R; ++p) {
+        if (p == c->rank) continue;
+        u64 ns = counts[(size_t)c->rank * R + p], nrv = counts[(size_t)p * R + c->rank];
+        if (ns) ncclSend(c->send_recs + (size_t)p * c->send_cap * W, ns * W, ncclUint64, p, c->comm, c->stream);
+        if (nrv) ncclRecv(c->recv_recs + roff * W, nrv * W, ncclUint64, p, c->comm, c->stream);
+        roff += nrv;
+    }
+    nr = ncclGroupEnd();
+    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "lookup request all-to-all failed: %s", ncclGetErrorString(nr));
+    if (recv_total) {
+        ProfScope ps(c, KMN_PROF_LOOKUP, recv_total);
+        KMN_DISPATCH_W(c, { k_lookup_words<W_><<<c->n_sms * 8, 256, 0, c->stream>>>(c->table, c->recv_recs, recv_total, (uint16_t *)c->lk_resp_out.p); });
+        c->launches++;
+        CK(c, cudaGetLastError());
+    }
+    ncclGroupStart();
+    roff = 0;
+    for (int p = 0; p < R; ++p) {
+        if (p == c->rank) continue;
+        u64 ns = counts[(size_t)c->rank * R + p], nrv = counts[(size_t)p * R + c->rank];
+        if (nrv) ncclSend((uint16_t *)c->lk_resp_out.p + roff, nrv * 2, ncclUint8, p, c->comm, c->stream);
+        if (ns) ncclRecv((uint16_t *)c->lk_resp_in.p + (size_t)p * c->send_cap, ns * 2, ncclUint8, p, c->comm, c->stream);
+        roff += nrv;
+    }
+    nr = ncclGroupEnd();
+    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "lookup answer all-to-all failed: %s", ncclGetErrorString(nr));
+    if (vals) {
+        dim3 grid(c->n_sms * 2, (unsigned)std::min(R, 8));
+        k_scatter_answers<<<grid, 256, 0, c->stream>>>((const uint16_t *)c->lk_resp_in.p, (const u64 *)c->lk_origin.p, c->send_cap,
+                                                       c->send_cursor, (u32)R, min_depth, vals);
+        c->launches++;
+        CK(c, cudaGetLastError());
+    }
+    CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)R * 8, c->stream));
+    return 0;
+}
+#endif
+
 int kmn_trim_batch(kmn_ctx *c, const uint8_t *bases, const uint64_t *read_off, uint64_t n_reads, const uint8_t *discarded,
                    uint32_t min_depth, int scoring, uint32_t *trim_off, uint32_t *trim_len, float *score, uint8_t *was_trimmed)
 {
     if (!c) return KMN_ERR_INVALID;
-    if (n_reads == 0) return 0;
-    if (!bases || !read_off || !trim_off || !trim_len || !score || !was_trimmed) return fail(c, KMN_ERR_INVALID, "null argument");
     if (scoring < 0 || scoring > 4) return fail(c, KMN_ERR_INVALID, "Invalid scoring type!");
-    if (c->nranks > 1) return fail(c, KMN_ERR_INVALID, "kmn_trim_batch with a communicator is not implemented yet");
     CK(c, cudaSetDevice(c->device));
     int r = drain(c); if (r) return r;
+#ifdef KMN_WITH_NCCL
+    if (c->nranks > 1 && n_reads == 0) {           // a rank without reads still serves the other ranks' requests
+        u64 rounds = 0;
+        r = allreduce_max_u64(c, 0, &rounds); if (r) return r;
+        for (u64 i = 0; i < rounds; ++i) { r = lookup_exchange(c, min_depth, nullptr); if (r) return r; }
+        return 0;
+    }
+#endif
+    if (n_reads == 0) return 0;
+    if (!bases || !read_off || !trim_off || !trim_len || !score || !was_trimmed) return fail(c, KMN_ERR_INVALID, "null argument");
     BatchPtrs bp;
     r = stage_inputs(c, bases, nullptr, read_off, n_reads, discarded, false, bp);
     if (r) return r;
@@ -740,12 +823,51 @@ int kmn_trim_batch(kmn_ctx *c, const uint8_t *bases, const uint64_t *read_off, u
     ParseArgs a;
     fill_parse_args(c, a, bp.bases, nullptr, bp.off, bp.disc, n_reads, bp.total_bytes);
     const int grid = c->n_sms * 8;
-    {
+    if (c->nranks > 1) {
+#ifdef KMN_WITH_NCCL
+        // rounds: read ranges whose k-mer positions fit one request region even if every k-mer had the same owner
+        r = ensure(c, c->lk_origin, (size_t)c->nranks * c->send_cap * 8); if (r) return r;
+        r = ensure(c, c->lk_resp_in, (size_t)c->nranks * c->send_cap * 2); if (r) return r;
+        std::vector<u64> hoff;
+        const u64 *ho = reinterpret_cast<const u64 *>(read_off);
+        if (!bp.off_on_host) {
+            hoff.resize(n_reads + 1);
+            CK(c, cudaMemcpyAsync(hoff.data(), bp.off, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+            CK(c, cudaStreamSynchronize(c->stream));
+            ho = hoff.data();
+        }
+        std::vector<uint64_t> cuts(1, 0);
+        u64 acc = 0;
+        for (uint64_t q = 0; q < n_reads; ++q) {
+            u64 len = ho[q + 1] - ho[q];
+            u64 np = len >= c->o.kmer_size ? len - c->o.kmer_size + 1 : 0;
+            if (np > c->send_cap) return fail(c, KMN_ERR_INVALID, "read %llu has more k-mers than the request region (%llu)", (unsigned long long)q, (unsigned long long)c->send_cap);
+            if (acc + np > c->send_cap) { cuts.push_back(q); acc = 0; }
+            acc += np;
+        }
+        cuts.push_back(n_reads);
+        u64 rounds = 0;
+        r = allreduce_max_u64(c, cuts.size() - 1, &rounds); if (r) return r;
+        for (u64 i = 0; i < rounds; ++i) {
+            if (i + 1 < cuts.size()) {
+                ParseArgs ai = a;
+                ai.read_off = bp.off + cuts[i]; ai.discarded = bp.disc ? bp.disc + cuts[i] : nullptr; ai.n_reads = cuts[i + 1] - cuts[i];
+                ProfScope ps(c, KMN_PROF_LOOKUP, ai.n_reads);
+                KMN_DISPATCH_W(c, { k_lookup_vals_dist<W_><<<grid, 256, 0, c->stream>>>(ai, min_depth, (uint16_t *)c->vals.p, (u32 *)c->first_nx.p + cuts[i], (u64 *)c->lk_origin.p); });
+                c->launches++;
+                CK(c, cudaGetLastError());
+            }
+            r = lookup_exchange(c, min_depth, (uint16_t *)c->vals.p); if (r) return r;
+        }
+#else
+        return fail(c, KMN_ERR_COMM, "library built without NCCL");
+#endif
+    } else {
         ProfScope ps(c, KMN_PROF_LOOKUP, bp.total_bytes);
         KMN_DISPATCH_W(c, { k_lookup_vals<W_><<<grid, 256, 0, c->stream>>>(a, min_depth, (uint16_t *)c->vals.p, (u32 *)c->first_nx.p); });
+        c->launches++;
+        CK(c, cudaGetLastError());
     }
-    c->launches++;
-    CK(c, cudaGetLastError());
     TrimArgs t;
     t.read_off = bp.off; t.discarded = bp.disc; t.vals = (const uint16_t *)c->vals.p; t.first_nx = (const u32 *)c->first_nx.p;
     t.n_reads = n_reads; t.k = c->o.kmer_size; t.min_depth = min_depth; t.scoring = scoring;

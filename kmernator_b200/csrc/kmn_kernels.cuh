@@ -765,6 +765,78 @@ __global__ void __launch_bounds__(256) k_lookup_vals(ParseArgs a, u32 min_depth,
 }
 
 // ------------------------------------------------------------------------------------------------
+// K7a (multi-GPU): DistributedReadSelector::_batchKmerLookup (src/DistributedFunctions.h:877-902): a k-mer owned by
+// this rank is looked up locally; any other k-mer becomes a request (its key words) in the owner's send region, and the
+// place its answer belongs to (index into vals) is remembered in `origin` at the same position.  Requests and
+// answers travel as two all-to-alls in the same order, so no request id is needed (the reference sends
+// {requestId, k-mer} out and {requestId, score} back, :809-874).
+// ------------------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256) k_lookup_vals_dist(ParseArgs a, u32 min_depth, uint16_t *vals, u32 *first_nx, u64 *origin)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += stride) {
+        u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
+        u32 len = (u32)(o1 - o0);
+        bool disc = a.discarded && a.discarded[r];
+        Walker<W> st;
+        st.clear();
+        if (!disc && len >= a.k) {
+            st.template begin<false>(a, o0, len);
+            auto emit = [&](u32 i, const u64 (&key)[W], bool, float, bool, u32) {
+                const u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
+                const u32 own = owner_of(h, a.nranks);
+                if (own == a.rank) {
+                    u64 ph = place_hash<W>(key);
+                    u64 v = table_find<W>(a.table, part_of(ph, a.table.n_parts), home_slot(ph, a.table.part_slots), key, nullptr);
+                    u32 c = clamp_count(v);
+                    vals[o0 + i] = (uint16_t)(c >= min_depth ? c : 0u);
+                } else {
+                    const u64 pos = atomicAdd(&a.send_cursor[own], 1ull);
+                    if (pos < a.send_cap) {
+                        u64 *d = a.send_recs + ((size_t)own * a.send_cap + pos) * W;
+#pragma unroll
+                        for (int q = 0; q < W; ++q) d[q] = key[q];
+                        origin[(size_t)own * a.send_cap + pos] = o0 + i;
+                    }
+                }
+            };
+            while (st.j < st.len) walker_step<W, false, false>(st, a, nullptr, emit);
+        } else if (!disc) {
+            for (u32 j = 0; j < len; ++j) { u32 c = base_code(a.bases[o0 + j]); if (c == 4 && st.first_nx == 0) st.first_nx = j + 1; }
+        }
+        first_nx[r] = st.first_nx;
+    }
+}
+
+// owner side: answer the received requests (keys as W words each) in order
+template <int W>
+__global__ void __launch_bounds__(256) k_lookup_words(TableView t, const u64 *keys, u64 n, uint16_t *out)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 key[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) key[q] = keys[i * W + q];
+        u64 ph = place_hash<W>(key);
+        u64 v = table_find<W>(t, part_of(ph, t.n_parts), home_slot(ph, t.part_slots), key, nullptr);
+        out[i] = (uint16_t)clamp_count(v);
+    }
+}
+
+// requester side: put the answers where they belong (setKmerValues semantics: below min_depth -> 0)
+__global__ void __launch_bounds__(256) k_scatter_answers(const uint16_t *resp, const u64 *origin, u64 region_cap, const u64 *counts,
+                                                         u32 nranks, u32 min_depth, uint16_t *vals)
+{
+    for (u32 d = blockIdx.y; d < nranks; d += gridDim.y) {
+        const u64 n = counts[d];
+        for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+            const u32 c = resp[(size_t)d * region_cap + i];
+            vals[origin[(size_t)d * region_cap + i]] = (uint16_t)(c >= min_depth ? c : 0u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K7b: lookup pass, part 2.  One warp per read: longest run of vals >= min_depth over [0,numKmers)
 // (first-longest wins), score of the run, ReadTrimType after setTrimHeaders.
 // ReadSelector::trimReadByMinimumKmerScore / scoreReadByScoringType / setTrimHeaders / _setNumKmers
