@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--stage-keys", type=int, default=0)
     ap.add_argument("--slice-mb", type=int, default=32)
+    ap.add_argument("--pipe-batches", type=int, default=1, help="sub-batches of the parse/insert pipeline per step")
     ap.add_argument("--e2e-reads", type=int, default=20_000_000)
     ap.add_argument("--e2e-batch", type=int, default=2_000_000)
     ap.add_argument("--cpu-reads", type=int, default=400_000)
@@ -168,13 +169,8 @@ def main():
     # distinct k-mers ~ genome (coverage 60x) + ~30 error k-mers per substitution: 0.7 G for C2 -> 1.4 G slots at load 0.5
     est_distinct = int(genome_len / world * 1.02 + n_reads * READ_LEN * 0.001 * 31 * 1.05)
     table_slots = args.table_slots or int(est_distinct / 0.5)
-    free_b, _ = torch.cuda.mem_get_info(dev)
-    stage_keys = args.stage_keys
-    if not stage_keys:
-        budget = free_b - table_slots * 16 - (6 << 30)
-        if world > 1:
-            budget = int(budget * 0.55)
-        stage_keys = max(1 << 24, min(int(inst_per_rank * 1.02), int(budget / 8 / 1.13)))
+    # staging: two sets of stage_keys records; one set = one sub-batch of the parse/insert pipeline (default: 1/8 of the input)
+    stage_keys = args.stage_keys or int(inst_per_rank * 1.02 / args.pipe_batches)
     ctx = KM.Context(kmer_size=K, est_raw_kmers=inst_per_rank, table_slots=table_slots, stage_keys=stage_keys,
                      slice_bytes=args.slice_mb << 20, device=local_rank)
     if world > 1:

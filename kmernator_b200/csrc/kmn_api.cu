@@ -32,8 +32,11 @@ struct kmn_ctx {
     bool hasx = false, ext = false, weights = false;
     int RW = 1;
     int device = 0, n_sms = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_in_free[2] = {nullptr, nullptr};
+    cudaStream_t stream = nullptr;        // main stream: phase 1 (parse), scans, lookup pass; the one kmn_stream() returns
+    cudaStream_t s_insert = nullptr;      // phase 2 (insert) runs here so that it overlaps phase 1 of the next sub-batch
+    cudaStream_t s_copy = nullptr;        // H2D staging of host inputs, overlapping the kernels of the previous batch
+    bool pipeline = false;                // two staging sets + insert stream (KMN_PIPELINE=1); off: phase 2 follows phase 1 on the main stream
+    int n_sets = 1;
     std::string err;
     uint64_t launches = 0;
     // optional per-kernel timing
@@ -46,11 +49,17 @@ struct kmn_ctx {
     TableView table{};
     uint64_t n_slots = 0;
     size_t slot_bytes = 0;
-    // staging
-    StageView stage{};
-    uint64_t stage_keys = 0;          // total record capacity targeted before a drain
-    uint64_t staged_upper = 0;        // upper bound of records currently staged
+    // staging: two sets, so that phase 2 drains one while phase 1 fills the other
+    struct StageSet {
+        StageView v{};
+        uint64_t staged_upper = 0;    // upper bound of records currently staged in this set
+        cudaEvent_t ev_parsed = nullptr, ev_drained = nullptr;
+        bool drain_pending = false;   // a drain was submitted on s_insert and the main stream has not waited for it yet
+    } sets[2];
+    int cur = 0;
+    uint64_t stage_keys = 0;          // record capacity of ONE set (= the sub-batch size of the pipeline)
     u64 *chunk_start = nullptr, *next_item = nullptr;
+    int insert_ctas = 8;              // phase-2 CTAs per SM
     Counters *ctr = nullptr;
     double *ptab = nullptr;
     u64 *scratch = nullptr;           // small device scalars
@@ -58,8 +67,11 @@ struct kmn_ctx {
     int parse_tpb = 512;
     uint32_t nb_log2 = 1, zero_below = 0;
     size_t parse_smem = 0;
-    // input staging (host inputs)
-    DevBuf in_bases, in_quals, in_off, in_disc;
+    // input staging (host inputs), double-buffered: the copy of batch b+1 overlaps the kernels of batch b
+    DevBuf in_bases[2], in_quals[2], in_off[2], in_disc[2];
+    cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
+    bool in_used[2] = {false, false};
+    int in_cur = 0;
     // lookup pass scratch
     DevBuf vals, first_nx, out_off, out_len, out_score, out_trim, lk_keys, lk_out;
     DevBuf lk_origin, lk_resp_in, lk_resp_out;   // multi-GPU lookup pass: request origins, answers in / out
@@ -95,17 +107,17 @@ static int fail(kmn_ctx *c, int code, const char *fmt, ...)
 
 // RAII timer around one kernel launch (no-op unless profiling is enabled)
 struct ProfScope {
-    kmn_ctx *c; cudaEvent_t a = nullptr, b = nullptr; int kind; uint64_t units;
-    ProfScope(kmn_ctx *c_, int kind_, uint64_t units_) : c(c_), kind(kind_), units(units_)
+    kmn_ctx *c; cudaEvent_t a = nullptr, b = nullptr; int kind; uint64_t units; cudaStream_t st;
+    ProfScope(kmn_ctx *c_, int kind_, uint64_t units_, cudaStream_t st_ = nullptr) : c(c_), kind(kind_), units(units_), st(st_ ? st_ : c_->stream)
     {
         if (!c->prof_on) return;
         cudaEventCreate(&a); cudaEventCreate(&b);
-        cudaEventRecord(a, c->stream);
+        cudaEventRecord(a, st);
     }
     ~ProfScope()
     {
         if (!a) return;
-        cudaEventRecord(b, c->stream);
+        cudaEventRecord(b, st);
         c->prof_events.push_back({a, b, kind, units});
     }
 };
@@ -129,13 +141,19 @@ static bool is_device_ptr(const void *p)
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-// dispatch on (W, HASX, EXT, DIST)
+// dispatch on (W, HASX, EXT, DIST).  -DKMN_ONLY_W1 (developer builds) instantiates k <= 32 only.
+#ifdef KMN_ONLY_W1
+#define KMN_WIDE_CASES(...)
+#else
+#define KMN_WIDE_CASES(...)                                            \
+    case 2: { constexpr int W_ = 2; __VA_ARGS__; } break;              \
+    case 3: { constexpr int W_ = 3; __VA_ARGS__; } break;              \
+    case 4: { constexpr int W_ = 4; __VA_ARGS__; } break;
+#endif
 #define KMN_DISPATCH_W(c, ...)                                         \
     switch ((c)->W) {                                                  \
     case 1: { constexpr int W_ = 1; __VA_ARGS__; } break;              \
-    case 2: { constexpr int W_ = 2; __VA_ARGS__; } break;              \
-    case 3: { constexpr int W_ = 3; __VA_ARGS__; } break;              \
-    case 4: { constexpr int W_ = 4; __VA_ARGS__; } break;              \
+    KMN_WIDE_CASES(__VA_ARGS__)                                        \
     default: return fail(c, KMN_ERR_INVALID, "unsupported key width"); \
     }
 #define KMN_DISPATCH_X(c, ...)                                   \
@@ -194,12 +212,13 @@ static int plan_and_alloc(kmn_ctx *c)
     // is bounded by the shared memory the phase-1 bins need (>= 16 records per bin)
     int dev_smem = 0;
     CK(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    const size_t smem_avail = (size_t)dev_smem - 256 * sizeof(double) - 1024;
+    // phase 1 leaves 8 KB of the SM's shared memory to the co-resident phase-2 CTAs (static + per-CTA reserved)
+    const size_t smem_avail = (size_t)dev_smem - 256 * sizeof(double) - 1024 - 8192;
     const uint32_t slice = o.slice_bytes ? o.slice_bytes : (32u << 20);
     uint64_t part_slots = std::max<uint64_t>(slice / c->slot_bytes, 256);
     uint64_t n_parts = (slots + part_slots - 1) / part_slots;
-    // shared memory per partition with the minimum ring (2 blocks x 8 records): 2*(64*RW+4)+4 bytes
-    const uint64_t p_max = smem_avail / (2 * (64 * (size_t)c->RW + 4) + 4);
+    // shared memory per partition with the minimum ring (2 blocks x 8 records): 2*(64*RW+4)+8 bytes
+    const uint64_t p_max = smem_avail / (2 * (64 * (size_t)c->RW + 4) + 8);
     if (n_parts > p_max) n_parts = p_max;
     if (n_parts < 1) n_parts = 1;
     part_slots = (slots + n_parts - 1) / n_parts;
@@ -209,30 +228,40 @@ static int plan_and_alloc(kmn_ctx *c)
     c->table.part_slots = part_slots;
     c->table.n_parts = (u32)n_parts;
 
-    c->parse_tpb = 512;
     uint32_t nbl = 1;                       // ring blocks per bin: largest power of two that fits, at most 64
-    while (nbl < 6 && (uint64_t)n_parts * ((2ull << nbl) * (64 * (size_t)c->RW + 4) + 4) <= smem_avail) nbl++;
+    while (nbl < 6 && (uint64_t)n_parts * ((2ull << nbl) * (64 * (size_t)c->RW + 4) + 8) <= smem_avail) nbl++;
     c->nb_log2 = nbl;
-    c->parse_smem = 256 * sizeof(double) + (size_t)n_parts * ((1ull << nbl) * (64 * (size_t)c->RW + 4) + 4);
+    c->parse_smem = 256 * sizeof(double) + (size_t)n_parts * ((1ull << nbl) * (64 * (size_t)c->RW + 4) + 8);
 
     CK(c, cudaMalloc(&c->table.slots, slots * c->slot_bytes));
     if (c->weights) CK(c, cudaMalloc((void **)&c->table.wsum, slots * 4));
     if (c->ext) CK(c, cudaMalloc((void **)&c->table.ext, slots * 48));
 
-    // staging capacity
+    // staging capacity: stage_keys records per set.  Pipelined (two sets): one set is one sub-batch (phase 2 drains it
+    // while phase 1 fills the other), so the default aims at ~8 sub-batches over the expected input.  Otherwise one set
+    // that takes the whole expected input when memory allows: every drain streams the whole table through L2 once.
     CK(c, cudaMemGetInfo(&free_b, &total_b));
     uint64_t sk = o.stage_keys;
     if (!sk) {
-        sk = o.est_raw_kmers ? o.est_raw_kmers : (1ull << 22);
-        uint64_t lim = (uint64_t)(0.35 * (double)free_b / (double)(c->RW * 8));
+        sk = (o.est_raw_kmers ? o.est_raw_kmers : (1ull << 22)) / (c->pipeline ? 8 : 1);
+        uint64_t lim = (uint64_t)(0.35 * (double)free_b / (double)(c->RW * 8) / (double)c->n_sets);
         if (sk > lim) sk = lim;
     }
     if (sk < (1ull << 16)) sk = 1ull << 16;
     c->stage_keys = sk;
-    c->stage.part_cap = sk / n_parts + sk / n_parts / 8 + 4096;
-    CK(c, cudaMalloc((void **)&c->stage.recs, (size_t)n_parts * c->stage.part_cap * c->RW * 8));
-    CK(c, cudaMalloc((void **)&c->stage.cursor, n_parts * 8));
-    CK(c, cudaMalloc((void **)&c->chunk_start, (n_parts + 1) * 8));
+    const uint64_t n_cta = (uint64_t)c->n_sms;
+    const uint64_t per_sub = sk / n_parts / n_cta;
+    const uint64_t sub_cap = per_sub + per_sub / 8 + 8 * (uint64_t)std::sqrt((double)per_sub + 1.0) + 64;   // mean + slack for the spread
+    if (sub_cap >= (1ull << 31)) return fail(c, KMN_ERR_INVALID, "staging sub-region too large (%llu records)", (unsigned long long)sub_cap);
+    for (int si = 0; si < c->n_sets; ++si) {
+        kmn_ctx::StageSet &st = c->sets[si];
+        st.v.sub_cap = (u32)sub_cap; st.v.n_cta = (u32)n_cta;
+        CK(c, cudaMalloc((void **)&st.v.recs, (size_t)n_parts * n_cta * sub_cap * c->RW * 8));
+        CK(c, cudaMalloc((void **)&st.v.count, (size_t)n_parts * n_cta * 4));
+        CK(c, cudaEventCreateWithFlags(&st.ev_parsed, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&st.ev_drained, cudaEventDisableTiming));
+    }
+    CK(c, cudaMalloc((void **)&c->chunk_start, ((size_t)n_parts * n_cta + 1) * 8));
     CK(c, cudaMalloc((void **)&c->next_item, 8));
     CK(c, cudaMalloc((void **)&c->ctr, sizeof(Counters)));
     CK(c, cudaMalloc((void **)&c->scratch, 64));
@@ -252,16 +281,23 @@ static int plan_and_alloc(kmn_ctx *c)
     return 0;
 }
 
+static int wait_drains(kmn_ctx *c);
+
 int kmn_reset(kmn_ctx *c)
 {
     if (!c) return KMN_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    int r = wait_drains(c); if (r) return r;          // phase-2 work still in flight must not see the cleared table
     CK(c, cudaMemsetAsync(c->table.slots, 0, c->n_slots * c->slot_bytes, c->stream));
     if (c->table.wsum) CK(c, cudaMemsetAsync(c->table.wsum, 0, c->n_slots * 4, c->stream));
     if (c->table.ext) CK(c, cudaMemsetAsync(c->table.ext, 0, c->n_slots * 48, c->stream));
-    CK(c, cudaMemsetAsync(c->stage.cursor, 0, (size_t)c->table.n_parts * 8, c->stream));
+    for (int si = 0; si < c->n_sets; ++si) {
+        kmn_ctx::StageSet &st = c->sets[si];
+        CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)c->table.n_parts * st.v.n_cta * 4, c->stream));
+        st.staged_upper = 0;
+    }
     CK(c, cudaMemsetAsync(c->ctr, 0, sizeof(Counters), c->stream));
     if (c->send_cursor) CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)c->nranks * 8, c->stream));
-    c->staged_upper = 0;
     c->purged_depth = 0;
     c->finished = false;
     return 0;
@@ -301,6 +337,19 @@ int kmn_create(kmn_ctx **out, const kmn_opts *opts)
         if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "cudaGetDeviceProperties failed"); break; }
         c->n_sms = prop.multiProcessorCount;
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "stream create failed"); break; }
+        // tuning knobs (bench experiments only; the defaults are the measured best)
+        if (const char *e = getenv("KMN_PIPELINE")) c->pipeline = atoi(e) != 0;
+        c->n_sets = c->pipeline ? 2 : 1;
+        if (const char *e = getenv("KMN_INSERT_CTAS")) c->insert_ctas = std::max(1, atoi(e));
+        if (const char *e = getenv("KMN_PARSE_TPB")) c->parse_tpb = std::min(PARSE_TPB, std::max(32, atoi(e) / 32 * 32));
+        if (c->pipeline) {
+            if (cudaStreamCreateWithFlags(&c->s_insert, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "stream create failed"); break; }
+        } else c->s_insert = c->stream;
+        if (cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "stream create failed"); break; }
+        for (int i = 0; i < 2; ++i) {
+            cudaEventCreateWithFlags(&c->ev_in_ready[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&c->ev_in_free[i], cudaEventDisableTiming);
+        }
         rc = plan_and_alloc(c);
         if (rc) break;
         {
@@ -326,16 +375,24 @@ void kmn_destroy(kmn_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    if (c->s_insert) cudaStreamSynchronize(c->s_insert);
     if (c->stream) cudaStreamSynchronize(c->stream);
 #ifdef KMN_WITH_NCCL
     if (c->comm) ncclCommDestroy(c->comm);
 #endif
-    void *ptrs[] = {c->table.slots, c->table.wsum, c->table.ext, c->stage.recs, c->stage.cursor, c->chunk_start, c->next_item,
+    void *ptrs[] = {c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
+                    c->chunk_start, c->next_item,
                     c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts,
-                    c->in_bases.p, c->in_quals.p, c->in_off.p, c->in_disc.p, c->vals.p, c->first_nx.p, c->out_off.p,
+                    c->in_bases[0].p, c->in_quals[0].p, c->in_off[0].p, c->in_disc[0].p,
+                    c->in_bases[1].p, c->in_quals[1].p, c->in_off[1].p, c->in_disc[1].p, c->vals.p, c->first_nx.p, c->out_off.p,
                     c->lk_origin.p, c->lk_resp_in.p, c->lk_resp_out.p,
                     c->out_len.p, c->out_score.p, c->out_trim.p, c->lk_keys.p, c->lk_out.p};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &st : c->sets) { if (st.ev_parsed) cudaEventDestroy(st.ev_parsed); if (st.ev_drained) cudaEventDestroy(st.ev_drained); }
+    for (int i = 0; i < 2; ++i) { if (c->ev_in_ready[i]) cudaEventDestroy(c->ev_in_ready[i]); if (c->ev_in_free[i]) cudaEventDestroy(c->ev_in_free[i]); }
+    if (c->s_insert && c->s_insert != c->stream) cudaStreamDestroy(c->s_insert);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -343,33 +400,74 @@ void kmn_destroy(kmn_ctx *c)
 // ---------------------------------------------------------------------------------------------------------
 // phase 2: drain the staging regions into the table
 // ---------------------------------------------------------------------------------------------------------
-static int drain(kmn_ctx *c)
+// submit the drain of one staging set on the insert stream (after everything staged so far on the main stream)
+static int submit_drain(kmn_ctx *c, int i)
 {
-    if (c->staged_upper == 0) return 0;
-    k_build_worklist<<<1, 1024, 0, c->stream>>>(c->stage.cursor, c->stage.part_cap, c->table.n_parts, c->chunk_start, c->next_item);
+    kmn_ctx::StageSet &st = c->sets[i];
+    if (st.staged_upper == 0) return 0;
+    cudaStream_t si = c->s_insert;
+    if (si != c->stream) {
+        CK(c, cudaEventRecord(st.ev_parsed, c->stream));
+        CK(c, cudaStreamWaitEvent(si, st.ev_parsed, 0));
+    }
+    const u32 n_entries = c->table.n_parts * st.v.n_cta;
+    k_build_worklist<<<1, 1024, 0, si>>>(st.v.count, st.v.sub_cap, n_entries, c->chunk_start, c->next_item);
     c->launches++;
-    const int grid = c->n_sms * 8;
+    const int grid = c->n_sms * c->insert_ctas;
     {
-        ProfScope ps(c, KMN_PROF_INSERT, c->staged_upper);
+        ProfScope ps(c, KMN_PROF_INSERT, st.staged_upper, si);
         KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
-            k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, c->stream>>>(c->table, c->stage, c->chunk_start, c->next_item, c->ctr);
+            k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, si>>>(c->table, st.v, c->chunk_start, c->next_item, c->ctr);
         }));
     }
     c->launches++;
     CK(c, cudaGetLastError());
-    CK(c, cudaMemsetAsync(c->stage.cursor, 0, (size_t)c->table.n_parts * 8, c->stream));
-    c->staged_upper = 0;
+    CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)n_entries * 4, si));
+    if (si != c->stream) {
+        CK(c, cudaEventRecord(st.ev_drained, si));
+        st.drain_pending = true;
+    }
+    st.staged_upper = 0;
+    return 0;
+}
+
+// the main stream waits for every drain submitted so far
+static int wait_drains(kmn_ctx *c)
+{
+    for (auto &st : c->sets)
+        if (st.drain_pending) { CK(c, cudaStreamWaitEvent(c->stream, st.ev_drained, 0)); st.drain_pending = false; }
+    return 0;
+}
+
+// everything staged so far is in the table as far as later work on the main stream is concerned
+static int drain(kmn_ctx *c)
+{
+    int r = submit_drain(c, c->cur); if (r) return r;
+    return wait_drains(c);
+}
+
+// make room for n more records in the current set: when it would overflow, hand it to phase 2 and switch to the
+// other set (waiting, on the main stream, for that set's previous drain)
+static int stage_room(kmn_ctx *c, uint64_t n)
+{
+    if (c->sets[c->cur].staged_upper + n > c->stage_keys && c->sets[c->cur].staged_upper > 0) {
+        int r = submit_drain(c, c->cur); if (r) return r;
+        if (c->n_sets > 1) c->cur ^= 1;
+    }
+    kmn_ctx::StageSet &st = c->sets[c->cur];
+    if (st.drain_pending) { CK(c, cudaStreamWaitEvent(c->stream, st.ev_drained, 0)); st.drain_pending = false; }
     return 0;
 }
 
 static int count_positions(kmn_ctx *c, const u64 *off, const uint8_t *disc, uint64_t n_reads, uint64_t *out)
 {
-    CK(c, cudaMemsetAsync(c->scratch + 4, 0, 8, c->stream));
-    k_count_positions<<<c->n_sms * 4, 256, 0, c->stream>>>(off, disc, n_reads, c->o.kmer_size, c->scratch + 4);
+    // on the copy stream: sizing the next sub-batch must not wait behind the kernels queued on the main stream
+    CK(c, cudaMemsetAsync(c->scratch + 4, 0, 8, c->s_copy));
+    k_count_positions<<<c->n_sms * 4, 256, 0, c->s_copy>>>(off, disc, n_reads, c->o.kmer_size, c->scratch + 4);
     c->launches++;
     CK(c, cudaGetLastError());
-    CK(c, cudaMemcpyAsync(out, c->scratch + 4, 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaMemcpyAsync(out, c->scratch + 4, 8, cudaMemcpyDeviceToHost, c->s_copy));
+    CK(c, cudaStreamSynchronize(c->s_copy));
     return 0;
 }
 
@@ -384,7 +482,7 @@ static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, cons
     a.nb_log2 = c->nb_log2; a.zero_below = c->zero_below;
     a.nranks = (u32)c->nranks; a.rank = (u32)c->rank;
     a.use_lookup8 = c->o.hash_kind == KMN_HASH_LOOKUP8_HASH2;
-    a.table = c->table; a.stage = c->stage; a.ctr = c->ctr;
+    a.table = c->table; a.stage = c->sets[c->cur].v; a.ctr = c->ctr;
     a.send_recs = c->send_recs; a.send_cursor = c->send_cursor; a.send_cap = c->send_cap;
 }
 
@@ -449,10 +547,10 @@ static int exchange(kmn_ctx *c)
     if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "nccl all-to-all failed: %s", ncclGetErrorString(nr));
     CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)R * 8, c->stream));
     if (recv_total) {
-        if (c->staged_upper + recv_total > c->stage_keys) { int r = drain(c); if (r) return r; }
+        { int r = stage_room(c, recv_total); if (r) return r; }
         RouteArgs ra;
         ra.recs = c->recv_recs; ra.n_recs = recv_total; ra.nb_log2 = c->nb_log2; ra.pad = 0;
-        ra.table = c->table; ra.stage = c->stage; ra.ctr = c->ctr;
+        ra.table = c->table; ra.stage = c->sets[c->cur].v; ra.ctr = c->ctr;
         {
             ProfScope ps(c, KMN_PROF_ROUTE, recv_total);
             KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
@@ -461,7 +559,7 @@ static int exchange(kmn_ctx *c)
         }
         c->launches++;
         CK(c, cudaGetLastError());
-        c->staged_upper += recv_total;
+        c->sets[c->cur].staged_upper += recv_total;
     }
     return 0;
 #else
@@ -489,7 +587,7 @@ int kmn_comm_init(kmn_ctx *c, int rank, int nranks, const void *id128)
     if (!c) return KMN_ERR_INVALID;
 #ifdef KMN_WITH_NCCL
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, KMN_ERR_INVALID, "bad rank %d / %d", rank, nranks);
-    if (c->staged_upper) return fail(c, KMN_ERR_STATE, "kmn_comm_init after counting started");
+    if (c->sets[0].staged_upper || c->sets[1].staged_upper) return fail(c, KMN_ERR_STATE, "kmn_comm_init after counting started");
     c->rank = rank; c->nranks = nranks;
     if (nranks == 1) return 0;
     CK(c, cudaSetDevice(c->device));
@@ -497,7 +595,7 @@ int kmn_comm_init(kmn_ctx *c, int rank, int nranks, const void *id128)
     memcpy(&id, id128, 128);
     ncclResult_t nr = ncclCommInitRank(&c->comm, nranks, id, rank);
     if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclCommInitRank failed: %s", ncclGetErrorString(nr));
-    // send/recv regions: a batch is bounded by stage_keys/2 records, 1/nranks of which go to each peer on average
+    // send/recv regions: a launch is bounded by stage_keys/2 instances, 1/nranks of which go to each peer on average
     c->send_cap = c->stage_keys / 2 / (uint64_t)nranks * 3 / 2 + 65536;
     c->recv_cap = c->send_cap * (uint64_t)(nranks - 1);
     CK(c, cudaMalloc((void **)&c->send_recs, (size_t)nranks * c->send_cap * c->RW * 8));
@@ -519,10 +617,13 @@ struct BatchPtrs {
     const uint8_t *bases, *quals, *disc;
     const u64 *off;
     uint64_t total_bytes;
-    std::vector<u64> host_off;     // filled only when splitting is needed or offsets were on the host
     bool off_on_host;
+    int slot = -1;                 // input staging slot used for host inputs (-1: everything was already on the device)
 };
 
+// Host inputs are copied into one of two device staging slots on the copy stream, so the copy of this batch overlaps
+// the kernels of the previous one; the main stream waits for the copy, the copy waits until the slot's previous
+// batch has been consumed.
 static int stage_inputs(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, const uint64_t *read_off, uint64_t n_reads,
                         const uint8_t *discarded, bool need_quals, BatchPtrs &bp)
 {
@@ -530,39 +631,54 @@ static int stage_inputs(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, 
     u64 first = 0, last = 0;
     if (bp.off_on_host) { first = read_off[0]; last = read_off[n_reads]; }
     else {
-        CK(c, cudaMemcpyAsync(&first, read_off, 8, cudaMemcpyDeviceToHost, c->stream));
-        CK(c, cudaMemcpyAsync(&last, read_off + n_reads, 8, cudaMemcpyDeviceToHost, c->stream));
-        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, cudaMemcpyAsync(&first, read_off, 8, cudaMemcpyDeviceToHost, c->s_copy));
+        CK(c, cudaMemcpyAsync(&last, read_off + n_reads, 8, cudaMemcpyDeviceToHost, c->s_copy));
+        CK(c, cudaStreamSynchronize(c->s_copy));
     }
     if (first != 0) return fail(c, KMN_ERR_INVALID, "read_off[0] must be 0");
+    if (need_quals && !quals) return fail(c, KMN_ERR_INVALID, "quals is required");
     bp.total_bytes = last;
+    const bool h_bases = !is_device_ptr(bases), h_quals = need_quals && !is_device_ptr(quals), h_disc = discarded && !is_device_ptr(discarded);
+    bp.off = reinterpret_cast<const u64 *>(read_off); bp.bases = bases; bp.quals = need_quals ? quals : nullptr; bp.disc = discarded;
+    if (!(bp.off_on_host || h_bases || h_quals || h_disc)) return 0;
+    const int j = c->in_cur;
+    c->in_cur ^= 1;
+    bp.slot = j;
+    if (c->in_used[j]) CK(c, cudaStreamWaitEvent(c->s_copy, c->ev_in_free[j], 0));
+    cudaStream_t sc = c->s_copy;
     if (bp.off_on_host) {
-        int r = ensure(c, c->in_off, (n_reads + 1) * 8); if (r) return r;
-        CK(c, cudaMemcpyAsync(c->in_off.p, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-        bp.off = (const u64 *)c->in_off.p;
-    } else bp.off = reinterpret_cast<const u64 *>(read_off);
-    if (!is_device_ptr(bases)) {
-        int r = ensure(c, c->in_bases, last + 16); if (r) return r;
-        CK(c, cudaMemcpyAsync(c->in_bases.p, bases, last, cudaMemcpyHostToDevice, c->stream));
-        bp.bases = (const uint8_t *)c->in_bases.p;
-    } else bp.bases = bases;
-    bp.quals = nullptr;
-    if (need_quals) {
-        if (!quals) return fail(c, KMN_ERR_INVALID, "quals is required");
-        if (!is_device_ptr(quals)) {
-            int r = ensure(c, c->in_quals, last + 16); if (r) return r;
-            CK(c, cudaMemcpyAsync(c->in_quals.p, quals, last, cudaMemcpyHostToDevice, c->stream));
-            bp.quals = (const uint8_t *)c->in_quals.p;
-        } else bp.quals = quals;
+        int r = ensure(c, c->in_off[j], (n_reads + 1) * 8); if (r) return r;
+        CK(c, cudaMemcpyAsync(c->in_off[j].p, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, sc));
+        bp.off = (const u64 *)c->in_off[j].p;
     }
-    bp.disc = nullptr;
-    if (discarded) {
-        if (!is_device_ptr(discarded)) {
-            int r = ensure(c, c->in_disc, n_reads + 16); if (r) return r;
-            CK(c, cudaMemcpyAsync(c->in_disc.p, discarded, n_reads, cudaMemcpyHostToDevice, c->stream));
-            bp.disc = (const uint8_t *)c->in_disc.p;
-        } else bp.disc = discarded;
+    if (h_bases) {
+        int r = ensure(c, c->in_bases[j], last + 16); if (r) return r;
+        CK(c, cudaMemcpyAsync(c->in_bases[j].p, bases, last, cudaMemcpyHostToDevice, sc));
+        bp.bases = (const uint8_t *)c->in_bases[j].p;
     }
+    if (h_quals) {
+        int r = ensure(c, c->in_quals[j], last + 16); if (r) return r;
+        CK(c, cudaMemcpyAsync(c->in_quals[j].p, quals, last, cudaMemcpyHostToDevice, sc));
+        bp.quals = (const uint8_t *)c->in_quals[j].p;
+    }
+    if (h_disc) {
+        int r = ensure(c, c->in_disc[j], n_reads + 16); if (r) return r;
+        CK(c, cudaMemcpyAsync(c->in_disc[j].p, discarded, n_reads, cudaMemcpyHostToDevice, sc));
+        bp.disc = (const uint8_t *)c->in_disc[j].p;
+    }
+    CK(c, cudaEventRecord(c->ev_in_ready[j], sc));
+    CK(c, cudaStreamWaitEvent(c->stream, c->ev_in_ready[j], 0));
+    return 0;
+}
+
+// the kernels reading this batch's staging slot have been launched on the main stream: mark the slot reusable after
+// them, and return to the caller only once its host buffers have been read (it may overwrite them right away)
+static int release_inputs(kmn_ctx *c, const BatchPtrs &bp)
+{
+    if (bp.slot < 0) return 0;
+    CK(c, cudaEventRecord(c->ev_in_free[bp.slot], c->stream));
+    c->in_used[bp.slot] = true;
+    CK(c, cudaEventSynchronize(c->ev_in_ready[bp.slot]));
     return 0;
 }
 
@@ -577,9 +693,12 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
     BatchPtrs bp;
     int r = stage_inputs(c, bases, quals, read_off, n_reads, discarded, true, bp);
     if (r) return r;
-    // A launch may stage at most `limit` instances (staging capacity; multi-GPU: also bounds the send regions).
-    // The exact number of k-mer positions of a read range is computed on the device; ranges that do not fit are halved.
+    // A launch may stage at most `limit` instances (one staging set; multi-GPU: half of it, the other half takes the
+    // records received from the peers and the same bound sizes the send regions).  The exact number of k-mer
+    // positions of a read range is computed on the device; ranges that do not fit are halved.
     const uint64_t limit = std::max<uint64_t>(c->nranks > 1 ? c->stage_keys / 2 : c->stage_keys, 1);
+    const bool host_sizes = bp.off_on_host && (!discarded || !is_device_ptr(discarded));
+    if (!host_sizes && bp.slot >= 0) CK(c, cudaStreamSynchronize(c->s_copy));   // count_positions reads the staged copies
     struct Range { uint64_t r0, r1; };
     std::vector<Range> todo;
     todo.push_back({0, n_reads});
@@ -587,7 +706,7 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
         Range rg = todo.back();
         todo.pop_back();
         uint64_t npos = 0;
-        if (bp.off_on_host && (!discarded || !is_device_ptr(discarded))) {     // host offsets: no device round trip
+        if (host_sizes) {                                                      // host offsets: no device round trip
             const uint32_t k = c->o.kmer_size;
             for (uint64_t q = rg.r0; q < rg.r1; ++q) {
                 uint64_t len = read_off[q + 1] - read_off[q];
@@ -604,14 +723,14 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
             continue;
         }
         if (npos == 0) continue;
-        if (c->staged_upper + npos > c->stage_keys) { r = drain(c); if (r) return r; }
+        r = stage_room(c, npos); if (r) return r;
         ParseArgs a;
         fill_parse_args(c, a, bp.bases, bp.quals, bp.off + rg.r0, bp.disc ? bp.disc + rg.r0 : nullptr, rg.r1 - rg.r0, bp.total_bytes);
         r = launch_parse(c, a); if (r) return r;
-        c->staged_upper += npos;
+        c->sets[c->cur].staged_upper += npos;
         r = exchange(c); if (r) return r;
     }
-    return 0;
+    return release_inputs(c, bp);
 }
 
 static int launch_purge(kmn_ctx *c, uint32_t min_depth)
@@ -892,7 +1011,7 @@ int kmn_trim_batch(kmn_ctx *c, const uint8_t *bases, const uint64_t *read_off, u
         CK(c, cudaMemcpyAsync(was_trimmed, t.was_trimmed, n_reads, cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
     }
-    return 0;
+    return release_inputs(c, bp);
 }
 
 int kmn_export(kmn_ctx *c, uint32_t min_count, uint8_t *keys, uint16_t *count, uint16_t *dir, float *wsum, uint32_t *ext,
@@ -964,7 +1083,7 @@ int kmn_debug_kmers(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
     if (hash) CK(c, cudaMemcpyAsync(hash, dh, nk * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     cudaFree(dko); cudaFree(dk); cudaFree(df); cudaFree(dw); cudaFree(dh);
-    return 0;
+    return release_inputs(c, bp);
 }
 
 int kmn_profile_enable(kmn_ctx *c, int on)
@@ -979,6 +1098,7 @@ int kmn_profile_read(kmn_ctx *c, kmn_profile *out)
     if (!c || !out) return KMN_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
+    if (c->s_insert != c->stream) CK(c, cudaStreamSynchronize(c->s_insert));
     for (auto &e : c->prof_events) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e.a, e.b);
@@ -995,7 +1115,9 @@ int kmn_sync(kmn_ctx *c)
 {
     if (!c) return KMN_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->s_copy));
     CK(c, cudaStreamSynchronize(c->stream));
+    if (c->s_insert != c->stream) CK(c, cudaStreamSynchronize(c->s_insert));
     return 0;
 }
 

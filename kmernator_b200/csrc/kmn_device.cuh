@@ -35,9 +35,11 @@ struct TableView {
 };
 
 struct StageView {        // partitioned staging area of k-mer records (phase 1 -> phase 2)
-    u64 *recs;            // [n_parts][part_cap][RW]
-    u64 *cursor;          // [n_parts] records written (may exceed part_cap: excess went direct)
-    u64 part_cap;
+    u64 *recs;            // [n_parts][n_cta][sub_cap][RW]: every phase-1 CTA owns a private sub-region of every partition,
+                          // so a flush needs no global atomic (its position follows from the CTA-local sequence number)
+    u32 *count;           // [n_parts][n_cta] records written (may exceed sub_cap: the excess was inserted directly)
+    u32 sub_cap;          // records per sub-region
+    u32 n_cta;            // phase-1 grid size (one CTA per SM)
 };
 
 struct Counters {         // device-side statistics (src/KmerSpectrum.h:1590-1650)
@@ -216,9 +218,11 @@ __device__ __forceinline__ u64 ld_cg64(const void *p)
     return v;
 }
 
-template <int W>
+// PRE: the home slot's words were loaded by the caller (pv = value word, pk = first key word; lets a thread keep the
+// home-slot loads of several records in flight before it resolves any of them)
+template <int W, bool PRE = false>
 __device__ __forceinline__ int table_insert(const TableView &t, u32 part, u64 slot0, const u64 (&key)[W], u64 add,
-                                            u64 *slot_out, u32 *probes_out)
+                                            u64 *slot_out, u32 *probes_out, u64 pv = 0, u64 pk = 0)
 {
     Slot<W> *base = reinterpret_cast<Slot<W> *>(t.slots) + (u64)part * t.part_slots;
     u64 s = slot0;
@@ -227,7 +231,8 @@ __device__ __forceinline__ int table_insert(const TableView &t, u32 part, u64 sl
         Slot<W> *sl = base + s;
         if (W == 1) {
             u64 v, ck;
-            ld_slot16(sl, v, ck);
+            if (PRE && probes == 0) { v = pv; ck = pk; }
+            else ld_slot16(sl, v, ck);
             const u64 want = ~key[0];
             if (ck == 0) {
                 u64 old = atomicCAS(&sl->k[0], 0ull, want);
@@ -245,7 +250,7 @@ __device__ __forceinline__ int table_insert(const TableView &t, u32 part, u64 sl
                 return 0;
             }
         } else {
-            u64 v = ld_cg64(&sl->val);
+            u64 v = (PRE && probes == 0) ? pv : ld_cg64(&sl->val);
             if (v == 0) {
                 u64 old = atomicCAS(&sl->val, 0ull, VAL_LOCK);
                 if (old == 0ull) {

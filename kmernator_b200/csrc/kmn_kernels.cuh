@@ -120,17 +120,19 @@ __device__ __forceinline__ void insert_record(const TableView &t, const Rec<W, H
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory write-combining bins, lock free (no CTA barrier on the hot path).
+// shared-memory write-combining bins, lock free (no CTA barrier and no global atomic on the hot path).
 // Every table partition owns a ring of NB blocks x 8 records in shared memory.  A producer reserves a slot with one
 // shared atomicAdd, waits (rarely) until the ring block's previous incarnation has been flushed, writes its record and
-// commits.  Whoever commits the 8th record of a block flushes the whole block (64*RW contiguous bytes) to the
-// partition's staging region and bumps the block's generation.  state word: bits 0..7 commits, bits 8..31 generation.
+// commits.  Whoever commits the 8th record of a block flushes the whole block (64*RW contiguous bytes) to this CTA's
+// private sub-region of the partition's staging region; the destination follows from the block's sequence number, so
+// the flush is eight plain stores with nothing to wait for.  state word: bits 0..7 commits, bits 8..31 generation.
 // ------------------------------------------------------------------------------------------------
 static constexpr u32 BIN_BLK = 8;
 
 template <int RW>
 struct Bins {
-    u32 *res;      // [n_parts] slots reserved so far
+    u32 *res;      // [n_parts] slots reserved so far in this launch
+    u32 *base;     // [n_parts] records already in this CTA's sub-region when the launch started
     u32 *state;    // [n_parts][nb]
     u64 *ring;     // [n_parts][nb][8][RW]
     u32 n_parts, nb_log2;
@@ -140,22 +142,22 @@ struct LocalCtr { u64 raw, good, unique, full, direct, probes; };
 
 template <int W, bool HASX>
 __device__ __forceinline__ void flush_block(const Bins<Rec<W, HASX>::RW> &b, const StageView &st, const TableView &tab, u32 bin, u32 rb,
-                                            u32 count, LocalCtr &lc)
+                                            u32 blk_seq, u32 count, LocalCtr &lc)
 {
     constexpr int RW = Rec<W, HASX>::RW;
-    const u64 pos = atomicAdd(&st.cursor[bin], (u64)count);
+    const u64 pos = (u64)b.base[bin] + (u64)blk_seq * BIN_BLK;
     const u64 *src = b.ring + ((((size_t)bin << b.nb_log2) + rb) * BIN_BLK) * RW;
-    u64 *dst = st.recs + ((size_t)bin * st.part_cap + pos) * RW;
-    if (count == BIN_BLK && pos + BIN_BLK <= st.part_cap) {
+    u64 *dst = st.recs + (((size_t)bin * st.n_cta + blockIdx.x) * st.sub_cap + pos) * RW;
+    if (count == BIN_BLK && pos + BIN_BLK <= st.sub_cap) {
 #pragma unroll
         for (int i = 0; i < (int)BIN_BLK * RW; ++i) dst[i] = src[i];
         return;
     }
     for (u32 i = 0; i < count; ++i) {
-        if (pos + i < st.part_cap) {
+        if (pos + i < st.sub_cap) {
 #pragma unroll
             for (int q = 0; q < RW; ++q) dst[(size_t)i * RW + q] = src[(size_t)i * RW + q];
-        } else {                                                            // staging region full: insert directly
+        } else {                                                            // sub-region full: insert directly
             Rec<W, HASX> rec;
 #pragma unroll
             for (int q = 0; q < RW; ++q) rec.w[q] = src[(size_t)i * RW + q];
@@ -181,24 +183,25 @@ __device__ __forceinline__ void bins_put(const Bins<Rec<W, HASX>::RW> &b, const 
     const u32 c = atomicAdd((u32 *)stp, 1u) & 0xffu;
     if (c == BIN_BLK - 1) {                                                 // last committer flushes the block
         __threadfence_block();
-        flush_block<W, HASX>(b, st, tab, bin, rb, BIN_BLK, lc);
+        flush_block<W, HASX>(b, st, tab, bin, rb, blk, BIN_BLK, lc);
         __threadfence_block();
         atomicAdd((u32 *)stp, 256u - BIN_BLK);                              // commits -> 0, generation + 1
     }
 }
 
-// after the last producer is done (CTA barrier): partial blocks
+// after the last producer is done (CTA barrier): partial blocks, then the sub-region fill levels go back to global memory
 template <int W, bool HASX>
 __device__ __forceinline__ void bins_drain(const Bins<Rec<W, HASX>::RW> &b, const StageView &st, const TableView &tab, LocalCtr &lc)
 {
     for (u32 bin = threadIdx.x; bin < b.n_parts; bin += blockDim.x) {
         const u32 n = b.res[bin], part = n & 7u;
-        if (part) flush_block<W, HASX>(b, st, tab, bin, (n >> 3) & ((1u << b.nb_log2) - 1u), part, lc);
+        if (part) flush_block<W, HASX>(b, st, tab, bin, (n >> 3) & ((1u << b.nb_log2) - 1u), n >> 3, part, lc);
+        if (n) st.count[(size_t)bin * st.n_cta + blockIdx.x] = b.base[bin] + n;
     }
 }
 
 template <int RW>
-__device__ __forceinline__ Bins<RW> bins_init(unsigned char *smem_after_ptab, u32 n_parts, u32 nb_log2)
+__device__ __forceinline__ Bins<RW> bins_init(unsigned char *smem_after_ptab, const StageView &st, u32 n_parts, u32 nb_log2)
 {
     Bins<RW> b;
     b.n_parts = n_parts; b.nb_log2 = nb_log2;
@@ -206,8 +209,9 @@ __device__ __forceinline__ Bins<RW> bins_init(unsigned char *smem_after_ptab, u3
     b.ring = reinterpret_cast<u64 *>(smem_after_ptab);
     b.state = reinterpret_cast<u32 *>(b.ring + nblk * BIN_BLK * RW);
     b.res = b.state + nblk;
+    b.base = b.res + n_parts;
     for (size_t i = threadIdx.x; i < nblk; i += blockDim.x) b.state[i] = 0;
-    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) b.res[i] = 0;
+    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) { b.res[i] = 0; b.base[i] = st.count[(size_t)i * st.n_cta + blockIdx.x]; }
     return b;
 }
 
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(PARSE_TPB, 1) k_count_parse(ParseArgs a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *ptab = reinterpret_cast<double *>(smem_raw);
     for (u32 i = threadIdx.x; i < 256; i += blockDim.x) ptab[i] = a.ptab[i];
-    Bins<RW> bins = bins_init<RW>(smem_raw + 256 * sizeof(double), a.table.n_parts, a.nb_log2);
+    Bins<RW> bins = bins_init<RW>(smem_raw + 256 * sizeof(double), a.stage, a.table.n_parts, a.nb_log2);
     __syncthreads();
 
     LocalCtr lc{0, 0, 0, 0, 0, 0};
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(PARSE_TPB, 1) k_route_records(RouteArgs a)
 {
     constexpr int RW = Rec<W, HASX>::RW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Bins<RW> bins = bins_init<RW>(smem_raw + 256 * sizeof(double), a.table.n_parts, a.nb_log2);
+    Bins<RW> bins = bins_init<RW>(smem_raw + 256 * sizeof(double), a.stage, a.table.n_parts, a.nb_log2);
     __syncthreads();
     LocalCtr lc{0, 0, 0, 0, 0, 0};
     const u64 stride = (u64)gridDim.x * blockDim.x;
@@ -506,19 +510,19 @@ __global__ void __launch_bounds__(256) k_count_positions(const u64 *read_off, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// phase 2 work list: chunk_start[p] = first chunk index of partition p (exclusive scan), single CTA
+// phase 2 work list over the (partition, phase-1 CTA) sub-regions in partition-major order:
+// chunk_start[e] = first chunk index of sub-region e (exclusive scan), single CTA
 // ------------------------------------------------------------------------------------------------
-__global__ void k_build_worklist(const u64 *cursor, u64 part_cap, u32 n_parts, u64 *chunk_start, u64 *next_item)
+__global__ void k_build_worklist(const u32 *count, u32 sub_cap, u32 n_entries, u64 *chunk_start, u64 *next_item)
 {
     __shared__ u64 carry;
+    __shared__ u64 wsum[32];
     if (threadIdx.x == 0) { carry = 0; *next_item = 0; }
     __syncthreads();
-    for (u32 base = 0; base < n_parts; base += blockDim.x) {
+    for (u32 base = 0; base < n_entries; base += blockDim.x) {
         u32 p = base + threadIdx.x;
         u64 n = 0;
-        if (p < n_parts) { u64 c = cursor[p]; if (c > part_cap) c = part_cap; n = (c + INSERT_CHUNK - 1) / INSERT_CHUNK; }
-        // block-wide inclusive scan (simple: warp scan + shared partials)
-        __shared__ u64 wsum[32];
+        if (p < n_entries) { u32 c = count[p]; if (c > sub_cap) c = sub_cap; n = (c + INSERT_CHUNK - 1) / INSERT_CHUNK; }
         u64 v = n;
         const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -533,16 +537,16 @@ __global__ void k_build_worklist(const u64 *cursor, u64 part_cap, u32 n_parts, u
         }
         __syncthreads();
         u64 incl = v + (warp ? wsum[warp - 1] : 0) + carry;
-        if (p < n_parts) chunk_start[p] = incl - n;
+        if (p < n_entries) chunk_start[p] = incl - n;
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) carry = incl;
         __syncthreads();
     }
-    if (threadIdx.x == 0) chunk_start[n_parts] = carry;
+    if (threadIdx.x == 0) chunk_start[n_entries] = carry;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: phase 2 of the count pass.  Persistent CTAs take (partition, chunk) items in partition order from an
+// K3: phase 2 of the count pass.  Persistent CTAs take (sub-region, chunk) items in partition order from an
 // atomic ticket, so at any time the whole GPU works on at most ~2 neighbouring partitions whose table
 // slices (slice_bytes each) stay L2-resident.  Per record: 16-B slot load, then CAS (new key) or RED (hit).
 // Replaces KmerSpectrum::append (src/KmerSpectrum.h:1578-1668) + KmerMapByKmerArrayPair insert/find
@@ -553,21 +557,41 @@ __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, Stage
 {
     constexpr int RW = Rec<W, HASX>::RW;
     __shared__ u64 s_item;
+    __shared__ u32 s_entry;
     u64 n_unique = 0, n_full = 0, n_probes = 0;
-    const u64 total_items = chunk_start[t.n_parts];
+    const u32 n_entries = t.n_parts * st.n_cta;
+    const u64 total_items = chunk_start[n_entries];
     while (true) {
-        if (threadIdx.x == 0) s_item = atomicAdd(next_item, 1ull);
+        if (threadIdx.x == 0) {
+            const u64 it = atomicAdd(next_item, 1ull);
+            s_item = it;
+            if (it < total_items) {
+                // sub-region of this item = last e with chunk_start[e] <= item.  Sub-regions hold nearly equal numbers of
+                // chunks, so interpolate, bracket by galloping, then bisect (2-4 loads instead of log2(n_entries)).
+                u32 lo = (u32)(((unsigned __int128)it * n_entries) / total_items), hi;
+                if (lo >= n_entries) lo = n_entries - 1;
+                u32 step = 1;
+                if (chunk_start[lo] <= it) {
+                    hi = lo + 1;
+                    while (hi < n_entries && chunk_start[hi] <= it) { lo = hi; hi = hi + step > n_entries ? n_entries : hi + step; step <<= 1; }
+                } else {
+                    hi = lo;
+                    lo = lo >= 1 ? lo - 1 : 0;
+                    while (lo > 0 && chunk_start[lo] > it) { hi = lo; lo = lo > step ? lo - step : 0; step <<= 1; }
+                }
+                while (hi - lo > 1) { u32 mid = lo + ((hi - lo) >> 1); if (chunk_start[mid] <= it) lo = mid; else hi = mid; }
+                s_entry = lo;
+            }
+        }
         __syncthreads();
         const u64 item = s_item;
+        const u32 entry = s_entry;
         __syncthreads();
         if (item >= total_items) break;
-        // partition of this item: last p with chunk_start[p] <= item
-        u32 lo = 0, hi = t.n_parts;
-        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (chunk_start[mid] <= item) lo = mid; else hi = mid; }
-        const u32 part = lo;
-        u64 n = st.cursor[part]; if (n > st.part_cap) n = st.part_cap;
-        const u64 first = (item - chunk_start[part]) * INSERT_CHUNK;
-        const u64 *src = st.recs + ((size_t)part * st.part_cap + first) * RW;
+        const u32 part = entry / st.n_cta;
+        u64 n = st.count[entry]; if (n > st.sub_cap) n = st.sub_cap;
+        const u64 first = (item - chunk_start[entry]) * INSERT_CHUNK;
+        const u64 *src = st.recs + ((size_t)entry * st.sub_cap + first) * RW;
         const u64 cnt = n - first < (u64)INSERT_CHUNK ? n - first : (u64)INSERT_CHUNK;
         Rec<W, HASX> rec[INSERT_UNROLL];
         bool have[INSERT_UNROLL];
@@ -580,20 +604,31 @@ __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, Stage
                 for (int q = 0; q < RW; ++q) rec[u].w[q] = ld_nc64(src + idx * RW + q);
             }
         }
+        // home-slot loads of all records first (independent, all in flight together), then resolve one by one
+        u64 key[INSERT_UNROLL][W], home[INSERT_UNROLL], pv[INSERT_UNROLL], pk[INSERT_UNROLL];
+        bool fwd[INSERT_UNROLL]; float weight[INSERT_UNROLL]; u32 eb[INSERT_UNROLL];
+        const Slot<W> *pbase = reinterpret_cast<const Slot<W> *>(t.slots) + (u64)part * t.part_slots;
+#pragma unroll
+        for (int u = 0; u < INSERT_UNROLL; ++u) {
+            pv[u] = pk[u] = 0; home[u] = 0;
+            if (have[u]) {
+                rec[u].unpack(key[u], fwd[u], weight[u], eb[u]);
+                home[u] = home_slot(place_hash<W>(key[u]), t.part_slots);
+                if (W == 1) ld_slot16(pbase + home[u], pv[u], pk[u]);
+                else pv[u] = ld_cg64(&pbase[home[u]].val);
+            }
+        }
 #pragma unroll
         for (int u = 0; u < INSERT_UNROLL; ++u) {
             if (have[u]) {
-                u64 key[W]; bool fwd; float weight; u32 eb;
-                rec[u].unpack(key, fwd, weight, eb);
-                u64 ph = place_hash<W>(key);
                 u64 slot; u32 probes = 0;
-                int r = table_insert<W>(t, part, home_slot(ph, t.part_slots), key, 1ull | ((u64)(fwd ? 1u : 0u) << 32), &slot, &probes);
+                int r = table_insert<W, true>(t, part, home[u], key[u], 1ull | ((u64)(fwd[u] ? 1u : 0u) << 32), &slot, &probes, pv[u], pk[u]);
                 if (r < 0) { n_full++; continue; }
                 n_unique += (u64)r; n_probes += probes;
                 if (HASX) {
-                    if (t.wsum) atomicAdd(&t.wsum[slot], weight);
+                    if (t.wsum) atomicAdd(&t.wsum[slot], weight[u]);
                     if (t.ext) {
-                        u32 l = eb & 7u, rr = (eb >> 3) & 7u;
+                        u32 l = eb[u] & 7u, rr = (eb[u] >> 3) & 7u;
                         if (l < 6) atomicAdd(&t.ext[slot * 12 + l], 1u);
                         if (rr < 6) atomicAdd(&t.ext[slot * 12 + 6 + rr], 1u);
                     }
