@@ -41,8 +41,8 @@ def parse_args():
     ap.add_argument("--genome", type=int, default=250_000_000, help="genome length per GPU-worth of reads (60x coverage)")
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--stage-keys", type=int, default=0)
-    ap.add_argument("--slice-mb", type=int, default=32)
-    ap.add_argument("--pipe-batches", type=int, default=1, help="sub-batches of the parse/insert pipeline per step")
+    ap.add_argument("--slice-mb", type=int, default=64)
+    ap.add_argument("--pipe-batches", type=int, default=4, help="sub-batches of the parse/insert pipeline per step")
     ap.add_argument("--e2e-reads", type=int, default=20_000_000)
     ap.add_argument("--e2e-batch", type=int, default=2_000_000)
     ap.add_argument("--cpu-reads", type=int, default=400_000)

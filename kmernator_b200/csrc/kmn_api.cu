@@ -60,13 +60,15 @@ struct kmn_ctx {
     uint64_t stage_keys = 0;          // record capacity of ONE set (= the sub-batch size of the pipeline)
     u64 *chunk_start = nullptr, *next_item = nullptr;
     int insert_ctas = 8;              // phase-2 CTAs per SM
+    bool insert_pre = true;           // phase 2 keeps the home-slot loads of its 4 records in flight together
     Counters *ctr = nullptr;
     double *ptab = nullptr;
     u64 *scratch = nullptr;           // small device scalars
     // phase-1 launch geometry
-    int parse_tpb = 512;
-    uint32_t nb_log2 = 1, zero_below = 0;
-    size_t parse_smem = 0;
+    int n_cta = 0;                    // grid of k_kmer_scatter / k_route_records = staging sub-regions per partition
+    uint32_t zero_below = 0;
+    size_t scatter_smem = 0;
+    DevBuf mask, wts;                 // phase 1a -> 1b: "counted" bits (and fp32 weights for KMN_VALUE_WEIGHTS)
     // input staging (host inputs), double-buffered: the copy of batch b+1 overlaps the kernels of batch b
     DevBuf in_bases[2], in_quals[2], in_off[2], in_disc[2];
     cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
@@ -173,7 +175,7 @@ void kmn_default_opts(kmn_opts *o)
     o->min_depth = 2;               // src/KmerSpectrum.h:92
     o->hash_kind = KMN_HASH_LOOKUP3_HASHLITTLE2;
     o->value_kind = KMN_VALUE_DIR;
-    o->slice_bytes = 32u << 20;
+    o->slice_bytes = 64u << 20;
 }
 
 const char *kmn_last_error(const kmn_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -208,17 +210,14 @@ static int plan_and_alloc(kmn_ctx *c)
     }
     if (slots < 1024) slots = 1024;
 
-    // partitions: slice_bytes each so that one slice stays L2-resident during phase 2; the number of partitions
-    // is bounded by the shared memory the phase-1 bins need (>= 16 records per bin)
+    // partitions: slice_bytes each so that one slice stays L2-resident during phase 2; every phase-1 CTA keeps one
+    // 4-byte fill counter per partition in shared memory
     int dev_smem = 0;
     CK(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    // phase 1 leaves 8 KB of the SM's shared memory to the co-resident phase-2 CTAs (static + per-CTA reserved)
-    const size_t smem_avail = (size_t)dev_smem - 256 * sizeof(double) - 1024 - 8192;
-    const uint32_t slice = o.slice_bytes ? o.slice_bytes : (32u << 20);
+    const uint32_t slice = o.slice_bytes ? o.slice_bytes : (64u << 20);
     uint64_t part_slots = std::max<uint64_t>(slice / c->slot_bytes, 256);
     uint64_t n_parts = (slots + part_slots - 1) / part_slots;
-    // shared memory per partition with the minimum ring (2 blocks x 8 records): 2*(64*RW+4)+8 bytes
-    const uint64_t p_max = smem_avail / (2 * (64 * (size_t)c->RW + 4) + 8);
+    const uint64_t p_max = ((size_t)dev_smem / SCATTER_CTAS - 1024) / 4 - 32;
     if (n_parts > p_max) n_parts = p_max;
     if (n_parts < 1) n_parts = 1;
     part_slots = (slots + n_parts - 1) / n_parts;
@@ -227,11 +226,8 @@ static int plan_and_alloc(kmn_ctx *c)
     c->n_slots = slots;
     c->table.part_slots = part_slots;
     c->table.n_parts = (u32)n_parts;
-
-    uint32_t nbl = 1;                       // ring blocks per bin: largest power of two that fits, at most 64
-    while (nbl < 6 && (uint64_t)n_parts * ((2ull << nbl) * (64 * (size_t)c->RW + 4) + 8) <= smem_avail) nbl++;
-    c->nb_log2 = nbl;
-    c->parse_smem = 256 * sizeof(double) + (size_t)n_parts * ((1ull << nbl) * (64 * (size_t)c->RW + 4) + 8);
+    c->n_cta = c->n_sms * SCATTER_CTAS;
+    c->scatter_smem = (((size_t)n_parts + 31) & ~(size_t)31) * 4;
 
     CK(c, cudaMalloc(&c->table.slots, slots * c->slot_bytes));
     if (c->weights) CK(c, cudaMalloc((void **)&c->table.wsum, slots * 4));
@@ -249,13 +245,14 @@ static int plan_and_alloc(kmn_ctx *c)
     }
     if (sk < (1ull << 16)) sk = 1ull << 16;
     c->stage_keys = sk;
-    const uint64_t n_cta = (uint64_t)c->n_sms;
+    const uint64_t n_cta = (uint64_t)c->n_cta;
     const uint64_t per_sub = sk / n_parts / n_cta;
     const uint64_t sub_cap = per_sub + per_sub / 8 + 8 * (uint64_t)std::sqrt((double)per_sub + 1.0) + 64;   // mean + slack for the spread
     if (sub_cap >= (1ull << 31)) return fail(c, KMN_ERR_INVALID, "staging sub-region too large (%llu records)", (unsigned long long)sub_cap);
     for (int si = 0; si < c->n_sets; ++si) {
         kmn_ctx::StageSet &st = c->sets[si];
-        st.v.sub_cap = (u32)sub_cap; st.v.n_cta = (u32)n_cta;
+        st.v.sub_cap = (u32)sub_cap; st.v.n_cta = (u32)n_cta; st.v.n_parts = (u32)n_parts;
+        st.v.cta_major = getenv("KMN_PART_MAJOR") ? 0 : 1;
         CK(c, cudaMalloc((void **)&st.v.recs, (size_t)n_parts * n_cta * sub_cap * c->RW * 8));
         CK(c, cudaMalloc((void **)&st.v.count, (size_t)n_parts * n_cta * 4));
         CK(c, cudaEventCreateWithFlags(&st.ev_parsed, cudaEventDisableTiming));
@@ -306,14 +303,15 @@ int kmn_reset(kmn_ctx *c)
 template <int W, bool X>
 static int set_smem_attrs(kmn_ctx *c)
 {
-    size_t s = c->parse_smem;
-    CK(c, cudaFuncSetAttribute(k_count_parse<W, X, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s));
-    CK(c, cudaFuncSetAttribute(k_count_parse<W, X, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s));
+    const int s = (int)c->scatter_smem;
+    if (s <= 48 * 1024) return 0;
+    CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
+    CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
     if (X) {
-        CK(c, cudaFuncSetAttribute(k_count_parse<W, X, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s));
-        CK(c, cudaFuncSetAttribute(k_count_parse<W, X, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s));
+        CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
+        CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
     }
-    CK(c, cudaFuncSetAttribute(k_route_records<W, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s));
+    CK(c, cudaFuncSetAttribute(k_route_records<W, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
     return 0;
 }
 
@@ -341,7 +339,7 @@ int kmn_create(kmn_ctx **out, const kmn_opts *opts)
         if (const char *e = getenv("KMN_PIPELINE")) c->pipeline = atoi(e) != 0;
         c->n_sets = c->pipeline ? 2 : 1;
         if (const char *e = getenv("KMN_INSERT_CTAS")) c->insert_ctas = std::max(1, atoi(e));
-        if (const char *e = getenv("KMN_PARSE_TPB")) c->parse_tpb = std::min(PARSE_TPB, std::max(32, atoi(e) / 32 * 32));
+        if (const char *e = getenv("KMN_INSERT_PRE")) c->insert_pre = atoi(e) != 0;
         if (c->pipeline) {
             if (cudaStreamCreateWithFlags(&c->s_insert, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "stream create failed"); break; }
         } else c->s_insert = c->stream;
@@ -386,7 +384,7 @@ void kmn_destroy(kmn_ctx *c)
                     c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts,
                     c->in_bases[0].p, c->in_quals[0].p, c->in_off[0].p, c->in_disc[0].p,
                     c->in_bases[1].p, c->in_quals[1].p, c->in_off[1].p, c->in_disc[1].p, c->vals.p, c->first_nx.p, c->out_off.p,
-                    c->lk_origin.p, c->lk_resp_in.p, c->lk_resp_out.p,
+                    c->lk_origin.p, c->lk_resp_in.p, c->lk_resp_out.p, c->mask.p, c->wts.p,
                     c->out_len.p, c->out_score.p, c->out_trim.p, c->lk_keys.p, c->lk_out.p};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &st : c->sets) { if (st.ev_parsed) cudaEventDestroy(st.ev_parsed); if (st.ev_drained) cudaEventDestroy(st.ev_drained); }
@@ -417,7 +415,8 @@ static int submit_drain(kmn_ctx *c, int i)
     {
         ProfScope ps(c, KMN_PROF_INSERT, st.staged_upper, si);
         KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
-            k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, si>>>(c->table, st.v, c->chunk_start, c->next_item, c->ctr);
+            if (c->insert_pre) k_insert_staged<W_, X_, true><<<grid, INSERT_TPB, 0, si>>>(c->table, st.v, c->chunk_start, c->next_item, c->ctr);
+            else k_insert_staged<W_, X_, false><<<grid, INSERT_TPB, 0, si>>>(c->table, st.v, c->chunk_start, c->next_item, c->ctr);
         }));
     }
     c->launches++;
@@ -479,30 +478,42 @@ static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, cons
     a.n_reads = n_reads; a.total_bytes = total_bytes; a.ptab = c->ptab;
     a.k = c->o.kmer_size; a.kb = (u32)c->kb; a.pad = c->pad;
     a.min_weight = c->o.min_kmer_quality; a.start_char = c->o.fastq_start_char;
-    a.nb_log2 = c->nb_log2; a.zero_below = c->zero_below;
+    a.zero_below = c->zero_below; a.mask = (u32 *)c->mask.p; a.wts = c->weights ? (float *)c->wts.p : nullptr;
     a.nranks = (u32)c->nranks; a.rank = (u32)c->rank;
     a.use_lookup8 = c->o.hash_kind == KMN_HASH_LOOKUP8_HASH2;
+    a.l2_hints = getenv("KMN_NO_L2_HINTS") ? 0 : 1;
     a.table = c->table; a.stage = c->sets[c->cur].v; a.ctr = c->ctr;
     a.send_recs = c->send_recs; a.send_cursor = c->send_cursor; a.send_cap = c->send_cap;
 }
 
 static int launch_parse(kmn_ctx *c, const ParseArgs &a)
 {
-    const int grid = c->n_sms;
     const bool dist = c->nranks > 1;
-    ProfScope ps(c, KMN_PROF_PARSE, a.n_reads);
-    KMN_DISPATCH_W(c, {
-        if (!c->hasx) {
-            if (dist) k_count_parse<W_, false, false, true><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
-            else k_count_parse<W_, false, false, false><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
-        } else if (c->ext) {
-            if (dist) k_count_parse<W_, true, true, true><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
-            else k_count_parse<W_, true, true, false><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
-        } else {
-            if (dist) k_count_parse<W_, true, false, true><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
-            else k_count_parse<W_, true, false, false><<<grid, c->parse_tpb, c->parse_smem, c->stream>>>(a);
-        }
-    });
+    {   // phase 1a: weights -> "counted" bits
+        ProfScope ps(c, KMN_PROF_WEIGHT, a.n_reads);
+        const int grid = (int)std::min<uint64_t>((a.n_reads + MASK_TPB - 1) / MASK_TPB, (uint64_t)c->n_sms * 8);
+        if (c->weights) k_weight_mask<true><<<grid, MASK_TPB, 0, c->stream>>>(a);
+        else k_weight_mask<false><<<grid, MASK_TPB, 0, c->stream>>>(a);
+    }
+    c->launches++;
+    CK(c, cudaGetLastError());
+    {   // phase 1b: k-mers -> staging sub-regions (and send regions)
+        ProfScope ps(c, KMN_PROF_PARSE, a.n_reads);
+        const int grid = c->n_cta;
+        const size_t sm = c->scatter_smem;
+        KMN_DISPATCH_W(c, {
+            if (!c->hasx) {
+                if (dist) k_kmer_scatter<W_, false, false, true><<<grid, SCATTER_TPB, sm, c->stream>>>(a);
+                else k_kmer_scatter<W_, false, false, false><<<grid, SCATTER_TPB, sm, c->stream>>>(a);
+            } else if (c->ext) {
+                if (dist) k_kmer_scatter<W_, true, true, true><<<grid, SCATTER_TPB, sm, c->stream>>>(a);
+                else k_kmer_scatter<W_, true, true, false><<<grid, SCATTER_TPB, sm, c->stream>>>(a);
+            } else {
+                if (dist) k_kmer_scatter<W_, true, false, true><<<grid, SCATTER_TPB, sm, c->stream>>>(a);
+                else k_kmer_scatter<W_, true, false, false><<<grid, SCATTER_TPB, sm, c->stream>>>(a);
+            }
+        });
+    }
     c->launches++;
     CK(c, cudaGetLastError());
     return 0;
@@ -549,12 +560,12 @@ static int exchange(kmn_ctx *c)
     if (recv_total) {
         { int r = stage_room(c, recv_total); if (r) return r; }
         RouteArgs ra;
-        ra.recs = c->recv_recs; ra.n_recs = recv_total; ra.nb_log2 = c->nb_log2; ra.pad = 0;
+        ra.recs = c->recv_recs; ra.n_recs = recv_total;
         ra.table = c->table; ra.stage = c->sets[c->cur].v; ra.ctr = c->ctr;
         {
             ProfScope ps(c, KMN_PROF_ROUTE, recv_total);
             KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
-                k_route_records<W_, X_><<<c->n_sms, c->parse_tpb, c->parse_smem, c->stream>>>(ra);
+                k_route_records<W_, X_><<<c->n_cta, SCATTER_TPB, c->scatter_smem, c->stream>>>(ra);
             }));
         }
         c->launches++;
@@ -693,6 +704,10 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
     BatchPtrs bp;
     int r = stage_inputs(c, bases, quals, read_off, n_reads, discarded, true, bp);
     if (r) return r;
+    // phase 1a -> 1b scratch: one bit per base position of the batch (+ one fp32 per position for KMN_VALUE_WEIGHTS)
+    r = ensure(c, c->mask, (bp.total_bytes / 32 + 4) * 4); if (r) return r;
+    CK(c, cudaMemsetAsync(c->mask.p, 0, (bp.total_bytes / 32 + 4) * 4, c->stream));
+    if (c->weights) { r = ensure(c, c->wts, (bp.total_bytes + 4) * 4); if (r) return r; }
     // A launch may stage at most `limit` instances (one staging set; multi-GPU: half of it, the other half takes the
     // records received from the peers and the same bound sizes the send regions).  The exact number of k-mer
     // positions of a read range is computed on the device; ranges that do not fit are halved.

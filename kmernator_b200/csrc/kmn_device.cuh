@@ -39,7 +39,13 @@ struct StageView {        // partitioned staging area of k-mer records (phase 1 
                           // so a flush needs no global atomic (its position follows from the CTA-local sequence number)
     u32 *count;           // [n_parts][n_cta] records written (may exceed sub_cap: the excess was inserted directly)
     u32 sub_cap;          // records per sub-region
-    u32 n_cta;            // phase-1 grid size (one CTA per SM)
+    u32 n_cta;            // phase-1 grid size
+    u32 n_parts;
+    u32 cta_major;        // layout of recs: [cta][part] (a CTA's write frontier stays within few pages) or [part][cta]
+    __device__ __forceinline__ size_t sub_index(u32 part, u32 cta) const
+    {
+        return cta_major ? (size_t)cta * n_parts + part : (size_t)part * n_cta + cta;
+    }
 };
 
 struct Counters {         // device-side statistics (src/KmerSpectrum.h:1590-1650)

@@ -1,23 +1,32 @@
 // kmn_kernels.cuh -- sm_100a kernels of the k-mer spectrum path.
 //
-//   count pass  = k_count_parse  (phase 1: bases -> canonical k-mers -> weight test -> partitioned staging)
+//   count pass  = k_weight_mask  (phase 1a: quality weights along each read -> one "counted" bit per k-mer position)
+//               + k_kmer_scatter (phase 1b: bases -> canonical k-mers, position-parallel -> partitioned staging)
 //               + k_insert_staged (phase 2: per-partition inserts into an L2-resident table slice)
 //   lookup pass = k_lookup_vals + k_trim_score
 //   table scans = k_histogram, k_purge, k_export, k_count_singletons
 //
 // Why two phases: on B200 a 64-bit atomic to an HBM-resident table runs at ~20 G/s while the same
 // atomic to a <=64 MB (L2-resident) region runs at 60-190 G/s (profiles/r01_randacc_microbench.csv).
-// Phase 1 therefore scatters every k-mer into one of n_parts staging regions through shared-memory
-// write-combining bins, and phase 2 walks the regions in order so that only one table slice is hot.
+// Phase 1 therefore scatters every k-mer into one of n_parts staging regions (each phase-1 CTA owns a private
+// sub-region of every partition, addressed by shared-memory counters), and phase 2 walks the regions in order
+// so that only one table slice is hot.
 #pragma once
 #include "kmn_device.cuh"
 
 namespace kmn {
 
-static constexpr int PARSE_TPB = 512;      // threads per CTA in phase 1 (1 CTA per SM, bins own the shared memory)
+static constexpr int MASK_TPB = 256;       // phase 1a: one thread per read
+#ifndef KMN_SCATTER_TPB
+#define KMN_SCATTER_TPB 1024
+#define KMN_SCATTER_CTAS 1
+#endif
+static constexpr int SCATTER_TPB = KMN_SCATTER_TPB;    // phase 1b: one thread per read, SCATTER_CTAS CTAs per SM
+static constexpr int SCATTER_CTAS = KMN_SCATTER_CTAS;
 static constexpr int INSERT_TPB = 256;
 static constexpr int INSERT_UNROLL = 4;
 static constexpr int INSERT_CHUNK = INSERT_TPB * INSERT_UNROLL;
+static constexpr int INSERT_GROUP = 4;      // chunks per ticket
 
 struct ParseArgs {
     const uint8_t *bases;
@@ -31,10 +40,12 @@ struct ParseArgs {
     int pad;               // 64*W - 2k
     float min_weight;
     u32 start_char;
-    u32 nb_log2;           // log2(ring blocks per shared-memory bin)
     u32 zero_below;        // qualities below this value have probability 0
+    u32 *mask;             // phase 1a -> 1b: bit (read_off[r] + i) set iff k-mer i of read r is counted
+    float *wts;            // optional (KMN_VALUE_WEIGHTS): fp32 weight of k-mer i of read r at [read_off[r] + i]
     u32 nranks, rank;
     u32 use_lookup8;
+    u32 l2_hints;          // staging stores carry an L2 evict_last policy
     TableView table;
     StageView stage;
     Counters *ctr;
@@ -119,101 +130,7 @@ __device__ __forceinline__ void insert_record(const TableView &t, const Rec<W, H
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// shared-memory write-combining bins, lock free (no CTA barrier and no global atomic on the hot path).
-// Every table partition owns a ring of NB blocks x 8 records in shared memory.  A producer reserves a slot with one
-// shared atomicAdd, waits (rarely) until the ring block's previous incarnation has been flushed, writes its record and
-// commits.  Whoever commits the 8th record of a block flushes the whole block (64*RW contiguous bytes) to this CTA's
-// private sub-region of the partition's staging region; the destination follows from the block's sequence number, so
-// the flush is eight plain stores with nothing to wait for.  state word: bits 0..7 commits, bits 8..31 generation.
-// ------------------------------------------------------------------------------------------------
-static constexpr u32 BIN_BLK = 8;
-
-template <int RW>
-struct Bins {
-    u32 *res;      // [n_parts] slots reserved so far in this launch
-    u32 *base;     // [n_parts] records already in this CTA's sub-region when the launch started
-    u32 *state;    // [n_parts][nb]
-    u64 *ring;     // [n_parts][nb][8][RW]
-    u32 n_parts, nb_log2;
-};
-
 struct LocalCtr { u64 raw, good, unique, full, direct, probes; };
-
-template <int W, bool HASX>
-__device__ __forceinline__ void flush_block(const Bins<Rec<W, HASX>::RW> &b, const StageView &st, const TableView &tab, u32 bin, u32 rb,
-                                            u32 blk_seq, u32 count, LocalCtr &lc)
-{
-    constexpr int RW = Rec<W, HASX>::RW;
-    const u64 pos = (u64)b.base[bin] + (u64)blk_seq * BIN_BLK;
-    const u64 *src = b.ring + ((((size_t)bin << b.nb_log2) + rb) * BIN_BLK) * RW;
-    u64 *dst = st.recs + (((size_t)bin * st.n_cta + blockIdx.x) * st.sub_cap + pos) * RW;
-    if (count == BIN_BLK && pos + BIN_BLK <= st.sub_cap) {
-#pragma unroll
-        for (int i = 0; i < (int)BIN_BLK * RW; ++i) dst[i] = src[i];
-        return;
-    }
-    for (u32 i = 0; i < count; ++i) {
-        if (pos + i < st.sub_cap) {
-#pragma unroll
-            for (int q = 0; q < RW; ++q) dst[(size_t)i * RW + q] = src[(size_t)i * RW + q];
-        } else {                                                            // sub-region full: insert directly
-            Rec<W, HASX> rec;
-#pragma unroll
-            for (int q = 0; q < RW; ++q) rec.w[q] = src[(size_t)i * RW + q];
-            insert_record<W, HASX>(tab, rec, lc.unique, lc.full, lc.probes);
-            lc.direct++;
-        }
-    }
-}
-
-template <int W, bool HASX>
-__device__ __forceinline__ void bins_put(const Bins<Rec<W, HASX>::RW> &b, const StageView &st, const TableView &tab, u32 bin,
-                                         const Rec<W, HASX> &rec, LocalCtr &lc)
-{
-    constexpr int RW = Rec<W, HASX>::RW;
-    const u32 s = atomicAdd(&b.res[bin], 1u);
-    const u32 blk = s >> 3, rb = blk & ((1u << b.nb_log2) - 1u), inc = (blk >> b.nb_log2) & 0xffffffu;
-    volatile u32 *stp = &b.state[((size_t)bin << b.nb_log2) + rb];
-    while ((*stp >> 8) != inc) __nanosleep(20);                             // ring block still holds its previous incarnation
-    u64 *d = b.ring + (((((size_t)bin << b.nb_log2) + rb) * BIN_BLK) + (s & 7u)) * RW;
-#pragma unroll
-    for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
-    __threadfence_block();
-    const u32 c = atomicAdd((u32 *)stp, 1u) & 0xffu;
-    if (c == BIN_BLK - 1) {                                                 // last committer flushes the block
-        __threadfence_block();
-        flush_block<W, HASX>(b, st, tab, bin, rb, blk, BIN_BLK, lc);
-        __threadfence_block();
-        atomicAdd((u32 *)stp, 256u - BIN_BLK);                              // commits -> 0, generation + 1
-    }
-}
-
-// after the last producer is done (CTA barrier): partial blocks, then the sub-region fill levels go back to global memory
-template <int W, bool HASX>
-__device__ __forceinline__ void bins_drain(const Bins<Rec<W, HASX>::RW> &b, const StageView &st, const TableView &tab, LocalCtr &lc)
-{
-    for (u32 bin = threadIdx.x; bin < b.n_parts; bin += blockDim.x) {
-        const u32 n = b.res[bin], part = n & 7u;
-        if (part) flush_block<W, HASX>(b, st, tab, bin, (n >> 3) & ((1u << b.nb_log2) - 1u), n >> 3, part, lc);
-        if (n) st.count[(size_t)bin * st.n_cta + blockIdx.x] = b.base[bin] + n;
-    }
-}
-
-template <int RW>
-__device__ __forceinline__ Bins<RW> bins_init(unsigned char *smem_after_ptab, const StageView &st, u32 n_parts, u32 nb_log2)
-{
-    Bins<RW> b;
-    b.n_parts = n_parts; b.nb_log2 = nb_log2;
-    const size_t nblk = (size_t)n_parts << nb_log2;
-    b.ring = reinterpret_cast<u64 *>(smem_after_ptab);
-    b.state = reinterpret_cast<u32 *>(b.ring + nblk * BIN_BLK * RW);
-    b.res = b.state + nblk;
-    b.base = b.res + n_parts;
-    for (size_t i = threadIdx.x; i < nblk; i += blockDim.x) b.state[i] = 0;
-    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) { b.res[i] = 0; b.base[i] = st.count[(size_t)i * st.n_cta + blockIdx.x]; }
-    return b;
-}
 
 __device__ __forceinline__ void ctr_commit(Counters *ctr, LocalCtr lc)
 {
@@ -313,7 +230,8 @@ struct Walker {
 };
 
 // One step = up to 8 bases.  EMIT(i, key, fwd, weightf, good, extbyte) is called for every k-mer position i.
-template <int W, bool NEED_W, bool EXT, typename EMIT>
+// KEYS=false: weights only (the k-mer is not rolled; emit receives a zero key).
+template <int W, bool NEED_W, bool EXT, bool KEYS = true, typename EMIT>
 __device__ __forceinline__ void walker_step(Walker<W> &s, const ParseArgs &a, const double *ptab, EMIT &&emit)
 {
     const u32 k = a.k;
@@ -336,6 +254,24 @@ __device__ __forceinline__ void walker_step(Walker<W> &s, const ParseArgs &a, co
     u64 bnext = 0, qnext = 0;
     if (EXT) { bnext = s.sb.peek(); qnext = s.sqi.peek(); }
 
+    if (NEED_W && !KEYS && !EXT) {
+        // weights only: a whole step in which nothing can change the weight -- past the first window, no markup in or
+        // entering the window, every incoming quality equal to the outgoing one (x/x == 1.0 exactly), no zero-probability
+        // quality, no re-seed boundary, w != 0 -- repeats the previous k-mer's weight eight times.
+        const u32 i0 = j0 + 1 - k;
+        const u64 zb = 0x0101010101010101ull * a.zero_below;
+        const bool has_zero_q = (((qin - zb) & ~qin) & 0x8080808080808080ull) != 0ull;
+        if (j0 >= k && j0 + 8 <= s.len && (valid & 0x8080808080808080ull) == 0x8080808080808080ull && qdiff == 0ull && !has_zero_q &&
+            (i0 & 1023u) != 0u && (i0 & 1023u) <= 1016u && s.w != 0.0 && s.last_bad < (int)i0) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) emit(i0 + u, s.roll.f, true, s.wf, s.good, 0x3fu);
+            s.sb.advance();
+            s.sqi.advance(); s.sqo.advance();
+            s.j = j0 + 8;
+            return;
+        }
+    }
+
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         const u32 j = j0 + u;
@@ -346,7 +282,7 @@ __device__ __forceinline__ void walker_step(Walker<W> &s, const ParseArgs &a, co
                 if ((c == 'N' || c == 'X' || c == '.') && s.first_nx == 0) s.first_nx = j + 1;
             }
             const u32 out_code = (u32)(s.roll.f[0] >> 62);          // base leaving the window (left neighbour of the new k-mer)
-            s.roll.push((u32)(codes >> (8 * u)) & 3u, a.pad);
+            if (KEYS) s.roll.push((u32)(codes >> (8 * u)) & 3u, a.pad);
             const u32 i = j + 1 - k;                                // k-mer index (valid when j+1 >= k)
             if (NEED_W) {
                 const u32 qi = (u32)(qin >> (8 * u)) & 0xffu;
@@ -379,7 +315,7 @@ __device__ __forceinline__ void walker_step(Walker<W> &s, const ParseArgs &a, co
                 }
             }
             if (j + 1 >= k) {
-                const bool fwd = s.roll.fwd_is_least();
+                const bool fwd = KEYS ? s.roll.fwd_is_least() : true;
                 u32 eb = 0x3f;
                 if (EXT) {
                     // left = base i-1 (or X,20), right = base i+k (or X,20); N neighbours read as A   KmerReadUtils.h:224-236
@@ -408,91 +344,176 @@ __device__ __forceinline__ void walker_step(Walker<W> &s, const ParseArgs &a, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1+K2 (+K5 partition): phase 1 of the count pass.  One thread walks one read; k-mers that pass the weight
-// test are dropped into the lock-free shared-memory bins keyed by table partition and leave for the staging
-// regions in 8-record bursts.  Multi-GPU: records owned by another rank (owner = lookup3 hash,
-// src/Kmer.h:2284-2295) go to that rank's send region instead.
+// K2a: phase 1a of the count pass.  One thread walks one read and evaluates the reference's sequential weight
+// recurrence (a3, src/KmerReadUtils.h:176-248); the only thing the count pass needs from it is one bit per k-mer
+// position -- "(float)w > minimumWeight" (src/KmerSpectrum.h:1598, src/KmerTrackingData.h:354-364) -- which goes to a
+// bit array indexed by the k-mer's first base in the concatenated batch (and, for KMN_VALUE_WEIGHTS, the fp32
+// weight itself).  Splitting this off leaves phase 1b free of any sequential dependency along the read.
 // ------------------------------------------------------------------------------------------------
-template <int W, bool HASX, bool EXT, bool DIST>
-__global__ void __launch_bounds__(PARSE_TPB, 1) k_count_parse(ParseArgs a)
+template <bool WTS>
+__global__ void __launch_bounds__(MASK_TPB) k_weight_mask(ParseArgs a)
 {
-    constexpr int RW = Rec<W, HASX>::RW;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *ptab = reinterpret_cast<double *>(smem_raw);
+    __shared__ double ptab[256];
     for (u32 i = threadIdx.x; i < 256; i += blockDim.x) ptab[i] = a.ptab[i];
-    Bins<RW> bins = bins_init<RW>(smem_raw + 256 * sizeof(double), a.stage, a.table.n_parts, a.nb_log2);
     __syncthreads();
-
     LocalCtr lc{0, 0, 0, 0, 0, 0};
     const u64 stride = (u64)gridDim.x * blockDim.x;
-    Walker<W> st;
-    st.clear();
-
-    auto emit = [&](u32 /*i*/, const u64 (&key)[W], bool fwd, float wf, bool good, u32 eb) {
-        lc.raw++;
-        if (!good) return;
-        lc.good++;
-        Rec<W, HASX> rec;
-        rec.pack(key, fwd, wf, eb);
-        if (DIST) {
-            u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
-            u32 own = owner_of(h, a.nranks);
-            if (own != a.rank) {
-                u64 pos = atomicAdd(&a.send_cursor[own], 1ull);
-                if (pos < a.send_cap) {
-                    u64 *d = a.send_recs + ((size_t)own * a.send_cap + pos) * RW;
-#pragma unroll
-                    for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
-                }
-                return;
-            }
-        }
-        u64 ph = place_hash<W>(key);
-        bins_put<W, HASX>(bins, a.stage, a.table, part_of(ph, a.table.n_parts), rec, lc);
-    };
-
+    Walker<1> st;
     for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += stride) {
         const u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
         const u32 len = (u32)(o1 - o0);
         if (len < a.k || (a.discarded && a.discarded[r])) continue;
         st.template begin<true>(a, o0, len);
-        while (st.j < st.len) walker_step<W, true, EXT>(st, a, ptab, emit);
+        u64 curw = ~0ull;
+        u32 acc = 0;
+        auto emit = [&](u32 i, const u64 (&)[1], bool, float wf, bool good, u32) {
+            const u64 gb = o0 + i, w = gb >> 5;
+            if (w != curw) { if (acc) atomicOr(&a.mask[curw], acc); acc = 0; curw = w; }
+            if (good) { acc |= 1u << (u32)(gb & 31ull); lc.good++; }
+            if (WTS) a.wts[gb] = wf;
+            lc.raw++;
+        };
+        while (st.j < st.len) walker_step<1, true, false, false>(st, a, ptab, emit);
+        if (acc) atomicOr(&a.mask[curw], acc);
     }
-    __syncthreads();
-    bins_drain<W, HASX>(bins, a.stage, a.table, lc);
     ctr_commit(a.ctr, lc);
 }
 
 // ------------------------------------------------------------------------------------------------
-// multi-GPU: records received from other ranks are routed into the local staging regions through the
-// same shared-memory bins (the receiving half of MPIAllToAllMessageBuffer, src/MPIBuffer.h:412-1073).
+// staging write: position pos of this CTA's sub-region of partition `part`, or a direct insert when it is full
+// ------------------------------------------------------------------------------------------------
+// L2 eviction policies.  The staging stores are 8*RW-byte pieces of sectors that only become complete several
+// stores later; a sector evicted half-written costs a DRAM read-modify-write, so these stores ask L2 to keep their
+// lines (evict_last) while the streamed inputs are marked evict_first.
+__device__ __forceinline__ u64 l2_policy_evict_last()
+{
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_first()
+{
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_normal()
+{
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_hint64(u64 *p, u64 v, u64 policy)
+{
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(policy) : "memory");
+}
+
+template <int W, bool HASX>
+__device__ __forceinline__ void stage_put(const StageView &st, const TableView &tab, u32 *cnt, u32 part, const Rec<W, HASX> &rec, LocalCtr &lc,
+                                          u64 policy)
+{
+    constexpr int RW = Rec<W, HASX>::RW;
+    const u32 pos = atomicAdd(&cnt[part], 1u);
+    if (pos < st.sub_cap) {
+        u64 *d = st.recs + (st.sub_index(part, blockIdx.x) * st.sub_cap + pos) * RW;
+#pragma unroll
+        for (int q = 0; q < RW; ++q) st_hint64(d + q, rec.w[q], policy);
+    } else {
+        insert_record<W, HASX>(tab, rec, lc.unique, lc.full, lc.probes);
+        lc.direct++;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1+K2b (+K5 partition): phase 1b of the count pass.  One thread walks one read and rolls the canonical k-mer
+// (a1 TwoBitSequence::compressSequence src/TwoBitSequence.cpp:242-269, a2 KmerArrayPair::build src/Kmer.h:1323-1375,
+// buildLeastComplement :356-364) 8 bases per step; k-mers whose "counted" bit (phase 1a) is set go to this CTA's
+// sub-region of their table partition -- one shared-memory atomicAdd for the position, one 8*RW-byte store.
+// Multi-GPU: records owned by another rank (a5: owner = lookup3 hash, src/Kmer.h:2284-2295) go to that rank's
+// send region instead.
+// ------------------------------------------------------------------------------------------------
+template <int W, bool HASX, bool EXT, bool DIST>
+__global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(ParseArgs a)
+{
+    constexpr int RW = Rec<W, HASX>::RW;
+    extern __shared__ __align__(16) u32 smem_u32[];
+    const u32 n_parts = a.table.n_parts;
+    u32 *cnt = smem_u32;                                               // [n_parts] fill level of this CTA's sub-regions
+    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) cnt[i] = a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x];
+    __syncthreads();
+
+    LocalCtr lc{0, 0, 0, 0, 0, 0};
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 keep = a.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
+    Walker<W> st;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += stride) {
+        const u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
+        const u32 len = (u32)(o1 - o0);
+        if (len < a.k || (a.discarded && a.discarded[r])) continue;
+        st.template begin<EXT>(a, o0, len);
+        u64 curw = o0 >> 5;                                            // mask word holding the current position's bit
+        u32 mw = __ldg(&a.mask[curw]), mwn = __ldg(&a.mask[curw + 1]);
+        auto emit = [&](u32 i, const u64 (&key)[W], bool fwd, float, bool, u32 eb) {
+            const u64 gb = o0 + i, w = gb >> 5;
+            if (w != curw) { curw = w; mw = mwn; mwn = __ldg(&a.mask[w + 1]); }
+            if (!((mw >> (u32)(gb & 31ull)) & 1u)) return;
+            Rec<W, HASX> rec;
+            rec.pack(key, fwd, (HASX && a.wts) ? a.wts[gb] : 1.0f, eb);
+            if (DIST) {
+                const u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
+                const u32 own = owner_of(h, a.nranks);
+                if (own != a.rank) {
+                    const u64 pos = atomicAdd(&a.send_cursor[own], 1ull);
+                    if (pos < a.send_cap) {
+                        u64 *d = a.send_recs + ((size_t)own * a.send_cap + pos) * RW;
+#pragma unroll
+                        for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
+                    }
+                    return;
+                }
+            }
+            const u64 ph = place_hash<W>(key);
+            stage_put<W, HASX>(a.stage, a.table, cnt, part_of(ph, n_parts), rec, lc, keep);
+        };
+        while (st.j < st.len) walker_step<W, false, EXT>(st, a, nullptr, emit);
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x] = cnt[i];
+    ctr_commit(a.ctr, lc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU: records received from other ranks are routed into the local staging regions the same way
+// (the receiving half of MPIAllToAllMessageBuffer, src/MPIBuffer.h:412-1073).  Same grid as k_kmer_scatter.
 // ------------------------------------------------------------------------------------------------
 struct RouteArgs {
     const u64 *recs; u64 n_recs;
-    u32 nb_log2, pad;
     TableView table; StageView stage; Counters *ctr;
 };
 
 template <int W, bool HASX>
-__global__ void __launch_bounds__(PARSE_TPB, 1) k_route_records(RouteArgs a)
+__global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_route_records(RouteArgs a)
 {
     constexpr int RW = Rec<W, HASX>::RW;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Bins<RW> bins = bins_init<RW>(smem_raw + 256 * sizeof(double), a.stage, a.table.n_parts, a.nb_log2);
+    extern __shared__ __align__(16) u32 smem_u32[];
+    const u32 n_parts = a.table.n_parts;
+    u32 *cnt = smem_u32;
+    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) cnt[i] = a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x];
     __syncthreads();
     LocalCtr lc{0, 0, 0, 0, 0, 0};
     const u64 stride = (u64)gridDim.x * blockDim.x;
+    const u64 keep = l2_policy_evict_last();
     for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n_recs; idx += stride) {
         Rec<W, HASX> rec;
 #pragma unroll
         for (int q = 0; q < RW; ++q) rec.w[q] = ld_nc64(a.recs + idx * RW + q);
         u64 key[W]; bool fwd; float wt; u32 eb;
         rec.unpack(key, fwd, wt, eb);
-        u64 ph = place_hash<W>(key);
-        bins_put<W, HASX>(bins, a.stage, a.table, part_of(ph, a.table.n_parts), rec, lc);
+        const u64 ph = place_hash<W>(key);
+        stage_put<W, HASX>(a.stage, a.table, cnt, part_of(ph, n_parts), rec, lc, keep);
     }
     __syncthreads();
-    bins_drain<W, HASX>(bins, a.stage, a.table, lc);
+    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x] = cnt[i];
     ctr_commit(a.ctr, lc);
 }
 
@@ -552,7 +573,7 @@ __global__ void k_build_worklist(const u32 *count, u32 sub_cap, u32 n_entries, u
 // Replaces KmerSpectrum::append (src/KmerSpectrum.h:1578-1668) + KmerMapByKmerArrayPair insert/find
 // (src/Kmer.h:1491-1544,3095-3110) + TrackingData::track (src/KmerTrackingData.h:427-448,517-529).
 // ------------------------------------------------------------------------------------------------
-template <int W, bool HASX>
+template <int W, bool HASX, bool PRE>
 __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, StageView st, const u64 *chunk_start, u64 *next_item, Counters *ctr)
 {
     constexpr int RW = Rec<W, HASX>::RW;
@@ -562,36 +583,31 @@ __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, Stage
     const u32 n_entries = t.n_parts * st.n_cta;
     const u64 total_items = chunk_start[n_entries];
     while (true) {
+        // one ticket = INSERT_GROUP consecutive chunks; the sub-region of the first one is found by bisection (the upper
+        // levels of the search are the same lines for every ticket and stay in L1), the following ones by stepping
         if (threadIdx.x == 0) {
-            const u64 it = atomicAdd(next_item, 1ull);
+            const u64 it = atomicAdd(next_item, (u64)INSERT_GROUP);
             s_item = it;
             if (it < total_items) {
-                // sub-region of this item = last e with chunk_start[e] <= item.  Sub-regions hold nearly equal numbers of
-                // chunks, so interpolate, bracket by galloping, then bisect (2-4 loads instead of log2(n_entries)).
-                u32 lo = (u32)(((unsigned __int128)it * n_entries) / total_items), hi;
-                if (lo >= n_entries) lo = n_entries - 1;
-                u32 step = 1;
-                if (chunk_start[lo] <= it) {
-                    hi = lo + 1;
-                    while (hi < n_entries && chunk_start[hi] <= it) { lo = hi; hi = hi + step > n_entries ? n_entries : hi + step; step <<= 1; }
-                } else {
-                    hi = lo;
-                    lo = lo >= 1 ? lo - 1 : 0;
-                    while (lo > 0 && chunk_start[lo] > it) { hi = lo; lo = lo > step ? lo - step : 0; step <<= 1; }
-                }
-                while (hi - lo > 1) { u32 mid = lo + ((hi - lo) >> 1); if (chunk_start[mid] <= it) lo = mid; else hi = mid; }
+                u32 lo = 0, hi = n_entries;
+                while (hi - lo > 1) { const u32 mid = lo + ((hi - lo) >> 1); if (__ldg(&chunk_start[mid]) <= it) lo = mid; else hi = mid; }
                 s_entry = lo;
             }
         }
         __syncthreads();
-        const u64 item = s_item;
-        const u32 entry = s_entry;
+        const u64 item0 = s_item;
+        u32 entry = s_entry;
         __syncthreads();
+        if (item0 >= total_items) break;
+#pragma unroll 1
+      for (u32 g = 0; g < (u32)INSERT_GROUP; ++g) {
+        const u64 item = item0 + g;
         if (item >= total_items) break;
+        while (__ldg(&chunk_start[entry + 1]) <= item) ++entry;
         const u32 part = entry / st.n_cta;
         u64 n = st.count[entry]; if (n > st.sub_cap) n = st.sub_cap;
-        const u64 first = (item - chunk_start[entry]) * INSERT_CHUNK;
-        const u64 *src = st.recs + ((size_t)entry * st.sub_cap + first) * RW;
+        const u64 first = (item - __ldg(&chunk_start[entry])) * INSERT_CHUNK;
+        const u64 *src = st.recs + (st.sub_index(part, entry - part * st.n_cta) * st.sub_cap + first) * RW;
         const u64 cnt = n - first < (u64)INSERT_CHUNK ? n - first : (u64)INSERT_CHUNK;
         Rec<W, HASX> rec[INSERT_UNROLL];
         bool have[INSERT_UNROLL];
@@ -604,7 +620,7 @@ __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, Stage
                 for (int q = 0; q < RW; ++q) rec[u].w[q] = ld_nc64(src + idx * RW + q);
             }
         }
-        // home-slot loads of all records first (independent, all in flight together), then resolve one by one
+        // PRE: home-slot loads of all records first (independent, all in flight together), then resolve one by one
         u64 key[INSERT_UNROLL][W], home[INSERT_UNROLL], pv[INSERT_UNROLL], pk[INSERT_UNROLL];
         bool fwd[INSERT_UNROLL]; float weight[INSERT_UNROLL]; u32 eb[INSERT_UNROLL];
         const Slot<W> *pbase = reinterpret_cast<const Slot<W> *>(t.slots) + (u64)part * t.part_slots;
@@ -614,15 +630,17 @@ __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, Stage
             if (have[u]) {
                 rec[u].unpack(key[u], fwd[u], weight[u], eb[u]);
                 home[u] = home_slot(place_hash<W>(key[u]), t.part_slots);
-                if (W == 1) ld_slot16(pbase + home[u], pv[u], pk[u]);
-                else pv[u] = ld_cg64(&pbase[home[u]].val);
+                if (PRE) {
+                    if (W == 1) ld_slot16(pbase + home[u], pv[u], pk[u]);
+                    else pv[u] = ld_cg64(&pbase[home[u]].val);
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < INSERT_UNROLL; ++u) {
             if (have[u]) {
                 u64 slot; u32 probes = 0;
-                int r = table_insert<W, true>(t, part, home[u], key[u], 1ull | ((u64)(fwd[u] ? 1u : 0u) << 32), &slot, &probes, pv[u], pk[u]);
+                int r = table_insert<W, PRE>(t, part, home[u], key[u], 1ull | ((u64)(fwd[u] ? 1u : 0u) << 32), &slot, &probes, pv[u], pk[u]);
                 if (r < 0) { n_full++; continue; }
                 n_unique += (u64)r; n_probes += probes;
                 if (HASX) {
@@ -635,6 +653,7 @@ __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, Stage
                 }
             }
         }
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
