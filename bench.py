@@ -42,9 +42,9 @@ def parse_args():
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--stage-keys", type=int, default=0)
     ap.add_argument("--slice-mb", type=int, default=64)
-    ap.add_argument("--pipe-batches", type=int, default=4, help="sub-batches of the parse/insert pipeline per step")
-    ap.add_argument("--e2e-reads", type=int, default=20_000_000)
-    ap.add_argument("--e2e-batch", type=int, default=2_000_000)
+    ap.add_argument("--pipe-batches", type=int, default=8, help="sub-batches of the parse/insert pipeline per step")
+    ap.add_argument("--e2e-reads", type=int, default=0, help="reads per e2e step (0 = same as --reads)")
+    ap.add_argument("--e2e-batch", type=int, default=4_000_000)
     ap.add_argument("--cpu-reads", type=int, default=400_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -247,7 +247,7 @@ def main():
     # ---- e2e: host (pinned) buffers through the C ABI, H2D of every batch + D2H of the counters inside the timing ----
     e2e = None
     if not args.no_e2e:
-        n_e = min(args.e2e_reads, n_reads)
+        n_e = min(args.e2e_reads or n_reads, n_reads)
         hb = torch.empty(n_e * READ_LEN, dtype=torch.uint8, pin_memory=True)
         hq = torch.empty(n_e * READ_LEN, dtype=torch.uint8, pin_memory=True)
         hb.copy_(bases[: n_e * READ_LEN])

@@ -35,8 +35,8 @@ struct kmn_ctx {
     cudaStream_t stream = nullptr;        // main stream: phase 1 (parse), scans, lookup pass; the one kmn_stream() returns
     cudaStream_t s_insert = nullptr;      // phase 2 (insert) runs here so that it overlaps phase 1 of the next sub-batch
     cudaStream_t s_copy = nullptr;        // H2D staging of host inputs, overlapping the kernels of the previous batch
-    bool pipeline = false;                // two staging sets + insert stream (KMN_PIPELINE=1); off: phase 2 follows phase 1 on the main stream
-    int n_sets = 1;
+    bool pipeline = true;                 // two staging sets + insert stream (KMN_PIPELINE=0: one set, phase 2 follows phase 1 on the main stream)
+    int n_sets = 2;
     std::string err;
     uint64_t launches = 0;
     // optional per-kernel timing
@@ -82,7 +82,8 @@ struct kmn_ctx {
     // multi-GPU
     int rank = 0, nranks = 1;
     u64 *send_recs = nullptr, *send_cursor = nullptr, *recv_recs = nullptr, *all_counts = nullptr;
-    uint64_t send_cap = 0, recv_cap = 0;
+    u64 *seg_recs = nullptr; u32 *seg_count = nullptr;
+    uint64_t send_cap = 0, recv_cap = 0, seg_cap = 0;
 #ifdef KMN_WITH_NCCL
     ncclComm_t comm = nullptr;
 #endif
@@ -227,7 +228,7 @@ static int plan_and_alloc(kmn_ctx *c)
     c->table.part_slots = part_slots;
     c->table.n_parts = (u32)n_parts;
     c->n_cta = c->n_sms * SCATTER_CTAS;
-    c->scatter_smem = (((size_t)n_parts + 31) & ~(size_t)31) * 4;
+    c->scatter_smem = ((((size_t)n_parts + 31) & ~(size_t)31) + 64) * 4;      // partition counters + send-segment counters (<= 64 ranks)
 
     CK(c, cudaMalloc(&c->table.slots, slots * c->slot_bytes));
     if (c->weights) CK(c, cudaMalloc((void **)&c->table.wsum, slots * 4));
@@ -295,6 +296,7 @@ int kmn_reset(kmn_ctx *c)
     }
     CK(c, cudaMemsetAsync(c->ctr, 0, sizeof(Counters), c->stream));
     if (c->send_cursor) CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)c->nranks * 8, c->stream));
+    if (c->seg_count) CK(c, cudaMemsetAsync(c->seg_count, 0, (size_t)c->nranks * c->n_cta * 4, c->stream));
     c->purged_depth = 0;
     c->finished = false;
     return 0;
@@ -381,7 +383,7 @@ void kmn_destroy(kmn_ctx *c)
 #endif
     void *ptrs[] = {c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
                     c->chunk_start, c->next_item,
-                    c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts,
+                    c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts, c->seg_recs, c->seg_count,
                     c->in_bases[0].p, c->in_quals[0].p, c->in_off[0].p, c->in_disc[0].p,
                     c->in_bases[1].p, c->in_quals[1].p, c->in_off[1].p, c->in_disc[1].p, c->vals.p, c->first_nx.p, c->out_off.p,
                     c->lk_origin.p, c->lk_resp_in.p, c->lk_resp_out.p, c->mask.p, c->wts.p,
@@ -484,6 +486,7 @@ static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, cons
     a.l2_hints = getenv("KMN_NO_L2_HINTS") ? 0 : 1;
     a.table = c->table; a.stage = c->sets[c->cur].v; a.ctr = c->ctr;
     a.send_recs = c->send_recs; a.send_cursor = c->send_cursor; a.send_cap = c->send_cap;
+    a.seg_recs = c->seg_recs; a.seg_count = c->seg_count; a.seg_cap = (u32)c->seg_cap;
 }
 
 static int launch_parse(kmn_ctx *c, const ParseArgs &a)
@@ -529,11 +532,26 @@ static int exchange(kmn_ctx *c)
 #ifdef KMN_WITH_NCCL
     if (c->nranks <= 1) return 0;
     const int R = c->nranks;
+    // pack the per-CTA send segments into one contiguous buffer per destination
+    CK(c, cudaMemsetAsync(c->scratch + 5, 0, 8, c->stream));
+    CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)R * 8, c->stream));
+    {
+        ProfScope ps(c, KMN_PROF_ROUTE, 0);
+        k_compact_send<<<dim3((unsigned)c->n_cta, (unsigned)R), 256, 0, c->stream>>>(c->seg_recs, c->seg_count, (u32)c->seg_cap, (u32)c->n_cta, (u32)c->RW,
+                                                                                   c->send_recs, c->send_cap, c->send_cursor, c->scratch + 5);
+    }
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemsetAsync(c->seg_count, 0, (size_t)R * c->n_cta * 4, c->stream));
     ncclResult_t nr = ncclAllGather(c->send_cursor, c->all_counts, (size_t)R, ncclUint64, c->comm, c->stream);
     if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclAllGather failed: %s", ncclGetErrorString(nr));
     std::vector<u64> counts((size_t)R * R);
+    u64 seg_overflow = 0;
     CK(c, cudaMemcpyAsync(counts.data(), c->all_counts, counts.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(&seg_overflow, c->scratch + 5, 8, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
+    if (seg_overflow) return fail(c, KMN_ERR_COMM, "send segment overflow (%llu segments; capacity %llu records each); use smaller batches",
+                                  (unsigned long long)seg_overflow, (unsigned long long)c->seg_cap);
     // counts[src*R + dst]
     u64 recv_total = 0;
     for (int s = 0; s < R; ++s) {
@@ -597,7 +615,7 @@ int kmn_comm_init(kmn_ctx *c, int rank, int nranks, const void *id128)
 {
     if (!c) return KMN_ERR_INVALID;
 #ifdef KMN_WITH_NCCL
-    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, KMN_ERR_INVALID, "bad rank %d / %d", rank, nranks);
+    if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) return fail(c, KMN_ERR_INVALID, "bad rank %d / %d (at most 64 ranks)", rank, nranks);
     if (c->sets[0].staged_upper || c->sets[1].staged_upper) return fail(c, KMN_ERR_STATE, "kmn_comm_init after counting started");
     c->rank = rank; c->nranks = nranks;
     if (nranks == 1) return 0;
@@ -609,6 +627,10 @@ int kmn_comm_init(kmn_ctx *c, int rank, int nranks, const void *id128)
     // send/recv regions: a launch is bounded by stage_keys/2 instances, 1/nranks of which go to each peer on average
     c->send_cap = c->stage_keys / 2 / (uint64_t)nranks * 3 / 2 + 65536;
     c->recv_cap = c->send_cap * (uint64_t)(nranks - 1);
+    c->seg_cap = c->stage_keys / 2 / (uint64_t)nranks / (uint64_t)c->n_cta * 2 + 4096;
+    CK(c, cudaMalloc((void **)&c->seg_recs, (size_t)nranks * c->n_cta * c->seg_cap * c->RW * 8));
+    CK(c, cudaMalloc((void **)&c->seg_count, (size_t)nranks * c->n_cta * 4));
+    CK(c, cudaMemsetAsync(c->seg_count, 0, (size_t)nranks * c->n_cta * 4, c->stream));
     CK(c, cudaMalloc((void **)&c->send_recs, (size_t)nranks * c->send_cap * c->RW * 8));
     CK(c, cudaMalloc((void **)&c->recv_recs, (size_t)c->recv_cap * c->RW * 8));
     CK(c, cudaMalloc((void **)&c->send_cursor, (size_t)nranks * 8));

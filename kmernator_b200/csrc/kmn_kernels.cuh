@@ -13,6 +13,7 @@
 // so that only one table slice is hot.
 #pragma once
 #include "kmn_device.cuh"
+#include <cooperative_groups.h>
 
 namespace kmn {
 
@@ -49,8 +50,12 @@ struct ParseArgs {
     TableView table;
     StageView stage;
     Counters *ctr;
-    // multi-GPU: records owned by other ranks are appended to per-destination send regions
-    u64 *send_recs;        // [nranks][send_cap][RW]
+    // multi-GPU count pass: records owned by other ranks go to this CTA's segment of the destination's send region
+    u64 *seg_recs;         // [nranks][n_cta][seg_cap][RW]
+    u32 *seg_count;        // [nranks][n_cta]
+    u32 seg_cap;
+    // multi-GPU lookup pass: requests are appended to per-destination regions
+    u64 *send_recs;        // [nranks][send_cap][W]
     u64 *send_cursor;      // [nranks]
     u64 send_cap;
 };
@@ -439,14 +444,18 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
     extern __shared__ __align__(16) u32 smem_u32[];
     const u32 n_parts = a.table.n_parts;
     u32 *cnt = smem_u32;                                               // [n_parts] fill level of this CTA's sub-regions
+    u32 *scnt = smem_u32 + ((n_parts + 31u) & ~31u);                   // [nranks] fill level of this CTA's send segments
     for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) cnt[i] = a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x];
+    if (DIST) for (u32 i = threadIdx.x; i < a.nranks; i += blockDim.x) scnt[i] = a.seg_count[(size_t)i * gridDim.x + blockIdx.x];
     __syncthreads();
 
     LocalCtr lc{0, 0, 0, 0, 0, 0};
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const u64 keep = a.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
     Walker<W> st;
-    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += stride) {
+    // consecutive groups of 32 reads (one warp) go to different CTAs, so even a small batch spreads evenly over the
+    // per-CTA sub-regions / segments while a warp still streams one contiguous piece of the batch
+    for (u64 r = ((u64)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u); r < a.n_reads; r += stride) {
         const u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
         const u32 len = (u32)(o1 - o0);
         if (len < a.k || (a.discarded && a.discarded[r])) continue;
@@ -463,9 +472,15 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
                 const u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
                 const u32 own = owner_of(h, a.nranks);
                 if (own != a.rank) {
-                    const u64 pos = atomicAdd(&a.send_cursor[own], 1ull);
-                    if (pos < a.send_cap) {
-                        u64 *d = a.send_recs + ((size_t)own * a.send_cap + pos) * RW;
+                    // one shared atomicAdd per (converged lanes, destination) group
+                    namespace cg = cooperative_groups;
+                    auto grp = cg::labeled_partition(cg::coalesced_threads(), (int)own);
+                    u32 base = 0;
+                    if (grp.thread_rank() == 0) base = atomicAdd(&scnt[own], (u32)grp.size());
+                    base = grp.shfl(base, 0);
+                    const u32 pos = base + grp.thread_rank();
+                    if (pos < a.seg_cap) {
+                        u64 *d = a.seg_recs + (((size_t)own * gridDim.x + blockIdx.x) * a.seg_cap + pos) * RW;
 #pragma unroll
                         for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
                     }
@@ -479,7 +494,36 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
     }
     __syncthreads();
     for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x] = cnt[i];
+    if (DIST) for (u32 i = threadIdx.x; i < a.nranks; i += blockDim.x) a.seg_count[(size_t)i * gridDim.x + blockIdx.x] = scnt[i];
     ctr_commit(a.ctr, lc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU: the per-CTA send segments of every destination are packed into one contiguous send buffer per
+// destination (what the all-to-all ships).  grid = (n_cta, nranks).  send_cursor[d] = records for d; flag != 0 on overflow.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_compact_send(const u64 *seg_recs, const u32 *seg_count, u32 seg_cap, u32 n_cta, u32 rw,
+                                                      u64 *send_recs, u64 send_cap, u64 *send_cursor, u64 *flag)
+{
+    const u32 d = blockIdx.y, c = blockIdx.x;
+    __shared__ u64 part[8];
+    __shared__ u64 s_off;
+    u64 mine = 0;
+    for (u32 i = threadIdx.x; i < c; i += blockDim.x) { const u32 n = seg_count[(size_t)d * n_cta + i]; mine += n < seg_cap ? n : seg_cap; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) { u64 t = 0; for (int i = 0; i < 8; ++i) t += part[i]; s_off = t; }
+    __syncthreads();
+    const u64 off = s_off;
+    u32 n = seg_count[(size_t)d * n_cta + c];
+    if (n > seg_cap) { if (threadIdx.x == 0) atomicAdd(flag, 1ull); n = seg_cap; }
+    if (off + n > send_cap) { if (threadIdx.x == 0) atomicAdd(flag, 1ull); n = off < send_cap ? (u32)(send_cap - off) : 0u; }
+    const u64 *src = seg_recs + ((size_t)d * n_cta + c) * seg_cap * rw;
+    u64 *dst = send_recs + ((size_t)d * send_cap + off) * rw;
+    for (u64 i = threadIdx.x; i < (u64)n * rw; i += blockDim.x) dst[i] = src[i];
+    if (c == n_cta - 1 && threadIdx.x == 0) send_cursor[d] = off + n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -503,7 +547,7 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_route_records(Rou
     LocalCtr lc{0, 0, 0, 0, 0, 0};
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const u64 keep = l2_policy_evict_last();
-    for (u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x; idx < a.n_recs; idx += stride) {
+    for (u64 idx = (u64)blockIdx.x * 32u + (threadIdx.x & 31u) + (u64)(threadIdx.x >> 5) * 32u * gridDim.x; idx < a.n_recs; idx += stride) {
         Rec<W, HASX> rec;
 #pragma unroll
         for (int q = 0; q < RW; ++q) rec.w[q] = ld_nc64(a.recs + idx * RW + q);
