@@ -61,7 +61,7 @@ typedef struct {
     uint64_t est_raw_kmers;      /* KmerSpectrum ctor argument (src/KmerSpectrum.h:414-421); 0 = use table_slots     */
     uint64_t table_slots;        /* explicit table capacity (slots); 0 = derive from est_raw_kmers                   */
     uint64_t stage_keys;         /* capacity of the partitioned key staging area (k-mer instances); 0 = auto         */
-    uint32_t slice_bytes;        /* target bytes of one table partition (kept L2-resident); 0 = 64 MiB               */
+    uint32_t slice_bytes;        /* target bytes of one table group (the L2-resident unit of the staging); 0 = 64 MiB */
     uint32_t device;             /* CUDA device ordinal                                                              */
     uint32_t ignore_quality;     /* --ignore-quality: every base weight 1                                            */
     uint32_t reserved[7];
@@ -143,7 +143,7 @@ int  kmn_sync(kmn_ctx *ctx);
  * Off by default (events cost a few microseconds per launch).  kmn_profile_read synchronises, returns the sums
  * accumulated since the last read and clears them.                                                             */
 enum { KMN_PROF_PARSE = 0, KMN_PROF_INSERT = 1, KMN_PROF_ROUTE = 2, KMN_PROF_LOOKUP = 3, KMN_PROF_TRIM = 4, KMN_PROF_SCAN = 5,
-       KMN_PROF_WEIGHT = 6, KMN_PROF_KINDS = 8 };
+       KMN_PROF_WEIGHT = 6, KMN_PROF_SUBPART = 7, KMN_PROF_KINDS = 8 };
 typedef struct {
     double   ms[KMN_PROF_KINDS];        /* summed device time per kernel class                                  */
     uint64_t launches[KMN_PROF_KINDS];

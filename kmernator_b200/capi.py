@@ -18,7 +18,7 @@ EXPORTED = [
     "kmn_lookup", "kmn_trim_batch", "kmn_export", "kmn_debug_kmers", "kmn_sync", "kmn_stream", "kmn_launch_count",
     "kmn_profile_enable", "kmn_profile_read",
 ]
-PROF_KINDS = ["parse", "insert", "route", "lookup", "trim", "scan", "weight", "k7"]
+PROF_KINDS = ["parse", "insert", "route", "lookup", "trim", "scan", "weight", "subpart"]
 
 
 class KmnProfile(C.Structure):

@@ -59,6 +59,13 @@ struct kmn_ctx {
     int cur = 0;
     uint64_t stage_keys = 0;          // record capacity of ONE set (= the sub-batch size of the pipeline)
     u64 *chunk_start = nullptr, *next_item = nullptr;
+    // fast count path (k <= 31, plain values): level-2 staging by table slice + shared-memory counting (level 3)
+    bool fast = false;
+    bool tiles = false;               // phase 1b: position-parallel tile kernel instead of the per-read walker
+    bool table_clean = true;          // nothing has been written to the table since the last reset
+    Stage2View s2{};
+    u32 *item_entry = nullptr;        // flat work list of level 2
+    size_t sub_smem = 0, cnt_smem = 0, tile_smem = 0;
     int insert_ctas = 8;              // phase-2 CTAs per SM
     bool insert_pre = true;           // phase 2 keeps the home-slot loads of its 4 records in flight together
     Counters *ctr = nullptr;
@@ -211,24 +218,29 @@ static int plan_and_alloc(kmn_ctx *c)
     }
     if (slots < 1024) slots = 1024;
 
-    // partitions: slice_bytes each so that one slice stays L2-resident during phase 2; every phase-1 CTA keeps one
-    // 4-byte fill counter per partition in shared memory
+    // slices of <= SLICE_SLOTS slots (one slice fits in shared memory; probing wraps inside a slice), grouped into
+    // L2-sized groups of ~slice_bytes: the level-1 staging is partitioned by group and every phase-1 CTA keeps one
+    // 4-byte fill counter per group in shared memory
     int dev_smem = 0;
     CK(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    const uint32_t slice = o.slice_bytes ? o.slice_bytes : (64u << 20);
-    uint64_t part_slots = std::max<uint64_t>(slice / c->slot_bytes, 256);
+    const uint32_t gbytes = o.slice_bytes ? o.slice_bytes : (64u << 20);
+    uint64_t part_slots = std::min<uint64_t>(SLICE_SLOTS, slots);
     uint64_t n_parts = (slots + part_slots - 1) / part_slots;
-    const uint64_t p_max = ((size_t)dev_smem / SCATTER_CTAS - 1024) / 4 - 32;
-    if (n_parts > p_max) n_parts = p_max;
-    if (n_parts < 1) n_parts = 1;
-    part_slots = (slots + n_parts - 1) / n_parts;
-    if (part_slots >= (1ull << 32)) return fail(c, KMN_ERR_INVALID, "partition too large (%llu slots)", (unsigned long long)part_slots);
+    if (n_parts >= (1ull << 31)) return fail(c, KMN_ERR_INVALID, "table too large (%llu slices)", (unsigned long long)n_parts);
     slots = part_slots * n_parts;
+    uint32_t gshift = 0;
+    while (gshift < 11 && (part_slots * c->slot_bytes << (gshift + 1)) <= (uint64_t)gbytes) gshift++;     // <= 2048 slices per group
+    const uint64_t p_max = ((size_t)dev_smem / SCATTER_CTAS - 1024) / 4 - 32;
+    while (((n_parts + (1ull << gshift) - 1) >> gshift) > p_max) gshift++;
+    if (gshift > 11) c->fast = false;                      // level 2 sorts at most 2048 slices per group
+    const uint64_t n_groups = (n_parts + (1ull << gshift) - 1) >> gshift;
     c->n_slots = slots;
     c->table.part_slots = part_slots;
     c->table.n_parts = (u32)n_parts;
-    c->n_cta = c->n_sms * SCATTER_CTAS;
-    c->scatter_smem = ((((size_t)n_parts + 31) & ~(size_t)31) + 64) * 4;      // partition counters + send-segment counters (<= 64 ranks)
+    c->table.group_shift = gshift;
+    c->tiles = c->fast && getenv("KMN_TILES") && atoi(getenv("KMN_TILES")) != 0;
+    c->n_cta = c->tiles ? c->n_sms * 4 : c->n_sms * SCATTER_CTAS;
+    c->scatter_smem = ((((size_t)n_groups + 31) & ~(size_t)31) + 64) * 4;      // group counters + send-segment counters (<= 64 ranks)
 
     CK(c, cudaMalloc(&c->table.slots, slots * c->slot_bytes));
     if (c->weights) CK(c, cudaMalloc((void **)&c->table.wsum, slots * 4));
@@ -240,26 +252,43 @@ static int plan_and_alloc(kmn_ctx *c)
     CK(c, cudaMemGetInfo(&free_b, &total_b));
     uint64_t sk = o.stage_keys;
     if (!sk) {
-        sk = (o.est_raw_kmers ? o.est_raw_kmers : (1ull << 22)) / (c->pipeline ? 8 : 1);
-        uint64_t lim = (uint64_t)(0.35 * (double)free_b / (double)(c->RW * 8) / (double)c->n_sets);
+        sk = (o.est_raw_kmers ? o.est_raw_kmers : (1ull << 22)) / (c->pipeline ? 8 : (c->fast ? 4 : 1));
+        uint64_t lim = (uint64_t)(0.35 * (double)free_b / (double)(c->RW * 8) / (double)(c->fast ? 3 : c->n_sets));
         if (sk > lim) sk = lim;
     }
     if (sk < (1ull << 16)) sk = 1ull << 16;
     c->stage_keys = sk;
     const uint64_t n_cta = (uint64_t)c->n_cta;
-    const uint64_t per_sub = sk / n_parts / n_cta;
+    const uint64_t per_sub = sk / n_groups / n_cta;
     const uint64_t sub_cap = per_sub + per_sub / 8 + 8 * (uint64_t)std::sqrt((double)per_sub + 1.0) + 64;   // mean + slack for the spread
     if (sub_cap >= (1ull << 31)) return fail(c, KMN_ERR_INVALID, "staging sub-region too large (%llu records)", (unsigned long long)sub_cap);
     for (int si = 0; si < c->n_sets; ++si) {
         kmn_ctx::StageSet &st = c->sets[si];
-        st.v.sub_cap = (u32)sub_cap; st.v.n_cta = (u32)n_cta; st.v.n_parts = (u32)n_parts;
+        st.v.sub_cap = (u32)sub_cap; st.v.n_cta = (u32)n_cta; st.v.n_parts = (u32)n_groups;
         st.v.cta_major = getenv("KMN_PART_MAJOR") ? 0 : 1;
-        CK(c, cudaMalloc((void **)&st.v.recs, (size_t)n_parts * n_cta * sub_cap * c->RW * 8));
-        CK(c, cudaMalloc((void **)&st.v.count, (size_t)n_parts * n_cta * 4));
+        CK(c, cudaMalloc((void **)&st.v.recs, (size_t)n_groups * n_cta * sub_cap * c->RW * 8));
+        CK(c, cudaMalloc((void **)&st.v.count, (size_t)n_groups * n_cta * 4));
         CK(c, cudaEventCreateWithFlags(&st.ev_parsed, cudaEventDisableTiming));
         CK(c, cudaEventCreateWithFlags(&st.ev_drained, cudaEventDisableTiming));
     }
-    CK(c, cudaMalloc((void **)&c->chunk_start, ((size_t)n_parts * n_cta + 1) * 8));
+    if (c->fast) {
+        // level-2 buckets, one per slice: mean + slack for the spread of duplicate-heavy inputs; the excess is inserted directly
+        const uint64_t mean2 = sk / n_parts;
+        const uint64_t cap2 = mean2 + mean2 / 4 + 8 * (uint64_t)std::sqrt(8.0 * (double)mean2 + 1.0) + 64;
+        if (cap2 >= (1ull << 31)) return fail(c, KMN_ERR_INVALID, "level-2 bucket too large (%llu records)", (unsigned long long)cap2);
+        c->s2.cap = (u32)cap2;
+        CK(c, cudaMalloc((void **)&c->s2.recs, (size_t)n_parts * cap2 * 8));
+        CK(c, cudaMalloc((void **)&c->s2.count, (size_t)n_parts * 4));
+        c->sub_smem = (size_t)TS_TILE * 16 + ((size_t)1 << gshift) * 16;
+        c->cnt_smem = (size_t)part_slots * 16;
+        c->tile_smem = (size_t)TS_TILE * 16 + ((size_t)TS_TILE / 8 + 6) * 8 + ((size_t)TS_TILE / 32) * 4 + ((size_t)n_groups + 64) * 20 + 16;
+        CK(c, cudaFuncSetAttribute(k_subpartition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sub_smem));
+        CK(c, cudaFuncSetAttribute(k_count_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cnt_smem));
+        CK(c, cudaFuncSetAttribute(k_kmer_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tile_smem));
+        CK(c, cudaFuncSetAttribute(k_kmer_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tile_smem));
+        CK(c, cudaMalloc((void **)&c->item_entry, ((size_t)n_groups * n_cta * (sub_cap / TS_TILE + 2) + 16) * 4));
+    }
+    CK(c, cudaMalloc((void **)&c->chunk_start, ((size_t)n_groups * n_cta + 1) * 8));
     CK(c, cudaMalloc((void **)&c->next_item, 8));
     CK(c, cudaMalloc((void **)&c->ctr, sizeof(Counters)));
     CK(c, cudaMalloc((void **)&c->scratch, 64));
@@ -291,9 +320,11 @@ int kmn_reset(kmn_ctx *c)
     if (c->table.ext) CK(c, cudaMemsetAsync(c->table.ext, 0, c->n_slots * 48, c->stream));
     for (int si = 0; si < c->n_sets; ++si) {
         kmn_ctx::StageSet &st = c->sets[si];
-        CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)c->table.n_parts * st.v.n_cta * 4, c->stream));
+        CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)st.v.n_parts * st.v.n_cta * 4, c->stream));
         st.staged_upper = 0;
     }
+    if (c->s2.count) CK(c, cudaMemsetAsync(c->s2.count, 0, (size_t)c->table.n_parts * 4, c->stream));
+    c->table_clean = true;
     CK(c, cudaMemsetAsync(c->ctr, 0, sizeof(Counters), c->stream));
     if (c->send_cursor) CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)c->nranks * 8, c->stream));
     if (c->seg_count) CK(c, cudaMemsetAsync(c->seg_count, 0, (size_t)c->nranks * c->n_cta * 4, c->stream));
@@ -338,7 +369,13 @@ int kmn_create(kmn_ctx **out, const kmn_opts *opts)
         c->n_sms = prop.multiProcessorCount;
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "stream create failed"); break; }
         // tuning knobs (bench experiments only; the defaults are the measured best)
-        if (const char *e = getenv("KMN_PIPELINE")) c->pipeline = atoi(e) != 0;
+        // fast path: single-word keys whose record is the key alone; it runs phase 1 and phase 2 on one stream with one
+        // staging set (every kernel of it is throughput-bound by itself, and direct inserts of overflowing records are
+        // then never concurrent with a slice held in shared memory)
+        c->fast = opts->kmer_size < 32 && (opts->value_kind & (KMN_VALUE_DIR_EXT | KMN_VALUE_WEIGHTS)) == 0;
+        if (const char *e = getenv("KMN_FAST")) c->fast = c->fast && atoi(e) != 0;
+        if (c->fast) c->pipeline = false;
+        if (const char *e = getenv("KMN_PIPELINE")) c->pipeline = !c->fast && atoi(e) != 0;
         c->n_sets = c->pipeline ? 2 : 1;
         if (const char *e = getenv("KMN_INSERT_CTAS")) c->insert_ctas = std::max(1, atoi(e));
         if (const char *e = getenv("KMN_INSERT_PRE")) c->insert_pre = atoi(e) != 0;
@@ -382,7 +419,7 @@ void kmn_destroy(kmn_ctx *c)
     if (c->comm) ncclCommDestroy(c->comm);
 #endif
     void *ptrs[] = {c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
-                    c->chunk_start, c->next_item,
+                    c->chunk_start, c->next_item, c->s2.recs, c->s2.count, c->item_entry,
                     c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts, c->seg_recs, c->seg_count,
                     c->in_bases[0].p, c->in_quals[0].p, c->in_off[0].p, c->in_disc[0].p,
                     c->in_bases[1].p, c->in_quals[1].p, c->in_off[1].p, c->in_disc[1].p, c->vals.p, c->first_nx.p, c->out_off.p,
@@ -410,8 +447,29 @@ static int submit_drain(kmn_ctx *c, int i)
         CK(c, cudaEventRecord(st.ev_parsed, c->stream));
         CK(c, cudaStreamWaitEvent(si, st.ev_parsed, 0));
     }
-    const u32 n_entries = c->table.n_parts * st.v.n_cta;
-    k_build_worklist<<<1, 1024, 0, si>>>(st.v.count, st.v.sub_cap, n_entries, c->chunk_start, c->next_item);
+    const u32 n_entries = st.v.n_parts * st.v.n_cta;
+    if (c->fast) {
+        k_build_worklist<<<1, 1024, 0, si>>>(st.v.count, st.v.sub_cap, n_entries, (u32)TS_TILE, c->chunk_start, c->next_item);
+        k_fill_items<<<(n_entries + 255) / 256, 256, 0, si>>>(c->chunk_start, n_entries, c->item_entry);
+        c->launches += 2;
+        {
+            ProfScope ps(c, KMN_PROF_SUBPART, st.staged_upper, si);
+            k_subpartition<<<c->n_sms * 4, TS_TPB, c->sub_smem, si>>>(c->table, st.v, c->s2, c->chunk_start, c->item_entry, c->ctr);
+        }
+        c->launches++;
+        CK(c, cudaGetLastError());
+        {
+            ProfScope ps(c, KMN_PROF_INSERT, st.staged_upper, si);
+            const int ctas = (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(200 * 1024) / c->cnt_smem));
+            const int grid = (int)std::min<uint64_t>((uint64_t)c->n_sms * ctas, c->table.n_parts);
+            k_count_slices<<<grid, CNT_TPB, c->cnt_smem, si>>>(c->table, c->s2, c->table_clean ? 1u : 0u, c->ctr);
+        }
+        c->launches++;
+        CK(c, cudaGetLastError());
+        c->table_clean = false;
+        CK(c, cudaMemsetAsync(c->s2.count, 0, (size_t)c->table.n_parts * 4, si));
+    } else {
+    k_build_worklist<<<1, 1024, 0, si>>>(st.v.count, st.v.sub_cap, n_entries, (u32)INSERT_CHUNK, c->chunk_start, c->next_item);
     c->launches++;
     const int grid = c->n_sms * c->insert_ctas;
     {
@@ -423,6 +481,7 @@ static int submit_drain(kmn_ctx *c, int i)
     }
     c->launches++;
     CK(c, cudaGetLastError());
+    }
     CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)n_entries * 4, si));
     if (si != c->stream) {
         CK(c, cudaEventRecord(st.ev_drained, si));
@@ -489,7 +548,7 @@ static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, cons
     a.seg_recs = c->seg_recs; a.seg_count = c->seg_count; a.seg_cap = (u32)c->seg_cap;
 }
 
-static int launch_parse(kmn_ctx *c, const ParseArgs &a)
+static int launch_parse(kmn_ctx *c, const ParseArgs &a, uint64_t byte0, uint64_t byte1)
 {
     const bool dist = c->nranks > 1;
     {   // phase 1a: weights -> "counted" bits
@@ -500,6 +559,15 @@ static int launch_parse(kmn_ctx *c, const ParseArgs &a)
     }
     c->launches++;
     CK(c, cudaGetLastError());
+    if (c->tiles) {   // phase 1b, position-parallel over tiles of the byte range
+        TileArgs ta;
+        ta.byte0 = byte0; ta.byte1 = byte1;
+        ta.tile0 = byte0 / TS_TILE;
+        ta.n_tiles = byte1 > byte0 ? (byte1 - 1) / TS_TILE - ta.tile0 + 1 : 0;
+        ProfScope ps(c, KMN_PROF_PARSE, a.n_reads);
+        if (dist) k_kmer_tiles<true><<<c->n_cta, TS_TPB, c->tile_smem, c->stream>>>(a, ta);
+        else k_kmer_tiles<false><<<c->n_cta, TS_TPB, c->tile_smem, c->stream>>>(a, ta);
+    } else
     {   // phase 1b: k-mers -> staging sub-regions (and send regions)
         ProfScope ps(c, KMN_PROF_PARSE, a.n_reads);
         const int grid = c->n_cta;
@@ -727,8 +795,9 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
     int r = stage_inputs(c, bases, quals, read_off, n_reads, discarded, true, bp);
     if (r) return r;
     // phase 1a -> 1b scratch: one bit per base position of the batch (+ one fp32 per position for KMN_VALUE_WEIGHTS)
-    r = ensure(c, c->mask, (bp.total_bytes / 32 + 4) * 4); if (r) return r;
-    CK(c, cudaMemsetAsync(c->mask.p, 0, (bp.total_bytes / 32 + 4) * 4, c->stream));
+    const size_t mask_bytes = ((bp.total_bytes / TS_TILE + 1) * (TS_TILE / 32) + 4) * 4;    // whole tiles
+    r = ensure(c, c->mask, mask_bytes); if (r) return r;
+    CK(c, cudaMemsetAsync(c->mask.p, 0, mask_bytes, c->stream));
     if (c->weights) { r = ensure(c, c->wts, (bp.total_bytes + 4) * 4); if (r) return r; }
     // A launch may stage at most `limit` instances (one staging set; multi-GPU: half of it, the other half takes the
     // records received from the peers and the same bound sizes the send regions).  The exact number of k-mer
@@ -761,9 +830,18 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
         }
         if (npos == 0) continue;
         r = stage_room(c, npos); if (r) return r;
+        uint64_t byte0 = 0, byte1 = bp.total_bytes;
+        if (c->tiles && !(rg.r0 == 0 && rg.r1 == n_reads)) {            // byte range of a sub-range of the batch
+            if (bp.off_on_host) { byte0 = read_off[rg.r0]; byte1 = read_off[rg.r1]; }
+            else {
+                CK(c, cudaMemcpyAsync(&byte0, bp.off + rg.r0, 8, cudaMemcpyDeviceToHost, c->s_copy));
+                CK(c, cudaMemcpyAsync(&byte1, bp.off + rg.r1, 8, cudaMemcpyDeviceToHost, c->s_copy));
+                CK(c, cudaStreamSynchronize(c->s_copy));
+            }
+        }
         ParseArgs a;
         fill_parse_args(c, a, bp.bases, bp.quals, bp.off + rg.r0, bp.disc ? bp.disc + rg.r0 : nullptr, rg.r1 - rg.r0, bp.total_bytes);
-        r = launch_parse(c, a); if (r) return r;
+        r = launch_parse(c, a, byte0, byte1); if (r) return r;
         c->sets[c->cur].staged_upper += npos;
         r = exchange(c); if (r) return r;
     }
@@ -825,7 +903,7 @@ int kmn_get_stats(kmn_ctx *c, kmn_stats *out)
     CK(c, cudaStreamSynchronize(c->stream));
     memset(out, 0, sizeof *out);
     out->raw_kmers = h.raw; out->raw_good_kmers = h.raw_good; out->unique_kmers = h.unique; out->singleton_kmers = ls[1];
-    out->discarded_kmers = h.raw - h.raw_good; out->table_slots = c->n_slots; out->table_partitions = c->table.n_parts;
+    out->discarded_kmers = h.raw - h.raw_good; out->table_slots = c->n_slots; out->table_partitions = c->table.n_groups();
     out->direct_inserts = h.direct;
     return 0;
 }

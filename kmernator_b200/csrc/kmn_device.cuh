@@ -25,16 +25,21 @@ static constexpr u32 MAX_COUNT = 65535u;
 
 template <int W> struct Slot { u64 val; u64 k[W]; };   // W==1: 16 B, stored key is ~key (0 = empty)
 
+// The table is cut into n_parts SLICES of part_slots slots (<= SLICE_SLOTS, so one slice fits in shared memory); a key's
+// slice and home slot come from place_hash and probing wraps inside the slice.  2^group_shift consecutive slices form one
+// GROUP (~slice_bytes, L2-sized): the unit the level-1 staging is partitioned by.
 struct TableView {
     void *slots;          // Slot<W>[n_parts * part_slots]
     float *wsum;          // optional, per slot
     u32 *ext;             // optional, 12 per slot
-    u64 part_slots;       // slots per partition
-    u32 n_parts;
-    u32 pad;
+    u64 part_slots;       // slots per slice
+    u32 n_parts;          // slices
+    u32 group_shift;      // log2(slices per group)
+    __device__ __host__ __forceinline__ u32 n_groups() const { return (n_parts + (1u << group_shift) - 1u) >> group_shift; }
 };
+static constexpr u32 SLICE_SLOTS = 4096;   // 64 KB of 16-byte slots
 
-struct StageView {        // partitioned staging area of k-mer records (phase 1 -> phase 2)
+struct StageView {        // level-1 staging area of k-mer records, partitioned by table GROUP (phase 1 -> phase 2); n_parts = groups
     u64 *recs;            // [n_parts][n_cta][sub_cap][RW]: every phase-1 CTA owns a private sub-region of every partition,
                           // so a flush needs no global atomic (its position follows from the CTA-local sequence number)
     u32 *count;           // [n_parts][n_cta] records written (may exceed sub_cap: the excess was inserted directly)
@@ -46,6 +51,13 @@ struct StageView {        // partitioned staging area of k-mer records (phase 1 
     {
         return cta_major ? (size_t)cta * n_parts + part : (size_t)part * n_cta + cta;
     }
+};
+
+struct Stage2View {       // level-2 staging: the records of one drain, one bucket per table SLICE
+    u64 *recs;            // [n_slices][cap]
+    u32 *count;           // [n_slices] records written (may exceed cap: the excess was inserted directly)
+    u32 cap;
+    u32 pad;
 };
 
 struct Counters {         // device-side statistics (src/KmerSpectrum.h:1590-1650)

@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
 {
     constexpr int RW = Rec<W, HASX>::RW;
     extern __shared__ __align__(16) u32 smem_u32[];
-    const u32 n_parts = a.table.n_parts;
+    const u32 n_parts = a.stage.n_parts;                               // staging partitions = table groups
     u32 *cnt = smem_u32;                                               // [n_parts] fill level of this CTA's sub-regions
     u32 *scnt = smem_u32 + ((n_parts + 31u) & ~31u);                   // [nranks] fill level of this CTA's send segments
     for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) cnt[i] = a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x];
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
                 }
             }
             const u64 ph = place_hash<W>(key);
-            stage_put<W, HASX>(a.stage, a.table, cnt, part_of(ph, n_parts), rec, lc, keep);
+            stage_put<W, HASX>(a.stage, a.table, cnt, part_of(ph, a.table.n_parts) >> a.table.group_shift, rec, lc, keep);
         };
         while (st.j < st.len) walker_step<W, false, EXT>(st, a, nullptr, emit);
     }
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_route_records(Rou
 {
     constexpr int RW = Rec<W, HASX>::RW;
     extern __shared__ __align__(16) u32 smem_u32[];
-    const u32 n_parts = a.table.n_parts;
+    const u32 n_parts = a.stage.n_parts;
     u32 *cnt = smem_u32;
     for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) cnt[i] = a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x];
     __syncthreads();
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_route_records(Rou
         u64 key[W]; bool fwd; float wt; u32 eb;
         rec.unpack(key, fwd, wt, eb);
         const u64 ph = place_hash<W>(key);
-        stage_put<W, HASX>(a.stage, a.table, cnt, part_of(ph, n_parts), rec, lc, keep);
+        stage_put<W, HASX>(a.stage, a.table, cnt, part_of(ph, a.table.n_parts) >> a.table.group_shift, rec, lc, keep);
     }
     __syncthreads();
     for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x] = cnt[i];
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(256) k_count_positions(const u64 *read_off, co
 // phase 2 work list over the (partition, phase-1 CTA) sub-regions in partition-major order:
 // chunk_start[e] = first chunk index of sub-region e (exclusive scan), single CTA
 // ------------------------------------------------------------------------------------------------
-__global__ void k_build_worklist(const u32 *count, u32 sub_cap, u32 n_entries, u64 *chunk_start, u64 *next_item)
+__global__ void k_build_worklist(const u32 *count, u32 sub_cap, u32 n_entries, u32 chunk, u64 *chunk_start, u64 *next_item)
 {
     __shared__ u64 carry;
     __shared__ u64 wsum[32];
@@ -587,7 +587,7 @@ __global__ void k_build_worklist(const u32 *count, u32 sub_cap, u32 n_entries, u
     for (u32 base = 0; base < n_entries; base += blockDim.x) {
         u32 p = base + threadIdx.x;
         u64 n = 0;
-        if (p < n_entries) { u32 c = count[p]; if (c > sub_cap) c = sub_cap; n = (c + INSERT_CHUNK - 1) / INSERT_CHUNK; }
+        if (p < n_entries) { u32 c = count[p]; if (c > sub_cap) c = sub_cap; n = (c + chunk - 1) / chunk; }
         u64 v = n;
         const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, Stage
     __shared__ u64 s_item;
     __shared__ u32 s_entry;
     u64 n_unique = 0, n_full = 0, n_probes = 0;
-    const u32 n_entries = t.n_parts * st.n_cta;
+    const u32 n_entries = st.n_parts * st.n_cta;
     const u64 total_items = chunk_start[n_entries];
     while (true) {
         // one ticket = INSERT_GROUP consecutive chunks; the sub-region of the first one is found by bisection (the upper
@@ -666,14 +666,16 @@ __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, Stage
         }
         // PRE: home-slot loads of all records first (independent, all in flight together), then resolve one by one
         u64 key[INSERT_UNROLL][W], home[INSERT_UNROLL], pv[INSERT_UNROLL], pk[INSERT_UNROLL];
-        bool fwd[INSERT_UNROLL]; float weight[INSERT_UNROLL]; u32 eb[INSERT_UNROLL];
-        const Slot<W> *pbase = reinterpret_cast<const Slot<W> *>(t.slots) + (u64)part * t.part_slots;
+        bool fwd[INSERT_UNROLL]; float weight[INSERT_UNROLL]; u32 eb[INSERT_UNROLL]; u32 slice[INSERT_UNROLL];
 #pragma unroll
         for (int u = 0; u < INSERT_UNROLL; ++u) {
-            pv[u] = pk[u] = 0; home[u] = 0;
+            pv[u] = pk[u] = 0; home[u] = 0; slice[u] = 0;
             if (have[u]) {
                 rec[u].unpack(key[u], fwd[u], weight[u], eb[u]);
-                home[u] = home_slot(place_hash<W>(key[u]), t.part_slots);
+                const u64 ph = place_hash<W>(key[u]);
+                slice[u] = part_of(ph, t.n_parts);                 // a slice of group `part`
+                home[u] = home_slot(ph, t.part_slots);
+                const Slot<W> *pbase = reinterpret_cast<const Slot<W> *>(t.slots) + (u64)slice[u] * t.part_slots;
                 if (PRE) {
                     if (W == 1) ld_slot16(pbase + home[u], pv[u], pk[u]);
                     else pv[u] = ld_cg64(&pbase[home[u]].val);
@@ -684,7 +686,7 @@ __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, Stage
         for (int u = 0; u < INSERT_UNROLL; ++u) {
             if (have[u]) {
                 u64 slot; u32 probes = 0;
-                int r = table_insert<W, PRE>(t, part, home[u], key[u], 1ull | ((u64)(fwd[u] ? 1u : 0u) << 32), &slot, &probes, pv[u], pk[u]);
+                int r = table_insert<W, PRE>(t, slice[u], home[u], key[u], 1ull | ((u64)(fwd[u] ? 1u : 0u) << 32), &slot, &probes, pv[u], pk[u]);
                 if (r < 0) { n_full++; continue; }
                 n_unique += (u64)r; n_probes += probes;
                 if (HASX) {
@@ -709,6 +711,350 @@ __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, Stage
         if (n_unique) atomicAdd(&ctr->unique, n_unique);
         if (n_full) atomicAdd(&ctr->table_full, n_full);
         if (n_probes) atomicAdd(&ctr->probe_steps, n_probes);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast count path (k <= 31, plain TrackingDataWithDirection values): phase 2 in two levels, so that no k-mer instance
+// costs an individual L2/HBM transaction.  Measured on B200 (profiles/r01_randacc_microbench.csv): scattered 16-byte
+// loads run at ~145 G/s and scattered REDs at ~190 G/s even when L2-resident -- an SM-side limit on uncoalesced sector
+// requests -- so one load + one RED per instance caps the insert at ~77 G/s.  Here every instance is moved twice with
+// coalesced accesses (level 1: group, level 2: slice) and counted with shared-memory atomics (level 3).
+//
+// Level 2 (k_subpartition): a CTA takes a tile of SUB_TILE records of one group, counting-sorts it by slice in shared
+// memory (histogram -> scan -> scatter), reserves one range per slice bucket with a single global atomicAdd, and copies
+// the sorted tile out so that neighbouring lanes write neighbouring records of the same bucket.
+// ------------------------------------------------------------------------------------------------
+static constexpr int TS_TPB = 256;                   // threads of a tile-sorting CTA
+static constexpr int TS_R = 8;                       // records per thread
+static constexpr int TS_TILE = TS_TPB * TS_R;        // 2048 records per tile
+static constexpr int TS_MAX_BPT = 10;                // bins per thread in the scan: up to 2560 bins
+static constexpr u32 TS_NONE = 0xffffffffu;
+static constexpr int SUB_TILE = TS_TILE;
+
+__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *warp_sums /*[TS_TPB/32]*/)
+{
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += t; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        u32 t = lane < (TS_TPB >> 5) ? warp_sums[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 q = __shfl_up_sync(0xffffffffu, t, o); if (lane >= (u32)o) t += q; }
+        if (lane < (TS_TPB >> 5)) warp_sums[lane] = t;             // inclusive over warps
+    }
+    __syncthreads();
+    return incl - v + (warp ? warp_sums[warp - 1] : 0u);
+}
+
+// Counting sort of one tile by bin, then a copy-out in sorted order.  Every thread brings up to TS_R records with their
+// bins (TS_NONE = no record).  PRE: hist[0..nb) is zero and a barrier has been passed since it was zeroed.
+//   reserve(bin, n, &room) -> address of the tile's first record in the bin's output region (called once per non-empty
+//                             bin by the thread that owns the bin in the scan); room = records that still fit there
+//   overflow(rec, bin) is called for records beyond `room`
+// Leaves no barrier pending: the caller must pass a barrier before it touches hist/buf/dst again.
+template <typename RESERVE, typename OVERFLOW>
+__device__ __forceinline__ void tile_sort_flush(const u64 (&rec)[TS_R], const u32 (&bin)[TS_R], u32 nb, u64 *buf, u64 *dst, u32 *hist, u64 *gptr,
+                                                u32 *room, u32 *wsum, u32 *s_total, RESERVE &&reserve, OVERFLOW &&overflow)
+{
+    u32 rank[TS_R];
+#pragma unroll
+    for (int u = 0; u < TS_R; ++u) rank[u] = bin[u] != TS_NONE ? atomicAdd(&hist[bin[u]], 1u) : 0u;
+    __syncthreads();
+    {
+        const u32 bpt = (nb + TS_TPB - 1) / TS_TPB;
+        const u32 b0 = threadIdx.x * bpt;
+        u32 tot = 0;
+        for (u32 q = 0; q < bpt; ++q) if (b0 + q < nb) tot += hist[b0 + q];
+        u32 run = block_exclusive_scan(tot, wsum);
+        for (u32 q = 0; q < bpt; ++q) {
+            const u32 b = b0 + q;
+            if (b < nb) {
+                const u32 c = hist[b];
+                hist[b] = run;
+                if (c) { u32 rm; gptr[b] = (u64)reserve(b, c, rm); room[b] = rm; }
+                run += c;
+            }
+        }
+        if (threadIdx.x == TS_TPB - 1) *s_total = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < TS_R; ++u) {
+        if (bin[u] != TS_NONE) {
+            const u32 pos = hist[bin[u]] + rank[u];
+            buf[pos] = rec[u];
+            dst[pos] = rank[u] < room[bin[u]] ? gptr[bin[u]] + 8ull * rank[u] : (u64)bin[u];   // bins are small numbers, never an address
+        }
+    }
+    __syncthreads();
+    const u32 total = *s_total;
+    for (u32 j = threadIdx.x; j < total; j += TS_TPB) {
+        const u64 d = dst[j], r = buf[j];
+        if (d >= 65536ull) *reinterpret_cast<u64 *>(d) = r;
+        else overflow(r, (u32)d);
+    }
+}
+
+// flat work list of level 2: item_entry[i] = staging sub-region of tile i (tiles of a sub-region are consecutive)
+__global__ void __launch_bounds__(256) k_fill_items(const u64 *chunk_start, u32 n_entries, u32 *item_entry)
+{
+    for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n_entries; e += gridDim.x * blockDim.x)
+        for (u64 i = chunk_start[e]; i < chunk_start[e + 1]; ++i) item_entry[i] = e;
+}
+
+__global__ void __launch_bounds__(TS_TPB, 4) k_subpartition(TableView t, StageView st, Stage2View s2, const u64 *chunk_start, const u32 *item_entry,
+                                                             Counters *ctr)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);          // [TS_TILE] records, sorted by slice
+    u64 *dst = buf + TS_TILE;                              // [TS_TILE] destination address of buf[j]
+    const u32 gp = 1u << t.group_shift;
+    u64 *gptr = dst + TS_TILE;                             // [gp]
+    u32 *hist = reinterpret_cast<u32 *>(gptr + gp);        // [gp]
+    u32 *room = hist + gp;                                 // [gp]
+    __shared__ u32 s_wsum[TS_TPB / 32];
+    __shared__ u32 s_total;
+    const u32 n_entries = st.n_parts * st.n_cta;
+    const u64 total_items = chunk_start[n_entries];
+    LocalCtr lc{0, 0, 0, 0, 0, 0};
+    for (u64 item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const u32 entry = __ldg(&item_entry[item]);
+        const u32 group = entry / st.n_cta;
+        u64 n = st.count[entry]; if (n > st.sub_cap) n = st.sub_cap;
+        const u64 first = (item - __ldg(&chunk_start[entry])) * TS_TILE;
+        const u64 *src = st.recs + st.sub_index(group, entry - group * st.n_cta) * st.sub_cap + first;
+        const u32 cnt = (u32)(n - first < (u64)TS_TILE ? n - first : (u64)TS_TILE);
+        const u32 slice0 = group << t.group_shift;
+        u64 rec[TS_R]; u32 sub[TS_R];
+#pragma unroll
+        for (int u = 0; u < TS_R; ++u) {
+            const u32 idx = (u32)u * TS_TPB + threadIdx.x;
+            rec[u] = idx < cnt ? ld_nc64(src + idx) : 0ull;
+        }
+        for (u32 i = threadIdx.x; i < gp; i += TS_TPB) hist[i] = 0;
+        __syncthreads();                                   // also orders the previous tile's copy-out before this tile's writes
+#pragma unroll
+        for (int u = 0; u < TS_R; ++u) {
+            const u32 idx = (u32)u * TS_TPB + threadIdx.x;
+            sub[u] = TS_NONE;
+            if (idx < cnt) { const u64 key[1] = {rec[u] & ~1ull}; sub[u] = part_of(place_hash<1>(key), t.n_parts) - slice0; }
+        }
+        tile_sort_flush(rec, sub, gp, buf, dst, hist, gptr, room, s_wsum, &s_total,
+            [&](u32 b, u32 c, u32 &rm) -> u64 * {
+                const u32 base = atomicAdd(&s2.count[slice0 + b], c);
+                rm = base < s2.cap ? s2.cap - base : 0u;
+                return s2.recs + (u64)(slice0 + b) * s2.cap + base;
+            },
+            [&](u64 r, u32) {                              // bucket full: insert directly (nothing else touches the table now)
+                Rec<1, false> rr; rr.w[0] = r;
+                insert_record<1, false>(t, rr, lc.unique, lc.full, lc.probes);
+                lc.direct++;
+            });
+    }
+    ctr_commit(ctr, lc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast phase 1b (k_kmer_tiles): position-parallel k-mer extraction.  The batch's base bytes are cut into tiles of
+// TS_TILE positions; a CTA loads a tile (+ k-1 bytes of halo) and the tile's "counted" bits (phase 1a) into shared memory
+// with coalesced loads; every thread packs the 8+k-1 bases of its 8 consecutive positions to 2 bits (SWAR, a1:
+// TwoBitSequence::compressSequence src/TwoBitSequence.cpp:242-269), cuts the forward k-mer of each position out of the
+// packed window with a funnel shift, gets the reverse complement by bit reversal, takes the smaller (a2: KmerArrayPair::build,
+// buildLeastComplement src/Kmer.h:1323-1375,356-364) and hands the records to the tile sort, which writes each group's
+// records of the tile as one contiguous run into the CTA's sub-region of that group.  No read structure is needed: the
+// "counted" bit of a position is only set where a k-mer of a non-discarded read starts.
+// Multi-GPU: a record owned by another rank (a5: src/Kmer.h:2284-2295) sorts into bin n_groups + owner = that rank's send segment.
+// ------------------------------------------------------------------------------------------------
+struct TileArgs {
+    u64 byte0, byte1;      // positions [byte0, byte1) of the batch belong to this launch
+    u64 tile0;             // first tile (tile index = position / TS_TILE)
+    u64 n_tiles;
+};
+
+// 8 ASCII bases (little-endian in w: first base in the low byte) -> 16 bits, first base in the top two bits; markups -> A
+__device__ __forceinline__ u32 pack8(u64 w)
+{
+    const u64 up = w & 0xDFDFDFDFDFDFDFDFull;
+    const u64 valid = bytes_eq(up, 0x4141414141414141ull) | bytes_eq(up, 0x4343434343434343ull) |
+                      bytes_eq(up, 0x4747474747474747ull) | bytes_eq(up, 0x5454545454545454ull);
+    u64 c = (w >> 1) & 0x0303030303030303ull;
+    c ^= (c >> 1) & 0x0101010101010101ull;
+    c &= (valid >> 7) * 3ull;
+    c = ((c << 2) | (c >> 8)) & 0x000F000F000F000Full;            // nibble j = b(2j)<<2 | b(2j+1) at bit 16j
+    return (u32)((c * 0x1000010000100001ull) >> 48);
+}
+
+template <bool DIST>
+__global__ void __launch_bounds__(TS_TPB, 4) k_kmer_tiles(ParseArgs a, TileArgs ta)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);          // [TS_TILE]
+    u64 *dst = buf + TS_TILE;                              // [TS_TILE]
+    u64 *sb = dst + TS_TILE;                               // [TS_TILE/8 + 6] raw aligned words of the tile's bases (+ halo)
+    u32 *smask = reinterpret_cast<u32 *>(sb + TS_TILE / 8 + 6);   // [TS_TILE/32]
+    const u32 n_groups = a.stage.n_parts;
+    const u32 nb = n_groups + (DIST ? a.nranks : 0u);
+    u32 *hist = smask + TS_TILE / 32;                      // [nb]
+    u32 *room = hist + nb;                                 // [nb]
+    u32 *cnt = room + nb;                                  // [nb] fill level of this CTA's sub-regions / send segments
+    u64 *gptr = reinterpret_cast<u64 *>(cnt + nb + (nb & 1u));    // [nb]
+    __shared__ u32 s_wsum[TS_TPB / 32];
+    __shared__ u32 s_total;
+    for (u32 i = threadIdx.x; i < n_groups; i += TS_TPB) cnt[i] = a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x];
+    if (DIST) for (u32 i = threadIdx.x; i < a.nranks; i += TS_TPB) cnt[n_groups + i] = a.seg_count[(size_t)i * gridDim.x + blockIdx.x];
+    const u32 k = a.k;
+    const u64 keymask = ~0ull << a.pad;                    // top 2k bits
+    LocalCtr lc{0, 0, 0, 0, 0, 0};
+    const unsigned long long gbeg = (unsigned long long)a.bases, gend = gbeg + a.total_bytes;
+    for (u64 tile = ta.tile0 + blockIdx.x; tile < ta.tile0 + ta.n_tiles; tile += gridDim.x) {
+        const u64 g0 = tile * TS_TILE;
+        __syncthreads();                                   // previous tile's copy-out and window reads are complete
+        {   // aligned 8-byte words covering bytes [g0, g0 + TS_TILE + 40)
+            const unsigned long long A = gbeg + g0, A0 = A & ~7ull;
+            for (u32 i = threadIdx.x; i < TS_TILE / 8 + 6; i += TS_TPB) {
+                const unsigned long long q = A0 + 8ull * i;
+                sb[i] = (q + 8 > (gbeg & ~7ull) && q < ((gend + 7ull) & ~7ull)) ? ld_nc64(reinterpret_cast<const u64 *>(q)) : 0ull;
+            }
+            for (u32 i = threadIdx.x; i < TS_TILE / 32; i += TS_TPB) smask[i] = __ldg(&a.mask[(g0 >> 5) + i]);
+            for (u32 i = threadIdx.x; i < nb; i += TS_TPB) hist[i] = 0;
+        }
+        __syncthreads();
+        u64 rec[TS_R]; u32 bin[TS_R];
+#pragma unroll
+        for (int u = 0; u < TS_R; ++u) { rec[u] = 0; bin[u] = TS_NONE; }
+        const u32 p0 = threadIdx.x * TS_R;                 // first position of this thread inside the tile
+        u32 mbits = (smask[p0 >> 5] >> (p0 & 31u)) & 0xffu;
+        {   // positions outside [byte0, byte1) belong to another launch of the same batch
+            const u64 ap = g0 + p0;
+            if (ap + TS_R <= ta.byte0 || ap >= ta.byte1) mbits = 0;
+            else if (ap < ta.byte0 || ap + TS_R > ta.byte1) {
+#pragma unroll
+                for (int u = 0; u < TS_R; ++u) if (ap + u < ta.byte0 || ap + u >= ta.byte1) mbits &= ~(1u << u);
+            }
+        }
+        if (mbits) {
+            // the 40 bases starting at position p0: byte offset inside sb = (A & 7) + p0
+            const u32 bo = (u32)((gbeg + g0) & 7ull) + p0;
+            const u32 wi = bo >> 3, sh = (bo & 7u) * 8u;
+            u64 w[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) w[i] = sb[wi + i];
+            u32 v[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) v[i] = pack8(sh ? (w[i] >> sh) | (w[i + 1] << (64u - sh)) : w[i]);
+            const u64 hi = ((u64)v[0] << 48) | ((u64)v[1] << 32) | ((u64)v[2] << 16) | (u64)v[3];
+            const u64 lo = (u64)v[4] << 48;
+#pragma unroll
+            for (int u = 0; u < TS_R; ++u) {
+                if ((mbits >> u) & 1u) {
+                    const u64 f = (u ? (hi << (2 * u)) | (lo >> (64 - 2 * u)) : hi) & keymask;
+                    u64 r = __brevll(~(f >> a.pad) & (~0ull >> a.pad));               // reversed bits, left-aligned, pairs swapped
+                    r = ((r & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((r & 0x5555555555555555ull) << 1);
+                    const bool fwd = f <= r;
+                    const u64 key[1] = {fwd ? f : r};
+                    rec[u] = key[0] | (fwd ? 1ull : 0ull);
+                    u32 b = part_of(place_hash<1>(key), a.table.n_parts) >> a.table.group_shift;
+                    if (DIST) {
+                        const u64 h = a.use_lookup8 ? hash_lookup8<1>(key, (int)a.kb) : hash_lookup3<1>(key, (int)a.kb);
+                        const u32 own = owner_of(h, a.nranks);
+                        if (own != a.rank) b = n_groups + own;
+                    }
+                    bin[u] = b;
+                }
+            }
+        }
+        (void)k;
+        tile_sort_flush(rec, bin, nb, buf, dst, hist, gptr, room, s_wsum, &s_total,
+            [&](u32 b, u32 c, u32 &rm) -> u64 * {
+                const u32 base = cnt[b]; cnt[b] = base + c;
+                if (!DIST || b < n_groups) {
+                    rm = base < a.stage.sub_cap ? a.stage.sub_cap - base : 0u;
+                    return a.stage.recs + a.stage.sub_index(b, blockIdx.x) * a.stage.sub_cap + base;
+                }
+                rm = base < a.seg_cap ? a.seg_cap - base : 0u;
+                return a.seg_recs + ((size_t)(b - n_groups) * gridDim.x + blockIdx.x) * a.seg_cap + base;
+            },
+            [&](u64 r, u32 b) {
+                if (b < n_groups) {                        // sub-region full: insert directly
+                    Rec<1, false> rr; rr.w[0] = r;
+                    insert_record<1, false>(a.table, rr, lc.unique, lc.full, lc.probes);
+                    lc.direct++;
+                }                                          // a full send segment is reported by k_compact_send (count > capacity)
+            });
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < n_groups; i += TS_TPB) a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x] = cnt[i];
+    if (DIST) for (u32 i = threadIdx.x; i < a.nranks; i += TS_TPB) a.seg_count[(size_t)i * gridDim.x + blockIdx.x] = cnt[n_groups + i];
+    ctr_commit(a.ctr, lc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Level 3 (k_count_slices): one CTA per table slice.  The slice (<= 64 KB) is brought into shared memory with
+// coalesced 16-byte loads (or zero-filled while the table is still clean), the slice's bucket is streamed through it --
+// probe with LDS, claim with a 64-bit shared CAS, count with 32-bit shared atomic adds on the two halves of the value
+// word -- and the slice is written back whole.  Replaces KmerSpectrum::append (src/KmerSpectrum.h:1578-1668) +
+// KmerMapByKmerArrayPair insert/find (src/Kmer.h:1491-1544,3095-3110) + TrackingDataWithDirection::track
+// (src/KmerTrackingData.h:427-448,517-529).
+// ------------------------------------------------------------------------------------------------
+static constexpr int CNT_TPB = 512;
+
+__global__ void __launch_bounds__(CNT_TPB, 3) k_count_slices(TableView t, Stage2View s2, u32 table_clean, Counters *ctr)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 *sl4 = reinterpret_cast<uint4 *>(smem_raw);
+    u64 *sl = reinterpret_cast<u64 *>(smem_raw);               // slot s: sl[2s] = value word, sl[2s+1] = ~key
+    const u32 S = (u32)t.part_slots;
+    const bool clean = table_clean && ctr->direct == 0;        // no direct insert has touched the table since the reset
+    u64 n_unique = 0, n_full = 0;
+    for (u32 p = blockIdx.x; p < t.n_parts; p += gridDim.x) {
+        u32 n = s2.count[p];
+        if (n == 0) continue;                                  // uniform over the CTA
+        if (n > s2.cap) n = s2.cap;
+        uint4 *g = reinterpret_cast<uint4 *>(t.slots) + (u64)p * S;
+        if (clean) { for (u32 i = threadIdx.x; i < S; i += CNT_TPB) sl4[i] = make_uint4(0, 0, 0, 0); }
+        else { for (u32 i = threadIdx.x; i < S; i += CNT_TPB) sl4[i] = __ldcs(g + i); }
+        __syncthreads();
+        const u64 *src = s2.recs + (u64)p * s2.cap;
+        for (u32 i = threadIdx.x; i < n; i += CNT_TPB) {
+            const u64 rec = ld_nc64(src + i);
+            const u64 key[1] = {rec & ~1ull};
+            const u64 want = ~key[0];
+            u32 s = (u32)home_slot(place_hash<1>(key), S);
+            // the probe loop only reads and compares; the (converged) counting follows it
+            bool found = false;
+            for (u32 probes = 0; probes < S; ++probes) {
+                u64 ck = *reinterpret_cast<volatile u64 *>(&sl[2 * s + 1]);
+                if (ck == 0ull) {
+                    ck = atomicCAS(&sl[2 * s + 1], 0ull, want);
+                    if (ck == 0ull) { n_unique++; ck = want; }
+                }
+                if (ck == want) { found = true; break; }
+                s = s + 1 == S ? 0 : s + 1;
+            }
+            if (found) {
+                u32 *v32 = reinterpret_cast<u32 *>(&sl[2 * s]);
+                if (*reinterpret_cast<volatile u32 *>(v32) < MAX_COUNT) {
+                    atomicAdd(v32, 1u);
+                    if (rec & 1ull) atomicAdd(v32 + 1, 1u);
+                }
+            } else n_full++;
+        }
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < S; i += CNT_TPB) __stcs(g + i, sl4[i]);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_unique) atomicAdd(&ctr->unique, n_unique);
+        if (n_full) atomicAdd(&ctr->table_full, n_full);
     }
 }
 

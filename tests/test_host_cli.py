@@ -1,0 +1,94 @@
+"""The C++ host mirror (kmernator_b200/host): FilterReads built against the C ABI.
+
+CPU part: the driver builds, exposes the reference's option surface (names, defaults, prefix guessing, README aliases)
+and fails loudly without a GPU.  GPU part (-m gpu): the reference's own integration test, test/runFilterTests.sh:26,44-76 --
+FilterReads on test/1000.fastq must reproduce the four 1000-Filtered*.fastq goldens (`diff -w`)."""
+import os
+import subprocess
+
+import pytest
+
+from tests.gpu_util import has_gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def filter_reads():
+    from kmernator_b200 import build as kbuild
+    from kmernator_b200.host import build as hbuild
+    kbuild.build()
+    return hbuild.build()
+
+
+def _run(exe, args, cwd=None):
+    return subprocess.run([exe] + args, capture_output=True, text=True, cwd=cwd, timeout=600)
+
+
+def test_help_lists_reference_options(filter_reads):
+    p = _run(filter_reads, ["--help"])
+    assert p.returncode == 1                       # apps/FilterReads.cpp:85: `if (!parseOpts) exit(1)`
+    for flag, default in [("min-kmer-quality", "0.10"), ("min-depth", "2"), ("min-read-length", "0.40"), ("kmer-scoring-type", "MAX"),
+                          ("min-passing-in-pair", "1"), ("max-kmer-output-depth", "-1"), ("min-quality-score", "3"),
+                          ("fastq-output-base-quality", "33"), ("batch-size", "100000"), ("skip-artifact-filter", "0"),
+                          ("normalization-method", "RANDOM"), ("separate-outputs", "1"), ("kmers-per-bucket", "32"),
+                          ("mpi-buffer-size", "33554432"), ("artifact-edit-distance", "2")]:
+        assert "--%s arg (=%s)" % (flag, default) in p.stderr, flag
+
+
+def test_option_errors(filter_reads, golden_dir):
+    inp = os.path.join(golden_dir, "10.fastq")
+    assert "unrecognised option" in _run(filter_reads, ["--no-such-flag", "1", "31", inp]).stderr
+    assert "ambiguous" in _run(filter_reads, ["--min", "1", "31", inp]).stderr            # min-depth, min-read-length, ...
+    assert "not implemented by kmernator_b200" in _run(filter_reads, ["--variant-sigmas", "2", "31", inp]).stderr
+    assert "at least one input file" in _run(filter_reads, ["31"]).stderr
+
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful on a box without a GPU")
+def test_fails_loudly_without_gpu(filter_reads, golden_dir, tmp_path):
+    p = _run(filter_reads, ["--out", str(tmp_path / "x"), "31", os.path.join(golden_dir, "10.fastq")])
+    assert p.returncode == 1
+    assert "no CPU fallback" in p.stderr
+    assert not list(tmp_path.iterdir())
+
+
+CASES = [  # test/runFilterTests.sh:44-70
+    ("1000.fastq", "1000-Filtered-0.85.std.fastq", ["--fastq-output-base-quality", "33", "--min-read-length", "0.85"]),
+    ("1000.fastq", "1000-Filtered-0.85.fastq", ["--fastq-output-base-quality", "64", "--min-read-length", "0.85"]),
+    ("1000.std.fastq", "1000-Filtered-0.85.std.fastq", ["--fastq-output-base-quality", "33", "--min-read-length", "0.85"]),
+    ("1000.std.fastq", "1000-Filtered-0.85.fastq", ["--fastq-output-base-quality", "64", "--min-read-length", "0.85"]),
+    ("1000.fastq", "1000-Filtered-readlength.fastq", ["--fastq-output-base-quality", "64", "--min-read-length", "1"]),
+    ("1000.fastq", "1000-Filtered-readlength-both.fastq", ["--fastq-output-base-quality", "64", "--min-read-length", "1", "--min-passing-in-pair", "2"]),
+    ("1000.fastq", "1000-Filtered.fastq", ["--fastq-output-base-quality", "64", "--min-read-length", "25", "--thread", "2"]),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("inp,good,extra", CASES)
+def test_filter_reads_goldens(filter_reads, golden_dir, tmp_path, inp, good, extra):
+    out = str(tmp_path / "out")
+    # the fixed option set of test/runFilterTests.sh:26 (prefix-guessed --out as in the script)
+    args = extra + ["--kmer-scoring-type", "MEDIAN", "--mask-simple-repeats", "0", "--artifact-edit-distance", "1", "--out", out, "31", inp]
+    p = _run(filter_reads, args, cwd=golden_dir)
+    assert p.returncode == 0, p.stderr
+    got = open("%s-MinDepth2-%s" % (out, inp)).read().split()          # diff -w
+    want = open(os.path.join(golden_dir, good)).read().split()
+    assert got == want
+
+
+@pytest.mark.gpu
+def test_filter_reads_normalisation_and_aliases(filter_reads, golden_dir, tmp_path):
+    """--max-kmer-depth / --min-kmer-depth (README.md:125 spellings) are aliases; RANDOM normalisation with a fixed
+    seed keeps every read whose score is <= D and a subset of the others (src/ReadSelector.h:661-749)"""
+    out = str(tmp_path / "norm")
+    env = dict(os.environ, KMN_SEED="7")
+    args = ["--max-kmer-depth", "20", "--min-kmer-depth", "2", "--kmer-scoring-type", "MEDIAN", "--fastq-output-base-quality", "64",
+            "--out", out, "31", "1000.fastq"]
+    p = subprocess.run([filter_reads] + args, capture_output=True, text=True, cwd=golden_dir, env=env, timeout=600)
+    assert p.returncode == 0, p.stderr
+    text = open(out + "-MinDepth2-MaxDepth20-1000.fastq").read().split("\n")
+    hdrs = [l for l in text[0::4] if l]
+    full = open(os.path.join(golden_dir, "1000-Filtered-0.85.fastq")).read().split("\n")[0::4]
+    assert 0 < len(hdrs) < len([l for l in full if l])
+    p2 = subprocess.run([filter_reads] + args, capture_output=True, text=True, cwd=golden_dir, env=env, timeout=600)
+    assert p2.returncode == 0 and open(out + "-MinDepth2-MaxDepth20-1000.fastq").read().split("\n")[0::4][: len(hdrs)] == hdrs
