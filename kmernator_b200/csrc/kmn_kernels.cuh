@@ -1024,24 +1024,25 @@ __global__ void __launch_bounds__(CNT_TPB, 3) k_count_slices(TableView t, Stage2
             const u64 key[1] = {rec & ~1ull};
             const u64 want = ~key[0];
             u32 s = (u32)home_slot(place_hash<1>(key), S);
-            // the probe loop only reads and compares; the (converged) counting follows it
-            bool found = false;
+            bool done = false;
             for (u32 probes = 0; probes < S; ++probes) {
                 u64 ck = *reinterpret_cast<volatile u64 *>(&sl[2 * s + 1]);
                 if (ck == 0ull) {
-                    ck = atomicCAS(&sl[2 * s + 1], 0ull, want);
-                    if (ck == 0ull) { n_unique++; ck = want; }
+                    const u64 old = atomicCAS(&sl[2 * s + 1], 0ull, want);
+                    if (old == 0ull) { n_unique++; ck = want; } else ck = old;
                 }
-                if (ck == want) { found = true; break; }
+                if (ck == want) {
+                    u32 *v32 = reinterpret_cast<u32 *>(&sl[2 * s]);
+                    if (*reinterpret_cast<volatile u32 *>(v32) < MAX_COUNT) {
+                        atomicAdd(v32, 1u);
+                        if (rec & 1ull) atomicAdd(v32 + 1, 1u);
+                    }
+                    done = true;
+                    break;
+                }
                 s = s + 1 == S ? 0 : s + 1;
             }
-            if (found) {
-                u32 *v32 = reinterpret_cast<u32 *>(&sl[2 * s]);
-                if (*reinterpret_cast<volatile u32 *>(v32) < MAX_COUNT) {
-                    atomicAdd(v32, 1u);
-                    if (rec & 1ull) atomicAdd(v32 + 1, 1u);
-                }
-            } else n_full++;
+            if (!done) n_full++;
         }
         __syncthreads();
         for (u32 i = threadIdx.x; i < S; i += CNT_TPB) __stcs(g + i, sl4[i]);

@@ -82,13 +82,13 @@ def test_filter_reads_normalisation_and_aliases(filter_reads, golden_dir, tmp_pa
     seed keeps every read whose score is <= D and a subset of the others (src/ReadSelector.h:661-749)"""
     out = str(tmp_path / "norm")
     env = dict(os.environ, KMN_SEED="7")
-    args = ["--max-kmer-depth", "20", "--min-kmer-depth", "2", "--kmer-scoring-type", "MEDIAN", "--fastq-output-base-quality", "64",
+    args = ["--max-kmer-depth", "4", "--min-kmer-depth", "2", "--kmer-scoring-type", "MEDIAN", "--fastq-output-base-quality", "64",
             "--out", out, "31", "1000.fastq"]
     p = subprocess.run([filter_reads] + args, capture_output=True, text=True, cwd=golden_dir, env=env, timeout=600)
     assert p.returncode == 0, p.stderr
-    text = open(out + "-MinDepth2-MaxDepth20-1000.fastq").read().split("\n")
+    text = open(out + "-MinDepth2-MaxDepth4-1000.fastq").read().split("\n")
     hdrs = [l for l in text[0::4] if l]
     full = open(os.path.join(golden_dir, "1000-Filtered-0.85.fastq")).read().split("\n")[0::4]
     assert 0 < len(hdrs) < len([l for l in full if l])
     p2 = subprocess.run([filter_reads] + args, capture_output=True, text=True, cwd=golden_dir, env=env, timeout=600)
-    assert p2.returncode == 0 and open(out + "-MinDepth2-MaxDepth20-1000.fastq").read().split("\n")[0::4][: len(hdrs)] == hdrs
+    assert p2.returncode == 0 and open(out + "-MinDepth2-MaxDepth4-1000.fastq").read().split("\n")[0::4][: len(hdrs)] == hdrs
