@@ -25,16 +25,19 @@ def _nccl_flags():
     return []
 
 
-def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in DEPS):
-        return OUT
+def build(force=False, verbose=False, variant=None, extra=()):
+    """variant/extra: developer A/B builds (libkmernator_b200.<variant>.so with extra -D flags), selected at load time
+    with KMN_LIB_VARIANT=<variant>; the default library is the product."""
+    out = OUT if not variant else OUT[:-3] + "." + variant + ".so"
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in DEPS):
+        return out
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-o", OUT, SRC] + _nccl_flags()
+           "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-o", out, SRC] + _nccl_flags() + list(extra)
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

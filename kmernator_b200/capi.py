@@ -54,6 +54,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    global LIB_PATH
+    if os.environ.get("KMN_LIB_VARIANT"):      # developer A/B builds (kmernator_b200/build.py)
+        LIB_PATH = LIB_PATH[:-3] + "." + os.environ["KMN_LIB_VARIANT"] + ".so"
     if not os.path.exists(LIB_PATH):
         raise ImportError("kmernator_b200: %s not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(there is no CPU fallback)" % LIB_PATH)

@@ -59,15 +59,9 @@ struct kmn_ctx {
     int cur = 0;
     uint64_t stage_keys = 0;          // record capacity of ONE set (= the sub-batch size of the pipeline)
     u64 *chunk_start = nullptr, *next_item = nullptr;
-    // fast count path (k <= 31, plain values): level-2 staging by table slice + shared-memory counting (level 3)
-    bool fast = false;
-    bool tiles = false;               // phase 1b: position-parallel tile kernel instead of the per-read walker
-    bool table_clean = true;          // nothing has been written to the table since the last reset
-    Stage2View s2{};
-    u32 *item_entry = nullptr;        // flat work list of level 2
-    size_t sub_smem = 0, cnt_smem = 0, tile_smem = 0;
+    u64 *ent_ptr = nullptr; u32 *ent_cnt = nullptr;     // phase-2 work list entries (k_build_entries)
+    uint64_t n_groups = 0;
     int insert_ctas = 8;              // phase-2 CTAs per SM
-    bool insert_pre = true;           // phase 2 keeps the home-slot loads of its 4 records in flight together
     Counters *ctr = nullptr;
     double *ptab = nullptr;
     u64 *scratch = nullptr;           // small device scalars
@@ -91,6 +85,21 @@ struct kmn_ctx {
     u64 *send_recs = nullptr, *send_cursor = nullptr, *recv_recs = nullptr, *all_counts = nullptr;
     u64 *seg_recs = nullptr; u32 *seg_count = nullptr;
     uint64_t send_cap = 0, recv_cap = 0, seg_cap = 0;
+    // multi-GPU push path: phase 1 bins by (owner, group); the other owners' parts are written into their receive
+    // buffers over NVLink (peer pointers from CUDA IPC), sorted by group, and inserted from there
+    bool p2p = false;
+    cudaStream_t s_comm = nullptr;        // push kernels + the NCCL barriers of a round
+    void *recv_all = nullptr;             // [2 round buffers][nranks sources][push_cap records] + [2][nranks][n_groups+1] offsets
+    void *peer_all[KMN_MAX_PUSH_RANKS] = {nullptr};   // recv_all of every peer (cudaIpcOpenMemHandle)
+    uint64_t push_cap = 0;                // records per (round buffer, source)
+    size_t push_meta = 0;                 // u32 words of meta per (round buffer, source)
+    bool push_ce = true;                  // transport: copy engines move whole parts (default) / k_push_copy writes sorted runs
+    u32 *run_off = nullptr, *grp_off = nullptr;
+    u64 *flags = nullptr;                 // [0] records lost to a full remote sub-region, [1] records beyond push_cap
+    u64 *d_const = nullptr;               // [0] = 0, [1] = 1, [2] = barrier scratch, [3] = sum of "done" flags
+    uint64_t round = 0;
+    cudaEvent_t ev_pushed[2] = {nullptr, nullptr}, ev_rb_free[2] = {nullptr, nullptr}, ev_recv[2] = {nullptr, nullptr};
+    bool push_pending[2] = {false, false}, rb_busy[2] = {false, false};
 #ifdef KMN_WITH_NCCL
     ncclComm_t comm = nullptr;
 #endif
@@ -190,6 +199,47 @@ const char *kmn_last_error(const kmn_ctx *ctx) { return ctx ? ctx->err.c_str() :
 void *kmn_stream(kmn_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 uint64_t kmn_launch_count(const kmn_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+// staging capacity: stage_keys records per set.  Pipelined (two sets): one set is one sub-batch (phase 2 drains it while
+// phase 1 fills the other), so the default aims at ~8 sub-batches over the expected input.  On the multi-GPU push path a
+// set is cut by owner rank as well ([owner][cta][group] sub-regions) and one launch fills one set.
+static int alloc_stage_sets(kmn_ctx *c)
+{
+    size_t free_b = 0, total_b = 0;
+    for (int si = 0; si < 2; ++si) {
+        kmn_ctx::StageSet &st = c->sets[si];
+        if (st.v.recs) { CK(c, cudaFree(st.v.recs)); st.v.recs = nullptr; }
+        if (st.v.count) { CK(c, cudaFree(st.v.count)); st.v.count = nullptr; }
+    }
+    CK(c, cudaMemGetInfo(&free_b, &total_b));
+    const kmn_opts &o = c->o;
+    uint64_t sk = o.stage_keys;
+    if (!sk) {
+        sk = (o.est_raw_kmers ? o.est_raw_kmers : (1ull << 22)) / (c->pipeline ? 8 : 1);
+        uint64_t lim = (uint64_t)(0.35 * (double)free_b / (double)(c->RW * 8) / (double)c->n_sets);
+        if (sk > lim) sk = lim;
+    }
+    if (sk < (1ull << 16)) sk = 1ull << 16;
+    c->stage_keys = sk;
+    const uint64_t n_groups = c->n_groups, n_cta = (uint64_t)c->n_cta, n_own = c->p2p ? (uint64_t)c->nranks : 1;
+    const uint64_t per_sub = sk / n_groups / n_cta / n_own;
+    const uint64_t sub_cap = per_sub + per_sub / 8 + 8 * (uint64_t)std::sqrt((double)per_sub + 1.0) + 64;   // mean + slack for the spread
+    if (sub_cap >= (1ull << 31)) return fail(c, KMN_ERR_INVALID, "staging sub-region too large (%llu records)", (unsigned long long)sub_cap);
+    for (int si = 0; si < c->n_sets; ++si) {
+        kmn_ctx::StageSet &st = c->sets[si];
+        st.v.sub_cap = (u32)sub_cap; st.v.n_cta = (u32)n_cta; st.v.n_parts = (u32)n_groups;
+        st.v.n_owners = (u32)n_own; st.v.me = (u32)c->rank;
+        CK(c, cudaMalloc((void **)&st.v.recs, (size_t)n_own * n_groups * n_cta * sub_cap * c->RW * 8));
+        CK(c, cudaMalloc((void **)&st.v.count, (size_t)n_own * n_groups * n_cta * 4));
+        CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)n_own * n_groups * n_cta * 4, c->stream));
+        if (!st.ev_parsed) CK(c, cudaEventCreateWithFlags(&st.ev_parsed, cudaEventDisableTiming));
+        if (!st.ev_drained) CK(c, cudaEventCreateWithFlags(&st.ev_drained, cudaEventDisableTiming));
+        st.staged_upper = 0;
+    }
+    // phase-1 shared memory: one fill counter per (owner, group) bin + send-segment counters (<= 64 ranks)
+    c->scatter_smem = ((((size_t)n_groups * n_own + 31) & ~(size_t)31) + 64) * 4;
+    return 0;
+}
+
 static int plan_and_alloc(kmn_ctx *c)
 {
     const kmn_opts &o = c->o;
@@ -224,7 +274,7 @@ static int plan_and_alloc(kmn_ctx *c)
     int dev_smem = 0;
     CK(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     const uint32_t gbytes = o.slice_bytes ? o.slice_bytes : (64u << 20);
-    uint64_t part_slots = std::min<uint64_t>(SLICE_SLOTS, slots);
+    uint64_t part_slots = std::min<uint64_t>(SLICE_SLOTS, slots) & ~1ull;   // even: W == 1 probes aligned pairs of slots
     uint64_t n_parts = (slots + part_slots - 1) / part_slots;
     if (n_parts >= (1ull << 31)) return fail(c, KMN_ERR_INVALID, "table too large (%llu slices)", (unsigned long long)n_parts);
     slots = part_slots * n_parts;
@@ -232,63 +282,25 @@ static int plan_and_alloc(kmn_ctx *c)
     while (gshift < 11 && (part_slots * c->slot_bytes << (gshift + 1)) <= (uint64_t)gbytes) gshift++;     // <= 2048 slices per group
     const uint64_t p_max = ((size_t)dev_smem / SCATTER_CTAS - 1024) / 4 - 32;
     while (((n_parts + (1ull << gshift) - 1) >> gshift) > p_max) gshift++;
-    if (gshift > 11) c->fast = false;                      // level 2 sorts at most 2048 slices per group
     const uint64_t n_groups = (n_parts + (1ull << gshift) - 1) >> gshift;
     c->n_slots = slots;
     c->table.part_slots = part_slots;
     c->table.n_parts = (u32)n_parts;
     c->table.group_shift = gshift;
-    c->tiles = c->fast && getenv("KMN_TILES") && atoi(getenv("KMN_TILES")) != 0;
-    c->n_cta = c->tiles ? c->n_sms * 4 : c->n_sms * SCATTER_CTAS;
-    c->scatter_smem = ((((size_t)n_groups + 31) & ~(size_t)31) + 64) * 4;      // group counters + send-segment counters (<= 64 ranks)
+    c->n_cta = c->n_sms * SCATTER_CTAS;
 
     CK(c, cudaMalloc(&c->table.slots, slots * c->slot_bytes));
     if (c->weights) CK(c, cudaMalloc((void **)&c->table.wsum, slots * 4));
     if (c->ext) CK(c, cudaMalloc((void **)&c->table.ext, slots * 48));
 
-    // staging capacity: stage_keys records per set.  Pipelined (two sets): one set is one sub-batch (phase 2 drains it
-    // while phase 1 fills the other), so the default aims at ~8 sub-batches over the expected input.  Otherwise one set
-    // that takes the whole expected input when memory allows: every drain streams the whole table through L2 once.
-    CK(c, cudaMemGetInfo(&free_b, &total_b));
-    uint64_t sk = o.stage_keys;
-    if (!sk) {
-        sk = (o.est_raw_kmers ? o.est_raw_kmers : (1ull << 22)) / (c->pipeline ? 8 : (c->fast ? 4 : 1));
-        uint64_t lim = (uint64_t)(0.35 * (double)free_b / (double)(c->RW * 8) / (double)(c->fast ? 3 : c->n_sets));
-        if (sk > lim) sk = lim;
+    c->n_groups = n_groups;
+    { int r = alloc_stage_sets(c); if (r) return r; }
+    {
+        const size_t max_entries = (size_t)n_groups * (size_t)c->n_cta * KMN_MAX_PUSH_RANKS;
+        CK(c, cudaMalloc((void **)&c->chunk_start, (max_entries + 1) * 8));
+        CK(c, cudaMalloc((void **)&c->ent_ptr, max_entries * 8));
+        CK(c, cudaMalloc((void **)&c->ent_cnt, max_entries * 4));
     }
-    if (sk < (1ull << 16)) sk = 1ull << 16;
-    c->stage_keys = sk;
-    const uint64_t n_cta = (uint64_t)c->n_cta;
-    const uint64_t per_sub = sk / n_groups / n_cta;
-    const uint64_t sub_cap = per_sub + per_sub / 8 + 8 * (uint64_t)std::sqrt((double)per_sub + 1.0) + 64;   // mean + slack for the spread
-    if (sub_cap >= (1ull << 31)) return fail(c, KMN_ERR_INVALID, "staging sub-region too large (%llu records)", (unsigned long long)sub_cap);
-    for (int si = 0; si < c->n_sets; ++si) {
-        kmn_ctx::StageSet &st = c->sets[si];
-        st.v.sub_cap = (u32)sub_cap; st.v.n_cta = (u32)n_cta; st.v.n_parts = (u32)n_groups;
-        st.v.cta_major = getenv("KMN_PART_MAJOR") ? 0 : 1;
-        CK(c, cudaMalloc((void **)&st.v.recs, (size_t)n_groups * n_cta * sub_cap * c->RW * 8));
-        CK(c, cudaMalloc((void **)&st.v.count, (size_t)n_groups * n_cta * 4));
-        CK(c, cudaEventCreateWithFlags(&st.ev_parsed, cudaEventDisableTiming));
-        CK(c, cudaEventCreateWithFlags(&st.ev_drained, cudaEventDisableTiming));
-    }
-    if (c->fast) {
-        // level-2 buckets, one per slice: mean + slack for the spread of duplicate-heavy inputs; the excess is inserted directly
-        const uint64_t mean2 = sk / n_parts;
-        const uint64_t cap2 = mean2 + mean2 / 4 + 8 * (uint64_t)std::sqrt(8.0 * (double)mean2 + 1.0) + 64;
-        if (cap2 >= (1ull << 31)) return fail(c, KMN_ERR_INVALID, "level-2 bucket too large (%llu records)", (unsigned long long)cap2);
-        c->s2.cap = (u32)cap2;
-        CK(c, cudaMalloc((void **)&c->s2.recs, (size_t)n_parts * cap2 * 8));
-        CK(c, cudaMalloc((void **)&c->s2.count, (size_t)n_parts * 4));
-        c->sub_smem = (size_t)TS_TILE * 16 + ((size_t)1 << gshift) * 16;
-        c->cnt_smem = (size_t)part_slots * 16;
-        c->tile_smem = (size_t)TS_TILE * 16 + ((size_t)TS_TILE / 8 + 6) * 8 + ((size_t)TS_TILE / 32) * 4 + ((size_t)n_groups + 64) * 20 + 16;
-        CK(c, cudaFuncSetAttribute(k_subpartition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sub_smem));
-        CK(c, cudaFuncSetAttribute(k_count_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->cnt_smem));
-        CK(c, cudaFuncSetAttribute(k_kmer_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tile_smem));
-        CK(c, cudaFuncSetAttribute(k_kmer_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->tile_smem));
-        CK(c, cudaMalloc((void **)&c->item_entry, ((size_t)n_groups * n_cta * (sub_cap / TS_TILE + 2) + 16) * 4));
-    }
-    CK(c, cudaMalloc((void **)&c->chunk_start, ((size_t)n_groups * n_cta + 1) * 8));
     CK(c, cudaMalloc((void **)&c->next_item, 8));
     CK(c, cudaMalloc((void **)&c->ctr, sizeof(Counters)));
     CK(c, cudaMalloc((void **)&c->scratch, 64));
@@ -320,11 +332,10 @@ int kmn_reset(kmn_ctx *c)
     if (c->table.ext) CK(c, cudaMemsetAsync(c->table.ext, 0, c->n_slots * 48, c->stream));
     for (int si = 0; si < c->n_sets; ++si) {
         kmn_ctx::StageSet &st = c->sets[si];
-        CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)st.v.n_parts * st.v.n_cta * 4, c->stream));
+        CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)st.v.n_owners * st.v.n_parts * st.v.n_cta * 4, c->stream));
         st.staged_upper = 0;
     }
-    if (c->s2.count) CK(c, cudaMemsetAsync(c->s2.count, 0, (size_t)c->table.n_parts * 4, c->stream));
-    c->table_clean = true;
+    if (c->flags) CK(c, cudaMemsetAsync(c->flags, 0, 16, c->stream));
     CK(c, cudaMemsetAsync(c->ctr, 0, sizeof(Counters), c->stream));
     if (c->send_cursor) CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)c->nranks * 8, c->stream));
     if (c->seg_count) CK(c, cudaMemsetAsync(c->seg_count, 0, (size_t)c->nranks * c->n_cta * 4, c->stream));
@@ -338,13 +349,24 @@ static int set_smem_attrs(kmn_ctx *c)
 {
     const int s = (int)c->scatter_smem;
     if (s <= 48 * 1024) return 0;
-    CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
-    CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
+    CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
+    CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
+    CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
     if (X) {
-        CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
-        CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
+        CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
+        CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
+        CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
     }
     CK(c, cudaFuncSetAttribute(k_route_records<W, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
+    return 0;
+}
+
+static int apply_smem_attrs(kmn_ctx *c)
+{
+    const int msm = (int)((MASK_TPB / 32) * MASK_WBUF);
+    CK(c, cudaFuncSetAttribute(k_weight_mask<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, msm));
+    CK(c, cudaFuncSetAttribute(k_weight_mask<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, msm));
+    KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, { int r_ = set_smem_attrs<W_, X_>(c); if (r_) return r_; }));
     return 0;
 }
 
@@ -369,17 +391,9 @@ int kmn_create(kmn_ctx **out, const kmn_opts *opts)
         c->n_sms = prop.multiProcessorCount;
         if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "stream create failed"); break; }
         // tuning knobs (bench experiments only; the defaults are the measured best)
-        // two-level path (KMN_FAST=1): single-word keys whose record is the key alone; it runs phase 1 and phase 2 on one stream with one
-        // staging set (every kernel of it is throughput-bound by itself, and direct inserts of overflowing records are
-        // then never concurrent with a slice held in shared memory)
-        c->fast = false;                 // measured on C2: 400 ms/step against 377 ms for the generic path (profiles/r01_summary.md)
-        if (const char *e = getenv("KMN_FAST"))
-            c->fast = atoi(e) != 0 && opts->kmer_size < 32 && (opts->value_kind & (KMN_VALUE_DIR_EXT | KMN_VALUE_WEIGHTS)) == 0;
-        if (c->fast) c->pipeline = false;
-        if (const char *e = getenv("KMN_PIPELINE")) c->pipeline = !c->fast && atoi(e) != 0;
+        if (const char *e = getenv("KMN_PIPELINE")) c->pipeline = atoi(e) != 0;
         c->n_sets = c->pipeline ? 2 : 1;
         if (const char *e = getenv("KMN_INSERT_CTAS")) c->insert_ctas = std::max(1, atoi(e));
-        if (const char *e = getenv("KMN_INSERT_PRE")) c->insert_pre = atoi(e) != 0;
         if (c->pipeline) {
             if (cudaStreamCreateWithFlags(&c->s_insert, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "stream create failed"); break; }
         } else c->s_insert = c->stream;
@@ -390,12 +404,8 @@ int kmn_create(kmn_ctx **out, const kmn_opts *opts)
         }
         rc = plan_and_alloc(c);
         if (rc) break;
-        {
-            kmn_ctx *cc = c;
-            auto body = [&]() -> int { KMN_DISPATCH_W(cc, KMN_DISPATCH_X(cc, { int r_ = set_smem_attrs<W_, X_>(cc); if (r_) return r_; })); return 0; };
-            rc = body();
-            if (rc) break;
-        }
+        rc = apply_smem_attrs(c);
+        if (rc) break;
         rc = kmn_reset(c);
         if (rc) break;
         if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = fail(c, KMN_ERR_CUDA, "sync failed"); break; }
@@ -416,11 +426,14 @@ void kmn_destroy(kmn_ctx *c)
     if (c->s_copy) cudaStreamSynchronize(c->s_copy);
     if (c->s_insert) cudaStreamSynchronize(c->s_insert);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->s_comm) cudaStreamSynchronize(c->s_comm);
+    for (int p = 0; p < KMN_MAX_PUSH_RANKS; ++p) if (c->peer_all[p] && p != c->rank) cudaIpcCloseMemHandle(c->peer_all[p]);
+    if (c->p2p) { c->send_recs = nullptr; c->recv_recs = nullptr; }     // aliases of recv_all
 #ifdef KMN_WITH_NCCL
     if (c->comm) ncclCommDestroy(c->comm);
 #endif
-    void *ptrs[] = {c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
-                    c->chunk_start, c->next_item, c->s2.recs, c->s2.count, c->item_entry,
+    void *ptrs[] = {c->recv_all, c->run_off, c->grp_off, c->flags, c->d_const, c->ent_ptr, c->ent_cnt,c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
+                    c->chunk_start, c->next_item,
                     c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts, c->seg_recs, c->seg_count,
                     c->in_bases[0].p, c->in_quals[0].p, c->in_off[0].p, c->in_disc[0].p,
                     c->in_bases[1].p, c->in_quals[1].p, c->in_off[1].p, c->in_disc[1].p, c->vals.p, c->first_nx.p, c->out_off.p,
@@ -429,6 +442,12 @@ void kmn_destroy(kmn_ctx *c)
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &st : c->sets) { if (st.ev_parsed) cudaEventDestroy(st.ev_parsed); if (st.ev_drained) cudaEventDestroy(st.ev_drained); }
     for (int i = 0; i < 2; ++i) { if (c->ev_in_ready[i]) cudaEventDestroy(c->ev_in_ready[i]); if (c->ev_in_free[i]) cudaEventDestroy(c->ev_in_free[i]); }
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_pushed[i]) cudaEventDestroy(c->ev_pushed[i]);
+        if (c->ev_rb_free[i]) cudaEventDestroy(c->ev_rb_free[i]);
+        if (c->ev_recv[i]) cudaEventDestroy(c->ev_recv[i]);
+    }
+    if (c->s_comm) cudaStreamDestroy(c->s_comm);
     if (c->s_insert && c->s_insert != c->stream) cudaStreamDestroy(c->s_insert);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -438,51 +457,44 @@ void kmn_destroy(kmn_ctx *c)
 // ---------------------------------------------------------------------------------------------------------
 // phase 2: drain the staging regions into the table
 // ---------------------------------------------------------------------------------------------------------
+// phase 2 of one staging set (plus, on the push path, the receive buffer `rb` of this round) on stream si
+static int launch_insert(kmn_ctx *c, const StageView &v, int rb, uint64_t units, cudaStream_t si)
+{
+    RecvView rv{};
+    if (rb >= 0) {
+        const size_t R = (size_t)c->nranks;
+        rv.recs = (const u64 *)c->recv_all + (size_t)rb * R * c->push_cap * c->RW;
+        rv.meta = (const u32 *)((const u64 *)c->recv_all + 2 * R * c->push_cap * c->RW) + (size_t)rb * R * c->push_meta;
+        rv.cap = c->push_cap; rv.n_src = (u32)R; rv.me = (u32)c->rank; rv.mode = c->push_ce ? 1u : 0u;
+    }
+    const u32 n_entries = v.n_parts * (v.n_cta + (rv.n_src > 1 ? (rv.n_src - 1) * (rv.mode == 1 ? v.n_cta : 1u) : 0));
+    k_build_entries<<<std::min<u32>((n_entries + 255) / 256, (u32)c->n_sms * 4), 256, 0, si>>>(v, rv, (u32)c->RW, c->ent_ptr, c->ent_cnt);
+    k_build_worklist<<<1, 1024, 0, si>>>(c->ent_cnt, n_entries, (u32)INSERT_CHUNK, c->chunk_start, c->next_item);
+    c->launches += 2;
+    const int grid = c->n_sms * c->insert_ctas;
+    {
+        ProfScope ps(c, KMN_PROF_INSERT, units, si);
+        KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
+            k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, si>>>(c->table, c->ent_ptr, c->ent_cnt, n_entries, c->chunk_start, c->next_item, c->ctr);
+        }));
+    }
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return 0;
+}
+
 // submit the drain of one staging set on the insert stream (after everything staged so far on the main stream)
 static int submit_drain(kmn_ctx *c, int i)
 {
     kmn_ctx::StageSet &st = c->sets[i];
-    if (st.staged_upper == 0) return 0;
+    if (st.staged_upper == 0 || c->p2p) return 0;
     cudaStream_t si = c->s_insert;
     if (si != c->stream) {
         CK(c, cudaEventRecord(st.ev_parsed, c->stream));
         CK(c, cudaStreamWaitEvent(si, st.ev_parsed, 0));
     }
     const u32 n_entries = st.v.n_parts * st.v.n_cta;
-    if (c->fast) {
-        k_build_worklist<<<1, 1024, 0, si>>>(st.v.count, st.v.sub_cap, n_entries, (u32)TS_TILE, c->chunk_start, c->next_item);
-        k_fill_items<<<(n_entries + 255) / 256, 256, 0, si>>>(c->chunk_start, n_entries, c->item_entry);
-        c->launches += 2;
-        {
-            ProfScope ps(c, KMN_PROF_SUBPART, st.staged_upper, si);
-            k_subpartition<<<c->n_sms * 4, TS_TPB, c->sub_smem, si>>>(c->table, st.v, c->s2, c->chunk_start, c->item_entry, c->ctr);
-        }
-        c->launches++;
-        CK(c, cudaGetLastError());
-        {
-            ProfScope ps(c, KMN_PROF_INSERT, st.staged_upper, si);
-            const int ctas = (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(200 * 1024) / c->cnt_smem));
-            const int grid = (int)std::min<uint64_t>((uint64_t)c->n_sms * ctas, c->table.n_parts);
-            k_count_slices<<<grid, CNT_TPB, c->cnt_smem, si>>>(c->table, c->s2, c->table_clean ? 1u : 0u, c->ctr);
-        }
-        c->launches++;
-        CK(c, cudaGetLastError());
-        c->table_clean = false;
-        CK(c, cudaMemsetAsync(c->s2.count, 0, (size_t)c->table.n_parts * 4, si));
-    } else {
-    k_build_worklist<<<1, 1024, 0, si>>>(st.v.count, st.v.sub_cap, n_entries, (u32)INSERT_CHUNK, c->chunk_start, c->next_item);
-    c->launches++;
-    const int grid = c->n_sms * c->insert_ctas;
-    {
-        ProfScope ps(c, KMN_PROF_INSERT, st.staged_upper, si);
-        KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
-            if (c->insert_pre) k_insert_staged<W_, X_, true><<<grid, INSERT_TPB, 0, si>>>(c->table, st.v, c->chunk_start, c->next_item, c->ctr);
-            else k_insert_staged<W_, X_, false><<<grid, INSERT_TPB, 0, si>>>(c->table, st.v, c->chunk_start, c->next_item, c->ctr);
-        }));
-    }
-    c->launches++;
-    CK(c, cudaGetLastError());
-    }
+    { int r = launch_insert(c, st.v, -1, st.staged_upper, si); if (r) return r; }
     CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)n_entries * 4, si));
     if (si != c->stream) {
         CK(c, cudaEventRecord(st.ev_drained, si));
@@ -547,44 +559,38 @@ static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, cons
     a.table = c->table; a.stage = c->sets[c->cur].v; a.ctr = c->ctr;
     a.send_recs = c->send_recs; a.send_cursor = c->send_cursor; a.send_cap = c->send_cap;
     a.seg_recs = c->seg_recs; a.seg_count = c->seg_count; a.seg_cap = (u32)c->seg_cap;
+    a.flags = c->flags;
 }
 
-static int launch_parse(kmn_ctx *c, const ParseArgs &a, uint64_t byte0, uint64_t byte1)
+static int launch_parse(kmn_ctx *c, const ParseArgs &a)
 {
     const bool dist = c->nranks > 1;
     {   // phase 1a: weights -> "counted" bits
         ProfScope ps(c, KMN_PROF_WEIGHT, a.n_reads);
         const int grid = (int)std::min<uint64_t>((a.n_reads + MASK_TPB - 1) / MASK_TPB, (uint64_t)c->n_sms * 8);
-        if (c->weights) k_weight_mask<true><<<grid, MASK_TPB, 0, c->stream>>>(a);
-        else k_weight_mask<false><<<grid, MASK_TPB, 0, c->stream>>>(a);
+        const size_t sm = (size_t)(MASK_TPB / 32) * MASK_WBUF;
+        if (c->weights) k_weight_mask<true><<<grid, MASK_TPB, sm, c->stream>>>(a);
+        else k_weight_mask<false><<<grid, MASK_TPB, sm, c->stream>>>(a);
     }
     c->launches++;
     CK(c, cudaGetLastError());
-    if (c->tiles) {   // phase 1b, position-parallel over tiles of the byte range
-        TileArgs ta;
-        ta.byte0 = byte0; ta.byte1 = byte1;
-        ta.tile0 = byte0 / TS_TILE;
-        ta.n_tiles = byte1 > byte0 ? (byte1 - 1) / TS_TILE - ta.tile0 + 1 : 0;
-        ProfScope ps(c, KMN_PROF_PARSE, a.n_reads);
-        if (dist) k_kmer_tiles<true><<<c->n_cta, TS_TPB, c->tile_smem, c->stream>>>(a, ta);
-        else k_kmer_tiles<false><<<c->n_cta, TS_TPB, c->tile_smem, c->stream>>>(a, ta);
-    } else
-    {   // phase 1b: k-mers -> staging sub-regions (and send regions)
+    {   // phase 1b: k-mers -> staging sub-regions (and send segments / the other owners' parts of the set)
         ProfScope ps(c, KMN_PROF_PARSE, a.n_reads);
         const int grid = c->n_cta;
         const size_t sm = c->scatter_smem;
+        const int mode = !dist ? 0 : (c->p2p ? 2 : 1);
+#define KMN_SCATTER(X_, E_)                                                                          \
+        do {                                                                                         \
+            if (mode == 0) k_kmer_scatter<W_, X_, E_, 0><<<grid, SCATTER_TPB, sm, c->stream>>>(a);    \
+            else if (mode == 1) k_kmer_scatter<W_, X_, E_, 1><<<grid, SCATTER_TPB, sm, c->stream>>>(a); \
+            else k_kmer_scatter<W_, X_, E_, 2><<<grid, SCATTER_TPB, sm, c->stream>>>(a);              \
+        } while (0)
         KMN_DISPATCH_W(c, {
-            if (!c->hasx) {
-                if (dist) k_kmer_scatter<W_, false, false, true><<<grid, SCATTER_TPB, sm, c->stream>>>(a);
-                else k_kmer_scatter<W_, false, false, false><<<grid, SCATTER_TPB, sm, c->stream>>>(a);
-            } else if (c->ext) {
-                if (dist) k_kmer_scatter<W_, true, true, true><<<grid, SCATTER_TPB, sm, c->stream>>>(a);
-                else k_kmer_scatter<W_, true, true, false><<<grid, SCATTER_TPB, sm, c->stream>>>(a);
-            } else {
-                if (dist) k_kmer_scatter<W_, true, false, true><<<grid, SCATTER_TPB, sm, c->stream>>>(a);
-                else k_kmer_scatter<W_, true, false, false><<<grid, SCATTER_TPB, sm, c->stream>>>(a);
-            }
+            if (!c->hasx) KMN_SCATTER(false, false);
+            else if (c->ext) KMN_SCATTER(true, true);
+            else KMN_SCATTER(true, false);
         });
+#undef KMN_SCATTER
     }
     c->launches++;
     CK(c, cudaGetLastError());
@@ -666,6 +672,184 @@ static int exchange(kmn_ctx *c)
 #endif
 }
 
+#ifdef KMN_WITH_NCCL
+// ---------------------------------------------------------------------------------------------------------
+// multi-GPU push path.  Set-up: every rank allocates its receive buffers, exports them with CUDA IPC, and the handles
+// travel through the NCCL communicator itself; all ranks switch to the push path only if every rank could map every
+// peer (otherwise the NCCL all-to-all path above stays in charge).
+// ---------------------------------------------------------------------------------------------------------
+static int nccl_sum_u64(kmn_ctx *c, u64 mine, u64 *out, cudaStream_t st)
+{
+    CK(c, cudaMemcpyAsync(c->scratch + 6, &mine, 8, cudaMemcpyHostToDevice, st));
+    ncclResult_t nr = ncclAllReduce(c->scratch + 6, c->scratch + 7, 1, ncclUint64, ncclSum, c->comm, st);
+    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclAllReduce failed: %s", ncclGetErrorString(nr));
+    CK(c, cudaMemcpyAsync(out, c->scratch + 7, 8, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int setup_push(kmn_ctx *c)
+{
+    const int R = c->nranks;
+    c->p2p = false;
+    bool want = R <= KMN_MAX_PUSH_RANKS;
+    if (const char *e = getenv("KMN_P2P")) want = want && atoi(e) != 0;
+    const uint64_t G = c->n_groups;
+    c->push_ce = true;
+    if (const char *e = getenv("KMN_PUSH")) c->push_ce = strcmp(e, "kernel") != 0;
+    uint64_t cap = c->stage_keys / (uint64_t)R; cap += cap / 4 + 65536;
+    size_t meta_words = (size_t)G + 1;
+    const bool old_pipeline = c->pipeline;
+    const int old_sets = c->n_sets;
+    if (want) { c->pipeline = true; c->n_sets = 2; }
+    if (want && c->push_ce) {
+        // the receive buffer of a source is a verbatim copy of its part of the staging set: size the sets by owner first
+        c->p2p = true;
+        int r = alloc_stage_sets(c); if (r) return r;
+        c->p2p = false;
+        cap = (uint64_t)c->n_cta * G * c->sets[0].v.sub_cap;
+        meta_words = (size_t)G * c->n_cta;
+    }
+    const size_t rec_bytes = 2 * (size_t)R * cap * c->RW * 8, meta_bytes = 2 * (size_t)R * meta_words * 4;
+    u64 ok = want ? 1 : 0;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (ok && cudaMalloc(&c->recv_all, rec_bytes + meta_bytes + 256) != cudaSuccess) { cudaGetLastError(); c->recv_all = nullptr; ok = 0; }
+    if (ok && cudaIpcGetMemHandle(&mine, c->recv_all) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    // handles of all ranks
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    std::vector<cudaIpcMemHandle_t> all((size_t)R);
+    {
+        void *d = nullptr;
+        CK(c, cudaMalloc(&d, (size_t)(R + 1) * 64));
+        CK(c, cudaMemcpyAsync((char *)d + (size_t)R * 64, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+        ncclResult_t nr = ncclAllGather((char *)d + (size_t)R * 64, d, 64, ncclUint8, c->comm, c->stream);
+        if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclAllGather failed: %s", ncclGetErrorString(nr));
+        CK(c, cudaMemcpyAsync(all.data(), d, (size_t)R * 64, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, cudaFree(d));
+    }
+    u64 all_ok = 0;
+    { int r = nccl_sum_u64(c, ok, &all_ok, c->stream); if (r) return r; }
+    if (all_ok == (u64)R) {
+        for (int p = 0; p < R && ok; ++p) {
+            if (p == c->rank) { c->peer_all[p] = c->recv_all; continue; }
+            if (cudaIpcOpenMemHandle(&c->peer_all[p], all[(size_t)p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); c->peer_all[p] = nullptr; ok = 0; }
+        }
+    } else ok = 0;
+    { int r = nccl_sum_u64(c, ok, &all_ok, c->stream); if (r) return r; }
+    if (all_ok != (u64)R) {                       // somebody could not: everybody stays on the NCCL path
+        for (int p = 0; p < R; ++p) { if (p != c->rank && c->peer_all[p]) cudaIpcCloseMemHandle(c->peer_all[p]); c->peer_all[p] = nullptr; }
+        if (c->recv_all) { cudaFree(c->recv_all); c->recv_all = nullptr; }
+        cudaGetLastError();
+        c->pipeline = old_pipeline; c->n_sets = old_sets;
+        if (want && c->push_ce) { int r = alloc_stage_sets(c); if (r) return r; }      // back to sets with a single owner
+        return 0;
+    }
+    c->p2p = true;
+    c->push_cap = cap;
+    c->push_meta = meta_words;
+    if (!c->s_insert || c->s_insert == c->stream) CK(c, cudaStreamCreateWithFlags(&c->s_insert, cudaStreamNonBlocking));
+    CK(c, cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(c, cudaEventCreateWithFlags(&c->ev_pushed[i], cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_rb_free[i], cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_recv[i], cudaEventDisableTiming));
+    }
+    const size_t n_sub = (size_t)G * c->n_cta;
+    CK(c, cudaMalloc((void **)&c->run_off, (size_t)R * n_sub * 4));
+    CK(c, cudaMalloc((void **)&c->grp_off, (size_t)R * (G + 1) * 4));
+    CK(c, cudaMalloc((void **)&c->flags, 16));
+    CK(c, cudaMalloc((void **)&c->d_const, 32));
+    const u64 consts[4] = {0, 1, 0, 0};
+    CK(c, cudaMemcpyAsync(c->d_const, consts, 32, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemsetAsync(c->flags, 0, 16, c->stream));
+    CK(c, cudaMemsetAsync(c->recv_all, 0, rec_bytes + meta_bytes, c->stream));
+    if (!c->push_ce) { int r = alloc_stage_sets(c); if (r) return r; }      // sets cut by owner
+    { int r = apply_smem_attrs(c); if (r) return r; }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// One round of the push path: the set `si` (filled by phase 1 on the main stream, possibly empty) is pushed to its
+// owners, and phase 2 inserts this rank's own part plus what the peers pushed.  Every rank runs the same sequence of
+// rounds; `done` says this rank has no more input, and the sum of the flags comes back when `done_sum` is given.
+//   comm stream  : plan -> barrier A (peers' round buffer is free; carries the done flags) -> copy over NVLink -> barrier B
+//   insert stream: after barrier B: entries + work list + insert
+static int push_round(kmn_ctx *c, int si, bool done, u64 *done_sum)
+{
+    kmn_ctx::StageSet &st = c->sets[si];
+    const int R = c->nranks, rb = (int)(c->round & 1);
+    const size_t G = (size_t)c->n_groups;
+    cudaStream_t sc = c->s_comm, sins = c->s_insert;
+    CK(c, cudaEventRecord(st.ev_parsed, c->stream));
+    CK(c, cudaStreamWaitEvent(sc, st.ev_parsed, 0));
+    if (c->rb_busy[rb]) { CK(c, cudaStreamWaitEvent(sc, c->ev_rb_free[rb], 0)); c->rb_busy[rb] = false; }
+    if (!c->push_ce) { k_push_plan<<<R, 1024, 0, sc>>>(st.v, c->push_cap, c->run_off, c->grp_off, c->flags); c->launches++; }
+    ncclResult_t nr = ncclAllReduce(c->d_const + (done ? 1 : 0), c->d_const + 3, 1, ncclUint64, ncclSum, c->comm, sc);
+    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "push barrier failed: %s", ncclGetErrorString(nr));
+    if (c->push_ce) {
+        // copy engines: the part of every other owner (whole sub-region capacity) and its fill counters go to that
+        // owner's round buffer as they are; no SM takes part in the transfer
+        const size_t n_sub = G * c->n_cta, part = n_sub * st.v.sub_cap * c->RW;          // u64 words per owner part
+        ProfScope ps(c, KMN_PROF_ROUTE, 0, sc);
+        for (int q = 1; q < R; ++q) {
+            const int p = (c->rank + q) % R;                                             // start with a different peer on every rank
+            u64 *base = (u64 *)c->peer_all[p];
+            u64 *drec = base + ((size_t)rb * R + c->rank) * c->push_cap * c->RW;
+            u32 *dmeta = (u32 *)(base + 2 * (size_t)R * c->push_cap * c->RW) + ((size_t)rb * R + c->rank) * c->push_meta;
+            CK(c, cudaMemcpyAsync(drec, st.v.recs + (size_t)p * part, part * 8, cudaMemcpyDeviceToDevice, sc));
+            CK(c, cudaMemcpyAsync(dmeta, st.v.count + (size_t)p * n_sub, n_sub * 4, cudaMemcpyDeviceToDevice, sc));
+        }
+    } else {
+        PushPeers pp;
+        memset(&pp, 0, sizeof pp);
+        for (int p = 0; p < R; ++p) {
+            u64 *base = (u64 *)c->peer_all[p];
+            pp.recs[p] = base + ((size_t)rb * R + c->rank) * c->push_cap * c->RW;
+            pp.meta[p] = (u32 *)(base + 2 * (size_t)R * c->push_cap * c->RW) + ((size_t)rb * R + c->rank) * c->push_meta;
+        }
+        ProfScope ps(c, KMN_PROF_ROUTE, 0, sc);
+        k_push_copy<<<c->n_sms * 2, 128, 0, sc>>>(st.v, pp, c->push_cap, c->run_off, c->grp_off, (u32)c->RW);
+        c->launches++;
+    }
+    CK(c, cudaGetLastError());
+    {   // the other owners' fill counters of this set are consumed
+        const size_t n_sub = G * c->n_cta;
+        if (c->rank > 0) CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)c->rank * n_sub * 4, sc));
+        if (c->rank + 1 < R) CK(c, cudaMemsetAsync(st.v.count + (size_t)(c->rank + 1) * n_sub, 0, (size_t)(R - 1 - c->rank) * n_sub * 4, sc));
+    }
+    CK(c, cudaEventRecord(c->ev_pushed[si], sc));
+    c->push_pending[si] = true;
+    nr = ncclAllReduce(c->d_const, c->d_const + 2, 1, ncclUint64, ncclSum, c->comm, sc);
+    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "push barrier failed: %s", ncclGetErrorString(nr));
+    CK(c, cudaEventRecord(c->ev_recv[rb], sc));
+    CK(c, cudaStreamWaitEvent(sins, st.ev_parsed, 0));
+    CK(c, cudaStreamWaitEvent(sins, c->ev_recv[rb], 0));
+    { int r = launch_insert(c, st.v, rb, c->stage_keys, sins); if (r) return r; }
+    CK(c, cudaMemsetAsync(st.v.count + (size_t)c->rank * G * c->n_cta, 0, G * c->n_cta * 4, sins));
+    CK(c, cudaEventRecord(st.ev_drained, sins));
+    st.drain_pending = true;
+    CK(c, cudaEventRecord(c->ev_rb_free[rb], sins));
+    c->rb_busy[rb] = true;
+    c->round++;
+    if (done_sum) {
+        CK(c, cudaMemcpyAsync(done_sum, c->d_const + 3, 8, cudaMemcpyDeviceToHost, sc));
+        CK(c, cudaStreamSynchronize(sc));
+    }
+    return 0;
+}
+
+// phase 1 may write into set `si` again: its previous push and its previous insert are complete
+static int push_set_ready(kmn_ctx *c, int si)
+{
+    kmn_ctx::StageSet &st = c->sets[si];
+    if (c->push_pending[si]) { CK(c, cudaStreamWaitEvent(c->stream, c->ev_pushed[si], 0)); c->push_pending[si] = false; }
+    if (st.drain_pending) { CK(c, cudaStreamWaitEvent(c->stream, st.ev_drained, 0)); st.drain_pending = false; }
+    return 0;
+}
+#endif
+
 int kmn_comm_unique_id(void *id128)
 {
 #ifdef KMN_WITH_NCCL
@@ -693,18 +877,29 @@ int kmn_comm_init(kmn_ctx *c, int rank, int nranks, const void *id128)
     memcpy(&id, id128, 128);
     ncclResult_t nr = ncclCommInitRank(&c->comm, nranks, id, rank);
     if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclCommInitRank failed: %s", ncclGetErrorString(nr));
-    // send/recv regions: a launch is bounded by stage_keys/2 instances, 1/nranks of which go to each peer on average
+    CK(c, cudaMalloc((void **)&c->send_cursor, (size_t)nranks * 8));
+    CK(c, cudaMalloc((void **)&c->all_counts, (size_t)nranks * nranks * 8));
+    CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)nranks * 8, c->stream));
+    // request/answer regions of the lookup pass (and of the NCCL count path): a launch is bounded by stage_keys/2
+    // instances, 1/nranks of which go to each peer on average
     c->send_cap = c->stage_keys / 2 / (uint64_t)nranks * 3 / 2 + 65536;
     c->recv_cap = c->send_cap * (uint64_t)(nranks - 1);
+    { int r = setup_push(c); if (r) return r; }
+    if (c->p2p) {
+        // the lookup pass runs after the count pass: its request / receive regions reuse the two round buffers
+        const size_t half = (size_t)nranks * c->push_cap * c->RW;
+        if ((size_t)nranks * c->send_cap * c->RW > half) c->send_cap = half / ((size_t)nranks * c->RW);
+        c->recv_cap = c->send_cap * (uint64_t)(nranks - 1);
+        c->send_recs = (u64 *)c->recv_all;
+        c->recv_recs = (u64 *)c->recv_all + half;
+        return 0;
+    }
     c->seg_cap = c->stage_keys / 2 / (uint64_t)nranks / (uint64_t)c->n_cta * 2 + 4096;
     CK(c, cudaMalloc((void **)&c->seg_recs, (size_t)nranks * c->n_cta * c->seg_cap * c->RW * 8));
     CK(c, cudaMalloc((void **)&c->seg_count, (size_t)nranks * c->n_cta * 4));
     CK(c, cudaMemsetAsync(c->seg_count, 0, (size_t)nranks * c->n_cta * 4, c->stream));
     CK(c, cudaMalloc((void **)&c->send_recs, (size_t)nranks * c->send_cap * c->RW * 8));
     CK(c, cudaMalloc((void **)&c->recv_recs, (size_t)c->recv_cap * c->RW * 8));
-    CK(c, cudaMalloc((void **)&c->send_cursor, (size_t)nranks * 8));
-    CK(c, cudaMalloc((void **)&c->all_counts, (size_t)nranks * nranks * 8));
-    CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)nranks * 8, c->stream));
     return 0;
 #else
     (void)rank; (void)nranks; (void)id128;
@@ -791,19 +986,19 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
     if (n_reads && (!bases || !read_off)) return fail(c, KMN_ERR_INVALID, "null input");
     CK(c, cudaSetDevice(c->device));
     c->finished = false;
-    if (n_reads == 0) return c->nranks > 1 ? exchange(c) : 0;
+    if (n_reads == 0) return c->nranks > 1 && !c->p2p ? exchange(c) : 0;
     BatchPtrs bp;
     int r = stage_inputs(c, bases, quals, read_off, n_reads, discarded, true, bp);
     if (r) return r;
     // phase 1a -> 1b scratch: one bit per base position of the batch (+ one fp32 per position for KMN_VALUE_WEIGHTS)
-    const size_t mask_bytes = ((bp.total_bytes / TS_TILE + 1) * (TS_TILE / 32) + 4) * 4;    // whole tiles
+    const size_t mask_bytes = (bp.total_bytes / 32 + 4) * 4;
     r = ensure(c, c->mask, mask_bytes); if (r) return r;
     CK(c, cudaMemsetAsync(c->mask.p, 0, mask_bytes, c->stream));
     if (c->weights) { r = ensure(c, c->wts, (bp.total_bytes + 4) * 4); if (r) return r; }
     // A launch may stage at most `limit` instances (one staging set; multi-GPU: half of it, the other half takes the
     // records received from the peers and the same bound sizes the send regions).  The exact number of k-mer
     // positions of a read range is computed on the device; ranges that do not fit are halved.
-    const uint64_t limit = std::max<uint64_t>(c->nranks > 1 ? c->stage_keys / 2 : c->stage_keys, 1);
+    const uint64_t limit = std::max<uint64_t>(c->nranks > 1 && !c->p2p ? c->stage_keys / 2 : c->stage_keys, 1);
     const bool host_sizes = bp.off_on_host && (!discarded || !is_device_ptr(discarded));
     if (!host_sizes && bp.slot >= 0) CK(c, cudaStreamSynchronize(c->s_copy));   // count_positions reads the staged copies
     struct Range { uint64_t r0, r1; };
@@ -830,19 +1025,21 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
             continue;
         }
         if (npos == 0) continue;
-        r = stage_room(c, npos); if (r) return r;
-        uint64_t byte0 = 0, byte1 = bp.total_bytes;
-        if (c->tiles && !(rg.r0 == 0 && rg.r1 == n_reads)) {            // byte range of a sub-range of the batch
-            if (bp.off_on_host) { byte0 = read_off[rg.r0]; byte1 = read_off[rg.r1]; }
-            else {
-                CK(c, cudaMemcpyAsync(&byte0, bp.off + rg.r0, 8, cudaMemcpyDeviceToHost, c->s_copy));
-                CK(c, cudaMemcpyAsync(&byte1, bp.off + rg.r1, 8, cudaMemcpyDeviceToHost, c->s_copy));
-                CK(c, cudaStreamSynchronize(c->s_copy));
-            }
+#ifdef KMN_WITH_NCCL
+        if (c->p2p) {                                       // one launch = one round: fill a set, push it, insert
+            r = push_set_ready(c, c->cur); if (r) return r;
+            ParseArgs a;
+            fill_parse_args(c, a, bp.bases, bp.quals, bp.off + rg.r0, bp.disc ? bp.disc + rg.r0 : nullptr, rg.r1 - rg.r0, bp.total_bytes);
+            r = launch_parse(c, a); if (r) return r;
+            r = push_round(c, c->cur, false, nullptr); if (r) return r;
+            c->cur ^= 1;
+            continue;
         }
+#endif
+        r = stage_room(c, npos); if (r) return r;
         ParseArgs a;
         fill_parse_args(c, a, bp.bases, bp.quals, bp.off + rg.r0, bp.disc ? bp.disc + rg.r0 : nullptr, rg.r1 - rg.r0, bp.total_bytes);
-        r = launch_parse(c, a, byte0, byte1); if (r) return r;
+        r = launch_parse(c, a); if (r) return r;
         c->sets[c->cur].staged_upper += npos;
         r = exchange(c); if (r) return r;
     }
@@ -866,7 +1063,26 @@ int kmn_count_finish(kmn_ctx *c, int apply_purge)
 {
     if (!c) return KMN_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
-    int r = drain(c);
+    int r = 0;
+#ifdef KMN_WITH_NCCL
+    if (c->p2p && !c->finished) {
+        // empty rounds until every rank has said it is done (a rank that finishes early keeps receiving and inserting)
+        while (true) {
+            r = push_set_ready(c, c->cur); if (r) return r;
+            u64 n_done = 0;
+            r = push_round(c, c->cur, true, &n_done); if (r) return r;
+            c->cur ^= 1;
+            if (n_done == (u64)c->nranks) break;
+        }
+        r = wait_drains(c); if (r) return r;
+        u64 fl[2] = {0, 0};
+        CK(c, cudaMemcpyAsync(fl, c->flags, 16, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        if (fl[0] || fl[1]) return fail(c, KMN_ERR_COMM, "push path overflow: %llu records beyond a remote sub-region, %llu beyond the receive buffer "
+                                        "(skewed k-mer distribution); use smaller batches or KMN_P2P=0", (unsigned long long)fl[0], (unsigned long long)fl[1]);
+    }
+#endif
+    r = drain(c);
     if (r) return r;
     Counters h;
     CK(c, cudaMemcpyAsync(&h, c->ctr, sizeof h, cudaMemcpyDeviceToHost, c->stream));

@@ -39,25 +39,25 @@ struct TableView {
 };
 static constexpr u32 SLICE_SLOTS = 4096;   // 64 KB of 16-byte slots
 
-struct StageView {        // level-1 staging area of k-mer records, partitioned by table GROUP (phase 1 -> phase 2); n_parts = groups
-    u64 *recs;            // [n_parts][n_cta][sub_cap][RW]: every phase-1 CTA owns a private sub-region of every partition,
-                          // so a flush needs no global atomic (its position follows from the CTA-local sequence number)
-    u32 *count;           // [n_parts][n_cta] records written (may exceed sub_cap: the excess was inserted directly)
+struct StageView {        // level-1 staging area of k-mer records, partitioned by (owner rank,) table GROUP (phase 1 -> phase 2)
+    u64 *recs;            // [n_owners][n_cta][n_parts][sub_cap][RW]: every phase-1 CTA owns a private sub-region of every
+                          // (owner, group), so a flush needs no global atomic (its position follows from a CTA-local counter)
+    u32 *count;           // [n_owners][n_parts][n_cta] records written (may exceed sub_cap: the excess was inserted directly)
     u32 sub_cap;          // records per sub-region
     u32 n_cta;            // phase-1 grid size
-    u32 n_parts;
-    u32 cta_major;        // layout of recs: [cta][part] (a CTA's write frontier stays within few pages) or [part][cta]
-    __device__ __forceinline__ size_t sub_index(u32 part, u32 cta) const
-    {
-        return cta_major ? (size_t)cta * n_parts + part : (size_t)part * n_cta + cta;
-    }
-};
-
-struct Stage2View {       // level-2 staging: the records of one drain, one bucket per table SLICE
-    u64 *recs;            // [n_slices][cap]
-    u32 *count;           // [n_slices] records written (may exceed cap: the excess was inserted directly)
-    u32 cap;
+    u32 n_parts;          // table groups
     u32 pad;
+    u32 n_owners;         // 1, or the number of ranks when phase 1 bins by owner as well (multi-GPU push path)
+    u32 me;               // this rank (index of the local owner when n_owners > 1)
+    __device__ __host__ __forceinline__ u32 local_owner() const { return n_owners > 1 ? me : 0u; }
+    __device__ __host__ __forceinline__ size_t sub_index(u32 owner, u32 part, u32 cta) const
+    {
+        return ((size_t)owner * n_cta + cta) * n_parts + part;     // a CTA's write frontier stays within few pages
+    }
+    __device__ __host__ __forceinline__ size_t cnt_index(u32 owner, u32 part, u32 cta) const
+    {
+        return ((size_t)owner * n_parts + part) * n_cta + cta;
+    }
 };
 
 struct Counters {         // device-side statistics (src/KmerSpectrum.h:1590-1650)
@@ -219,7 +219,7 @@ struct Roll {
 };
 
 // ------------------------------------------------------------------------------------------------
-// K3. table insert: open addressing, linear probing inside one partition.
+// K3. table insert: open addressing, linear probing inside one slice (part_slots is even).
 // W==1: slot {val, ~key}; claim by 64-bit atomicCAS on the key word, then one RED on the value word.
 // W>=2: slot {val, key[W]}; claim by CAS(val: 0 -> LOCK), write key words, publish with READY.
 // add = 1 | (isFwd << 32)
@@ -236,63 +236,83 @@ __device__ __forceinline__ u64 ld_cg64(const void *p)
     return v;
 }
 
-// PRE: the home slot's words were loaded by the caller (pv = value word, pk = first key word; lets a thread keep the
-// home-slot loads of several records in flight before it resolves any of them)
+// W == 1: two 16-byte slots share one 32-byte sector, so the probe unit is an aligned PAIR of slots fetched with one
+// 256-bit load: linear probing that starts at the even slot below the home slot and looks at two slots per sector request.
+__device__ __forceinline__ void ld_pair32(const void *p, u64 &v0, u64 &k0, u64 &v1, u64 &k1)
+{
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(k0), "=l"(v1), "=l"(k1) : "l"(p));
+}
+
+__device__ __forceinline__ u32 pair_sat(u64 v0, u64 v1) { return ((u32)v0 >= MAX_COUNT ? 1u : 0u) | ((u32)v1 >= MAX_COUNT ? 2u : 0u); }
+
+// PRE: the home probe was loaded by the caller (W == 1: key words of the home pair in pk0/pk1 and "count saturated" bits
+// in psat; W >= 2: the value word in pk0), which lets a thread keep the home loads of several records in flight before
+// it resolves any of them
 template <int W, bool PRE = false>
 __device__ __forceinline__ int table_insert(const TableView &t, u32 part, u64 slot0, const u64 (&key)[W], u64 add,
-                                            u64 *slot_out, u32 *probes_out, u64 pv = 0, u64 pk = 0)
+                                            u64 *slot_out, u32 *probes_out, u64 pk0 = 0, u64 pk1 = 0, u32 psat = 0)
 {
     Slot<W> *base = reinterpret_cast<Slot<W> *>(t.slots) + (u64)part * t.part_slots;
-    u64 s = slot0;
     const u64 S = t.part_slots;
+    if (W == 1) {
+        u64 s = slot0 & ~1ull;
+        const u64 want = ~key[0];
+        for (u64 probes = 0; probes < S; probes += 2) {
+            Slot<W> *sl = base + s;
+            u64 k0, k1;
+            u32 sat;
+            if (PRE && probes == 0) { k0 = pk0; k1 = pk1; sat = psat; }
+            else { u64 v0, v1; ld_pair32(sl, v0, k0, v1, k1); sat = pair_sat(v0, v1); }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                u64 ck = h ? k1 : k0;
+                bool full = (sat >> h) & 1u;
+                if (ck == 0) {
+                    const u64 old = atomicCAS(&sl[h].k[0], 0ull, want);
+                    if (old == 0ull) {
+                        atomicAdd(&sl[h].val, add);
+                        *slot_out = (u64)part * S + s + h; *probes_out = (u32)probes + h;
+                        return 1;
+                    }
+                    ck = old; full = false;
+                }
+                if (ck == want) {
+                    if (!full) atomicAdd(&sl[h].val, add);
+                    *slot_out = (u64)part * S + s + h; *probes_out = (u32)probes + h;
+                    return 0;
+                }
+            }
+            s = s + 2 >= S ? 0 : s + 2;
+        }
+        return -1;
+    }
+    u64 s = slot0;
     for (u64 probes = 0; probes < S; ++probes) {
         Slot<W> *sl = base + s;
-        if (W == 1) {
-            u64 v, ck;
-            if (PRE && probes == 0) { v = pv; ck = pk; }
-            else ld_slot16(sl, v, ck);
-            const u64 want = ~key[0];
-            if (ck == 0) {
-                u64 old = atomicCAS(&sl->k[0], 0ull, want);
-                if (old == 0ull) {
-                    atomicAdd(&sl->val, add);
-                    *slot_out = (u64)part * S + s; *probes_out = (u32)probes;
-                    return 1;
-                }
-                ck = old;
-                v = 0;
-            }
-            if (ck == want) {
-                if ((u32)v < MAX_COUNT) atomicAdd(&sl->val, add);
-                *slot_out = (u64)part * S + s; *probes_out = (u32)probes;
-                return 0;
-            }
-        } else {
-            u64 v = (PRE && probes == 0) ? pv : ld_cg64(&sl->val);
-            if (v == 0) {
-                u64 old = atomicCAS(&sl->val, 0ull, VAL_LOCK);
-                if (old == 0ull) {
+        u64 v = (PRE && probes == 0) ? pk0 : ld_cg64(&sl->val);
+        if (v == 0) {
+            u64 old = atomicCAS(&sl->val, 0ull, VAL_LOCK);
+            if (old == 0ull) {
 #pragma unroll
-                    for (int i = 0; i < W; ++i) sl->k[i] = key[i];
-                    __threadfence();
-                    atomicExch(&sl->val, VAL_READY | add);
-                    *slot_out = (u64)part * S + s; *probes_out = (u32)probes;
-                    return 1;
-                }
-                v = old;
-            }
-            while (!(v & VAL_READY)) {            // another thread is publishing this slot
-                __nanosleep(32);
-                v = ld_cg64(&sl->val);
-            }
-            bool eq = true;
-#pragma unroll
-            for (int i = 0; i < W; ++i) eq = eq && (ld_cg64(&sl->k[i]) == key[i]);
-            if (eq) {
-                if ((u32)v < MAX_COUNT) atomicAdd(&sl->val, add);
+                for (int i = 0; i < W; ++i) sl->k[i] = key[i];
+                __threadfence();
+                atomicExch(&sl->val, VAL_READY | add);
                 *slot_out = (u64)part * S + s; *probes_out = (u32)probes;
-                return 0;
+                return 1;
             }
+            v = old;
+        }
+        while (!(v & VAL_READY)) {            // another thread is publishing this slot
+            __nanosleep(32);
+            v = ld_cg64(&sl->val);
+        }
+        bool eq = true;
+#pragma unroll
+        for (int i = 0; i < W; ++i) eq = eq && (ld_cg64(&sl->k[i]) == key[i]);
+        if (eq) {
+            if ((u32)v < MAX_COUNT) atomicAdd(&sl->val, add);
+            *slot_out = (u64)part * S + s; *probes_out = (u32)probes;
+            return 0;
         }
         s = s + 1 == S ? 0 : s + 1;
     }
@@ -304,23 +324,30 @@ template <int W>
 __device__ __forceinline__ u64 table_find(const TableView &t, u32 part, u64 slot0, const u64 (&key)[W], u64 *slot_out)
 {
     const Slot<W> *base = reinterpret_cast<const Slot<W> *>(t.slots) + (u64)part * t.part_slots;
-    u64 s = slot0;
     const u64 S = t.part_slots;
+    if (W == 1) {
+        u64 s = slot0 & ~1ull;
+        const u64 want = ~key[0];
+        for (u64 probes = 0; probes < S; probes += 2) {
+            u64 v0, k0, v1, k1;
+            ld_pair32(base + s, v0, k0, v1, k1);
+            if (k0 == want) { if (slot_out) *slot_out = (u64)part * S + s; return v0; }
+            if (k0 == 0) return 0;
+            if (k1 == want) { if (slot_out) *slot_out = (u64)part * S + s + 1; return v1; }
+            if (k1 == 0) return 0;
+            s = s + 2 >= S ? 0 : s + 2;
+        }
+        return 0;
+    }
+    u64 s = slot0;
     for (u64 probes = 0; probes < S; ++probes) {
         const Slot<W> *sl = base + s;
-        if (W == 1) {
-            u64 v, ck;
-            ld_slot16(sl, v, ck);
-            if (ck == 0) return 0;
-            if (ck == ~key[0]) { if (slot_out) *slot_out = (u64)part * S + s; return v; }
-        } else {
-            u64 v = ld_cg64(&sl->val);
-            if (v == 0) return 0;
-            bool eq = true;
+        u64 v = ld_cg64(&sl->val);
+        if (v == 0) return 0;
+        bool eq = true;
 #pragma unroll
-            for (int i = 0; i < W; ++i) eq = eq && (ld_cg64(&sl->k[i]) == key[i]);
-            if (eq) { if (slot_out) *slot_out = (u64)part * S + s; return v; }
-        }
+        for (int i = 0; i < W; ++i) eq = eq && (ld_cg64(&sl->k[i]) == key[i]);
+        if (eq) { if (slot_out) *slot_out = (u64)part * S + s; return v; }
         s = s + 1 == S ? 0 : s + 1;
     }
     return 0;

@@ -24,10 +24,17 @@ static constexpr int MASK_TPB = 256;       // phase 1a: one thread per read
 #endif
 static constexpr int SCATTER_TPB = KMN_SCATTER_TPB;    // phase 1b: one thread per read, SCATTER_CTAS CTAs per SM
 static constexpr int SCATTER_CTAS = KMN_SCATTER_CTAS;
+#ifndef KMN_INSERT_MIN_CTAS
+#define KMN_INSERT_MIN_CTAS 4
+#endif
 static constexpr int INSERT_TPB = 256;
-static constexpr int INSERT_UNROLL = 4;
+#ifndef KMN_INSERT_UNROLL
+#define KMN_INSERT_UNROLL 2
+#endif
+static constexpr int INSERT_UNROLL = KMN_INSERT_UNROLL;
 static constexpr int INSERT_CHUNK = INSERT_TPB * INSERT_UNROLL;
 static constexpr int INSERT_GROUP = 4;      // chunks per ticket
+#define KMN_MAX_PUSH_RANKS 16               // ranks of the NVLink push path (kernel-parameter arrays of peer pointers)
 
 struct ParseArgs {
     const uint8_t *bases;
@@ -55,6 +62,7 @@ struct ParseArgs {
     u32 *seg_count;        // [nranks][n_cta]
     u32 seg_cap;
     // multi-GPU lookup pass: requests are appended to per-destination regions
+    u64 *flags;            // [0] += records lost to a full remote-owner sub-region (push path; reported by kmn_count_finish)
     u64 *send_recs;        // [nranks][send_cap][W]
     u64 *send_cursor;      // [nranks]
     u64 send_cap;
@@ -349,38 +357,179 @@ __device__ __forceinline__ void walker_step(Walker<W> &s, const ParseArgs &a, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2a: phase 1a of the count pass.  One thread walks one read and evaluates the reference's sequential weight
-// recurrence (a3, src/KmerReadUtils.h:176-248); the only thing the count pass needs from it is one bit per k-mer
-// position -- "(float)w > minimumWeight" (src/KmerSpectrum.h:1598, src/KmerTrackingData.h:354-364) -- which goes to a
-// bit array indexed by the k-mer's first base in the concatenated batch (and, for KMN_VALUE_WEIGHTS, the fp32
-// weight itself).  Splitting this off leaves phase 1b free of any sequential dependency along the read.
+// K2a: phase 1a of the count pass.  Evaluates the reference's sequential weight recurrence (a3,
+// src/KmerReadUtils.h:176-248); the only thing the count pass needs from it is one bit per k-mer position --
+// "(float)w > minimumWeight" (src/KmerSpectrum.h:1598, src/KmerTrackingData.h:354-364) -- which goes to a bit array
+// indexed by the k-mer's first base in the concatenated batch (and, for KMN_VALUE_WEIGHTS, the fp32 weight itself).
+//
+// Most reads of a modern run are UNIFORM: every base is ACGT and every quality byte is the same value q.  For such a
+// read the recurrence never changes the weight: it is seeded with p[q]*p[q]*...*p[q] (k factors, left to right), every
+// later step multiplies by p[q]/p[q] (skipped by the reference's own `if change != 1`-free arithmetic: x/x == 1.0
+// exactly), and the periodic re-seed (i%1024==0) recomputes the same left-to-right product.  So a warp first
+// classifies 32 reads with SWAR compares (one lane per read), uniform reads set their whole bit range at once from a
+// 256-entry table of those products, and the others are queued in shared memory and walked 32 at a time -- the
+// sequential walker then runs with all lanes busy instead of diverging on every step.
 // ------------------------------------------------------------------------------------------------
+template <bool WTS>
+__device__ __forceinline__ void weight_walk_read(const ParseArgs &a, const double *ptab, u64 r, LocalCtr &lc)
+{
+    const u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
+    const u32 len = (u32)(o1 - o0);
+    Walker<1> st;
+    st.template begin<true>(a, o0, len);
+    u64 curw = ~0ull;
+    u32 acc = 0;
+    auto emit = [&](u32 i, const u64 (&)[1], bool, float wf, bool good, u32) {
+        const u64 gb = o0 + i, w = gb >> 5;
+        if (w != curw) { if (acc) atomicOr(&a.mask[curw], acc); acc = 0; curw = w; }
+        if (good) { acc |= 1u << (u32)(gb & 31ull); lc.good++; }
+        if (WTS) a.wts[gb] = wf;
+        lc.raw++;
+    };
+    while (st.j < st.len) walker_step<1, true, false, false>(st, a, ptab, emit);
+    if (acc) atomicOr(&a.mask[curw], acc);
+}
+
+// sets bits [b0, b0+n) of the mask (neighbouring reads share the boundary words)
+__device__ __forceinline__ void mask_set_range(u32 *mask, u64 b0, u32 n)
+{
+    u64 w = b0 >> 5;
+    u32 sh = (u32)(b0 & 31ull);
+    while (n) {
+        const u32 take = min(n, 32u - sh);
+        const u32 bits = (take == 32u ? 0xffffffffu : ((1u << take) - 1u)) << sh;
+        atomicOr(&mask[w], bits);
+        n -= take; sh = 0; ++w;
+    }
+}
+
+static constexpr u32 MASK_WBUF = 8192 + 64;      // bytes of one warp's staging buffer: 32 reads of up to 256 bases
+
+// coalesced copy of the 16-byte blocks that hold bytes [b0, b1) of buf into a warp's shared buffer; returns the offset of
+// byte b0 inside the buffer.  Only blocks containing at least one valid byte are touched.
+__device__ __forceinline__ u32 warp_stage_bytes(const uint8_t *buf, u64 b0, u64 b1, uint4 *dst, u32 lane)
+{
+    const unsigned long long a0 = (unsigned long long)buf + b0, a1 = (unsigned long long)buf + b1;
+    const unsigned long long blk0 = a0 & ~15ull;
+    const u32 n_blk = (u32)((a1 - blk0 + 15ull) >> 4);
+    for (u32 i = lane; i < n_blk; i += 32) dst[i] = __ldg(reinterpret_cast<const uint4 *>(blk0) + i);
+    return (u32)(a0 - blk0);
+}
+
+// true iff some byte of the lane's read [pos, pos+len) in the shared buffer differs from pat (pat_valid: ACGT test instead)
+template <bool BASES>
+__device__ __forceinline__ bool smem_scan_read(const u64 *buf64, u32 pos, u32 len, u64 qpat)
+{
+    u32 wi = pos >> 3;
+    const u32 sh = (pos & 7u) * 8u;
+    u64 w0 = buf64[wi];
+    u64 bad = 0;
+    for (u32 j = 0; j < len && !bad; j += 8) {
+        const u64 w1 = buf64[++wi];
+        const u64 x = sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0;
+        w0 = w1;
+        const u32 nb = len - j;
+        const u64 m = nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1ull);
+        if (BASES) {
+            const u64 up = x & 0xDFDFDFDFDFDFDFDFull;
+            const u64 valid = bytes_eq(up, 0x4141414141414141ull) | bytes_eq(up, 0x4343434343434343ull) |
+                              bytes_eq(up, 0x4747474747474747ull) | bytes_eq(up, 0x5454545454545454ull);
+            bad = (~valid & 0x8080808080808080ull) & m;
+        } else bad = (x ^ qpat) & m;
+    }
+    return bad != 0;
+}
+
 template <bool WTS>
 __global__ void __launch_bounds__(MASK_TPB) k_weight_mask(ParseArgs a)
 {
     __shared__ double ptab[256];
-    for (u32 i = threadIdx.x; i < 256; i += blockDim.x) ptab[i] = a.ptab[i];
+    __shared__ float powk[256];                       // (float)(p[q] * p[q] * ... ), k factors, left to right
+    __shared__ u64 queue[MASK_TPB / 32][64];          // per-warp queue of non-uniform reads
+    extern __shared__ __align__(16) unsigned char mask_smem[];   // [warps][MASK_WBUF] staging buffers
+    for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
+        const double p = a.ptab[i];
+        ptab[i] = p;
+        double w = p;
+        for (u32 q = 1; q < a.k; ++q) w = w * p;
+        powk[i] = (float)w;
+    }
     __syncthreads();
     LocalCtr lc{0, 0, 0, 0, 0, 0};
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    Walker<1> st;
-    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += stride) {
-        const u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
-        const u32 len = (u32)(o1 - o0);
-        if (len < a.k || (a.discarded && a.discarded[r])) continue;
-        st.template begin<true>(a, o0, len);
-        u64 curw = ~0ull;
-        u32 acc = 0;
-        auto emit = [&](u32 i, const u64 (&)[1], bool, float wf, bool good, u32) {
-            const u64 gb = o0 + i, w = gb >> 5;
-            if (w != curw) { if (acc) atomicOr(&a.mask[curw], acc); acc = 0; curw = w; }
-            if (good) { acc |= 1u << (u32)(gb & 31ull); lc.good++; }
-            if (WTS) a.wts[gb] = wf;
-            lc.raw++;
-        };
-        while (st.j < st.len) walker_step<1, true, false, false>(st, a, ptab, emit);
-        if (acc) atomicOr(&a.mask[curw], acc);
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u64 n_warps = (u64)gridDim.x * (MASK_TPB / 32);
+    u64 *q = queue[warp];
+    uint4 *wbuf = reinterpret_cast<uint4 *>(mask_smem + (size_t)warp * MASK_WBUF);
+    const u64 *wbuf64 = reinterpret_cast<const u64 *>(wbuf);
+    u32 qn = 0;
+    for (u64 base = ((u64)blockIdx.x * (MASK_TPB / 32) + warp) * 32u; base < a.n_reads; base += n_warps * 32u) {
+        const u64 r = base + lane;
+        const u32 nr = (u32)min((u64)32, a.n_reads - base);
+        // offsets of the round's reads: lane l holds read_off[base + l], B1 = end of the last read
+        const u64 o0 = lane < nr ? a.read_off[r] : 0ull;
+        const u64 B0 = __shfl_sync(0xffffffffu, o0, 0);
+        const u64 B1 = a.read_off[base + nr];
+        const u64 nxt = __shfl_down_sync(0xffffffffu, o0, 1);
+        const u64 o1 = lane + 1 < nr ? nxt : B1;
+        const u32 len = lane < nr ? (u32)(o1 - o0) : 0u;
+        const bool live = lane < nr && len >= a.k && !(a.discarded && a.discarded[r]);
+        bool slow = false;
+        u64 q0 = 0;
+        if (B1 - B0 + 32 <= MASK_WBUF) {
+            // the round's bytes go through shared memory with coalesced 16-byte loads: qualities first, then bases
+            __syncwarp();
+            u32 sh0 = warp_stage_bytes(a.quals, B0, B1, wbuf, lane);
+            __syncwarp();
+            if (live) {
+                const u32 pos = sh0 + (u32)(o0 - B0);
+                q0 = (wbuf64[pos >> 3] >> ((pos & 7u) * 8u)) & 0xffull;
+                slow = smem_scan_read<false>(wbuf64, pos, len, q0 * 0x0101010101010101ull);
+            }
+            __syncwarp();
+            sh0 = warp_stage_bytes(a.bases, B0, B1, wbuf, lane);
+            __syncwarp();
+            if (live && !slow) slow = smem_scan_read<true>(wbuf64, sh0 + (u32)(o0 - B0), len, 0);
+        } else if (live) {
+            // long reads: per-lane streams over global memory
+            Stream sb, sq;
+            sb.init(a.bases, (long long)o0, a.total_bytes);
+            sq.init(a.quals, (long long)o0, a.total_bytes);
+            q0 = sq.get() & 0xffull;
+            const u64 qpat = q0 * 0x0101010101010101ull;
+            u64 bad = 0;
+            for (u32 j = 0; j < len && !bad; j += 8) {
+                sb.prefetch(a.bases, a.total_bytes);
+                sq.prefetch(a.quals, a.total_bytes);
+                const u64 bw = sb.get(), qw = sq.get();
+                const u32 nb = len - j;
+                const u64 m = nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1ull);
+                const u64 up = bw & 0xDFDFDFDFDFDFDFDFull;
+                const u64 valid = bytes_eq(up, 0x4141414141414141ull) | bytes_eq(up, 0x4343434343434343ull) |
+                                  bytes_eq(up, 0x4747474747474747ull) | bytes_eq(up, 0x5454545454545454ull);
+                bad = ((qw ^ qpat) | (~valid & 0x8080808080808080ull)) & m;
+                sb.advance(); sq.advance();
+            }
+            slow = bad != 0;
+        }
+        if (live && !slow) {
+            // uniform read: every k-mer has the weight p[q]^k (evaluated left to right)
+            const u32 n = len - a.k + 1;
+            const float wf = powk[q0];
+            lc.raw += n;
+            if (wf > a.min_weight) { lc.good += n; mask_set_range(a.mask, o0, n); }
+            if (WTS) for (u32 i = 0; i < n; ++i) a.wts[o0 + i] = wf;
+        }
+        const u32 bal = __ballot_sync(0xffffffffu, slow);
+        if (slow) q[qn + __popc(bal & ((1u << lane) - 1u))] = r;
+        qn += __popc(bal);
+        __syncwarp();
+        if (qn >= 32) {
+            qn -= 32;
+            weight_walk_read<WTS>(a, ptab, q[qn + lane], lc);
+            __syncwarp();
+        }
     }
+    if (lane < qn) weight_walk_read<WTS>(a, ptab, q[lane], lc);
     ctr_commit(a.ctr, lc);
 }
 
@@ -413,14 +562,15 @@ __device__ __forceinline__ void st_hint64(u64 *p, u64 v, u64 policy)
     asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(policy) : "memory");
 }
 
+// cbase = this CTA's sub-region of group 0 of the local owner (the sub-regions of one CTA and owner are contiguous)
 template <int W, bool HASX>
-__device__ __forceinline__ void stage_put(const StageView &st, const TableView &tab, u32 *cnt, u32 part, const Rec<W, HASX> &rec, LocalCtr &lc,
+__device__ __forceinline__ void stage_put(u64 *cbase, u32 sub_cap, const TableView &tab, u32 *cnt, u32 part, const Rec<W, HASX> &rec, LocalCtr &lc,
                                           u64 policy)
 {
     constexpr int RW = Rec<W, HASX>::RW;
     const u32 pos = atomicAdd(&cnt[part], 1u);
-    if (pos < st.sub_cap) {
-        u64 *d = st.recs + (st.sub_index(part, blockIdx.x) * st.sub_cap + pos) * RW;
+    if (pos < sub_cap) {
+        u64 *d = cbase + ((size_t)part * sub_cap + pos) * RW;
 #pragma unroll
         for (int q = 0; q < RW; ++q) st_hint64(d + q, rec.w[q], policy);
     } else {
@@ -437,19 +587,30 @@ __device__ __forceinline__ void stage_put(const StageView &st, const TableView &
 // Multi-GPU: records owned by another rank (a5: owner = lookup3 hash, src/Kmer.h:2284-2295) go to that rank's
 // send region instead.
 // ------------------------------------------------------------------------------------------------
-template <int W, bool HASX, bool EXT, bool DIST>
+// DIST: 0 = single GPU; 1 = records of other owners go to per-CTA send segments (NCCL all-to-all path); 2 = every record
+// is binned by (owner, group) into this CTA's sub-region of the owner's part of the staging set (push path: the parts of
+// the other owners are copied into their receive buffers over NVLink, already sorted by group)
+template <int W, bool HASX, bool EXT, int DIST>
 __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(ParseArgs a)
 {
     constexpr int RW = Rec<W, HASX>::RW;
     extern __shared__ __align__(16) u32 smem_u32[];
     const u32 n_parts = a.stage.n_parts;                               // staging partitions = table groups
-    u32 *cnt = smem_u32;                                               // [n_parts] fill level of this CTA's sub-regions
-    u32 *scnt = smem_u32 + ((n_parts + 31u) & ~31u);                   // [nranks] fill level of this CTA's send segments
-    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) cnt[i] = a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x];
-    if (DIST) for (u32 i = threadIdx.x; i < a.nranks; i += blockDim.x) scnt[i] = a.seg_count[(size_t)i * gridDim.x + blockIdx.x];
+    const u32 n_bins = DIST == 2 ? n_parts * a.nranks : n_parts;       // (owner, group) bins on the push path
+    const u32 lo = a.stage.local_owner();
+    u32 *cnt = smem_u32;                                               // [n_bins] fill level of this CTA's sub-regions
+    u32 *scnt = smem_u32 + ((n_bins + 31u) & ~31u);                    // [nranks] fill level of this CTA's send segments (DIST 1)
+    for (u32 i = threadIdx.x; i < n_bins; i += blockDim.x) {
+        const u32 o = DIST == 2 ? i / n_parts : lo, g = DIST == 2 ? i - o * n_parts : i;
+        cnt[i] = a.stage.count[a.stage.cnt_index(o, g, blockIdx.x)];
+    }
+    if (DIST == 1) for (u32 i = threadIdx.x; i < a.nranks; i += blockDim.x) scnt[i] = a.seg_count[(size_t)i * gridDim.x + blockIdx.x];
     __syncthreads();
 
     LocalCtr lc{0, 0, 0, 0, 0, 0};
+    u64 lost = 0;
+    const u32 sub_cap = a.stage.sub_cap;
+    u64 *const cbase = a.stage.recs + a.stage.sub_index(lo, 0, blockIdx.x) * sub_cap * RW;
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const u64 keep = a.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
     Walker<W> st;
@@ -468,9 +629,23 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
             if (!((mw >> (u32)(gb & 31ull)) & 1u)) return;
             Rec<W, HASX> rec;
             rec.pack(key, fwd, (HASX && a.wts) ? a.wts[gb] : 1.0f, eb);
-            if (DIST) {
+            const u64 ph = place_hash<W>(key);
+            const u32 group = part_of(ph, a.table.n_parts) >> a.table.group_shift;
+            if (DIST != 0) {
                 const u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
                 const u32 own = owner_of(h, a.nranks);
+                if (DIST == 2) {
+                    const u32 pos = atomicAdd(&cnt[own * n_parts + group], 1u);
+                    if (pos < sub_cap) {
+                        u64 *d = a.stage.recs + (a.stage.sub_index(own, group, blockIdx.x) * sub_cap + pos) * RW;
+#pragma unroll
+                        for (int q = 0; q < RW; ++q) st_hint64(d + q, rec.w[q], keep);
+                    } else if (own == a.rank) {
+                        insert_record<W, HASX>(a.table, rec, lc.unique, lc.full, lc.probes);
+                        lc.direct++;
+                    } else lost++;
+                    return;
+                }
                 if (own != a.rank) {
                     // one shared atomicAdd per (converged lanes, destination) group
                     namespace cg = cooperative_groups;
@@ -487,15 +662,108 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
                     return;
                 }
             }
-            const u64 ph = place_hash<W>(key);
-            stage_put<W, HASX>(a.stage, a.table, cnt, part_of(ph, a.table.n_parts) >> a.table.group_shift, rec, lc, keep);
+            stage_put<W, HASX>(cbase, sub_cap, a.table, cnt, group, rec, lc, keep);
         };
         while (st.j < st.len) walker_step<W, false, EXT>(st, a, nullptr, emit);
     }
     __syncthreads();
-    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x] = cnt[i];
-    if (DIST) for (u32 i = threadIdx.x; i < a.nranks; i += blockDim.x) a.seg_count[(size_t)i * gridDim.x + blockIdx.x] = scnt[i];
+    for (u32 i = threadIdx.x; i < n_bins; i += blockDim.x) {
+        const u32 o = DIST == 2 ? i / n_parts : lo, g = DIST == 2 ? i - o * n_parts : i;
+        a.stage.count[a.stage.cnt_index(o, g, blockIdx.x)] = cnt[i];
+    }
+    if (DIST == 1) for (u32 i = threadIdx.x; i < a.nranks; i += blockDim.x) a.seg_count[(size_t)i * gridDim.x + blockIdx.x] = scnt[i];
+    if (DIST == 2 && lost) atomicAdd(a.flags, lost);
     ctr_commit(a.ctr, lc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU push path (DIST 2), sender side.  After phase 1 the part of the staging set that belongs to owner o holds
+// o's records in n_parts x n_cta sub-regions.  k_push_plan gives every sub-region its place in one contiguous run per
+// owner, ordered by group (so the owner's phase 2 can read group g of every source as one slice of the run);
+// k_push_copy then writes the runs and their per-group offsets straight into the owners' receive buffers through
+// peer pointers: the all-to-all of MPIAllToAllMessageBuffer (src/MPIBuffer.h:588-600,872-892) as coalesced stores over
+// NVLink, with no send buffer, no count exchange and no routing pass on the receiver.
+// ------------------------------------------------------------------------------------------------
+struct PushPeers { u64 *recs[KMN_MAX_PUSH_RANKS]; u32 *meta[KMN_MAX_PUSH_RANKS]; };   // receive buffer + meta of rank o, slot of this rank
+
+__global__ void __launch_bounds__(1024) k_push_plan(StageView st, u64 recv_cap, u32 *run_off, u32 *grp_off, u64 *flags)
+{
+    // one CTA per owner: exclusive prefix over its sub-regions in (group, cta) order
+    const u32 o = blockIdx.x;
+    if (o == st.me) return;
+    __shared__ u64 carry;
+    __shared__ u64 wsum[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const u32 n = st.n_parts * st.n_cta;
+    const u32 *count = st.count + (size_t)o * n;
+    u32 *ro = run_off + (size_t)o * n;
+    u32 *go = grp_off + (size_t)o * (st.n_parts + 1);
+    for (u32 base = 0; base < n; base += blockDim.x) {
+        const u32 p = base + threadIdx.x;
+        u64 c = 0;
+        if (p < n) { c = count[p]; if (c > st.sub_cap) c = st.sub_cap; }
+        u64 v = c;
+        const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u64 x = __shfl_up_sync(0xffffffffu, v, d); if (lane >= (u32)d) v += x; }
+        if (lane == 31) wsum[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            u64 x = wsum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u64 y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (u32)d) x += y; }
+            wsum[lane] = x;
+        }
+        __syncthreads();
+        const u64 incl = v + (warp ? wsum[warp - 1] : 0) + carry;
+        if (p < n) {
+            u64 excl = incl - c;
+            if (excl > recv_cap) excl = recv_cap;                    // the copy clamps at the capacity and reports it
+            ro[p] = (u32)excl;
+            if (p % st.n_cta == 0) go[p / st.n_cta] = (u32)excl;
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        u64 tot = carry;
+        if (tot > recv_cap) { atomicAdd(flags + 1, tot - recv_cap); tot = recv_cap; }
+        go[st.n_parts] = (u32)tot;
+    }
+}
+
+__global__ void __launch_bounds__(128, 16) k_push_copy(StageView st, PushPeers peers, u64 recv_cap, const u32 *run_off, const u32 *grp_off, u32 rw)
+{
+    const u32 n = st.n_parts * st.n_cta;
+    const u32 lane = threadIdx.x & 31u;
+    const u64 n_warps = (u64)gridDim.x * (blockDim.x >> 5);
+    const u64 total = (u64)st.n_owners * n;
+    for (u64 e = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < total; e += n_warps) {
+        const u32 o = (u32)(e / n), p = (u32)(e - (u64)o * n);
+        if (o == st.me) continue;
+        const u32 g = p / st.n_cta, c = p - g * st.n_cta;
+        u64 cnt = st.count[(size_t)o * n + p];
+        if (cnt > st.sub_cap) cnt = st.sub_cap;
+        const u64 off = run_off[(size_t)o * n + p];
+        if (off + cnt > recv_cap) cnt = recv_cap - off;
+        const u64 *src = st.recs + st.sub_index(o, g, c) * st.sub_cap * rw;
+        u64 *dst = peers.recs[o] + off * rw;
+        const u64 words = cnt * rw;
+        u64 i = lane;
+        for (; i + 96 < words; i += 128) {                        // four independent 8-byte loads per lane in flight
+            const u64 x0 = ld_nc64(src + i), x1 = ld_nc64(src + i + 32), x2 = ld_nc64(src + i + 64), x3 = ld_nc64(src + i + 96);
+            dst[i] = x0; dst[i + 32] = x1; dst[i + 64] = x2; dst[i + 96] = x3;
+        }
+        for (; i < words; i += 32) dst[i] = ld_nc64(src + i);
+    }
+    // per-group offsets of this rank's run, for the receiver's work list
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < (u64)st.n_owners * (st.n_parts + 1); i += (u64)gridDim.x * blockDim.x) {
+        const u32 o = (u32)(i / (st.n_parts + 1));
+        if (o == st.me) continue;
+        peers.meta[o][i - (u64)o * (st.n_parts + 1)] = grp_off[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -542,11 +810,12 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_route_records(Rou
     extern __shared__ __align__(16) u32 smem_u32[];
     const u32 n_parts = a.stage.n_parts;
     u32 *cnt = smem_u32;
-    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) cnt[i] = a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x];
+    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) cnt[i] = a.stage.count[a.stage.cnt_index(a.stage.local_owner(), i, blockIdx.x)];
     __syncthreads();
     LocalCtr lc{0, 0, 0, 0, 0, 0};
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const u64 keep = l2_policy_evict_last();
+    u64 *const cbase = a.stage.recs + a.stage.sub_index(a.stage.local_owner(), 0, blockIdx.x) * a.stage.sub_cap * RW;
     for (u64 idx = (u64)blockIdx.x * 32u + (threadIdx.x & 31u) + (u64)(threadIdx.x >> 5) * 32u * gridDim.x; idx < a.n_recs; idx += stride) {
         Rec<W, HASX> rec;
 #pragma unroll
@@ -554,10 +823,10 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_route_records(Rou
         u64 key[W]; bool fwd; float wt; u32 eb;
         rec.unpack(key, fwd, wt, eb);
         const u64 ph = place_hash<W>(key);
-        stage_put<W, HASX>(a.stage, a.table, cnt, part_of(ph, a.table.n_parts) >> a.table.group_shift, rec, lc, keep);
+        stage_put<W, HASX>(cbase, a.stage.sub_cap, a.table, cnt, part_of(ph, a.table.n_parts) >> a.table.group_shift, rec, lc, keep);
     }
     __syncthreads();
-    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x] = cnt[i];
+    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) a.stage.count[a.stage.cnt_index(a.stage.local_owner(), i, blockIdx.x)] = cnt[i];
     ctr_commit(a.ctr, lc);
 }
 
@@ -575,20 +844,22 @@ __global__ void __launch_bounds__(256) k_count_positions(const u64 *read_off, co
 }
 
 // ------------------------------------------------------------------------------------------------
-// phase 2 work list over the (partition, phase-1 CTA) sub-regions in partition-major order:
-// chunk_start[e] = first chunk index of sub-region e (exclusive scan), single CTA
+// phase 2 work list: chunk_start[e] = first chunk index of entry e (exclusive scan over the entries of k_build_entries),
+// single CTA
 // ------------------------------------------------------------------------------------------------
-__global__ void k_build_worklist(const u32 *count, u32 sub_cap, u32 n_entries, u32 chunk, u64 *chunk_start, u64 *next_item)
+__global__ void k_build_worklist(const u32 *ent_cnt, u32 n_entries, u32 chunk, u64 *chunk_start, u64 *next_item)
 {
+    constexpr u32 IPT = 4;                       // entries per thread and step
     __shared__ u64 carry;
     __shared__ u64 wsum[32];
     if (threadIdx.x == 0) { carry = 0; *next_item = 0; }
     __syncthreads();
-    for (u32 base = 0; base < n_entries; base += blockDim.x) {
-        u32 p = base + threadIdx.x;
-        u64 n = 0;
-        if (p < n_entries) { u32 c = count[p]; if (c > sub_cap) c = sub_cap; n = (c + chunk - 1) / chunk; }
-        u64 v = n;
+    for (u32 base = 0; base < n_entries; base += blockDim.x * IPT) {
+        const u32 p0 = base + threadIdx.x * IPT;
+        u64 n[IPT], tot = 0;
+#pragma unroll
+        for (u32 q = 0; q < IPT; ++q) { n[q] = p0 + q < n_entries ? (ent_cnt[p0 + q] + chunk - 1) / chunk : 0; tot += n[q]; }
+        u64 v = tot;
         const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { u64 t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (u32)o) v += t; }
@@ -601,8 +872,10 @@ __global__ void k_build_worklist(const u32 *count, u32 sub_cap, u32 n_entries, u
             wsum[lane] = t;
         }
         __syncthreads();
-        u64 incl = v + (warp ? wsum[warp - 1] : 0) + carry;
-        if (p < n_entries) chunk_start[p] = incl - n;
+        const u64 incl = v + (warp ? wsum[warp - 1] : 0) + carry;
+        u64 run = incl - tot;
+#pragma unroll
+        for (u32 q = 0; q < IPT; ++q) { if (p0 + q < n_entries) chunk_start[p0 + q] = run; run += n[q]; }
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) carry = incl;
         __syncthreads();
@@ -610,24 +883,112 @@ __global__ void k_build_worklist(const u32 *count, u32 sub_cap, u32 n_entries, u
     if (threadIdx.x == 0) chunk_start[n_entries] = carry;
 }
 
+// phase-2 work list entries, group-major: for table group g first the n_cta local sub-regions of the staging set, then
+// (multi-GPU) one run per peer rank inside the receive buffer that peer pushed its records of this round into.
+// ent_ptr[e] = address of the entry's first record, ent_cnt[e] = its records.
 // ------------------------------------------------------------------------------------------------
-// K3: phase 2 of the count pass.  Persistent CTAs take (sub-region, chunk) items in partition order from an
-// atomic ticket, so at any time the whole GPU works on at most ~2 neighbouring partitions whose table
-// slices (slice_bytes each) stay L2-resident.  Per record: 16-B slot load, then CAS (new key) or RED (hit).
+struct RecvView {
+    const u64 *recs;      // [n_src][cap][RW]   this round's receive buffer (written by the peers over NVLink)
+    const u32 *meta;      // mode 0: [n_src][n_parts + 1] record offset of every group inside the source's run (exclusive prefix)
+                          // mode 1: [n_src][n_parts][n_cta] fill counters of the source's sub-regions
+    u64 cap;              // records per source
+    u32 n_src;            // ranks (0 = single GPU: no remote entries); the slot of this rank itself is unused
+    u32 me;
+    u32 mode;             // 0: one run per source, sorted by group (k_push_copy)
+                          // 1: verbatim copy of the source's [cta][group][sub_cap] part of its staging set (copy engines)
+    u32 pad;
+};
+
+__global__ void __launch_bounds__(256) k_build_entries(StageView st, RecvView rv, u32 rw, u64 *ent_ptr, u32 *ent_cnt)
+{
+    const u32 n_rem = rv.n_src > 1 ? (rv.n_src - 1) * (rv.mode == 1 ? st.n_cta : 1u) : 0;
+    const u32 per_group = st.n_cta + n_rem;
+    const u32 n_entries = st.n_parts * per_group;
+    const u32 lo = st.local_owner();
+    for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n_entries; e += gridDim.x * blockDim.x) {
+        const u32 g = e / per_group, j = e - g * per_group;
+        if (j < st.n_cta) {
+            u32 n = st.count[st.cnt_index(lo, g, j)];
+            if (n > st.sub_cap) n = st.sub_cap;                    // the excess was inserted directly by phase 1
+            ent_cnt[e] = n;
+            ent_ptr[e] = (u64)(st.recs + st.sub_index(lo, g, j) * st.sub_cap * rw);
+        } else if (rv.mode == 1) {
+            const u32 jj = j - st.n_cta;
+            u32 src = jj / st.n_cta;
+            const u32 cta = jj - src * st.n_cta;
+            if (src >= rv.me) ++src;
+            u32 n = rv.meta[((size_t)src * st.n_parts + g) * st.n_cta + cta];
+            if (n > st.sub_cap) n = st.sub_cap;
+            ent_cnt[e] = n;
+            ent_ptr[e] = (u64)(rv.recs + ((size_t)src * rv.cap + ((size_t)cta * st.n_parts + g) * st.sub_cap) * rw);
+        } else {
+            u32 src = j - st.n_cta;
+            if (src >= rv.me) ++src;
+            const u32 *m = rv.meta + (size_t)src * (st.n_parts + 1);
+            const u32 o0 = m[g], o1 = m[g + 1];
+            ent_cnt[e] = o1 - o0;
+            ent_ptr[e] = (u64)(rv.recs + ((size_t)src * rv.cap + o0) * rw);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: phase 2 of the count pass.  Persistent CTAs take (entry, chunk) items in group order from an atomic ticket, so at
+// any time the whole GPU works on at most ~2 neighbouring groups whose table slices (slice_bytes each) stay L2-resident.
 // Replaces KmerSpectrum::append (src/KmerSpectrum.h:1578-1668) + KmerMapByKmerArrayPair insert/find
 // (src/Kmer.h:1491-1544,3095-3110) + TrackingData::track (src/KmerTrackingData.h:427-448,517-529).
+//
+// The kernel is bound by dependent L2 round trips, not by instruction issue (ncu: 0.35 IPC per scheduler, long-scoreboard
+// stalls), so for single-word keys every thread runs its INSERT_UNROLL records through the probe sequence in LOCKSTEP:
+// one pass issues the next memory operation of every unresolved record (pair load, or CAS on an empty slot), the next
+// pass consumes all the answers.  A chunk then costs as many round trips as its longest probe chain (2-3) instead of
+// one chain after the other, and the records of the next chunk are already in flight while this one is resolved.
 // ------------------------------------------------------------------------------------------------
-template <int W, bool HASX, bool PRE>
-__global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, StageView st, const u64 *chunk_start, u64 *next_item, Counters *ctr)
+template <int W, bool HASX>
+__device__ __forceinline__ void track_extras(const TableView &t, u64 slot, float weight, u32 eb)
+{
+    if (HASX) {
+        if (t.wsum) atomicAdd(&t.wsum[slot], weight);
+        if (t.ext) {
+            const u32 l = eb & 7u, rr = (eb >> 3) & 7u;
+            if (l < 6) atomicAdd(&t.ext[slot * 12 + l], 1u);
+            if (rr < 6) atomicAdd(&t.ext[slot * 12 + 6 + rr], 1u);
+        }
+    }
+}
+
+template <int W, bool HASX>
+__global__ void __launch_bounds__(INSERT_TPB, KMN_INSERT_MIN_CTAS) k_insert_staged(TableView t, const u64 *ent_ptr, const u32 *ent_cnt, u32 n_entries,
+                                                                                    const u64 *chunk_start, u64 *next_item, Counters *ctr)
 {
     constexpr int RW = Rec<W, HASX>::RW;
+    constexpr int U = INSERT_UNROLL;
     __shared__ u64 s_item;
     __shared__ u32 s_entry;
     u64 n_unique = 0, n_full = 0, n_probes = 0;
-    const u32 n_entries = st.n_parts * st.n_cta;
     const u64 total_items = chunk_start[n_entries];
+
+    // chunk `item` of the work list: first record and record count (entry = hint, moved forward to the item's entry)
+    auto locate = [&](u64 item, u32 &entry, const u64 *&src, u32 &cnt) {
+        while (__ldg(&chunk_start[entry + 1]) <= item) ++entry;
+        const u64 first = (item - __ldg(&chunk_start[entry])) * INSERT_CHUNK;
+        const u64 n = __ldg(&ent_cnt[entry]);
+        src = reinterpret_cast<const u64 *>(__ldg(&ent_ptr[entry])) + first * RW;
+        cnt = (u32)(n - first < (u64)INSERT_CHUNK ? n - first : (u64)INSERT_CHUNK);
+    };
+    auto load = [&](const u64 *src, u32 cnt, Rec<W, HASX> (&r)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const u32 idx = (u32)u * INSERT_TPB + threadIdx.x;
+            if (idx < cnt) {
+#pragma unroll
+                for (int q = 0; q < RW; ++q) r[u].w[q] = ld_nc64(src + (size_t)idx * RW + q);
+            }
+        }
+    };
+
     while (true) {
-        // one ticket = INSERT_GROUP consecutive chunks; the sub-region of the first one is found by bisection (the upper
+        // one ticket = INSERT_GROUP consecutive chunks; the entry of the first one is found by bisection (the upper
         // levels of the search are the same lines for every ticket and stay in L1), the following ones by stepping
         if (threadIdx.x == 0) {
             const u64 it = atomicAdd(next_item, (u64)INSERT_GROUP);
@@ -643,63 +1004,105 @@ __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, Stage
         u32 entry = s_entry;
         __syncthreads();
         if (item0 >= total_items) break;
+        Rec<W, HASX> rec[U];
+        const u64 *src; u32 cnt;
+        locate(item0, entry, src, cnt);
+        load(src, cnt, rec);
 #pragma unroll 1
-      for (u32 g = 0; g < (u32)INSERT_GROUP; ++g) {
-        const u64 item = item0 + g;
-        if (item >= total_items) break;
-        while (__ldg(&chunk_start[entry + 1]) <= item) ++entry;
-        const u32 part = entry / st.n_cta;
-        u64 n = st.count[entry]; if (n > st.sub_cap) n = st.sub_cap;
-        const u64 first = (item - __ldg(&chunk_start[entry])) * INSERT_CHUNK;
-        const u64 *src = st.recs + (st.sub_index(part, entry - part * st.n_cta) * st.sub_cap + first) * RW;
-        const u64 cnt = n - first < (u64)INSERT_CHUNK ? n - first : (u64)INSERT_CHUNK;
-        Rec<W, HASX> rec[INSERT_UNROLL];
-        bool have[INSERT_UNROLL];
+        for (u32 g = 0; g < (u32)INSERT_GROUP; ++g) {
+            const u64 item = item0 + g;
+            if (item >= total_items) break;
+            Rec<W, HASX> rec_n[U];
+            u32 cnt_n = 0;
+            if (g + 1 < (u32)INSERT_GROUP && item + 1 < total_items) { locate(item + 1, entry, src, cnt_n); load(src, cnt_n, rec_n); }
+
+            if constexpr (W == 1) {
+                // lockstep probing.  state: 0 done, 1 pair load in flight, 2/3 CAS on slot 0/1 of the pair in flight
+                u64 want[U], k0[U], k1[U], add[U];
+                Slot<1> *sbase[U];
+                u32 s[U], pr[U], state[U], sat[U];
+                float weight[U]; u32 eb[U];
+                const u32 S = (u32)t.part_slots;
 #pragma unroll
-        for (int u = 0; u < INSERT_UNROLL; ++u) {
-            u64 idx = (u64)u * INSERT_TPB + threadIdx.x;
-            have[u] = idx < cnt;
-            if (have[u]) {
-#pragma unroll
-                for (int q = 0; q < RW; ++q) rec[u].w[q] = ld_nc64(src + idx * RW + q);
-            }
-        }
-        // PRE: home-slot loads of all records first (independent, all in flight together), then resolve one by one
-        u64 key[INSERT_UNROLL][W], home[INSERT_UNROLL], pv[INSERT_UNROLL], pk[INSERT_UNROLL];
-        bool fwd[INSERT_UNROLL]; float weight[INSERT_UNROLL]; u32 eb[INSERT_UNROLL]; u32 slice[INSERT_UNROLL];
-#pragma unroll
-        for (int u = 0; u < INSERT_UNROLL; ++u) {
-            pv[u] = pk[u] = 0; home[u] = 0; slice[u] = 0;
-            if (have[u]) {
-                rec[u].unpack(key[u], fwd[u], weight[u], eb[u]);
-                const u64 ph = place_hash<W>(key[u]);
-                slice[u] = part_of(ph, t.n_parts);                 // a slice of group `part`
-                home[u] = home_slot(ph, t.part_slots);
-                const Slot<W> *pbase = reinterpret_cast<const Slot<W> *>(t.slots) + (u64)slice[u] * t.part_slots;
-                if (PRE) {
-                    if (W == 1) ld_slot16(pbase + home[u], pv[u], pk[u]);
-                    else pv[u] = ld_cg64(&pbase[home[u]].val);
+                for (int u = 0; u < U; ++u) {
+                    state[u] = 0; pr[u] = 0; sat[u] = 0; k0[u] = k1[u] = 0; want[u] = 0; add[u] = 0; s[u] = 0; sbase[u] = nullptr; weight[u] = 0.f; eb[u] = 0;
+                    if ((u32)u * INSERT_TPB + threadIdx.x < cnt) {
+                        u64 key[1]; bool fwd;
+                        rec[u].unpack(key, fwd, weight[u], eb[u]);
+                        const u64 ph = place_hash<1>(key);
+                        sbase[u] = reinterpret_cast<Slot<1> *>(t.slots) + (u64)part_of(ph, t.n_parts) * S;
+                        s[u] = (u32)home_slot(ph, S) & ~1u;
+                        want[u] = ~key[0];
+                        add[u] = 1ull | ((u64)(fwd ? 1u : 0u) << 32);
+                        state[u] = 1;
+                        u64 v0, v1;
+                        ld_pair32(sbase[u] + s[u], v0, k0[u], v1, k1[u]);
+                        sat[u] = pair_sat(v0, v1);
+                    }
                 }
-            }
-        }
+                while (true) {
+                    bool pending = false;
 #pragma unroll
-        for (int u = 0; u < INSERT_UNROLL; ++u) {
-            if (have[u]) {
-                u64 slot; u32 probes = 0;
-                int r = table_insert<W, PRE>(t, slice[u], home[u], key[u], 1ull | ((u64)(fwd[u] ? 1u : 0u) << 32), &slot, &probes, pv[u], pk[u]);
-                if (r < 0) { n_full++; continue; }
-                n_unique += (u64)r; n_probes += probes;
-                if (HASX) {
-                    if (t.wsum) atomicAdd(&t.wsum[slot], weight[u]);
-                    if (t.ext) {
-                        u32 l = eb[u] & 7u, rr = (eb[u] >> 3) & 7u;
-                        if (l < 6) atomicAdd(&t.ext[slot * 12 + l], 1u);
-                        if (rr < 6) atomicAdd(&t.ext[slot * 12 + 6 + rr], 1u);
+                    for (int u = 0; u < U; ++u) {             // consume the answers
+                        if (state[u] == 0) continue;
+                        Slot<1> *pair = sbase[u] + s[u];
+                        int hit = -1;                          // slot of the pair that now holds this key
+                        bool fresh = false;
+                        if (state[u] == 1) {
+                            if (k0[u] == want[u]) hit = 0;
+                            else if (k0[u] == 0) state[u] = 2;
+                            else if (k1[u] == want[u]) hit = 1;
+                            else if (k1[u] == 0) state[u] = 3;
+                            else state[u] = 4;                 // both slots hold other keys: next pair
+                        } else {                               // CAS answer is in k0
+                            const u64 old = k0[u];
+                            const int h = (int)state[u] - 2;
+                            if (old == 0 || old == want[u]) { hit = h; fresh = old == 0; sat[u] = 0; }
+                            else if (h == 0) {                 // slot 0 went to another key meanwhile; slot 1 as loaded before
+                                if (k1[u] == want[u]) hit = 1;
+                                else if (k1[u] == 0) state[u] = 3;
+                                else state[u] = 4;
+                            } else state[u] = 4;
+                        }
+                        if (hit >= 0) {
+                            if (!((sat[u] >> hit) & 1u)) atomicAdd(&pair[hit].val, add[u]);
+                            if (fresh) n_unique++;
+                            n_probes += pr[u] + (u32)hit;
+                            track_extras<1, HASX>(t, (u64)(pair - reinterpret_cast<Slot<1> *>(t.slots)) + (u64)hit, weight[u], eb[u]);
+                            state[u] = 0;
+                        } else if (state[u] == 4) {
+                            pr[u] += 2;
+                            s[u] = s[u] + 2 >= S ? 0 : s[u] + 2;
+                            if (pr[u] >= S) { n_full++; state[u] = 0; } else state[u] = 1;
+                        }
+                        pending = pending || state[u] != 0;
+                    }
+                    if (!pending) break;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {             // issue the next operation of every unresolved record
+                        if (state[u] == 1) { u64 v0, v1; ld_pair32(sbase[u] + s[u], v0, k0[u], v1, k1[u]); sat[u] = pair_sat(v0, v1); }
+                        else if (state[u] >= 2) k0[u] = atomicCAS(&sbase[u][s[u] + (state[u] - 2)].k[0], 0ull, want[u]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if ((u32)u * INSERT_TPB + threadIdx.x < cnt) {
+                        u64 key[W]; bool fwd; float weight; u32 eb;
+                        rec[u].unpack(key, fwd, weight, eb);
+                        const u64 ph = place_hash<W>(key);
+                        u64 slot; u32 probes = 0;
+                        const int r = table_insert<W>(t, part_of(ph, t.n_parts), home_slot(ph, t.part_slots), key, 1ull | ((u64)(fwd ? 1u : 0u) << 32), &slot, &probes);
+                        if (r < 0) { n_full++; continue; }
+                        n_unique += (u64)r; n_probes += probes;
+                        track_extras<W, HASX>(t, slot, weight, eb);
                     }
                 }
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u) rec[u] = rec_n[u];
+            cnt = cnt_n;
         }
-      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -711,351 +1114,6 @@ __global__ void __launch_bounds__(INSERT_TPB) k_insert_staged(TableView t, Stage
         if (n_unique) atomicAdd(&ctr->unique, n_unique);
         if (n_full) atomicAdd(&ctr->table_full, n_full);
         if (n_probes) atomicAdd(&ctr->probe_steps, n_probes);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fast count path (k <= 31, plain TrackingDataWithDirection values): phase 2 in two levels, so that no k-mer instance
-// costs an individual L2/HBM transaction.  Measured on B200 (profiles/r01_randacc_microbench.csv): scattered 16-byte
-// loads run at ~145 G/s and scattered REDs at ~190 G/s even when L2-resident -- an SM-side limit on uncoalesced sector
-// requests -- so one load + one RED per instance caps the insert at ~77 G/s.  Here every instance is moved twice with
-// coalesced accesses (level 1: group, level 2: slice) and counted with shared-memory atomics (level 3).
-//
-// Level 2 (k_subpartition): a CTA takes a tile of SUB_TILE records of one group, counting-sorts it by slice in shared
-// memory (histogram -> scan -> scatter), reserves one range per slice bucket with a single global atomicAdd, and copies
-// the sorted tile out so that neighbouring lanes write neighbouring records of the same bucket.
-// ------------------------------------------------------------------------------------------------
-static constexpr int TS_TPB = 256;                   // threads of a tile-sorting CTA
-static constexpr int TS_R = 8;                       // records per thread
-static constexpr int TS_TILE = TS_TPB * TS_R;        // 2048 records per tile
-static constexpr int TS_MAX_BPT = 10;                // bins per thread in the scan: up to 2560 bins
-static constexpr u32 TS_NONE = 0xffffffffu;
-static constexpr int SUB_TILE = TS_TILE;
-
-__device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *warp_sums /*[TS_TPB/32]*/)
-{
-    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    u32 incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const u32 t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (u32)o) incl += t; }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        u32 t = lane < (TS_TPB >> 5) ? warp_sums[lane] : 0u;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const u32 q = __shfl_up_sync(0xffffffffu, t, o); if (lane >= (u32)o) t += q; }
-        if (lane < (TS_TPB >> 5)) warp_sums[lane] = t;             // inclusive over warps
-    }
-    __syncthreads();
-    return incl - v + (warp ? warp_sums[warp - 1] : 0u);
-}
-
-// Counting sort of one tile by bin, then a copy-out in sorted order.  Every thread brings up to TS_R records with their
-// bins (TS_NONE = no record).  PRE: hist[0..nb) is zero and a barrier has been passed since it was zeroed.
-//   reserve(bin, n, &room) -> address of the tile's first record in the bin's output region (called once per non-empty
-//                             bin by the thread that owns the bin in the scan); room = records that still fit there
-//   overflow(rec, bin) is called for records beyond `room`
-// Leaves no barrier pending: the caller must pass a barrier before it touches hist/buf/dst again.
-template <typename RESERVE, typename OVERFLOW>
-__device__ __forceinline__ void tile_sort_flush(const u64 (&rec)[TS_R], const u32 (&bin)[TS_R], u32 nb, u64 *buf, u64 *dst, u32 *hist, u64 *gptr,
-                                                u32 *room, u32 *wsum, u32 *s_total, RESERVE &&reserve, OVERFLOW &&overflow)
-{
-    u32 rank[TS_R];
-#pragma unroll
-    for (int u = 0; u < TS_R; ++u) rank[u] = bin[u] != TS_NONE ? atomicAdd(&hist[bin[u]], 1u) : 0u;
-    __syncthreads();
-    {
-        const u32 bpt = (nb + TS_TPB - 1) / TS_TPB;
-        const u32 b0 = threadIdx.x * bpt;
-        u32 tot = 0;
-        for (u32 q = 0; q < bpt; ++q) if (b0 + q < nb) tot += hist[b0 + q];
-        u32 run = block_exclusive_scan(tot, wsum);
-        for (u32 q = 0; q < bpt; ++q) {
-            const u32 b = b0 + q;
-            if (b < nb) {
-                const u32 c = hist[b];
-                hist[b] = run;
-                if (c) { u32 rm; gptr[b] = (u64)reserve(b, c, rm); room[b] = rm; }
-                run += c;
-            }
-        }
-        if (threadIdx.x == TS_TPB - 1) *s_total = run;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < TS_R; ++u) {
-        if (bin[u] != TS_NONE) {
-            const u32 pos = hist[bin[u]] + rank[u];
-            buf[pos] = rec[u];
-            dst[pos] = rank[u] < room[bin[u]] ? gptr[bin[u]] + 8ull * rank[u] : (u64)bin[u];   // bins are small numbers, never an address
-        }
-    }
-    __syncthreads();
-    const u32 total = *s_total;
-    for (u32 j = threadIdx.x; j < total; j += TS_TPB) {
-        const u64 d = dst[j], r = buf[j];
-        if (d >= 65536ull) *reinterpret_cast<u64 *>(d) = r;
-        else overflow(r, (u32)d);
-    }
-}
-
-// flat work list of level 2: item_entry[i] = staging sub-region of tile i (tiles of a sub-region are consecutive)
-__global__ void __launch_bounds__(256) k_fill_items(const u64 *chunk_start, u32 n_entries, u32 *item_entry)
-{
-    for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n_entries; e += gridDim.x * blockDim.x)
-        for (u64 i = chunk_start[e]; i < chunk_start[e + 1]; ++i) item_entry[i] = e;
-}
-
-__global__ void __launch_bounds__(TS_TPB, 4) k_subpartition(TableView t, StageView st, Stage2View s2, const u64 *chunk_start, const u32 *item_entry,
-                                                             Counters *ctr)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *buf = reinterpret_cast<u64 *>(smem_raw);          // [TS_TILE] records, sorted by slice
-    u64 *dst = buf + TS_TILE;                              // [TS_TILE] destination address of buf[j]
-    const u32 gp = 1u << t.group_shift;
-    u64 *gptr = dst + TS_TILE;                             // [gp]
-    u32 *hist = reinterpret_cast<u32 *>(gptr + gp);        // [gp]
-    u32 *room = hist + gp;                                 // [gp]
-    __shared__ u32 s_wsum[TS_TPB / 32];
-    __shared__ u32 s_total;
-    const u32 n_entries = st.n_parts * st.n_cta;
-    const u64 total_items = chunk_start[n_entries];
-    LocalCtr lc{0, 0, 0, 0, 0, 0};
-    for (u64 item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const u32 entry = __ldg(&item_entry[item]);
-        const u32 group = entry / st.n_cta;
-        u64 n = st.count[entry]; if (n > st.sub_cap) n = st.sub_cap;
-        const u64 first = (item - __ldg(&chunk_start[entry])) * TS_TILE;
-        const u64 *src = st.recs + st.sub_index(group, entry - group * st.n_cta) * st.sub_cap + first;
-        const u32 cnt = (u32)(n - first < (u64)TS_TILE ? n - first : (u64)TS_TILE);
-        const u32 slice0 = group << t.group_shift;
-        u64 rec[TS_R]; u32 sub[TS_R];
-#pragma unroll
-        for (int u = 0; u < TS_R; ++u) {
-            const u32 idx = (u32)u * TS_TPB + threadIdx.x;
-            rec[u] = idx < cnt ? ld_nc64(src + idx) : 0ull;
-        }
-        for (u32 i = threadIdx.x; i < gp; i += TS_TPB) hist[i] = 0;
-        __syncthreads();                                   // also orders the previous tile's copy-out before this tile's writes
-#pragma unroll
-        for (int u = 0; u < TS_R; ++u) {
-            const u32 idx = (u32)u * TS_TPB + threadIdx.x;
-            sub[u] = TS_NONE;
-            if (idx < cnt) { const u64 key[1] = {rec[u] & ~1ull}; sub[u] = part_of(place_hash<1>(key), t.n_parts) - slice0; }
-        }
-        tile_sort_flush(rec, sub, gp, buf, dst, hist, gptr, room, s_wsum, &s_total,
-            [&](u32 b, u32 c, u32 &rm) -> u64 * {
-                const u32 base = atomicAdd(&s2.count[slice0 + b], c);
-                rm = base < s2.cap ? s2.cap - base : 0u;
-                return s2.recs + (u64)(slice0 + b) * s2.cap + base;
-            },
-            [&](u64 r, u32) {                              // bucket full: insert directly (nothing else touches the table now)
-                Rec<1, false> rr; rr.w[0] = r;
-                insert_record<1, false>(t, rr, lc.unique, lc.full, lc.probes);
-                lc.direct++;
-            });
-    }
-    ctr_commit(ctr, lc);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Fast phase 1b (k_kmer_tiles): position-parallel k-mer extraction.  The batch's base bytes are cut into tiles of
-// TS_TILE positions; a CTA loads a tile (+ k-1 bytes of halo) and the tile's "counted" bits (phase 1a) into shared memory
-// with coalesced loads; every thread packs the 8+k-1 bases of its 8 consecutive positions to 2 bits (SWAR, a1:
-// TwoBitSequence::compressSequence src/TwoBitSequence.cpp:242-269), cuts the forward k-mer of each position out of the
-// packed window with a funnel shift, gets the reverse complement by bit reversal, takes the smaller (a2: KmerArrayPair::build,
-// buildLeastComplement src/Kmer.h:1323-1375,356-364) and hands the records to the tile sort, which writes each group's
-// records of the tile as one contiguous run into the CTA's sub-region of that group.  No read structure is needed: the
-// "counted" bit of a position is only set where a k-mer of a non-discarded read starts.
-// Multi-GPU: a record owned by another rank (a5: src/Kmer.h:2284-2295) sorts into bin n_groups + owner = that rank's send segment.
-// ------------------------------------------------------------------------------------------------
-struct TileArgs {
-    u64 byte0, byte1;      // positions [byte0, byte1) of the batch belong to this launch
-    u64 tile0;             // first tile (tile index = position / TS_TILE)
-    u64 n_tiles;
-};
-
-// 8 ASCII bases (little-endian in w: first base in the low byte) -> 16 bits, first base in the top two bits; markups -> A
-__device__ __forceinline__ u32 pack8(u64 w)
-{
-    const u64 up = w & 0xDFDFDFDFDFDFDFDFull;
-    const u64 valid = bytes_eq(up, 0x4141414141414141ull) | bytes_eq(up, 0x4343434343434343ull) |
-                      bytes_eq(up, 0x4747474747474747ull) | bytes_eq(up, 0x5454545454545454ull);
-    u64 c = (w >> 1) & 0x0303030303030303ull;
-    c ^= (c >> 1) & 0x0101010101010101ull;
-    c &= (valid >> 7) * 3ull;
-    c = ((c << 2) | (c >> 8)) & 0x000F000F000F000Full;            // nibble j = b(2j)<<2 | b(2j+1) at bit 16j
-    return (u32)((c * 0x1000010000100001ull) >> 48);
-}
-
-template <bool DIST>
-__global__ void __launch_bounds__(TS_TPB, 4) k_kmer_tiles(ParseArgs a, TileArgs ta)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *buf = reinterpret_cast<u64 *>(smem_raw);          // [TS_TILE]
-    u64 *dst = buf + TS_TILE;                              // [TS_TILE]
-    u64 *sb = dst + TS_TILE;                               // [TS_TILE/8 + 6] raw aligned words of the tile's bases (+ halo)
-    u32 *smask = reinterpret_cast<u32 *>(sb + TS_TILE / 8 + 6);   // [TS_TILE/32]
-    const u32 n_groups = a.stage.n_parts;
-    const u32 nb = n_groups + (DIST ? a.nranks : 0u);
-    u32 *hist = smask + TS_TILE / 32;                      // [nb]
-    u32 *room = hist + nb;                                 // [nb]
-    u32 *cnt = room + nb;                                  // [nb] fill level of this CTA's sub-regions / send segments
-    u64 *gptr = reinterpret_cast<u64 *>(cnt + nb + (nb & 1u));    // [nb]
-    __shared__ u32 s_wsum[TS_TPB / 32];
-    __shared__ u32 s_total;
-    for (u32 i = threadIdx.x; i < n_groups; i += TS_TPB) cnt[i] = a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x];
-    if (DIST) for (u32 i = threadIdx.x; i < a.nranks; i += TS_TPB) cnt[n_groups + i] = a.seg_count[(size_t)i * gridDim.x + blockIdx.x];
-    const u32 k = a.k;
-    const u64 keymask = ~0ull << a.pad;                    // top 2k bits
-    LocalCtr lc{0, 0, 0, 0, 0, 0};
-    const unsigned long long gbeg = (unsigned long long)a.bases, gend = gbeg + a.total_bytes;
-    for (u64 tile = ta.tile0 + blockIdx.x; tile < ta.tile0 + ta.n_tiles; tile += gridDim.x) {
-        const u64 g0 = tile * TS_TILE;
-        __syncthreads();                                   // previous tile's copy-out and window reads are complete
-        {   // aligned 8-byte words covering bytes [g0, g0 + TS_TILE + 40)
-            const unsigned long long A = gbeg + g0, A0 = A & ~7ull;
-            for (u32 i = threadIdx.x; i < TS_TILE / 8 + 6; i += TS_TPB) {
-                const unsigned long long q = A0 + 8ull * i;
-                sb[i] = (q + 8 > (gbeg & ~7ull) && q < ((gend + 7ull) & ~7ull)) ? ld_nc64(reinterpret_cast<const u64 *>(q)) : 0ull;
-            }
-            for (u32 i = threadIdx.x; i < TS_TILE / 32; i += TS_TPB) smask[i] = __ldg(&a.mask[(g0 >> 5) + i]);
-            for (u32 i = threadIdx.x; i < nb; i += TS_TPB) hist[i] = 0;
-        }
-        __syncthreads();
-        u64 rec[TS_R]; u32 bin[TS_R];
-#pragma unroll
-        for (int u = 0; u < TS_R; ++u) { rec[u] = 0; bin[u] = TS_NONE; }
-        const u32 p0 = threadIdx.x * TS_R;                 // first position of this thread inside the tile
-        u32 mbits = (smask[p0 >> 5] >> (p0 & 31u)) & 0xffu;
-        {   // positions outside [byte0, byte1) belong to another launch of the same batch
-            const u64 ap = g0 + p0;
-            if (ap + TS_R <= ta.byte0 || ap >= ta.byte1) mbits = 0;
-            else if (ap < ta.byte0 || ap + TS_R > ta.byte1) {
-#pragma unroll
-                for (int u = 0; u < TS_R; ++u) if (ap + u < ta.byte0 || ap + u >= ta.byte1) mbits &= ~(1u << u);
-            }
-        }
-        if (mbits) {
-            // the 40 bases starting at position p0: byte offset inside sb = (A & 7) + p0
-            const u32 bo = (u32)((gbeg + g0) & 7ull) + p0;
-            const u32 wi = bo >> 3, sh = (bo & 7u) * 8u;
-            u64 w[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) w[i] = sb[wi + i];
-            u32 v[5];
-#pragma unroll
-            for (int i = 0; i < 5; ++i) v[i] = pack8(sh ? (w[i] >> sh) | (w[i + 1] << (64u - sh)) : w[i]);
-            const u64 hi = ((u64)v[0] << 48) | ((u64)v[1] << 32) | ((u64)v[2] << 16) | (u64)v[3];
-            const u64 lo = (u64)v[4] << 48;
-#pragma unroll
-            for (int u = 0; u < TS_R; ++u) {
-                if ((mbits >> u) & 1u) {
-                    const u64 f = (u ? (hi << (2 * u)) | (lo >> (64 - 2 * u)) : hi) & keymask;
-                    u64 r = __brevll(~(f >> a.pad) & (~0ull >> a.pad));               // reversed bits, left-aligned, pairs swapped
-                    r = ((r & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((r & 0x5555555555555555ull) << 1);
-                    const bool fwd = f <= r;
-                    const u64 key[1] = {fwd ? f : r};
-                    rec[u] = key[0] | (fwd ? 1ull : 0ull);
-                    u32 b = part_of(place_hash<1>(key), a.table.n_parts) >> a.table.group_shift;
-                    if (DIST) {
-                        const u64 h = a.use_lookup8 ? hash_lookup8<1>(key, (int)a.kb) : hash_lookup3<1>(key, (int)a.kb);
-                        const u32 own = owner_of(h, a.nranks);
-                        if (own != a.rank) b = n_groups + own;
-                    }
-                    bin[u] = b;
-                }
-            }
-        }
-        (void)k;
-        tile_sort_flush(rec, bin, nb, buf, dst, hist, gptr, room, s_wsum, &s_total,
-            [&](u32 b, u32 c, u32 &rm) -> u64 * {
-                const u32 base = cnt[b]; cnt[b] = base + c;
-                if (!DIST || b < n_groups) {
-                    rm = base < a.stage.sub_cap ? a.stage.sub_cap - base : 0u;
-                    return a.stage.recs + a.stage.sub_index(b, blockIdx.x) * a.stage.sub_cap + base;
-                }
-                rm = base < a.seg_cap ? a.seg_cap - base : 0u;
-                return a.seg_recs + ((size_t)(b - n_groups) * gridDim.x + blockIdx.x) * a.seg_cap + base;
-            },
-            [&](u64 r, u32 b) {
-                if (b < n_groups) {                        // sub-region full: insert directly
-                    Rec<1, false> rr; rr.w[0] = r;
-                    insert_record<1, false>(a.table, rr, lc.unique, lc.full, lc.probes);
-                    lc.direct++;
-                }                                          // a full send segment is reported by k_compact_send (count > capacity)
-            });
-    }
-    __syncthreads();
-    for (u32 i = threadIdx.x; i < n_groups; i += TS_TPB) a.stage.count[(size_t)i * a.stage.n_cta + blockIdx.x] = cnt[i];
-    if (DIST) for (u32 i = threadIdx.x; i < a.nranks; i += TS_TPB) a.seg_count[(size_t)i * gridDim.x + blockIdx.x] = cnt[n_groups + i];
-    ctr_commit(a.ctr, lc);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Level 3 (k_count_slices): one CTA per table slice.  The slice (<= 64 KB) is brought into shared memory with
-// coalesced 16-byte loads (or zero-filled while the table is still clean), the slice's bucket is streamed through it --
-// probe with LDS, claim with a 64-bit shared CAS, count with 32-bit shared atomic adds on the two halves of the value
-// word -- and the slice is written back whole.  Replaces KmerSpectrum::append (src/KmerSpectrum.h:1578-1668) +
-// KmerMapByKmerArrayPair insert/find (src/Kmer.h:1491-1544,3095-3110) + TrackingDataWithDirection::track
-// (src/KmerTrackingData.h:427-448,517-529).
-// ------------------------------------------------------------------------------------------------
-static constexpr int CNT_TPB = 512;
-
-__global__ void __launch_bounds__(CNT_TPB, 3) k_count_slices(TableView t, Stage2View s2, u32 table_clean, Counters *ctr)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint4 *sl4 = reinterpret_cast<uint4 *>(smem_raw);
-    u64 *sl = reinterpret_cast<u64 *>(smem_raw);               // slot s: sl[2s] = value word, sl[2s+1] = ~key
-    const u32 S = (u32)t.part_slots;
-    const bool clean = table_clean && ctr->direct == 0;        // no direct insert has touched the table since the reset
-    u64 n_unique = 0, n_full = 0;
-    for (u32 p = blockIdx.x; p < t.n_parts; p += gridDim.x) {
-        u32 n = s2.count[p];
-        if (n == 0) continue;                                  // uniform over the CTA
-        if (n > s2.cap) n = s2.cap;
-        uint4 *g = reinterpret_cast<uint4 *>(t.slots) + (u64)p * S;
-        if (clean) { for (u32 i = threadIdx.x; i < S; i += CNT_TPB) sl4[i] = make_uint4(0, 0, 0, 0); }
-        else { for (u32 i = threadIdx.x; i < S; i += CNT_TPB) sl4[i] = __ldcs(g + i); }
-        __syncthreads();
-        const u64 *src = s2.recs + (u64)p * s2.cap;
-        for (u32 i = threadIdx.x; i < n; i += CNT_TPB) {
-            const u64 rec = ld_nc64(src + i);
-            const u64 key[1] = {rec & ~1ull};
-            const u64 want = ~key[0];
-            u32 s = (u32)home_slot(place_hash<1>(key), S);
-            bool done = false;
-            for (u32 probes = 0; probes < S; ++probes) {
-                u64 ck = *reinterpret_cast<volatile u64 *>(&sl[2 * s + 1]);
-                if (ck == 0ull) {
-                    const u64 old = atomicCAS(&sl[2 * s + 1], 0ull, want);
-                    if (old == 0ull) { n_unique++; ck = want; } else ck = old;
-                }
-                if (ck == want) {
-                    u32 *v32 = reinterpret_cast<u32 *>(&sl[2 * s]);
-                    if (*reinterpret_cast<volatile u32 *>(v32) < MAX_COUNT) {
-                        atomicAdd(v32, 1u);
-                        if (rec & 1ull) atomicAdd(v32 + 1, 1u);
-                    }
-                    done = true;
-                    break;
-                }
-                s = s + 1 == S ? 0 : s + 1;
-            }
-            if (!done) n_full++;
-        }
-        __syncthreads();
-        for (u32 i = threadIdx.x; i < S; i += CNT_TPB) __stcs(g + i, sl4[i]);
-        __syncthreads();
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
-        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (n_unique) atomicAdd(&ctr->unique, n_unique);
-        if (n_full) atomicAdd(&ctr->table_full, n_full);
     }
 }
 
