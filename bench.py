@@ -283,7 +283,8 @@ def main():
     # ---- e2e: host (pinned) buffers through the C ABI, H2D of every batch + D2H of the counters inside the timing ----
     e2e = None
     if not args.no_e2e:
-        n_e = min(args.e2e_reads or n_reads, n_reads)
+        # multi-GPU: a bounded sample per rank keeps the pinned host memory of N ranks on one box small
+        n_e = min(args.e2e_reads or (n_reads if world == 1 else max(n_reads // world, args.e2e_batch)), n_reads)
         hb = torch.empty(n_e * READ_LEN, dtype=torch.uint8, pin_memory=True)
         hq = torch.empty(n_e * READ_LEN, dtype=torch.uint8, pin_memory=True)
         hb.copy_(bases[: n_e * READ_LEN])

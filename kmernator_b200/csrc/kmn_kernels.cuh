@@ -276,7 +276,7 @@ __device__ __forceinline__ void walker_step(Walker<W> &s, const ParseArgs &a, co
         const bool has_zero_q = (((qin - zb) & ~qin) & 0x8080808080808080ull) != 0ull;
         if (j0 >= k && j0 + 8 <= s.len && (valid & 0x8080808080808080ull) == 0x8080808080808080ull && qdiff == 0ull && !has_zero_q &&
             (i0 & 1023u) != 0u && (i0 & 1023u) <= 1016u && s.w != 0.0 && s.last_bad < (int)i0) {
-#pragma unroll
+#pragma unroll 1
             for (int u = 0; u < 8; ++u) emit(i0 + u, s.roll.f, true, s.wf, s.good, 0x3fu);
             s.sb.advance();
             s.sqi.advance(); s.sqo.advance();
@@ -285,8 +285,9 @@ __device__ __forceinline__ void walker_step(Walker<W> &s, const ParseArgs &a, co
         }
     }
 
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    // the weights-only walker (KEYS == false) keeps this loop rolled: unrolled it is 110 KB of code and the kernel
+    // stalls on instruction fetch (ncu: "no instruction" was the top stall); the k-mer walkers want it unrolled
+    auto per_base = [&](const int u) {
         const u32 j = j0 + u;
         if (j < s.len) {
             if (!((valid >> (8 * u + 7)) & 1ull)) {                 // markup (rare)
@@ -350,6 +351,13 @@ __device__ __forceinline__ void walker_step(Walker<W> &s, const ParseArgs &a, co
                 emit(i, fwd ? s.roll.f : s.roll.r, fwd, NEED_W ? s.wf : 1.0f, NEED_W ? s.good : true, eb);
             }
         }
+    };
+    if constexpr (KEYS) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) per_base(u);
+    } else {
+#pragma unroll 1
+        for (int u = 0; u < 8; ++u) per_base(u);
     }
     s.sb.advance();
     if (NEED_Q) { s.sqi.advance(); s.sqo.advance(); }
@@ -462,7 +470,10 @@ __global__ void __launch_bounds__(MASK_TPB) k_weight_mask(ParseArgs a)
     uint4 *wbuf = reinterpret_cast<uint4 *>(mask_smem + (size_t)warp * MASK_WBUF);
     const u64 *wbuf64 = reinterpret_cast<const u64 *>(wbuf);
     u32 qn = 0;
-    for (u64 base = ((u64)blockIdx.x * (MASK_TPB / 32) + warp) * 32u; base < a.n_reads; base += n_warps * 32u) {
+    u64 base = ((u64)blockIdx.x * (MASK_TPB / 32) + warp) * 32u;
+    while (true) {
+        const bool more = base < a.n_reads;             // warp-uniform
+        if (more) {
         const u64 r = base + lane;
         const u32 nr = (u32)min((u64)32, a.n_reads - base);
         // offsets of the round's reads: lane l holds read_off[base + l], B1 = end of the last read
@@ -523,13 +534,17 @@ __global__ void __launch_bounds__(MASK_TPB) k_weight_mask(ParseArgs a)
         if (slow) q[qn + __popc(bal & ((1u << lane) - 1u))] = r;
         qn += __popc(bal);
         __syncwarp();
-        if (qn >= 32) {
-            qn -= 32;
-            weight_walk_read<WTS>(a, ptab, q[qn + lane], lc);
+        base += n_warps * 32u;
+        }
+        // one call site for the sequential walker (its code is large): a full warp of queued reads, or the rest at the end
+        if (qn >= 32 || (!more && qn > 0)) {
+            const u32 n = qn < 32u ? qn : 32u;
+            qn -= n;
+            if (lane < n) weight_walk_read<WTS>(a, ptab, q[qn + lane], lc);
             __syncwarp();
         }
+        if (!more && qn == 0) break;
     }
-    if (lane < qn) weight_walk_read<WTS>(a, ptab, q[lane], lc);
     ctr_commit(a.ctr, lc);
 }
 
@@ -621,14 +636,16 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
         const u32 len = (u32)(o1 - o0);
         if (len < a.k || (a.discarded && a.discarded[r])) continue;
         st.template begin<EXT>(a, o0, len);
-        u64 curw = o0 >> 5;                                            // mask word holding the current position's bit
-        u32 mw = __ldg(&a.mask[curw]), mwn = __ldg(&a.mask[curw + 1]);
+        // "counted" bits of phase 1a: a 64-bit window (mask words curw, curw+1) plus the following word, which is
+        // requested one whole step before it can be needed so that its latency never sits on the critical path
+        u64 curw = o0 >> 5;
+        u64 mbits = (u64)__ldg(&a.mask[curw]) | ((u64)__ldg(&a.mask[curw + 1]) << 32);
+        u32 pend = __ldg(&a.mask[curw + 2]);
+        u32 bits8 = 0, ifirst = 0;                                     // bits of k-mers ifirst .. ifirst+7 (this step's)
         auto emit = [&](u32 i, const u64 (&key)[W], bool fwd, float, bool, u32 eb) {
-            const u64 gb = o0 + i, w = gb >> 5;
-            if (w != curw) { curw = w; mw = mwn; mwn = __ldg(&a.mask[w + 1]); }
-            if (!((mw >> (u32)(gb & 31ull)) & 1u)) return;
+            if (!((bits8 >> (i - ifirst)) & 1u)) return;
             Rec<W, HASX> rec;
-            rec.pack(key, fwd, (HASX && a.wts) ? a.wts[gb] : 1.0f, eb);
+            rec.pack(key, fwd, (HASX && a.wts) ? a.wts[o0 + i] : 1.0f, eb);
             const u64 ph = place_hash<W>(key);
             const u32 group = part_of(ph, a.table.n_parts) >> a.table.group_shift;
             if (DIST != 0) {
@@ -664,7 +681,15 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
             }
             stage_put<W, HASX>(cbase, sub_cap, a.table, cnt, group, rec, lc, keep);
         };
-        while (st.j < st.len) walker_step<W, false, EXT>(st, a, nullptr, emit);
+        while (st.j < st.len) {
+            ifirst = st.j + 1 >= a.k ? st.j + 1 - a.k : 0u;            // first k-mer this step can emit
+            const u64 gb0 = o0 + ifirst;
+            if ((gb0 >> 5) != curw) { mbits = (mbits >> 32) | ((u64)pend << 32); ++curw; }
+            const u32 nxt = __ldg(&a.mask[curw + 2]);
+            bits8 = (u32)(mbits >> (u32)(gb0 & 31ull)) & 0xffu;
+            walker_step<W, false, EXT>(st, a, nullptr, emit);
+            pend = nxt;
+        }
     }
     __syncthreads();
     for (u32 i = threadIdx.x; i < n_bins; i += blockDim.x) {
