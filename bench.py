@@ -253,6 +253,15 @@ def main():
                        "frac": ALGO_BYTES_PER_INSTANCE * inst_per_rank / (ms_per_step * 1e-3) / 1e9 / peak},
     }
 
+    # ---- multi-GPU: the exchange (records pushed to their owners over NVLink), against 900 GB/s per direction ----
+    exchange = None
+    rt = prof.get("route")
+    if world > 1 and rt and rt["ms"] > 0 and rt["units"] > 0:
+        gbps = rt["units"] / (rt["ms"] * 1e-3) / 1e9
+        exchange = {"bytes_per_step_per_gpu": rt["units"] / args.steps, "copy_ms_per_step": rt["ms"] / args.steps, "GBps_while_copying": gbps,
+                    "frac_of_nvlink_900GBps": gbps / 900.0, "share_of_step": rt["ms"] / ms,
+                    "note": "copy-engine pushes of whole staging parts (capacity, incl. slack), overlapped with phase 1/2 on other streams"}
+
     # ---- lookup pass (FilterReads pass 2: per-read min-depth trim + score), device-resident reads, single GPU only ----
     lookup = None
     if world == 1 and not args.no_lookup:
@@ -343,7 +352,7 @@ def main():
                        "table_partitions": stats["table_partitions"], "stage_keys": stage_keys, "slice_mb": args.slice_mb,
                        "l2_policy": "inputs (30 GB) and table (>20 GB) exceed the 126 MB L2; table cleared every step",
                        "parallelism": "owner-sharded x%d" % world if world > 1 else "single GPU"},
-            "roofline": roofline, "lookup_pass": lookup, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "exchange": exchange, "lookup_pass": lookup, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "stats": {k: int(v) for k, v in stats.items()},
             "profile_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},

@@ -89,6 +89,8 @@ struct kmn_ctx {
     // buffers over NVLink (peer pointers from CUDA IPC), sorted by group, and inserted from there
     bool p2p = false;
     cudaStream_t s_comm = nullptr;        // push kernels + the NCCL barriers of a round
+    cudaStream_t s_comm2 = nullptr;       // second copy stream: half of the peers, so two copy engines feed NVLink at once
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void *recv_all = nullptr;             // [2 round buffers][nranks sources][push_cap records] + [2][nranks][n_groups+1] offsets
     void *peer_all[KMN_MAX_PUSH_RANKS] = {nullptr};   // recv_all of every peer (cudaIpcOpenMemHandle)
     uint64_t push_cap = 0;                // records per (round buffer, source)
@@ -98,6 +100,8 @@ struct kmn_ctx {
     u64 *flags = nullptr;                 // [0] records lost to a full remote sub-region, [1] records beyond push_cap
     u64 *d_const = nullptr;               // [0] = 0, [1] = 1, [2] = barrier scratch, [3] = sum of "done" flags
     uint64_t round = 0;
+    int round_split = 1;                  // launches per kernel class and round (KMN_ROUND_SPLIT; measured: no gain)
+    uint32_t cta_rot = 0;                 // first CTA of the next phase-1b launch
     cudaEvent_t ev_pushed[2] = {nullptr, nullptr}, ev_rb_free[2] = {nullptr, nullptr}, ev_recv[2] = {nullptr, nullptr};
     bool push_pending[2] = {false, false}, rb_busy[2] = {false, false};
 #ifdef KMN_WITH_NCCL
@@ -301,7 +305,7 @@ static int plan_and_alloc(kmn_ctx *c)
         CK(c, cudaMalloc((void **)&c->ent_ptr, max_entries * 8));
         CK(c, cudaMalloc((void **)&c->ent_cnt, max_entries * 4));
     }
-    CK(c, cudaMalloc((void **)&c->next_item, 8));
+    CK(c, cudaMalloc((void **)&c->next_item, 64));
     CK(c, cudaMalloc((void **)&c->ctr, sizeof(Counters)));
     CK(c, cudaMalloc((void **)&c->scratch, 64));
     CK(c, cudaMalloc((void **)&c->ptab, 256 * sizeof(double)));
@@ -427,6 +431,9 @@ void kmn_destroy(kmn_ctx *c)
     if (c->s_insert) cudaStreamSynchronize(c->s_insert);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->s_comm) cudaStreamSynchronize(c->s_comm);
+    if (c->s_comm2) { cudaStreamSynchronize(c->s_comm2); cudaStreamDestroy(c->s_comm2); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (int p = 0; p < KMN_MAX_PUSH_RANKS; ++p) if (c->peer_all[p] && p != c->rank) cudaIpcCloseMemHandle(c->peer_all[p]);
     if (c->p2p) { c->send_recs = nullptr; c->recv_recs = nullptr; }     // aliases of recv_all
 #ifdef KMN_WITH_NCCL
@@ -472,13 +479,14 @@ static int launch_insert(kmn_ctx *c, const StageView &v, int rb, uint64_t units,
     k_build_worklist<<<1, 1024, 0, si>>>(c->ent_cnt, n_entries, (u32)INSERT_CHUNK, c->chunk_start, c->next_item);
     c->launches += 2;
     const int grid = c->n_sms * c->insert_ctas;
-    {
-        ProfScope ps(c, KMN_PROF_INSERT, units, si);
+    const u32 n_split = rb >= 0 ? (u32)c->round_split : 1u;
+    for (u32 sp = 0; sp < n_split; ++sp) {
+        ProfScope ps(c, KMN_PROF_INSERT, sp == 0 ? units : 0, si);
         KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
-            k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, si>>>(c->table, c->ent_ptr, c->ent_cnt, n_entries, c->chunk_start, c->next_item, c->ctr);
+            k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, si>>>(c->table, c->ent_ptr, c->ent_cnt, n_entries, c->chunk_start, c->next_item, c->ctr, sp, n_split);
         }));
+        c->launches++;
     }
-    c->launches++;
     CK(c, cudaGetLastError());
     return 0;
 }
@@ -560,6 +568,8 @@ static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, cons
     a.send_recs = c->send_recs; a.send_cursor = c->send_cursor; a.send_cap = c->send_cap;
     a.seg_recs = c->seg_recs; a.seg_count = c->seg_count; a.seg_cap = (u32)c->seg_cap;
     a.flags = c->flags;
+    a.cta_rot = c->cta_rot;
+    c->cta_rot = (uint32_t)((c->cta_rot + (n_reads + 31) / 32) % (uint64_t)std::max(1, c->n_cta));
 }
 
 static int launch_parse(kmn_ctx *c, const ParseArgs &a)
@@ -750,7 +760,17 @@ static int setup_push(kmn_ctx *c)
     c->push_cap = cap;
     c->push_meta = meta_words;
     if (!c->s_insert || c->s_insert == c->stream) CK(c, cudaStreamCreateWithFlags(&c->s_insert, cudaStreamNonBlocking));
-    CK(c, cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
+    {   // the barrier kernels of a round are tiny but sit behind long persistent kernels: give them the first free SM
+        int lo_pri = 0, hi_pri = 0;
+        CK(c, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        CK(c, cudaStreamCreateWithPriority(&c->s_comm, cudaStreamNonBlocking, hi_pri));
+    }
+    if (const char *e = getenv("KMN_ROUND_SPLIT")) c->round_split = std::min(8, std::max(1, atoi(e)));
+    if (getenv("KMN_TWO_COPY_STREAMS")) {
+        CK(c, cudaStreamCreateWithFlags(&c->s_comm2, cudaStreamNonBlocking));
+        CK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CK(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
     for (int i = 0; i < 2; ++i) {
         CK(c, cudaEventCreateWithFlags(&c->ev_pushed[i], cudaEventDisableTiming));
         CK(c, cudaEventCreateWithFlags(&c->ev_rb_free[i], cudaEventDisableTiming));
@@ -792,15 +812,19 @@ static int push_round(kmn_ctx *c, int si, bool done, u64 *done_sum)
         // copy engines: the part of every other owner (whole sub-region capacity) and its fill counters go to that
         // owner's round buffer as they are; no SM takes part in the transfer
         const size_t n_sub = G * c->n_cta, part = n_sub * st.v.sub_cap * c->RW;          // u64 words per owner part
-        ProfScope ps(c, KMN_PROF_ROUTE, 0, sc);
+        ProfScope ps(c, KMN_PROF_ROUTE, (uint64_t)(R - 1) * (part * 8 + n_sub * 4), sc);      // units = bytes leaving this GPU
+        const bool two = c->s_comm2 != nullptr && R > 2;
+        if (two) { CK(c, cudaEventRecord(c->ev_fork, sc)); CK(c, cudaStreamWaitEvent(c->s_comm2, c->ev_fork, 0)); }
         for (int q = 1; q < R; ++q) {
             const int p = (c->rank + q) % R;                                             // start with a different peer on every rank
+            cudaStream_t scp = (two && (q & 1) == 0) ? c->s_comm2 : sc;
             u64 *base = (u64 *)c->peer_all[p];
             u64 *drec = base + ((size_t)rb * R + c->rank) * c->push_cap * c->RW;
             u32 *dmeta = (u32 *)(base + 2 * (size_t)R * c->push_cap * c->RW) + ((size_t)rb * R + c->rank) * c->push_meta;
-            CK(c, cudaMemcpyAsync(drec, st.v.recs + (size_t)p * part, part * 8, cudaMemcpyDeviceToDevice, sc));
-            CK(c, cudaMemcpyAsync(dmeta, st.v.count + (size_t)p * n_sub, n_sub * 4, cudaMemcpyDeviceToDevice, sc));
+            CK(c, cudaMemcpyAsync(drec, st.v.recs + (size_t)p * part, part * 8, cudaMemcpyDeviceToDevice, scp));
+            CK(c, cudaMemcpyAsync(dmeta, st.v.count + (size_t)p * n_sub, n_sub * 4, cudaMemcpyDeviceToDevice, scp));
         }
+        if (two) { CK(c, cudaEventRecord(c->ev_join, c->s_comm2)); CK(c, cudaStreamWaitEvent(sc, c->ev_join, 0)); }
     } else {
         PushPeers pp;
         memset(&pp, 0, sizeof pp);
@@ -1028,9 +1052,14 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
 #ifdef KMN_WITH_NCCL
         if (c->p2p) {                                       // one launch = one round: fill a set, push it, insert
             r = push_set_ready(c, c->cur); if (r) return r;
-            ParseArgs a;
-            fill_parse_args(c, a, bp.bases, bp.quals, bp.off + rg.r0, bp.disc ? bp.disc + rg.r0 : nullptr, rg.r1 - rg.r0, bp.total_bytes);
-            r = launch_parse(c, a); if (r) return r;
+            const uint64_t nr = rg.r1 - rg.r0, ns = (uint64_t)std::max(1, c->round_split);
+            for (uint64_t sp = 0; sp < ns; ++sp) {            // same set, several launches (see round_split)
+                const uint64_t q0 = rg.r0 + nr * sp / ns, q1 = rg.r0 + nr * (sp + 1) / ns;
+                if (q1 == q0) continue;
+                ParseArgs a;
+                fill_parse_args(c, a, bp.bases, bp.quals, bp.off + q0, bp.disc ? bp.disc + q0 : nullptr, q1 - q0, bp.total_bytes);
+                r = launch_parse(c, a); if (r) return r;
+            }
             r = push_round(c, c->cur, false, nullptr); if (r) return r;
             c->cur ^= 1;
             continue;
@@ -1430,6 +1459,7 @@ int kmn_profile_read(kmn_ctx *c, kmn_profile *out)
     if (!c || !out) return KMN_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
+    if (c->s_comm) CK(c, cudaStreamSynchronize(c->s_comm));
     if (c->s_insert != c->stream) CK(c, cudaStreamSynchronize(c->s_insert));
     for (auto &e : c->prof_events) {
         float ms = 0.f;
@@ -1449,6 +1479,7 @@ int kmn_sync(kmn_ctx *c)
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->s_copy));
     CK(c, cudaStreamSynchronize(c->stream));
+    if (c->s_comm) CK(c, cudaStreamSynchronize(c->s_comm));
     if (c->s_insert != c->stream) CK(c, cudaStreamSynchronize(c->s_insert));
     return 0;
 }

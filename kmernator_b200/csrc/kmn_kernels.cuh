@@ -54,6 +54,8 @@ struct ParseArgs {
     u32 nranks, rank;
     u32 use_lookup8;
     u32 l2_hints;          // staging stores carry an L2 evict_last policy
+    u32 cta_rot;           // phase 1b: the warp-sized pieces of this launch are dealt to CTAs starting at this CTA, so that a
+                           // sequence of small launches fills the per-CTA sub-regions evenly instead of always the first ones
     TableView table;
     StageView stage;
     Counters *ctr;
@@ -631,7 +633,8 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
     Walker<W> st;
     // consecutive groups of 32 reads (one warp) go to different CTAs, so even a small batch spreads evenly over the
     // per-CTA sub-regions / segments while a warp still streams one contiguous piece of the batch
-    for (u64 r = ((u64)(threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u); r < a.n_reads; r += stride) {
+    const u32 vblock = (blockIdx.x + gridDim.x - a.cta_rot % gridDim.x) % gridDim.x;
+    for (u64 r = ((u64)(threadIdx.x >> 5) * gridDim.x + vblock) * 32u + (threadIdx.x & 31u); r < a.n_reads; r += stride) {
         const u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
         const u32 len = (u32)(o1 - o0);
         if (len < a.k || (a.discarded && a.discarded[r])) continue;
@@ -877,7 +880,8 @@ __global__ void k_build_worklist(const u32 *ent_cnt, u32 n_entries, u32 chunk, u
     constexpr u32 IPT = 4;                       // entries per thread and step
     __shared__ u64 carry;
     __shared__ u64 wsum[32];
-    if (threadIdx.x == 0) { carry = 0; *next_item = 0; }
+    if (threadIdx.x == 0) carry = 0;
+    if (threadIdx.x < 8) next_item[threadIdx.x] = 0;          // one ticket counter per launch of a split phase 2
     __syncthreads();
     for (u32 base = 0; base < n_entries; base += blockDim.x * IPT) {
         const u32 p0 = base + threadIdx.x * IPT;
@@ -984,14 +988,21 @@ __device__ __forceinline__ void track_extras(const TableView &t, u64 slot, float
 
 template <int W, bool HASX>
 __global__ void __launch_bounds__(INSERT_TPB, KMN_INSERT_MIN_CTAS) k_insert_staged(TableView t, const u64 *ent_ptr, const u32 *ent_cnt, u32 n_entries,
-                                                                                    const u64 *chunk_start, u64 *next_item, Counters *ctr)
+                                                                                    const u64 *chunk_start, u64 *next_item, Counters *ctr,
+                                                                                    u32 split, u32 n_split)
 {
     constexpr int RW = Rec<W, HASX>::RW;
     constexpr int U = INSERT_UNROLL;
     __shared__ u64 s_item;
     __shared__ u32 s_entry;
     u64 n_unique = 0, n_full = 0, n_probes = 0;
-    const u64 total_items = chunk_start[n_entries];
+    // this launch covers the items [item_lo, total_items) of the work list's `split`-th part (the multi-GPU rounds cut
+    // phase 2 into several launches so that the small barrier kernels of the next round are not stuck behind it)
+    const u64 all_items = chunk_start[n_entries];
+    const u64 per_split = ((all_items + n_split - 1) / n_split + INSERT_GROUP - 1) / INSERT_GROUP * INSERT_GROUP;
+    const u64 item_lo = min(all_items, per_split * split);
+    const u64 total_items = min(all_items, item_lo + per_split);
+    next_item += split;
 
     // chunk `item` of the work list: first record and record count (entry = hint, moved forward to the item's entry)
     auto locate = [&](u64 item, u32 &entry, const u64 *&src, u32 &cnt) {
@@ -1016,7 +1027,7 @@ __global__ void __launch_bounds__(INSERT_TPB, KMN_INSERT_MIN_CTAS) k_insert_stag
         // one ticket = INSERT_GROUP consecutive chunks; the entry of the first one is found by bisection (the upper
         // levels of the search are the same lines for every ticket and stay in L1), the following ones by stepping
         if (threadIdx.x == 0) {
-            const u64 it = atomicAdd(next_item, (u64)INSERT_GROUP);
+            const u64 it = item_lo + atomicAdd(next_item, (u64)INSERT_GROUP);
             s_item = it;
             if (it < total_items) {
                 u32 lo = 0, hi = n_entries;

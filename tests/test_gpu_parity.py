@@ -172,6 +172,21 @@ def test_count_table_synthetic(K, k, n_reads, kw):
     ctx.close()
 
 
+def test_many_small_batches_spread_over_ctas(K):
+    """--batch-size-like input (MPI path of the reference: 8192 reads per batch, src/DistributedFunctions.h:360): a
+    long sequence of small batches must fill the per-CTA staging sub-regions evenly (no direct inserts) and count right"""
+    n_reads, per = 24000, 400
+    bases, q, off = synth.reads_numpy(n_reads, 150, 30000, seed=9, err=0.002, lowq=0.001)
+    ctx = K.Context(kmer_size=31, table_slots=1 << 22, stage_keys=1 << 22)
+    for r0 in range(0, n_reads, per):
+        b0, b1 = int(off[r0]), int(off[r0 + per])
+        ctx.count_batch(bases[b0:b1], q[b0:b1], np.ascontiguousarray(off[r0:r0 + per + 1] - off[r0]))
+    ctx.count_finish(apply_purge=False)
+    assert ctx.stats()["direct_inserts"] == 0
+    assert_tables_equal(ctx.export(), oracle_table(bases, q, off, 31, threads=4).export())
+    ctx.close()
+
+
 def test_count_saturation(K):
     """uint16 saturating count (KmerTrackingData.h:306): 70000 copies of one read -> every count == 65535"""
     seq = b"ACGTTGCAAGGCTTAACCGGATATCGCGATTACGGATCCA"
