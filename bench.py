@@ -243,7 +243,12 @@ def main():
     achieved = ALGO_BYTES_PER_INSERT * ins_units_per_launch / (ins_ms_per_launch * 1e-3) / 1e9 if ins["ms"] else 0.0
     roofline = {
         "bound": "hbm", "kernel": "k_insert_staged", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one k_insert_staged launch of this workload (1.477 G records),
+        # ncu --set full, profiles/r01ah_ncu_insert_c2_selected.csv: 31.0 GB read + 9.35 GB written.  Far below the
+        # algorithmic 64 B per record because the table group being filled stays L2-resident (the design's point).
+        "traffic": 40.35e9 if (world == 1 and n_reads == 100_000_000) else None, "traffic_unit": "bytes per launch",
+        "algorithmic_bytes_per_launch": ALGO_BYTES_PER_INSERT * ins_units_per_launch, "peak_source": peak_src,
         "algorithmic_bytes_per_unit": ALGO_BYTES_PER_INSERT, "units_per_launch": ins_units_per_launch,
         "ms_per_launch": ins_ms_per_launch, "launches": ins["launches"],
         "share_of_step": ins["ms"] / ms if ms else None,

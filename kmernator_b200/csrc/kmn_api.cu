@@ -60,6 +60,7 @@ struct kmn_ctx {
     uint64_t stage_keys = 0;          // record capacity of ONE set (= the sub-batch size of the pipeline)
     u64 *chunk_start = nullptr, *next_item = nullptr;
     u64 *ent_ptr = nullptr; u32 *ent_cnt = nullptr;     // phase-2 work list entries (k_build_entries)
+    u32 *coarse = nullptr;                              // entry of every 64th chunk of the work list
     uint64_t n_groups = 0;
     int insert_ctas = 8;              // phase-2 CTAs per SM
     Counters *ctr = nullptr;
@@ -304,6 +305,10 @@ static int plan_and_alloc(kmn_ctx *c)
         CK(c, cudaMalloc((void **)&c->chunk_start, (max_entries + 1) * 8));
         CK(c, cudaMalloc((void **)&c->ent_ptr, max_entries * 8));
         CK(c, cudaMalloc((void **)&c->ent_cnt, max_entries * 4));
+        // chunks of one drain <= records of a set / chunk + one partial chunk per entry (sets never grow after this point:
+        // the owner-cut sets of the multi-GPU paths hold the same stage_keys)
+        const size_t max_chunks = (size_t)(2 * c->stage_keys + (64ull << 20)) / INSERT_CHUNK + max_entries;
+        CK(c, cudaMalloc((void **)&c->coarse, ((max_chunks >> COARSE_SHIFT) + 16) * 4));
     }
     CK(c, cudaMalloc((void **)&c->next_item, 64));
     CK(c, cudaMalloc((void **)&c->ctr, sizeof(Counters)));
@@ -439,7 +444,7 @@ void kmn_destroy(kmn_ctx *c)
 #ifdef KMN_WITH_NCCL
     if (c->comm) ncclCommDestroy(c->comm);
 #endif
-    void *ptrs[] = {c->recv_all, c->run_off, c->grp_off, c->flags, c->d_const, c->ent_ptr, c->ent_cnt,c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
+    void *ptrs[] = {c->recv_all, c->run_off, c->grp_off, c->flags, c->d_const, c->ent_ptr, c->ent_cnt, c->coarse,c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
                     c->chunk_start, c->next_item,
                     c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts, c->seg_recs, c->seg_count,
                     c->in_bases[0].p, c->in_quals[0].p, c->in_off[0].p, c->in_disc[0].p,
@@ -476,14 +481,14 @@ static int launch_insert(kmn_ctx *c, const StageView &v, int rb, uint64_t units,
     }
     const u32 n_entries = v.n_parts * (v.n_cta + (rv.n_src > 1 ? (rv.n_src - 1) * (rv.mode == 1 ? v.n_cta : 1u) : 0));
     k_build_entries<<<std::min<u32>((n_entries + 255) / 256, (u32)c->n_sms * 4), 256, 0, si>>>(v, rv, (u32)c->RW, c->ent_ptr, c->ent_cnt);
-    k_build_worklist<<<1, 1024, 0, si>>>(c->ent_cnt, n_entries, (u32)INSERT_CHUNK, c->chunk_start, c->next_item);
+    k_build_worklist<<<1, 1024, 0, si>>>(c->ent_cnt, n_entries, (u32)INSERT_CHUNK, c->chunk_start, c->next_item, c->coarse);
     c->launches += 2;
     const int grid = c->n_sms * c->insert_ctas;
     const u32 n_split = rb >= 0 ? (u32)c->round_split : 1u;
     for (u32 sp = 0; sp < n_split; ++sp) {
         ProfScope ps(c, KMN_PROF_INSERT, sp == 0 ? units : 0, si);
         KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
-            k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, si>>>(c->table, c->ent_ptr, c->ent_cnt, n_entries, c->chunk_start, c->next_item, c->ctr, sp, n_split);
+            k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, si>>>(c->table, c->ent_ptr, c->ent_cnt, n_entries, c->chunk_start, c->coarse, c->next_item, c->ctr, sp, n_split);
         }));
         c->launches++;
     }

@@ -33,7 +33,8 @@ static constexpr int INSERT_TPB = 256;
 #endif
 static constexpr int INSERT_UNROLL = KMN_INSERT_UNROLL;
 static constexpr int INSERT_CHUNK = INSERT_TPB * INSERT_UNROLL;
-static constexpr int INSERT_GROUP = 4;      // chunks per ticket
+static constexpr int INSERT_GROUP = 4;      // chunks per ticket (8 measured no better)
+static constexpr int COARSE_SHIFT = 6;      // work-list index: one cell per 64 chunks
 #define KMN_MAX_PUSH_RANKS 16               // ranks of the NVLink push path (kernel-parameter arrays of peer pointers)
 
 struct ParseArgs {
@@ -875,7 +876,9 @@ __global__ void __launch_bounds__(256) k_count_positions(const u64 *read_off, co
 // phase 2 work list: chunk_start[e] = first chunk index of entry e (exclusive scan over the entries of k_build_entries),
 // single CTA
 // ------------------------------------------------------------------------------------------------
-__global__ void k_build_worklist(const u32 *ent_cnt, u32 n_entries, u32 chunk, u64 *chunk_start, u64 *next_item)
+// coarse[c] = the entry that holds chunk c << COARSE_SHIFT: a ticket finds its entry with one load and a bisection over
+// the few entries of its cell instead of a bisection over the whole list (which the whole CTA would wait for)
+__global__ void k_build_worklist(const u32 *ent_cnt, u32 n_entries, u32 chunk, u64 *chunk_start, u64 *next_item, u32 *coarse)
 {
     constexpr u32 IPT = 4;                       // entries per thread and step
     __shared__ u64 carry;
@@ -904,7 +907,14 @@ __global__ void k_build_worklist(const u32 *ent_cnt, u32 n_entries, u32 chunk, u
         const u64 incl = v + (warp ? wsum[warp - 1] : 0) + carry;
         u64 run = incl - tot;
 #pragma unroll
-        for (u32 q = 0; q < IPT; ++q) { if (p0 + q < n_entries) chunk_start[p0 + q] = run; run += n[q]; }
+        for (u32 q = 0; q < IPT; ++q) {
+            if (p0 + q < n_entries) {
+                chunk_start[p0 + q] = run;
+                const u64 step = 1ull << COARSE_SHIFT;
+                for (u64 m = (run + step - 1) & ~(step - 1); m < run + n[q]; m += step) coarse[m >> COARSE_SHIFT] = p0 + q;
+            }
+            run += n[q];
+        }
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) carry = incl;
         __syncthreads();
@@ -988,8 +998,8 @@ __device__ __forceinline__ void track_extras(const TableView &t, u64 slot, float
 
 template <int W, bool HASX>
 __global__ void __launch_bounds__(INSERT_TPB, KMN_INSERT_MIN_CTAS) k_insert_staged(TableView t, const u64 *ent_ptr, const u32 *ent_cnt, u32 n_entries,
-                                                                                    const u64 *chunk_start, u64 *next_item, Counters *ctr,
-                                                                                    u32 split, u32 n_split)
+                                                                                    const u64 *chunk_start, const u32 *coarse, u64 *next_item,
+                                                                                    Counters *ctr, u32 split, u32 n_split)
 {
     constexpr int RW = Rec<W, HASX>::RW;
     constexpr int U = INSERT_UNROLL;
@@ -1024,13 +1034,15 @@ __global__ void __launch_bounds__(INSERT_TPB, KMN_INSERT_MIN_CTAS) k_insert_stag
     };
 
     while (true) {
-        // one ticket = INSERT_GROUP consecutive chunks; the entry of the first one is found by bisection (the upper
-        // levels of the search are the same lines for every ticket and stay in L1), the following ones by stepping
+        // one ticket = INSERT_GROUP consecutive chunks; the entry of the first one comes from the coarse index (one load,
+        // then a bisection over the entries of that cell), the following ones by stepping
         if (threadIdx.x == 0) {
             const u64 it = item_lo + atomicAdd(next_item, (u64)INSERT_GROUP);
             s_item = it;
             if (it < total_items) {
-                u32 lo = 0, hi = n_entries;
+                const u64 cell = it >> COARSE_SHIFT, n_cells = (all_items + (1ull << COARSE_SHIFT) - 1) >> COARSE_SHIFT;
+                u32 lo = __ldg(&coarse[cell]);
+                u32 hi = cell + 1 < n_cells ? __ldg(&coarse[cell + 1]) + 1u : n_entries;
                 while (hi - lo > 1) { const u32 mid = lo + ((hi - lo) >> 1); if (__ldg(&chunk_start[mid]) <= it) lo = mid; else hi = mid; }
                 s_entry = lo;
             }
