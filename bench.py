@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lookup", action="store_true")
+    ap.add_argument("--no-checks", action="store_true")
     ap.add_argument("--lookup-reads", type=int, default=20_000_000)
     return ap.parse_args()
 
@@ -258,6 +259,26 @@ def main():
                        "frac": ALGO_BYTES_PER_INSTANCE * inst_per_rank / (ms_per_step * 1e-3) / 1e9 / peak},
     }
 
+    # ---- full-size parity properties (untimed): every counted instance is in the table exactly once ----
+    checks = None
+    if not args.no_checks:
+        ctx.reset()
+        ctx.count_batch(bases, quals, off_u64, n_reads=n_reads)
+        ctx.count_finish(apply_purge=False)
+        st0 = ctx.stats()
+        hist = ctx.histogram().astype(np.float64)           # all-reduced over ranks; exact in fp64 below 2^53
+        sum_counts = float((hist * np.arange(65536, dtype=np.float64)).sum())
+        tot = torch.tensor([st0["raw_kmers"], st0["raw_good_kmers"], st0["unique_kmers"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        raw_all, good_all, uniq_all = (float(x) for x in tot.tolist())
+        checks = {"instances_presented": raw_all, "instances_counted": good_all, "sum_of_table_counts": sum_counts,
+                  "distinct_kmers": uniq_all, "histogram_entries": float(hist.sum()),
+                  "sum_counts_equals_counted_instances": bool(sum_counts == good_all and hist[65535] == 0),
+                  "histogram_entries_equal_distinct": bool(hist.sum() == uniq_all),
+                  "presented_equals_reads_x_kmers": bool(raw_all == float(inst_per_rank) * world)}
+        step_device()                                        # leave the purged table of a normal step for the lookup pass
+
     # ---- multi-GPU: the exchange (records pushed to their owners over NVLink), against 900 GB/s per direction ----
     exchange = None
     rt = prof.get("route")
@@ -291,6 +312,8 @@ def main():
         lookup = {"value": n_lk / (lms * 1e-3), "unit": "kmer lookups/s", "reads": n_l, "ms_per_pass": lms,
                   "algorithmic_bytes_per_lookup": 33.25, "achieved_GBps": 33.25 * n_lk / (lms * 1e-3) / 1e9,
                   "frac_of_hbm_peak": 33.25 * n_lk / (lms * 1e-3) / 1e9 / peak,
+                  # scattered 16-byte loads from a 16 GiB table on this GPU (profiles/r01_randacc_microbench.csv): 18.3 G/s
+                  "x_measured_random_load_rate": n_lk / (lms * 1e-3) / 18.3e9,
                   "kept_reads_full_length": int((outs[1] == READ_LEN).sum().item()),
                   "profile_ms_per_pass": {k: v["ms"] / args.steps for k, v in lprof.items()}}
 
@@ -357,7 +380,7 @@ def main():
                        "table_partitions": stats["table_partitions"], "stage_keys": stage_keys, "slice_mb": args.slice_mb,
                        "l2_policy": "inputs (30 GB) and table (>20 GB) exceed the 126 MB L2; table cleared every step",
                        "parallelism": "owner-sharded x%d" % world if world > 1 else "single GPU"},
-            "roofline": roofline, "exchange": exchange, "lookup_pass": lookup, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "checks": checks, "exchange": exchange, "lookup_pass": lookup, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "stats": {k: int(v) for k, v in stats.items()},
             "profile_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},

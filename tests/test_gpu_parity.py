@@ -187,6 +187,37 @@ def test_many_small_batches_spread_over_ctas(K):
     ctx.close()
 
 
+def test_large_scale_invariants(K):
+    """sizes the oracle cannot finish: size-independent properties on 3 M reads generated in HBM --
+    every counted instance is in the table exactly once, a second build of the same input gives the same spectrum,
+    the min-depth-2 purge removes exactly the singletons"""
+    import torch
+    n_reads = 3_000_000
+    bases, quals, off = synth.reads_torch(n_reads, 150, 7_500_000, seed=5, device="cuda", read_seed=6)
+    ctx = K.Context(kmer_size=31, est_raw_kmers=n_reads * 120, table_slots=1 << 27, stage_keys=n_reads * 120 // 5)
+    hists = []
+    for _ in range(2):
+        ctx.reset()
+        ctx.count_batch(bases, quals, off, n_reads=n_reads)
+        ctx.count_finish(apply_purge=False)
+        st = ctx.stats()
+        h = ctx.histogram()
+        hists.append(h)
+        assert st["raw_kmers"] == n_reads * 120 and st["direct_inserts"] == 0
+        assert int((h.astype(np.float64) * np.arange(65536)).sum()) == st["raw_good_kmers"] and h[65535] == 0
+        assert int(h.sum()) == st["unique_kmers"] and int(h[1]) == st["singleton_kmers"]
+    assert (hists[0] == hists[1]).all()
+    ctx.purge_min_depth(2)
+    hp = ctx.histogram()
+    assert hp[1] == 0 and (hp[2:] == hists[0][2:]).all()
+    # the lookup pass sees what the table holds: a read made of genomic k-mers (depth 60) keeps its full length
+    outs = ctx.trim_batch(bases[: 150 * 100_000], off[: 100_001], 2, "MAX", n_reads=100_000)
+    assert (outs[1] == 150).mean() > 0.7 and outs[2].max() <= 65535
+    ctx.close()
+    del bases, quals, off
+    torch.cuda.empty_cache()
+
+
 def test_count_saturation(K):
     """uint16 saturating count (KmerTrackingData.h:306): 70000 copies of one read -> every count == 65535"""
     seq = b"ACGTTGCAAGGCTTAACCGGATATCGCGATTACGGATCCA"
