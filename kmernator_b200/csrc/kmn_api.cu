@@ -817,7 +817,7 @@ static int push_round(kmn_ctx *c, int si, bool done, u64 *done_sum)
         // copy engines: the part of every other owner (whole sub-region capacity) and its fill counters go to that
         // owner's round buffer as they are; no SM takes part in the transfer
         const size_t n_sub = G * c->n_cta, part = n_sub * st.v.sub_cap * c->RW;          // u64 words per owner part
-        ProfScope ps(c, KMN_PROF_ROUTE, (uint64_t)(R - 1) * (part * 8 + n_sub * 4), sc);      // units = bytes leaving this GPU
+        ProfScope ps(c, KMN_PROF_ROUTE, (uint64_t)(R - 1) * ((done ? 0 : part * 8) + n_sub * 4), sc);   // units = bytes leaving this GPU
         const bool two = c->s_comm2 != nullptr && R > 2;
         if (two) { CK(c, cudaEventRecord(c->ev_fork, sc)); CK(c, cudaStreamWaitEvent(c->s_comm2, c->ev_fork, 0)); }
         for (int q = 1; q < R; ++q) {
@@ -826,7 +826,8 @@ static int push_round(kmn_ctx *c, int si, bool done, u64 *done_sum)
             u64 *base = (u64 *)c->peer_all[p];
             u64 *drec = base + ((size_t)rb * R + c->rank) * c->push_cap * c->RW;
             u32 *dmeta = (u32 *)(base + 2 * (size_t)R * c->push_cap * c->RW) + ((size_t)rb * R + c->rank) * c->push_meta;
-            CK(c, cudaMemcpyAsync(drec, st.v.recs + (size_t)p * part, part * 8, cudaMemcpyDeviceToDevice, scp));
+            // a finishing round (this rank has no more input) has nothing staged: only the (zero) counters travel
+            if (!done) CK(c, cudaMemcpyAsync(drec, st.v.recs + (size_t)p * part, part * 8, cudaMemcpyDeviceToDevice, scp));
             CK(c, cudaMemcpyAsync(dmeta, st.v.count + (size_t)p * n_sub, n_sub * 4, cudaMemcpyDeviceToDevice, scp));
         }
         if (two) { CK(c, cudaEventRecord(c->ev_join, c->s_comm2)); CK(c, cudaStreamWaitEvent(sc, c->ev_join, 0)); }
