@@ -225,10 +225,6 @@ struct Roll {
 // add = 1 | (isFwd << 32)
 // returns: 0 updated existing, 1 claimed new, -1 partition full
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ld_slot16(const void *p, u64 &a, u64 &b)
-{
-    asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
-}
 __device__ __forceinline__ u64 ld_cg64(const void *p)
 {
     u64 v;

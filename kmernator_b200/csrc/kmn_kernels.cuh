@@ -1,23 +1,25 @@
 // kmn_kernels.cuh -- sm_100a kernels of the k-mer spectrum path.
 //
-//   count pass  = k_weight_mask  (phase 1a: quality weights along each read -> one "counted" bit per k-mer position)
-//               + k_kmer_scatter (phase 1b: bases -> canonical k-mers, position-parallel -> partitioned staging)
-//               + k_insert_staged (phase 2: per-partition inserts into an L2-resident table slice)
-//   lookup pass = k_lookup_vals + k_trim_score
-//   table scans = k_histogram, k_purge, k_export, k_count_singletons
+//   count pass  = k_weight_mask   (phase 1a: quality weights along each read -> one "counted" bit per k-mer position)
+//               + k_kmer_scatter  (phase 1b: bases -> canonical k-mers -> staging set partitioned by (owner,) table group)
+//               + k_build_entries / k_build_worklist / k_insert_staged (phase 2: group by group into L2-resident slices)
+//   multi-GPU   = k_push_plan / k_push_copy (records to their owners' receive buffers over NVLink; the default transport
+//                 uses copy engines instead), k_compact_send / k_route_records (NCCL fallback path)
+//   lookup pass = k_lookup_vals (+ _dist / k_lookup_words / k_scatter_answers) + k_trim_score
+//   table scans = k_histogram, k_purge, k_export, k_count_live
 //
 // Why two phases: on B200 a 64-bit atomic to an HBM-resident table runs at ~20 G/s while the same
 // atomic to a <=64 MB (L2-resident) region runs at 60-190 G/s (profiles/r01_randacc_microbench.csv).
 // Phase 1 therefore scatters every k-mer into one of n_parts staging regions (each phase-1 CTA owns a private
 // sub-region of every partition, addressed by shared-memory counters), and phase 2 walks the regions in order
-// so that only one table slice is hot.
+// so that only one table group is hot.
 #pragma once
 #include "kmn_device.cuh"
 #include <cooperative_groups.h>
 
 namespace kmn {
 
-static constexpr int MASK_TPB = 256;       // phase 1a: one thread per read
+static constexpr int MASK_TPB = 256;       // phase 1a: one warp per 32 reads
 #ifndef KMN_SCATTER_TPB
 #define KMN_SCATTER_TPB 1024
 #define KMN_SCATTER_CTAS 1
