@@ -116,7 +116,9 @@ int  kmn_purge_min_depth(kmn_ctx *ctx, uint32_t min_depth);
 int  kmn_histogram(kmn_ctx *ctx, uint64_t *hist65536, double *wsum65536);
 
 /* getElementIfExists(kmer).value().getCount()              src/ReadSelector.h:924-931
- * keys: n * key_bytes reference-format bytes (canonical); counts: n x u16 (0 = absent or purged).          */
+ * keys: n * key_bytes reference-format bytes (canonical); counts: n x u16 (0 = absent or purged).
+ * With a communicator the call is collective (every rank calls it, n may be 0): keys travel to their owners and the
+ * counts come back, as DistributedReadSelector::_batchKmerLookup does (src/DistributedFunctions.h:877-902).  */
 int  kmn_lookup(kmn_ctx *ctx, const uint8_t *keys, uint64_t n, uint16_t *counts);
 
 /* ReadSelector::scoreAndTrimReads(minDepth)               src/ReadSelector.h:1182-1209 (+:948-1180),

@@ -1186,13 +1186,52 @@ int kmn_histogram(kmn_ctx *c, uint64_t *hist, double *wsum)
     return 0;
 }
 
+#ifdef KMN_WITH_NCCL
+static int allreduce_max_u64(kmn_ctx *c, u64 mine, u64 *out);
+static int lookup_exchange(kmn_ctx *c, uint32_t min_depth, uint16_t *vals);
+#endif
+
 int kmn_lookup(kmn_ctx *c, const uint8_t *keys, uint64_t n, uint16_t *counts)
 {
     if (!c || (n && (!keys || !counts))) return KMN_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     int r = drain(c); if (r) return r;
+#ifdef KMN_WITH_NCCL
+    if (c->nranks > 1) {
+        // collective: every rank calls it (n may be 0); keys go to their owners in rounds of at most send_cap keys,
+        // as DistributedReadSelector::_batchKmerLookup does per batch (src/DistributedFunctions.h:877-902)
+        const u64 per = std::max<u64>(1, c->send_cap);
+        u64 rounds = 0;
+        r = allreduce_max_u64(c, (n + per - 1) / per, &rounds); if (r) return r;
+        if (rounds == 0) return 0;
+        r = ensure(c, c->lk_origin, (size_t)c->nranks * c->send_cap * 8); if (r) return r;
+        r = ensure(c, c->lk_resp_in, (size_t)c->nranks * c->send_cap * 2); if (r) return r;
+        const uint8_t *dk = keys;
+        if (n && !is_device_ptr(keys)) {
+            r = ensure(c, c->lk_keys, n * c->kb); if (r) return r;
+            CK(c, cudaMemcpyAsync(c->lk_keys.p, keys, n * c->kb, cudaMemcpyHostToDevice, c->stream));
+            dk = (const uint8_t *)c->lk_keys.p;
+        }
+        uint16_t *dout = counts;
+        const bool out_host = n && !is_device_ptr(counts);
+        if (out_host) { r = ensure(c, c->lk_out, n * 2); if (r) return r; dout = (uint16_t *)c->lk_out.p; }
+        ParseArgs a;
+        fill_parse_args(c, a, nullptr, nullptr, nullptr, nullptr, 0, 0);
+        for (u64 i = 0; i < rounds; ++i) {
+            const u64 k0 = std::min<u64>(n, i * per), k1 = std::min<u64>(n, (i + 1) * per);
+            if (k1 > k0) {
+                KMN_DISPATCH_W(c, { k_lookup_keys_dist<W_><<<c->n_sms * 8, 256, 0, c->stream>>>(a, dk + k0 * c->kb, k1 - k0, dout + k0, (u64 *)c->lk_origin.p); });
+                c->launches++;
+                CK(c, cudaGetLastError());
+            }
+            r = lookup_exchange(c, 0, k1 > k0 ? dout + k0 : nullptr); if (r) return r;
+        }
+        if (out_host) CK(c, cudaMemcpyAsync(counts, dout, n * 2, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+#endif
     if (n == 0) return 0;
-    if (c->nranks > 1) return fail(c, KMN_ERR_INVALID, "kmn_lookup with a communicator is not implemented yet (keys must be looked up on their owner)");
     const uint8_t *dk = keys;
     if (!is_device_ptr(keys)) {
         r = ensure(c, c->lk_keys, n * c->kb); if (r) return r;

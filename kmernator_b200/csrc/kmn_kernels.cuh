@@ -1285,6 +1285,33 @@ __global__ void __launch_bounds__(256) k_lookup_keys(TableView t, const uint8_t 
     }
 }
 
+// kmn_lookup with a communicator: a key owned by this rank is answered locally, any other key becomes a request in its
+// owner's send region (same protocol as k_lookup_vals_dist: key words out, u16 counts back in request order)
+template <int W>
+__global__ void __launch_bounds__(256) k_lookup_keys_dist(ParseArgs a, const uint8_t *keys, u64 n, uint16_t *out, u64 *origin)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 key[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) key[q] = 0;
+        for (u32 b = 0; b < a.kb; ++b) key[b >> 3] |= (u64)keys[i * a.kb + b] << (56 - 8 * (b & 7));
+        const u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
+        const u32 own = owner_of(h, a.nranks);
+        if (own == a.rank) {
+            const u64 ph = place_hash<W>(key);
+            out[i] = (uint16_t)clamp_count(table_find<W>(a.table, part_of(ph, a.table.n_parts), home_slot(ph, a.table.part_slots), key, nullptr));
+        } else {
+            const u64 pos = atomicAdd(&a.send_cursor[own], 1ull);
+            if (pos < a.send_cap) {
+                u64 *d = a.send_recs + ((size_t)own * a.send_cap + pos) * W;
+#pragma unroll
+                for (int q = 0; q < W; ++q) d[q] = key[q];
+                origin[(size_t)own * a.send_cap + pos] = i;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K7a: lookup pass, part 1.  One thread walks one read (no weights), probes the table for every
 // canonical k-mer and writes value(kmer) = count if count >= min_depth else 0 (setKmerValues,

@@ -77,6 +77,19 @@ def main():
         exact = np.bincount(o["count"], minlength=65536).astype(np.uint64)
         assert (hist == exact).all()
 
+        # kmn_lookup with a communicator (collective; getElementIfExists on a distributed map): every rank asks for a
+        # different sample of the k-mers, most of them owned by other ranks, plus keys that are in no table
+        okeys, ocnt = o["keys"], o["count"]
+        sel = np.arange(rank, len(okeys), 5)[:3000]
+        absent = np.random.default_rng(100 + rank).integers(0, 256, (40, okeys.shape[1]), dtype=np.uint8)
+        absent[:, -1] &= np.uint8((0xFF << (2 * ((4 - k % 4) % 4))) & 0xFF)
+        lut = {bytes(x): int(cn) for x, cn in zip(okeys, ocnt)}
+        ask = np.concatenate([okeys[sel], absent])
+        want = np.concatenate([ocnt[sel], np.array([lut.get(bytes(x), 0) for x in absent], dtype=ocnt.dtype)])
+        got_counts = ctx.lookup(ask if rank != world - 1 or not uneven else ask[:0])
+        if not (uneven and rank == world - 1):
+            assert (got_counts == want).all(), (k, "lookup")
+
         # lookup pass on this rank's reads, against the oracle on the same reads
         ctx.purge_min_depth(2)
         osp.purge_min_depth(2)
