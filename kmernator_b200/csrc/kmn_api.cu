@@ -336,6 +336,8 @@ int kmn_reset(kmn_ctx *c)
     if (!c) return KMN_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     int r = wait_drains(c); if (r) return r;          // phase-2 work still in flight must not see the cleared table
+    for (int si = 0; si < 2; ++si)                     // nor may a push still read the fill counters cleared below
+        if (c->push_pending[si]) { CK(c, cudaStreamWaitEvent(c->stream, c->ev_pushed[si], 0)); c->push_pending[si] = false; }
     CK(c, cudaMemsetAsync(c->table.slots, 0, c->n_slots * c->slot_bytes, c->stream));
     if (c->table.wsum) CK(c, cudaMemsetAsync(c->table.wsum, 0, c->n_slots * 4, c->stream));
     if (c->table.ext) CK(c, cudaMemsetAsync(c->table.ext, 0, c->n_slots * 48, c->stream));
@@ -710,6 +712,11 @@ static int setup_push(kmn_ctx *c)
     bool want = R <= KMN_MAX_PUSH_RANKS;
     if (const char *e = getenv("KMN_P2P")) want = want && atoi(e) != 0;
     const uint64_t G = c->n_groups;
+    {   // phase 1 keeps one shared-memory counter per (owner, group) bin
+        int dev_smem = 0;
+        CK(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+        if ((G * (uint64_t)R + 128) * 4 > (uint64_t)dev_smem / SCATTER_CTAS - 2048) want = false;
+    }
     c->push_ce = true;
     if (const char *e = getenv("KMN_PUSH")) c->push_ce = strcmp(e, "kernel") != 0;
     uint64_t cap = c->stage_keys / (uint64_t)R; cap += cap / 4 + 65536;
