@@ -214,6 +214,9 @@ static int alloc_stage_sets(kmn_ctx *c)
         kmn_ctx::StageSet &st = c->sets[si];
         if (st.v.recs) { CK(c, cudaFree(st.v.recs)); st.v.recs = nullptr; }
         if (st.v.count) { CK(c, cudaFree(st.v.count)); st.v.count = nullptr; }
+        if (st.v.ovf_recs) { CK(c, cudaFree(st.v.ovf_recs)); st.v.ovf_recs = nullptr; }
+        if (st.v.ovf_count) { CK(c, cudaFree(st.v.ovf_count)); st.v.ovf_count = nullptr; }
+        st.v.ovf_cap = 0;
     }
     CK(c, cudaMemGetInfo(&free_b, &total_b));
     const kmn_opts &o = c->o;
@@ -236,6 +239,13 @@ static int alloc_stage_sets(kmn_ctx *c)
         CK(c, cudaMalloc((void **)&st.v.recs, (size_t)n_own * n_groups * n_cta * sub_cap * c->RW * 8));
         CK(c, cudaMalloc((void **)&st.v.count, (size_t)n_own * n_groups * n_cta * 4));
         CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)n_own * n_groups * n_cta * 4, c->stream));
+        if (n_own > 1 && c->push_ce) {
+            // overflow list per owner: records of other owners whose sub-region was full travel ungrouped behind the part
+            st.v.ovf_cap = (u32)std::min<uint64_t>(65536 + sk / n_own / 256, 1u << 30);
+            CK(c, cudaMalloc((void **)&st.v.ovf_recs, (size_t)n_own * st.v.ovf_cap * c->RW * 8));
+            CK(c, cudaMalloc((void **)&st.v.ovf_count, (size_t)n_own * 4));
+            CK(c, cudaMemsetAsync(st.v.ovf_count, 0, (size_t)n_own * 4, c->stream));
+        }
         if (!st.ev_parsed) CK(c, cudaEventCreateWithFlags(&st.ev_parsed, cudaEventDisableTiming));
         if (!st.ev_drained) CK(c, cudaEventCreateWithFlags(&st.ev_drained, cudaEventDisableTiming));
         st.staged_upper = 0;
@@ -301,7 +311,7 @@ static int plan_and_alloc(kmn_ctx *c)
     c->n_groups = n_groups;
     { int r = alloc_stage_sets(c); if (r) return r; }
     {
-        const size_t max_entries = (size_t)n_groups * (size_t)c->n_cta * KMN_MAX_PUSH_RANKS;
+        const size_t max_entries = (size_t)n_groups * (size_t)c->n_cta * KMN_MAX_PUSH_RANKS + 64;
         CK(c, cudaMalloc((void **)&c->chunk_start, (max_entries + 1) * 8));
         CK(c, cudaMalloc((void **)&c->ent_ptr, max_entries * 8));
         CK(c, cudaMalloc((void **)&c->ent_cnt, max_entries * 4));
@@ -344,6 +354,7 @@ int kmn_reset(kmn_ctx *c)
     for (int si = 0; si < c->n_sets; ++si) {
         kmn_ctx::StageSet &st = c->sets[si];
         CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)st.v.n_owners * st.v.n_parts * st.v.n_cta * 4, c->stream));
+        if (st.v.ovf_count) CK(c, cudaMemsetAsync(st.v.ovf_count, 0, (size_t)st.v.n_owners * 4, c->stream));
         st.staged_upper = 0;
     }
     if (c->flags) CK(c, cudaMemsetAsync(c->flags, 0, 16, c->stream));
@@ -446,7 +457,7 @@ void kmn_destroy(kmn_ctx *c)
 #ifdef KMN_WITH_NCCL
     if (c->comm) ncclCommDestroy(c->comm);
 #endif
-    void *ptrs[] = {c->recv_all, c->run_off, c->grp_off, c->flags, c->d_const, c->ent_ptr, c->ent_cnt, c->coarse,c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
+    void *ptrs[] = {c->sets[0].v.ovf_recs, c->sets[0].v.ovf_count, c->sets[1].v.ovf_recs, c->sets[1].v.ovf_count, c->recv_all, c->run_off, c->grp_off, c->flags, c->d_const, c->ent_ptr, c->ent_cnt, c->coarse,c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
                     c->chunk_start, c->next_item,
                     c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts, c->seg_recs, c->seg_count,
                     c->in_bases[0].p, c->in_quals[0].p, c->in_off[0].p, c->in_disc[0].p,
@@ -480,8 +491,10 @@ static int launch_insert(kmn_ctx *c, const StageView &v, int rb, uint64_t units,
         rv.recs = (const u64 *)c->recv_all + (size_t)rb * R * c->push_cap * c->RW;
         rv.meta = (const u32 *)((const u64 *)c->recv_all + 2 * R * c->push_cap * c->RW) + (size_t)rb * R * c->push_meta;
         rv.cap = c->push_cap; rv.n_src = (u32)R; rv.me = (u32)c->rank; rv.mode = c->push_ce ? 1u : 0u;
+        rv.ovf_cap = v.ovf_cap; rv.part_recs = (u64)v.n_cta * v.n_parts * v.sub_cap; rv.meta_stride = c->push_meta;
     }
-    const u32 n_entries = v.n_parts * (v.n_cta + (rv.n_src > 1 ? (rv.n_src - 1) * (rv.mode == 1 ? v.n_cta : 1u) : 0));
+    const u32 n_entries = v.n_parts * (v.n_cta + (rv.n_src > 1 ? (rv.n_src - 1) * (rv.mode == 1 ? v.n_cta : 1u) : 0)) +
+                          (rv.mode == 1 && rv.n_src > 1 ? rv.n_src - 1 : 0u);
     k_build_entries<<<std::min<u32>((n_entries + 255) / 256, (u32)c->n_sms * 4), 256, 0, si>>>(v, rv, (u32)c->RW, c->ent_ptr, c->ent_cnt);
     k_build_worklist<<<1, 1024, 0, si>>>(c->ent_cnt, n_entries, (u32)INSERT_CHUNK, c->chunk_start, c->next_item, c->coarse);
     c->launches += 2;
@@ -575,8 +588,12 @@ static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, cons
     a.send_recs = c->send_recs; a.send_cursor = c->send_cursor; a.send_cap = c->send_cap;
     a.seg_recs = c->seg_recs; a.seg_count = c->seg_count; a.seg_cap = (u32)c->seg_cap;
     a.flags = c->flags;
+    // pieces of 32 reads for large launches; smaller pieces when that would leave CTAs without work (at least 2 per CTA)
+    uint32_t ps = 5;
+    while (ps > 0 && (n_reads >> ps) < 2ull * (uint64_t)std::max(1, c->n_cta)) --ps;
+    a.piece_shift = ps;
     a.cta_rot = c->cta_rot;
-    c->cta_rot = (uint32_t)((c->cta_rot + (n_reads + 31) / 32) % (uint64_t)std::max(1, c->n_cta));
+    c->cta_rot = (uint32_t)((c->cta_rot + ((n_reads + (1ull << ps) - 1) >> ps)) % (uint64_t)std::max(1, c->n_cta));
 }
 
 static int launch_parse(kmn_ctx *c, const ParseArgs &a)
@@ -729,8 +746,8 @@ static int setup_push(kmn_ctx *c)
         c->p2p = true;
         int r = alloc_stage_sets(c); if (r) return r;
         c->p2p = false;
-        cap = (uint64_t)c->n_cta * G * c->sets[0].v.sub_cap;
-        meta_words = (size_t)G * c->n_cta;
+        cap = (uint64_t)c->n_cta * G * c->sets[0].v.sub_cap + c->sets[0].v.ovf_cap;
+        meta_words = (size_t)G * c->n_cta + 1;
     }
     const size_t rec_bytes = 2 * (size_t)R * cap * c->RW * 8, meta_bytes = 2 * (size_t)R * meta_words * 4;
     u64 ok = want ? 1 : 0;
@@ -750,6 +767,20 @@ static int setup_push(kmn_ctx *c)
         CK(c, cudaMemcpyAsync(all.data(), d, (size_t)R * 64, cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
         CK(c, cudaFree(d));
+    }
+    {   // the peers write straight into each other's buffers: the layout (groups, CTAs, sub-region capacity, record
+        // width) must be the same on every rank, otherwise everybody stays on the NCCL path, which re-buckets on arrival
+        u64 geo[6] = {G, (u64)c->n_cta, (u64)c->sets[0].v.sub_cap, (u64)c->RW, cap, (u64)meta_words};
+        void *d = nullptr;
+        CK(c, cudaMalloc(&d, (size_t)(R + 1) * sizeof geo));
+        CK(c, cudaMemcpyAsync((char *)d + (size_t)R * sizeof geo, geo, sizeof geo, cudaMemcpyHostToDevice, c->stream));
+        ncclResult_t nr = ncclAllGather((char *)d + (size_t)R * sizeof geo, d, 6, ncclUint64, c->comm, c->stream);
+        if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclAllGather failed: %s", ncclGetErrorString(nr));
+        std::vector<u64> allgeo((size_t)R * 6);
+        CK(c, cudaMemcpyAsync(allgeo.data(), d, (size_t)R * sizeof geo, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, cudaFree(d));
+        for (int p = 0; p < R; ++p) if (memcmp(&allgeo[(size_t)p * 6], geo, sizeof geo) != 0) ok = 0;
     }
     u64 all_ok = 0;
     { int r = nccl_sum_u64(c, ok, &all_ok, c->stream); if (r) return r; }
@@ -834,8 +865,12 @@ static int push_round(kmn_ctx *c, int si, bool done, u64 *done_sum)
             u64 *drec = base + ((size_t)rb * R + c->rank) * c->push_cap * c->RW;
             u32 *dmeta = (u32 *)(base + 2 * (size_t)R * c->push_cap * c->RW) + ((size_t)rb * R + c->rank) * c->push_meta;
             // a finishing round (this rank has no more input) has nothing staged: only the (zero) counters travel
-            if (!done) CK(c, cudaMemcpyAsync(drec, st.v.recs + (size_t)p * part, part * 8, cudaMemcpyDeviceToDevice, scp));
+            if (!done) {
+                CK(c, cudaMemcpyAsync(drec, st.v.recs + (size_t)p * part, part * 8, cudaMemcpyDeviceToDevice, scp));
+                if (st.v.ovf_cap) CK(c, cudaMemcpyAsync(drec + part, st.v.ovf_recs + (size_t)p * st.v.ovf_cap * c->RW, (size_t)st.v.ovf_cap * c->RW * 8, cudaMemcpyDeviceToDevice, scp));
+            }
             CK(c, cudaMemcpyAsync(dmeta, st.v.count + (size_t)p * n_sub, n_sub * 4, cudaMemcpyDeviceToDevice, scp));
+            if (st.v.ovf_cap) CK(c, cudaMemcpyAsync(dmeta + n_sub, st.v.ovf_count + p, 4, cudaMemcpyDeviceToDevice, scp));
         }
         if (two) { CK(c, cudaEventRecord(c->ev_join, c->s_comm2)); CK(c, cudaStreamWaitEvent(sc, c->ev_join, 0)); }
     } else {
@@ -855,6 +890,7 @@ static int push_round(kmn_ctx *c, int si, bool done, u64 *done_sum)
         const size_t n_sub = G * c->n_cta;
         if (c->rank > 0) CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)c->rank * n_sub * 4, sc));
         if (c->rank + 1 < R) CK(c, cudaMemsetAsync(st.v.count + (size_t)(c->rank + 1) * n_sub, 0, (size_t)(R - 1 - c->rank) * n_sub * 4, sc));
+        if (st.v.ovf_count) CK(c, cudaMemsetAsync(st.v.ovf_count, 0, (size_t)R * 4, sc));
     }
     CK(c, cudaEventRecord(c->ev_pushed[si], sc));
     c->push_pending[si] = true;

@@ -49,6 +49,10 @@ struct StageView {        // level-1 staging area of k-mer records, partitioned 
     u32 pad;
     u32 n_owners;         // 1, or the number of ranks when phase 1 bins by owner as well (multi-GPU push path)
     u32 me;               // this rank (index of the local owner when n_owners > 1)
+    u64 *ovf_recs;        // [n_owners][ovf_cap][RW] records of OTHER owners that found their sub-region full (skewed input:
+    u32 *ovf_count;       // [n_owners]              one read with very many k-mers, few distinct bins); shipped ungrouped
+    u32 ovf_cap;          // 0: no overflow list (a full remote sub-region is then an error)
+    u32 pad2;
     __device__ __host__ __forceinline__ u32 local_owner() const { return n_owners > 1 ? me : 0u; }
     __device__ __host__ __forceinline__ size_t sub_index(u32 owner, u32 part, u32 cta) const
     {

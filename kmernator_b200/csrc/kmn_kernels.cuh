@@ -57,8 +57,10 @@ struct ParseArgs {
     u32 nranks, rank;
     u32 use_lookup8;
     u32 l2_hints;          // staging stores carry an L2 evict_last policy
-    u32 cta_rot;           // phase 1b: the warp-sized pieces of this launch are dealt to CTAs starting at this CTA, so that a
+    u32 cta_rot;           // phase 1b: the pieces of this launch are dealt to CTAs starting at this CTA, so that a
                            // sequence of small launches fills the per-CTA sub-regions evenly instead of always the first ones
+    u32 piece_shift;       // log2(reads per piece), 5 for large launches; small launches use smaller pieces so that they
+                           // still spread over all CTAs (the sub-region capacities assume an even spread)
     TableView table;
     StageView stage;
     Counters *ctr;
@@ -637,7 +639,13 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
     // consecutive groups of 32 reads (one warp) go to different CTAs, so even a small batch spreads evenly over the
     // per-CTA sub-regions / segments while a warp still streams one contiguous piece of the batch
     const u32 vblock = (blockIdx.x + gridDim.x - a.cta_rot % gridDim.x) % gridDim.x;
-    for (u64 r = ((u64)(threadIdx.x >> 5) * gridDim.x + vblock) * 32u + (threadIdx.x & 31u); r < a.n_reads; r += stride) {
+    // piece q of a sweep goes to warp slot q % T (T slots = CTAs x warps, CTA index fastest), lanes take 32/p pieces of p reads
+    const u32 p_shift = a.piece_shift, lane_in = threadIdx.x & 31u;
+    const u64 n_slots = (u64)gridDim.x * (blockDim.x >> 5);
+    const u64 in_sweep = (((u64)(lane_in >> p_shift) * n_slots + (u64)(threadIdx.x >> 5) * gridDim.x + vblock) << p_shift) + (lane_in & ((1u << p_shift) - 1u));
+    for (u64 sweep0 = 0; sweep0 < a.n_reads; sweep0 += stride) {
+        const u64 r = sweep0 + in_sweep;
+        if (r >= a.n_reads) continue;
         const u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
         const u32 len = (u32)(o1 - o0);
         if (len < a.k || (a.discarded && a.discarded[r])) continue;
@@ -666,7 +674,14 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
                     } else if (own == a.rank) {
                         insert_record<W, HASX>(a.table, rec, lc.unique, lc.full, lc.probes);
                         lc.direct++;
-                    } else lost++;
+                    } else {                                           // full remote sub-region: the owner's overflow list
+                        const u32 op = a.stage.ovf_cap ? atomicAdd(&a.stage.ovf_count[own], 1u) : 0u;
+                        if (op < a.stage.ovf_cap) {
+                            u64 *d = a.stage.ovf_recs + ((size_t)own * a.stage.ovf_cap + op) * RW;
+#pragma unroll
+                            for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
+                        } else lost++;
+                    }
                     return;
                 }
                 if (own != a.rank) {
@@ -936,17 +951,30 @@ struct RecvView {
     u32 n_src;            // ranks (0 = single GPU: no remote entries); the slot of this rank itself is unused
     u32 me;
     u32 mode;             // 0: one run per source, sorted by group (k_push_copy)
-                          // 1: verbatim copy of the source's [cta][group][sub_cap] part of its staging set (copy engines)
-    u32 pad;
+                          // 1: verbatim copy of the source's [cta][group][sub_cap] part of its staging set (copy engines),
+                          //    followed by the source's overflow list for this rank (ovf_cap records, ungrouped)
+    u32 ovf_cap;
+    u64 part_recs;        // mode 1: records of the part proper (n_cta * n_parts * sub_cap)
+    u64 meta_stride;      // u32 words of meta per source (mode 1: n_parts * n_cta counters + the overflow count)
 };
 
 __global__ void __launch_bounds__(256) k_build_entries(StageView st, RecvView rv, u32 rw, u64 *ent_ptr, u32 *ent_cnt)
 {
     const u32 n_rem = rv.n_src > 1 ? (rv.n_src - 1) * (rv.mode == 1 ? st.n_cta : 1u) : 0;
     const u32 per_group = st.n_cta + n_rem;
-    const u32 n_entries = st.n_parts * per_group;
+    const u32 n_grouped = st.n_parts * per_group;
+    const u32 n_entries = n_grouped + (rv.mode == 1 && rv.n_src > 1 ? rv.n_src - 1 : 0u);   // + one overflow list per peer
     const u32 lo = st.local_owner();
     for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n_entries; e += gridDim.x * blockDim.x) {
+        if (e >= n_grouped) {                                      // ungrouped records (any group): still exact, just not L2-friendly
+            u32 src = e - n_grouped;
+            if (src >= rv.me) ++src;
+            u32 n = rv.meta[(size_t)src * rv.meta_stride + (size_t)st.n_parts * st.n_cta];
+            if (n > rv.ovf_cap) n = rv.ovf_cap;
+            ent_cnt[e] = n;
+            ent_ptr[e] = (u64)(rv.recs + ((size_t)src * rv.cap + rv.part_recs) * rw);
+            continue;
+        }
         const u32 g = e / per_group, j = e - g * per_group;
         if (j < st.n_cta) {
             u32 n = st.count[st.cnt_index(lo, g, j)];
@@ -958,7 +986,7 @@ __global__ void __launch_bounds__(256) k_build_entries(StageView st, RecvView rv
             u32 src = jj / st.n_cta;
             const u32 cta = jj - src * st.n_cta;
             if (src >= rv.me) ++src;
-            u32 n = rv.meta[((size_t)src * st.n_parts + g) * st.n_cta + cta];
+            u32 n = rv.meta[(size_t)src * rv.meta_stride + (size_t)g * st.n_cta + cta];
             if (n > st.sub_cap) n = st.sub_cap;
             ent_cnt[e] = n;
             ent_ptr[e] = (u64)(rv.recs + ((size_t)src * rv.cap + ((size_t)cta * st.n_parts + g) * st.sub_cap) * rw);

@@ -6,10 +6,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 BIN = os.path.join(HERE, "bin")
 FILTER_READS = os.path.join(BIN, "FilterReads")
+FILTER_READS_P = os.path.join(BIN, "FilterReads-P")
 
 
 def _deps():
-    d = [os.path.join(HERE, "apps", "FilterReads.cpp"), os.path.join(os.path.dirname(PKG), "include", "kmernator_b200.h")]
+    d = [os.path.join(HERE, "apps", f) for f in ("FilterReads.cpp", "FilterReads-P.cpp", "FilterReads.h")]
+    d.append(os.path.join(os.path.dirname(PKG), "include", "kmernator_b200.h"))
     kd = os.path.join(HERE, "kmernator")
     return d + [os.path.join(kd, f) for f in os.listdir(kd) if f.endswith(".h")]
 
@@ -19,11 +21,12 @@ def build(force=False):
     if not os.path.exists(lib):
         raise ImportError("kmernator_b200.host: %s not built (build the CUDA library first)" % lib)
     os.makedirs(BIN, exist_ok=True)
-    if not force and os.path.exists(FILTER_READS) and all(os.path.getmtime(FILTER_READS) >= os.path.getmtime(d) for d in _deps()):
-        return FILTER_READS
-    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-o", FILTER_READS, os.path.join(HERE, "apps", "FilterReads.cpp"),
-           "-L" + PKG, "-l:libkmernator_b200.so", "-Wl,-rpath,$ORIGIN/../..", "-Wl,-rpath-link," + PKG]
-    subprocess.check_call(cmd)
+    for exe, src in ((FILTER_READS, "FilterReads.cpp"), (FILTER_READS_P, "FilterReads-P.cpp")):
+        if not force and os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in _deps()):
+            continue
+        cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", exe, os.path.join(HERE, "apps", src),
+               "-L" + PKG, "-l:libkmernator_b200.so", "-Wl,-rpath,$ORIGIN/../..", "-Wl,-rpath-link," + PKG]
+        subprocess.check_call(cmd)
     return FILTER_READS
 
 

@@ -10,6 +10,7 @@
 #ifndef KMERNATOR_HOST_KMERSPECTRUM_H
 #define KMERNATOR_HOST_KMERSPECTRUM_H
 
+#include <algorithm>
 #include <cmath>
 #include <iomanip>
 #include <sstream>
@@ -20,6 +21,7 @@
 #include "Log.h"
 #include "Options.h"
 #include "ReadSet.h"
+#include "World.h"
 
 #define KMN_CHECK(ctx, call)                                                                        \
     do {                                                                                            \
@@ -37,6 +39,10 @@ class KmerSpectrum {
 public:
     KmerMapHandle weak;
 
+    // distributed: every rank sizes its table for the largest local estimate, so that all ranks have the same table and
+    // staging geometry (DistributedKmerSpectrum::estimateRawKmers(world, reads), src/DistributedFunctions.h:154-161)
+    static unsigned long estimateRawKmers(World &world, const ReadSet &reads) { return world.allMax(estimateRawKmers(reads)); }
+
     // (avgLen - k + 1) * numReads, at least 128                          src/KmerSpectrum.h:573-584
     static unsigned long estimateRawKmers(const ReadSet &reads)
     {
@@ -45,6 +51,18 @@ public:
         unsigned long avg = reads.getBaseCount() / reads.getSize();
         unsigned long kmers = avg >= k ? (avg - k + 1) * reads.getSize() : 0;
         return kmers < 128 ? 128 : kmers;
+    }
+
+    // KS spectrum(world, rawKmers): one context per rank on its local GPU, joined to the library's communicator with an
+    // NCCL id that rank 0 creates and the world hands round      src/DistributedFunctions.h:126-131, src/MPIUtils.h:256-391
+    KmerSpectrum(World &world, unsigned long rawKmers, unsigned int valueKind = KMN_VALUE_DIR) : KmerSpectrum(rawKmers, world.localRank(), valueKind)
+    {
+        if (!weak.ctx || world.size() == 1) return;
+        std::string id(128, '\0');
+        if (world.rank() == 0 && kmn_comm_unique_id(&id[0]) != 0) LOG_THROW("kmn_comm_unique_id failed");
+        id = world.broadcast(id);
+        if (id.size() != 128) LOG_THROW("bad communicator id from rank 0");
+        KMN_CHECK(weak.ctx, kmn_comm_init(weak.ctx, world.rank(), world.size(), id.data()));
     }
 
     explicit KmerSpectrum(unsigned long rawKmers = 0, int device = 0, unsigned int valueKind = KMN_VALUE_DIR) : _rawKmers(rawKmers)
@@ -91,8 +109,12 @@ public:
         std::string bases, quals;
         std::vector<uint64_t> off;
         std::vector<uint8_t> disc;
-        for (ReadSet::ReadSetSizeType r0 = 0; r0 < n; r0 += batch) {
-            ReadSet::ReadSetSizeType r1 = r0 + batch < n ? r0 + batch : n;
+        // distributed: every rank makes the same number of calls (a rank that has run out of reads passes empty batches),
+        // as every MPI rank must keep calling sendReceive in the reference (src/DistributedFunctions.h:436-447)
+        unsigned long nBatches = (n + batch - 1) / batch;
+        if (World::instance()) nBatches = World::instance()->allMax(nBatches);
+        for (unsigned long b = 0; b < nBatches; ++b) {
+            const ReadSet::ReadSetSizeType r0 = std::min<ReadSet::ReadSetSizeType>(n, b * batch), r1 = std::min<ReadSet::ReadSetSizeType>(n, r0 + batch);
             reads.concat(r0, r1, bases, quals, off, disc);
             KMN_CHECK(weak.ctx, kmn_count_batch(weak.ctx, (const uint8_t *)bases.data(), (const uint8_t *)quals.data(), off.data(), r1 - r0, disc.data()));
         }

@@ -33,11 +33,13 @@ public:
             std::shared_ptr<std::ofstream> of(new std::ofstream(fn.c_str()));
             if (!of->good()) LOG_THROW("Could not open " << fn << " for writing");
             LOG_VERBOSE(1, "Writing to " << fn);
+            created().push_back(fn);
             it = _map.insert(std::make_pair(key, of)).first;
         }
         return *it->second;
     }
     void clear() { _map.clear(); }
+    static std::vector<std::string> &created() { static std::vector<std::string> v; return v; }   // every file opened so far
 private:
     std::string _prefix, _suffix;
     std::map<std::string, std::shared_ptr<std::ofstream> > _map;
@@ -115,10 +117,14 @@ public:
         std::vector<uint8_t> disc, wasTrimmed;
         std::vector<uint32_t> toff, tlen;
         std::vector<float> score;
-        for (ReadSetSizeType r0 = 0; r0 < n; r0 += batch) {
-            const ReadSetSizeType r1 = r0 + batch < n ? r0 + batch : n, m = r1 - r0;
+        // distributed: the lookup is collective (keys travel to their owners), so every rank makes the same number of
+        // calls, with empty batches once it has run out of reads   DistributedReadSelector, src/DistributedFunctions.h:903-1045
+        unsigned long nBatches = (n + batch - 1) / batch;
+        if (World::instance()) nBatches = World::instance()->allMax(nBatches);
+        for (unsigned long bi = 0; bi < nBatches; ++bi) {
+            const ReadSetSizeType r0 = std::min<ReadSetSizeType>(n, bi * batch), r1 = std::min<ReadSetSizeType>(n, r0 + batch), m = r1 - r0;
             _reads.concat(r0, r1, bases, quals, off, disc);
-            toff.resize(m); tlen.resize(m); score.resize(m); wasTrimmed.resize(m);
+            toff.resize(m + 1); tlen.resize(m + 1); score.resize(m + 1); wasTrimmed.resize(m + 1);
             KMN_CHECK(_map.ctx, kmn_trim_batch(_map.ctx, (const uint8_t *)bases.data(), off.data(), m, disc.data(), (uint32_t)minimumKmerScore,
                                                (int)scoring, toff.data(), tlen.data(), score.data(), wasTrimmed.data()));
             for (ReadSetSizeType i = 0; i < m; ++i) {

@@ -118,8 +118,28 @@ public:
             }
             if (!hdr.empty()) tmp.push_back(makeRead(hdr, seq, std::string(seq.size(), (char)Read::REF_QUAL), fileNum));
         } else if (first != EOF) LOG_THROW("Unrecognised sequence file format: " << path);
-        const size_t n = tmp.size(), a = n * (size_t)rank / (size_t)size, b = n * (size_t)(rank + 1) / (size_t)size;
+        // contiguous slice of the records; a cut never separates two mates (the reference's readers re-synchronise on
+        // record and pair boundaries after seeking, src/ReadFileReader.h:379-398)
+        const size_t n = tmp.size();
+        size_t a = n * (size_t)rank / (size_t)size, b = n * (size_t)(rank + 1) / (size_t)size;
+        if (size > 1) { a = pairAlignedCut(tmp, a); b = pairAlignedCut(tmp, b); }
         for (size_t i = a; i < b; ++i) append(tmp[i]);
+    }
+    // first index >= cut that does not separate record cut-1 from its mate at cut.  Mates are adjacent records, so the
+    // records before the cut are paired off from the start of the file exactly as identifyPairs() does
+    static size_t pairAlignedCut(const std::vector<Read> &v, size_t cut)
+    {
+        if (cut == 0 || cut >= v.size()) return cut;
+        size_t i = 0;
+        while (i < cut) {
+            if (i + 1 < v.size()) {
+                std::string c1, c2;
+                const int n1 = readNum(v[i], c1), n2 = readNum(v[i + 1], c2);
+                if (n1 && n2 && n1 != n2 && c1 == c2) { i += 2; continue; }
+            }
+            ++i;
+        }
+        return i;
     }
     void append(const Read &r)
     {

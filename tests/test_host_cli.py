@@ -25,6 +25,30 @@ def _run(exe, args, cwd=None):
     return subprocess.run([exe] + args, capture_output=True, text=True, cwd=cwd, timeout=600)
 
 
+def _run_ranks(exe, args, world, cwd, comm_dir, gpus=False):
+    """one process per rank, as torchrun / mpirun would start them (RANK / WORLD_SIZE / LOCAL_RANK)"""
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r if gpus else 0), KMN_COMM_DIR=comm_dir)
+        procs.append(subprocess.Popen([exe] + args, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=600) for p in procs]
+    return [(p.returncode, o[1]) for p, o in zip(procs, outs)]
+
+
+def test_filter_reads_p_without_kmers_matches_serial(filter_reads, golden_dir, tmp_path):
+    """FilterReads-P with kmer-size 0 needs no GPU (artifact filter + length filter only): three ranks, each on its
+    pair-aligned slice of the input, joined in rank order, write exactly what the serial driver writes
+    (the reference's criterion for the distributed app, test/runFilterTests.sh:93-116)"""
+    exe_p = filter_reads + "-P"
+    args = ["--fastq-output-base-quality", "64", "--min-read-length", "25"]
+    p = _run(filter_reads, args + ["--out", str(tmp_path / "serial"), "0", "1000.fastq"], cwd=golden_dir)
+    assert p.returncode == 0, p.stderr
+    res = _run_ranks(exe_p, args + ["--out", str(tmp_path / "par"), "0", "1000.fastq"], 3, golden_dir, str(tmp_path / "comm"))
+    assert all(rc == 0 for rc, _ in res), res
+    assert open(str(tmp_path / "par-1000.fastq")).read() == open(str(tmp_path / "serial-1000.fastq")).read()
+    assert not os.path.exists(str(tmp_path / "comm")) and not os.path.exists(str(tmp_path / "par-1000.fastq.rank1"))
+
+
 def test_help_lists_reference_options(filter_reads):
     p = _run(filter_reads, ["--help"])
     assert p.returncode == 1                       # apps/FilterReads.cpp:85: `if (!parseOpts) exit(1)`
@@ -73,6 +97,23 @@ def test_filter_reads_goldens(filter_reads, golden_dir, tmp_path, inp, good, ext
     assert p.returncode == 0, p.stderr
     got = open("%s-MinDepth2-%s" % (out, inp)).read().split()          # diff -w
     want = open(os.path.join(golden_dir, good)).read().split()
+    assert got == want
+
+
+@pytest.mark.gpu
+def test_filter_reads_p_two_ranks_reproduce_the_golden(filter_reads, golden_dir, tmp_path):
+    """the reference's own test of the distributed app (test/runFilterTests.sh:93-116): FilterReads-P on two ranks (two
+    GPUs, table sharded by hash owner, collective lookup pass) writes the golden file of the serial run"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "out")
+    args = ["--fastq-output-base-quality", "64", "--min-read-length", "25", "--kmer-scoring-type", "MEDIAN", "--mask-simple-repeats", "0",
+            "--artifact-edit-distance", "1", "--out", out, "31", "1000.fastq"]
+    res = _run_ranks(filter_reads + "-P", args, 2, golden_dir, str(tmp_path / "comm"), gpus=True)
+    assert all(rc == 0 for rc, _ in res), res
+    got = open(out + "-MinDepth2-1000.fastq").read().split()
+    want = open(os.path.join(golden_dir, "1000-Filtered.fastq")).read().split()
     assert got == want
 
 
