@@ -185,3 +185,45 @@ def test_count_saturation_and_stats():
     assert len(e["count"]) == len(seq) - 30 and (e["count"] == 65535).all()
     st = s.stats()
     assert st["raw"] == n * 10 and st["raw_good"] == n * 10 and st["unique"] == 10 and st["singleton"] == 0
+
+
+def test_oracle_counts_vs_independent_bruteforce_on_skewed_input():
+    """BASELINE config 4 scaled down (skewed abundances: a few genomes sampled 1x..200x): the C restatement against an
+    independent pure-Python count of canonical k-mers (strings and a dict; no packing, no hashing, no rolling), for a
+    single-word, an exactly-32 and a multi-word k.  Every base has a high quality, so a k-mer counts iff it has no
+    non-ACGT character (markup -> weight 0, src/KmerReadUtils.h:218-222)."""
+    rng = np.random.default_rng(11)
+    genomes = ["".join("ACGT"[c] for c in rng.integers(0, 4, n)) for n in (900, 700, 500, 400)]
+    depth = [1, 6, 40, 200]
+    comp = str.maketrans("ACGT", "TGCA")
+    reads = []
+    for g, d in zip(genomes, depth):
+        for _ in range(d * len(g) // 100):
+            s = int(rng.integers(0, len(g) - 100))
+            r = g[s:s + 100]
+            if rng.random() < 0.5:
+                r = r.translate(comp)[::-1]
+            if rng.random() < 0.1:
+                p = int(rng.integers(0, 100))
+                r = r[:p] + "N" + r[p + 1:]
+            reads.append(r)
+    bases, quals, off = oracle.concat_reads([r.encode() for r in reads])
+    for k in (21, 32, 45):
+        want = {}
+        for r in reads:
+            for i in range(len(r) - k + 1):
+                f = r[i:i + k]
+                if "N" in f:
+                    continue
+                rc = f.translate(comp)[::-1]
+                c = min(f, rc)
+                want[c] = want.get(c, 0) + 1
+        s = oracle.OracleSpectrum(k, est_distinct=1 << 14)
+        s.add_reads(bases, quals, off)
+        e = s.export()
+        got = {}
+        for key, cnt in zip(e["keys"], e["count"]):
+            bits = "".join(format(b, "08b") for b in key.tobytes())
+            got["".join("ACGT"[int(bits[2 * j:2 * j + 2], 2)] for j in range(k))] = int(cnt)
+        assert got == want
+        assert max(want.values()) > 150          # the skew is real: some k-mers are two orders deeper than others
