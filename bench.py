@@ -234,8 +234,24 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # the phase-2 kernel is timed inside a long step: prefer a sustained HBM figure, then the plain one, then any HBM key
+    def _num(v):
+        return float(v) if isinstance(v, (int, float)) and not isinstance(v, bool) and v > 0 else None
+    flat = {}
+    for k_, v_ in (peaks.items() if isinstance(peaks, dict) else []):
+        if isinstance(v_, dict):
+            for k2, v2 in v_.items():
+                flat["%s.%s" % (k_, k2)] = v2
+        else:
+            flat[k_] = v_
+    cands = [k_ for k_ in flat if "hbm" in k_.lower() and _num(flat[k_])]
+    cands.sort(key=lambda k_: (0 if "sustain" in k_.lower() else 1 if k_ == "hbm_gbs" else 2, k_))
+    if cands:
+        peak, peak_src = _num(flat[cands[0]]), "measured (MEASURED_PEAKS.json %s)" % cands[0]
+        if peak < 100:                       # a TB/s figure
+            peak *= 1000.0
+    else:
+        peak, peak_src = 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
     ins = prof.get("insert", {"ms": 0.0, "launches": 0, "units": 0})
     par = prof.get("parse", {"ms": 0.0, "launches": 0, "units": 0})
     good_per_step = stats["raw_good_kmers"]              # instances actually inserted in the last step
