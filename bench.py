@@ -345,7 +345,9 @@ def main():
         torch.cuda.synchronize()
         hbn, hqn = hb.numpy(), hq.numpy()
         bsz = args.e2e_batch
-        hoff = (np.arange(bsz + 1, dtype=np.uint64) * READ_LEN)
+        hoff_t = torch.empty(bsz + 1, dtype=torch.int64, pin_memory=True)      # offsets are an input too: pinned like the bases
+        hoff_t.copy_(torch.arange(bsz + 1, dtype=torch.int64) * READ_LEN)
+        hoff = hoff_t.numpy()
 
         def step_e2e():
             ctx.reset()
