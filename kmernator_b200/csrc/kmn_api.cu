@@ -1,6 +1,8 @@
 // kmn_api.cu -- host side of the C ABI declared in include/kmernator_b200.h.
-// Owns the device memory plan (count table, partitioned staging, input staging), launches the kernels of
-// kmn_kernels.cuh on one stream, and runs the NCCL exchange of the owner-sharded build.
+// Owns the device memory plan (count table, staging sets cut by owner and table group, input staging, receive buffers),
+// launches the kernels of kmn_kernels.cuh (phase 1 on the main stream, phase 2 on the insert stream, pushes and round
+// barriers on the comm stream, H2D staging on the copy stream) and runs the multi-GPU build: records pushed into their
+// owners' receive buffers over NVLink through CUDA-IPC peer memory, or the NCCL all-to-all when peers cannot be mapped.
 #include "../../include/kmernator_b200.h"
 #include "kmn_kernels.cuh"
 
