@@ -70,8 +70,10 @@ struct kmn_ctx {
     u64 *scratch = nullptr;           // small device scalars
     // phase-1 launch geometry
     int n_cta = 0;                    // grid of k_kmer_scatter / k_route_records = staging sub-regions per partition
+    int scatter_tpb = 512, scatter_ctas = 2;   // phase-1b CTA size and CTAs per SM (KMN_SCATTER_TPB / KMN_SCATTER_CTAS)
+    uint32_t ring_R = 0;              // record slots per bin ring in phase 1b (0: no rings, every record stored directly)
     uint32_t zero_below = 0;
-    size_t scatter_smem = 0;
+    size_t scatter_smem = 0, route_smem = 0;
     DevBuf mask, wts;                 // phase 1a -> 1b: "counted" bits (and fp32 weights for KMN_VALUE_WEIGHTS)
     // input staging (host inputs), double-buffered: the copy of batch b+1 overlaps the kernels of batch b
     DevBuf in_bases[2], in_quals[2], in_off[2], in_disc[2];
@@ -232,7 +234,8 @@ static int alloc_stage_sets(kmn_ctx *c)
     c->stage_keys = sk;
     const uint64_t n_groups = c->n_groups, n_cta = (uint64_t)c->n_cta, n_own = c->p2p ? (uint64_t)c->nranks : 1;
     const uint64_t per_sub = sk / n_groups / n_cta / n_own;
-    const uint64_t sub_cap = per_sub + per_sub / 8 + 8 * (uint64_t)std::sqrt((double)per_sub + 1.0) + 64;   // mean + slack for the spread
+    // mean + slack for the spread; a multiple of 4 records, so that every sub-region starts on a 32-byte sector boundary
+    const uint64_t sub_cap = (per_sub + per_sub / 8 + 8 * (uint64_t)std::sqrt((double)per_sub + 1.0) + 64 + 3) & ~3ull;
     if (sub_cap >= (1ull << 31)) return fail(c, KMN_ERR_INVALID, "staging sub-region too large (%llu records)", (unsigned long long)sub_cap);
     for (int si = 0; si < c->n_sets; ++si) {
         kmn_ctx::StageSet &st = c->sets[si];
@@ -252,8 +255,24 @@ static int alloc_stage_sets(kmn_ctx *c)
         if (!st.ev_drained) CK(c, cudaEventCreateWithFlags(&st.ev_drained, cudaEventDisableTiming));
         st.staged_upper = 0;
     }
-    // phase-1 shared memory: one fill counter per (owner, group) bin + send-segment counters (<= 64 ranks)
-    c->scatter_smem = ((((size_t)n_groups * n_own + 31) & ~(size_t)31) + 64) * 4;
+    // phase-1 shared memory: per (owner, group) bin a position counter, a flush mark and a ring of R record slots
+    // (+ send-segment counters, <= 64 ranks).  R = the largest power of two that fits, at most 64; below 4 no rings.
+    {
+        int dev_smem = 0, sm_smem = 0;
+        CK(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+        CK(c, cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
+        const size_t budget = std::min<size_t>((size_t)dev_smem, ((size_t)sm_smem - 1024u * (size_t)c->scatter_ctas) / (size_t)c->scatter_ctas) - 256;
+        const size_t n_bins = (size_t)n_groups * n_own, n_pad = (n_bins + 31) & ~(size_t)31;
+        const size_t hdr = (2 * n_pad + 64 + 32) * 4;
+        uint32_t R = 64;
+        if (const char *e = getenv("KMN_RING")) R = (uint32_t)std::max(0, atoi(e));
+        while (R >= 4 && hdr + n_bins * R * c->RW * 8 > budget) R >>= 1;
+        if (R < 4 || (R & (R - 1))) R = 0;
+        if (hdr > budget) return fail(c, KMN_ERR_INVALID, "too many staging bins (%zu) for the phase-1 shared memory", n_bins);
+        c->ring_R = R;
+        c->scatter_smem = hdr + n_bins * R * c->RW * 8;
+        c->route_smem = (n_pad + 64) * 4;
+    }
     return 0;
 }
 
@@ -297,14 +316,17 @@ static int plan_and_alloc(kmn_ctx *c)
     slots = part_slots * n_parts;
     uint32_t gshift = 0;
     while (gshift < 11 && (part_slots * c->slot_bytes << (gshift + 1)) <= (uint64_t)gbytes) gshift++;     // <= 2048 slices per group
-    const uint64_t p_max = ((size_t)dev_smem / SCATTER_CTAS - 1024) / 4 - 32;
+    if (const char *e = getenv("KMN_SCATTER_TPB")) c->scatter_tpb = std::min(SCATTER_MAX_TPB, std::max(64, atoi(e) & ~31));
+    if (const char *e = getenv("KMN_SCATTER_CTAS")) c->scatter_ctas = std::max(1, atoi(e));
+    if (c->scatter_tpb * c->scatter_ctas > 2048) c->scatter_ctas = 2048 / c->scatter_tpb;
+    const uint64_t p_max = ((size_t)dev_smem / c->scatter_ctas - 2048) / 8 - 64;      // counter + flush mark per bin
     while (((n_parts + (1ull << gshift) - 1) >> gshift) > p_max) gshift++;
     const uint64_t n_groups = (n_parts + (1ull << gshift) - 1) >> gshift;
     c->n_slots = slots;
     c->table.part_slots = part_slots;
     c->table.n_parts = (u32)n_parts;
     c->table.group_shift = gshift;
-    c->n_cta = c->n_sms * SCATTER_CTAS;
+    c->n_cta = c->n_sms * c->scatter_ctas;
 
     CK(c, cudaMalloc(&c->table.slots, slots * c->slot_bytes));
     if (c->weights) CK(c, cudaMalloc((void **)&c->table.wsum, slots * 4));
@@ -371,7 +393,7 @@ int kmn_reset(kmn_ctx *c)
 template <int W, bool X>
 static int set_smem_attrs(kmn_ctx *c)
 {
-    const int s = (int)c->scatter_smem;
+    const int s = (int)std::max(c->scatter_smem, c->route_smem);
     if (s <= 48 * 1024) return 0;
     CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
     CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
@@ -594,6 +616,7 @@ static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, cons
     uint32_t ps = 5;
     while (ps > 0 && (n_reads >> ps) < 2ull * (uint64_t)std::max(1, c->n_cta)) --ps;
     a.piece_shift = ps;
+    a.ring_R = c->ring_R;
     a.cta_rot = c->cta_rot;
     c->cta_rot = (uint32_t)((c->cta_rot + ((n_reads + (1ull << ps) - 1) >> ps)) % (uint64_t)std::max(1, c->n_cta));
 }
@@ -617,9 +640,9 @@ static int launch_parse(kmn_ctx *c, const ParseArgs &a)
         const int mode = !dist ? 0 : (c->p2p ? 2 : 1);
 #define KMN_SCATTER(X_, E_)                                                                          \
         do {                                                                                         \
-            if (mode == 0) k_kmer_scatter<W_, X_, E_, 0><<<grid, SCATTER_TPB, sm, c->stream>>>(a);    \
-            else if (mode == 1) k_kmer_scatter<W_, X_, E_, 1><<<grid, SCATTER_TPB, sm, c->stream>>>(a); \
-            else k_kmer_scatter<W_, X_, E_, 2><<<grid, SCATTER_TPB, sm, c->stream>>>(a);              \
+            if (mode == 0) k_kmer_scatter<W_, X_, E_, 0><<<grid, c->scatter_tpb, sm, c->stream>>>(a);    \
+            else if (mode == 1) k_kmer_scatter<W_, X_, E_, 1><<<grid, c->scatter_tpb, sm, c->stream>>>(a); \
+            else k_kmer_scatter<W_, X_, E_, 2><<<grid, c->scatter_tpb, sm, c->stream>>>(a);              \
         } while (0)
         KMN_DISPATCH_W(c, {
             if (!c->hasx) KMN_SCATTER(false, false);
@@ -694,7 +717,7 @@ static int exchange(kmn_ctx *c)
         {
             ProfScope ps(c, KMN_PROF_ROUTE, recv_total);
             KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
-                k_route_records<W_, X_><<<c->n_cta, SCATTER_TPB, c->scatter_smem, c->stream>>>(ra);
+                k_route_records<W_, X_><<<c->n_cta, ROUTE_TPB, c->route_smem, c->stream>>>(ra);
             }));
         }
         c->launches++;
@@ -734,7 +757,7 @@ static int setup_push(kmn_ctx *c)
     {   // phase 1 keeps one shared-memory counter per (owner, group) bin
         int dev_smem = 0;
         CK(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-        if ((G * (uint64_t)R + 128) * 4 > (uint64_t)dev_smem / SCATTER_CTAS - 2048) want = false;
+        if ((G * (uint64_t)R + 128) * 8 > (uint64_t)dev_smem / c->scatter_ctas - 4096) want = false;
     }
     c->push_ce = true;
     if (const char *e = getenv("KMN_PUSH")) c->push_ce = strcmp(e, "kernel") != 0;

@@ -20,12 +20,8 @@
 namespace kmn {
 
 static constexpr int MASK_TPB = 256;       // phase 1a: one warp per 32 reads
-#ifndef KMN_SCATTER_TPB
-#define KMN_SCATTER_TPB 1024
-#define KMN_SCATTER_CTAS 1
-#endif
-static constexpr int SCATTER_TPB = KMN_SCATTER_TPB;    // phase 1b: one thread per read, SCATTER_CTAS CTAs per SM
-static constexpr int SCATTER_CTAS = KMN_SCATTER_CTAS;
+static constexpr int SCATTER_MAX_TPB = 1024;           // phase 1b: one thread per read; CTA size and CTAs per SM are chosen at run time
+static constexpr int ROUTE_TPB = 1024;
 #ifndef KMN_INSERT_MIN_CTAS
 #define KMN_INSERT_MIN_CTAS 4
 #endif
@@ -61,6 +57,7 @@ struct ParseArgs {
                            // sequence of small launches fills the per-CTA sub-regions evenly instead of always the first ones
     u32 piece_shift;       // log2(reads per piece), 5 for large launches; small launches use smaller pieces so that they
                            // still spread over all CTAs (the sub-region capacities assume an even spread)
+    u32 ring_R;            // phase 1b: record slots of one bin's shared-memory ring (power of two >= 4; 0 = no rings)
     TableView table;
     StageView stage;
     Counters *ctr;
@@ -604,38 +601,57 @@ __device__ __forceinline__ void stage_put(u64 *cbase, u32 sub_cap, const TableVi
 // ------------------------------------------------------------------------------------------------
 // K1+K2b (+K5 partition): phase 1b of the count pass.  One thread walks one read and rolls the canonical k-mer
 // (a1 TwoBitSequence::compressSequence src/TwoBitSequence.cpp:242-269, a2 KmerArrayPair::build src/Kmer.h:1323-1375,
-// buildLeastComplement :356-364) 8 bases per step; k-mers whose "counted" bit (phase 1a) is set go to this CTA's
-// sub-region of their table partition -- one shared-memory atomicAdd for the position, one 8*RW-byte store.
-// Multi-GPU: records owned by another rank (a5: owner = lookup3 hash, src/Kmer.h:2284-2295) go to that rank's
-// send region instead.
+// buildLeastComplement :356-364) 8 bases per step; k-mers whose "counted" bit (phase 1a) is set become records of this
+// CTA's sub-region of their (owner,) table group.
+//
+// What bounds this kernel on B200 is the SM's store path to L2: it moves one 32-byte SECTOR per ~3.5 cycles whether the
+// store fills the sector or only 8 bytes of it (bench/micro/lsu.cu: a shared atomic + one scattered 8-byte store per record
+// runs at 64-100 G records/s, the shared atomic + a shared store alone at 940 G/s).  So records are write-combined in shared
+// memory: every bin has a ring of R record slots addressed by the record's position in the bin's sub-region (position p
+// lives in ring slot p mod R until it is flushed), the position comes from one shared atomicAdd, and after every walker
+// step of the CTA (a ROUND: at most 8 records per thread) one thread per bin moves the bin's complete, aligned groups of
+// four records to global memory as whole sectors.  A record that finds its ring full (more than R records of one bin in
+// a round: skewed input) is stored directly, which is merely slower.
+// Multi-GPU: DIST 2 bins by (owner, group) (a5: owner = lookup3 hash, src/Kmer.h:2284-2295) into this CTA's sub-region of
+// the owner's part of the staging set (push path); DIST 1 (NCCL all-to-all path) writes records of other owners to
+// per-CTA send segments instead.
 // ------------------------------------------------------------------------------------------------
-// DIST: 0 = single GPU; 1 = records of other owners go to per-CTA send segments (NCCL all-to-all path); 2 = every record
-// is binned by (owner, group) into this CTA's sub-region of the owner's part of the staging set (push path: the parts of
-// the other owners are copied into their receive buffers over NVLink, already sorted by group)
+__device__ __forceinline__ void st_sector(u64 *dst, const u64 *src_smem)      // 32 bytes, both 32-byte aligned
+{
+    const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(src_smem), y = *reinterpret_cast<const ulonglong2 *>(src_smem + 2);
+    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(x.x), "l"(x.y), "l"(y.x), "l"(y.y) : "memory");
+}
+
 template <int W, bool HASX, bool EXT, int DIST>
-__global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(ParseArgs a)
+__global__ void __launch_bounds__(1024, 1) k_kmer_scatter(ParseArgs a)
 {
     constexpr int RW = Rec<W, HASX>::RW;
-    extern __shared__ __align__(16) u32 smem_u32[];
+    extern __shared__ __align__(32) unsigned char smem_raw[];
     const u32 n_parts = a.stage.n_parts;                               // staging partitions = table groups
     const u32 n_bins = DIST == 2 ? n_parts * a.nranks : n_parts;       // (owner, group) bins on the push path
+    const u32 n_pad = (n_bins + 31u) & ~31u;
     const u32 lo = a.stage.local_owner();
-    u32 *cnt = smem_u32;                                               // [n_bins] fill level of this CTA's sub-regions
-    u32 *scnt = smem_u32 + ((n_bins + 31u) & ~31u);                    // [nranks] fill level of this CTA's send segments (DIST 1)
+    u32 *cnt = reinterpret_cast<u32 *>(smem_raw);                      // [n_bins] records given a position so far (may exceed sub_cap)
+    u32 *fl = cnt + n_pad;                                             // [n_bins] positions below fl are in global memory
+    u32 *scnt = fl + n_pad;                                            // [32 or nranks] fill level of this CTA's send segments (DIST 1)
+    u64 *ring = reinterpret_cast<u64 *>(scnt + ((DIST == 1 ? a.nranks + 31u : 31u) & ~31u) + 32u);
+    const u32 R = a.ring_R;                                            // power of two >= 4, or 0: every record is stored directly
+    const u32 sub_cap = a.stage.sub_cap;
     for (u32 i = threadIdx.x; i < n_bins; i += blockDim.x) {
         const u32 o = DIST == 2 ? i / n_parts : lo, g = DIST == 2 ? i - o * n_parts : i;
-        cnt[i] = a.stage.count[a.stage.cnt_index(o, g, blockIdx.x)];
+        const u32 c0 = a.stage.count[a.stage.cnt_index(o, g, blockIdx.x)];
+        cnt[i] = c0;
+        fl[i] = c0 < sub_cap ? c0 : sub_cap;
     }
     if (DIST == 1) for (u32 i = threadIdx.x; i < a.nranks; i += blockDim.x) scnt[i] = a.seg_count[(size_t)i * gridDim.x + blockIdx.x];
     __syncthreads();
 
     LocalCtr lc{0, 0, 0, 0, 0, 0};
     u64 lost = 0;
-    const u32 sub_cap = a.stage.sub_cap;
-    u64 *const cbase = a.stage.recs + a.stage.sub_index(lo, 0, blockIdx.x) * sub_cap * RW;
     const u64 stride = (u64)gridDim.x * blockDim.x;
     const u64 keep = a.l2_hints ? l2_policy_evict_last() : l2_policy_evict_normal();
     Walker<W> st;
+    st.clear();
     // consecutive groups of 32 reads (one warp) go to different CTAs, so even a small batch spreads evenly over the
     // per-CTA sub-regions / segments while a warp still streams one contiguous piece of the batch
     const u32 vblock = (blockIdx.x + gridDim.x - a.cta_rot % gridDim.x) % gridDim.x;
@@ -643,66 +659,119 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
     const u32 p_shift = a.piece_shift, lane_in = threadIdx.x & 31u;
     const u64 n_slots = (u64)gridDim.x * (blockDim.x >> 5);
     const u64 in_sweep = (((u64)(lane_in >> p_shift) * n_slots + (u64)(threadIdx.x >> 5) * gridDim.x + vblock) << p_shift) + (lane_in & ((1u << p_shift) - 1u));
-    for (u64 sweep0 = 0; sweep0 < a.n_reads; sweep0 += stride) {
-        const u64 r = sweep0 + in_sweep;
-        if (r >= a.n_reads) continue;
-        const u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
-        const u32 len = (u32)(o1 - o0);
-        if (len < a.k || (a.discarded && a.discarded[r])) continue;
-        st.template begin<EXT>(a, o0, len);
-        // "counted" bits of phase 1a: a 64-bit window (mask words curw, curw+1) plus the following word, which is
-        // requested one whole step before it can be needed so that its latency never sits on the critical path
-        u64 curw = o0 >> 5;
-        u64 mbits = (u64)__ldg(&a.mask[curw]) | ((u64)__ldg(&a.mask[curw + 1]) << 32);
-        u32 pend = __ldg(&a.mask[curw + 2]);
-        u32 bits8 = 0, ifirst = 0;                                     // bits of k-mers ifirst .. ifirst+7 (this step's)
-        auto emit = [&](u32 i, const u64 (&key)[W], bool fwd, float, bool, u32 eb) {
-            if (!((bits8 >> (i - ifirst)) & 1u)) return;
-            Rec<W, HASX> rec;
-            rec.pack(key, fwd, (HASX && a.wts) ? a.wts[o0 + i] : 1.0f, eb);
-            const u64 ph = place_hash<W>(key);
-            const u32 group = part_of(ph, a.table.n_parts) >> a.table.group_shift;
-            if (DIST != 0) {
-                const u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
-                const u32 own = owner_of(h, a.nranks);
-                if (DIST == 2) {
-                    const u32 pos = atomicAdd(&cnt[own * n_parts + group], 1u);
-                    if (pos < sub_cap) {
-                        u64 *d = a.stage.recs + (a.stage.sub_index(own, group, blockIdx.x) * sub_cap + pos) * RW;
+
+    // sub-region of bin b in the staging set
+    auto sub_base = [&](u32 b) -> u64 * {
+        const u32 o = DIST == 2 ? b / n_parts : lo, g = DIST == 2 ? b - o * n_parts : b;
+        return a.stage.recs + a.stage.sub_index(o, g, blockIdx.x) * sub_cap * RW;
+    };
+    // one thread per bin: complete aligned groups of four records leave the ring as whole sectors (everything when `all`)
+    auto flush = [&](bool all) {
+        for (u32 b = threadIdx.x; b < n_bins; b += blockDim.x) {
+            u32 c = cnt[b];
+            if (c > sub_cap) c = sub_cap;
+            const u32 f = fl[b];
+            if (c <= f) continue;
+            u32 end, nfl;
+            if (c - f > R) { end = f + R; nfl = c; }                   // the ring overflowed: positions >= f + R were stored directly
+            else { end = all ? c : (c & ~3u); nfl = end; }
+            if (end <= f) continue;
+            u64 *g = sub_base(b);
+            const u64 *rb = ring + (size_t)b * R * RW;
+            u32 pos = f;
+            for (; pos < end && (pos & 3u); ++pos) {
 #pragma unroll
-                        for (int q = 0; q < RW; ++q) st_hint64(d + q, rec.w[q], keep);
-                    } else if (own == a.rank) {
-                        insert_record<W, HASX>(a.table, rec, lc.unique, lc.full, lc.probes);
-                        lc.direct++;
-                    } else {                                           // full remote sub-region: the owner's overflow list
-                        const u32 op = a.stage.ovf_cap ? atomicAdd(&a.stage.ovf_count[own], 1u) : 0u;
-                        if (op < a.stage.ovf_cap) {
-                            u64 *d = a.stage.ovf_recs + ((size_t)own * a.stage.ovf_cap + op) * RW;
-#pragma unroll
-                            for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
-                        } else lost++;
-                    }
-                    return;
-                }
-                if (own != a.rank) {
-                    // one shared atomicAdd per (converged lanes, destination) group
-                    namespace cg = cooperative_groups;
-                    auto grp = cg::labeled_partition(cg::coalesced_threads(), (int)own);
-                    u32 base = 0;
-                    if (grp.thread_rank() == 0) base = atomicAdd(&scnt[own], (u32)grp.size());
-                    base = grp.shfl(base, 0);
-                    const u32 pos = base + grp.thread_rank();
-                    if (pos < a.seg_cap) {
-                        u64 *d = a.seg_recs + (((size_t)own * gridDim.x + blockIdx.x) * a.seg_cap + pos) * RW;
-#pragma unroll
-                        for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
-                    }
-                    return;
-                }
+                for (int q = 0; q < RW; ++q) g[(size_t)pos * RW + q] = rb[(size_t)(pos & (R - 1u)) * RW + q];
             }
-            stage_put<W, HASX>(cbase, sub_cap, a.table, cnt, group, rec, lc, keep);
-        };
-        while (st.j < st.len) {
+            for (; pos + 4u <= end; pos += 4u) {
+#pragma unroll
+                for (int q = 0; q < RW; ++q) st_sector(g + (size_t)pos * RW + 4 * q, rb + (size_t)(pos & (R - 1u)) * RW + 4 * q);
+            }
+            for (; pos < end; ++pos) {
+#pragma unroll
+                for (int q = 0; q < RW; ++q) g[(size_t)pos * RW + q] = rb[(size_t)(pos & (R - 1u)) * RW + q];
+            }
+            fl[b] = nfl;
+        }
+    };
+
+    u64 sweep0 = 0, o0 = 0;
+    bool active = false, exhausted = false;
+    u64 curw = 0, mbits = 0;
+    u32 pend = 0, bits8 = 0, ifirst = 0;                               // bits of k-mers ifirst .. ifirst+7 (this step's)
+    auto emit = [&](u32 i, const u64 (&key)[W], bool fwd, float, bool, u32 eb) {
+        if (!((bits8 >> (i - ifirst)) & 1u)) return;
+        Rec<W, HASX> rec;
+        rec.pack(key, fwd, (HASX && a.wts) ? a.wts[o0 + i] : 1.0f, eb);
+        const u64 ph = place_hash<W>(key);
+        const u32 group = part_of(ph, a.table.n_parts) >> a.table.group_shift;
+        u32 own = lo;
+        if (DIST != 0) {
+            const u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
+            own = owner_of(h, a.nranks);
+            if (DIST == 1 && own != a.rank) {
+                // one shared atomicAdd per (converged lanes, destination) group
+                namespace cg = cooperative_groups;
+                auto grp = cg::labeled_partition(cg::coalesced_threads(), (int)own);
+                u32 base = 0;
+                if (grp.thread_rank() == 0) base = atomicAdd(&scnt[own], (u32)grp.size());
+                base = grp.shfl(base, 0);
+                const u32 pos = base + grp.thread_rank();
+                if (pos < a.seg_cap) {
+                    u64 *d = a.seg_recs + (((size_t)own * gridDim.x + blockIdx.x) * a.seg_cap + pos) * RW;
+#pragma unroll
+                    for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
+                }
+                return;
+            }
+        }
+        const u32 bin = DIST == 2 ? own * n_parts + group : group;
+        const u32 p = atomicAdd(&cnt[bin], 1u);
+        if (p < sub_cap) {
+            if (p - fl[bin] < R) {
+                u64 *d = ring + ((size_t)bin * R + (p & (R - 1u))) * RW;
+#pragma unroll
+                for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
+            } else {
+                u64 *d = sub_base(bin) + (size_t)p * RW;
+#pragma unroll
+                for (int q = 0; q < RW; ++q) st_hint64(d + q, rec.w[q], keep);
+            }
+        } else if (DIST != 2 || own == a.rank) {                       // full sub-region: straight into the table
+            insert_record<W, HASX>(a.table, rec, lc.unique, lc.full, lc.probes);
+            lc.direct++;
+        } else {                                                       // full remote sub-region: the owner's overflow list
+            const u32 op = a.stage.ovf_cap ? atomicAdd(&a.stage.ovf_count[own], 1u) : 0u;
+            if (op < a.stage.ovf_cap) {
+                u64 *d = a.stage.ovf_recs + ((size_t)own * a.stage.ovf_cap + op) * RW;
+#pragma unroll
+                for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
+            } else lost++;
+        }
+    };
+
+    while (true) {
+        if (!active && !exhausted) {                                   // next read of this thread
+            while (sweep0 < a.n_reads) {
+                const u64 r = sweep0 + in_sweep;
+                sweep0 += stride;
+                if (r >= a.n_reads) continue;
+                const u64 b0 = a.read_off[r], b1 = a.read_off[r + 1];
+                const u32 len = (u32)(b1 - b0);
+                if (len < a.k || (a.discarded && a.discarded[r])) continue;
+                o0 = b0;
+                st.template begin<EXT>(a, b0, len);
+                // "counted" bits of phase 1a: a 64-bit window (mask words curw, curw+1) plus the following word, which is
+                // requested one whole step before it can be needed so that its latency never sits on the critical path
+                curw = b0 >> 5;
+                mbits = (u64)__ldg(&a.mask[curw]) | ((u64)__ldg(&a.mask[curw + 1]) << 32);
+                pend = __ldg(&a.mask[curw + 2]);
+                active = true;
+                break;
+            }
+            if (!active) exhausted = true;
+        }
+        if (active) {                                                  // one step: up to 8 bases, up to 8 records
             ifirst = st.j + 1 >= a.k ? st.j + 1 - a.k : 0u;            // first k-mer this step can emit
             const u64 gb0 = o0 + ifirst;
             if ((gb0 >> 5) != curw) { mbits = (mbits >> 32) | ((u64)pend << 32); ++curw; }
@@ -710,8 +779,13 @@ __global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_kmer_scatter(Pars
             bits8 = (u32)(mbits >> (u32)(gb0 & 31ull)) & 0xffu;
             walker_step<W, false, EXT>(st, a, nullptr, emit);
             pend = nxt;
+            if (st.j >= st.len) active = false;
         }
+        __syncthreads();
+        if (R) flush(false);
+        if (!__syncthreads_or((active || !exhausted) ? 1 : 0)) break;
     }
+    if (R) flush(true);
     __syncthreads();
     for (u32 i = threadIdx.x; i < n_bins; i += blockDim.x) {
         const u32 o = DIST == 2 ? i / n_parts : lo, g = DIST == 2 ? i - o * n_parts : i;
@@ -850,7 +924,7 @@ struct RouteArgs {
 };
 
 template <int W, bool HASX>
-__global__ void __launch_bounds__(SCATTER_TPB, SCATTER_CTAS) k_route_records(RouteArgs a)
+__global__ void __launch_bounds__(ROUTE_TPB, 1) k_route_records(RouteArgs a)
 {
     constexpr int RW = Rec<W, HASX>::RW;
     extern __shared__ __align__(16) u32 smem_u32[];

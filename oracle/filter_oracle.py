@@ -197,3 +197,117 @@ def meraculous_counts(recs, k=21, start=33, min_quality=2, min_kmer_quality=0.0,
         graph.append(km + "\t" + " ".join(str(int(x)) for x in ext) + " 0")
         graph.append(rc + "\t" + " ".join(str(x) for x in re) + " 0")
     return sorted(set(counts)), sorted(set(graph))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a12: RANDOM coverage normalisation (src/ReadSelector.h:661-749).  IntRand is boost::random::mt19937 behind a
+# uniform_int_distribution<uint32_t> over its full range (src/Utils.h:1147), i.e. the raw 32-bit outputs of MT19937; the
+# reference seeds it from time(NULL), so parity = identical decisions for an injected draw sequence.
+# ---------------------------------------------------------------------------------------------------------
+class MT19937:
+    """Matsumoto & Nishimura's reference generator (init_genrand / genrand_int32), what std::mt19937(seed) and
+    boost::random::mt19937(seed) implement; mt19937()() with the default seed 5489 gives 4123659995 as its 10000th output."""
+
+    def __init__(self, seed=5489):
+        self.mt = [0] * 624
+        self.mt[0] = seed & 0xFFFFFFFF
+        for i in range(1, 624):
+            self.mt[i] = (1812433253 * (self.mt[i - 1] ^ (self.mt[i - 1] >> 30)) + i) & 0xFFFFFFFF
+        self.idx = 624
+
+    def __call__(self):
+        if self.idx >= 624:
+            mt = self.mt
+            for k in range(624):
+                y = (mt[k] & 0x80000000) | (mt[(k + 1) % 624] & 0x7FFFFFFF)
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ (0x9908B0DF if y & 1 else 0)
+            self.idx = 0
+        y = self.mt[self.idx]
+        self.idx += 1
+        y ^= y >> 11
+        y ^= (y << 7) & 0x9D2C5680
+        y ^= (y << 15) & 0xEFC60000
+        y ^= y >> 18
+        return y & 0xFFFFFFFF
+
+
+def choose_read(score, target_depth, use_logscale, draw):
+    """ReadSelector::chooseRead (src/ReadSelector.h:661-672).  `draw` is called only when score > target_depth."""
+    if score <= target_depth:
+        return True
+    choice = draw() % score
+    if use_logscale:
+        return choice <= target_depth * np.log(np.float32(score) / np.float32(target_depth))
+    return choice <= target_depth
+
+
+def pick_coverage_normalized_subset(scores, passes, pairs, target_depth, by_pair, both_pass, draw, use_logscale=False):
+    """ReadSelector::pickCoverageNormalizedSubset (src/ReadSelector.h:673-749), single thread (pairs in order, one RNG
+    stream).  scores[i] = ReadTrimType::score of read i, passes[i] = isPassingRead(i, minimumScore, minimumLength),
+    pairs = [(i, j|None)].  Returns the picked read indexes in pick order after optimizePickOrder (ascending)."""
+    picked = []
+    for i, j in pairs:
+        s1 = int(scores[i]) if passes[i] else -1                       # (long) of a float: truncation
+        s2 = int(scores[j]) if (j is not None and passes[j]) else -1
+        if by_pair:
+            p1, p2 = passes[i], (passes[j] if j is not None else False)
+            if not ((p1 and p2) if (j is not None and both_pass) else (p1 or p2)):        # isPassingPair :558-568
+                continue
+            if both_pass and (s1 <= 0 or s2 <= 0):
+                continue
+            if s1 <= 0 and s2 <= 0:
+                continue
+            if choose_read(max(s1, s2), target_depth, use_logscale, draw):
+                picked.append(i)
+                if j is not None:
+                    picked.append(j)
+        else:
+            if s1 > 0 and choose_read(s1, target_depth, use_logscale, draw):
+                picked.append(i)
+            if s2 > 0 and choose_read(s2, target_depth, use_logscale, draw):
+                picked.append(j)
+    return sorted(picked)
+
+
+def expected_kept_fraction(scores, target_depth):
+    """sum over reads of P(kept) = min(1, (D+1)/s): rand() % s <= D holds for D+1 of the s residues."""
+    s = np.asarray(scores, dtype=np.float64)
+    p = np.where(s > target_depth, (target_depth + 1.0) / np.maximum(s, 1.0), 1.0)
+    return float(p.sum()), float((p * (1.0 - p)).sum())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# a9: text of KmerSpectrum::Histogram::toString (src/KmerSpectrum.h:987-1035) from the three bucket columns
+# ---------------------------------------------------------------------------------------------------------
+def format_histogram(visits, visited_count, visited_weight, zoom_max=256):
+    """visits/visited_count/visited_weight: bucket arrays as filled by Histogram::addRecord (:964-975); the text is what
+    finish() + toString() print: fixed, setprecision(3); integer members print as integers, doubles with 3 decimals."""
+    zoom_log_skip = 7                                                  # (uint)(log(zoomMax+1)/log 2 - 1) for 255 and 256
+    n = len(visits)
+    cum = [0] * n
+    count, total_count, total_weight, last = 0, 0.0, 0.0, 0
+    for i in range(n - 1, -1, -1):
+        count += int(visits[i])
+        cum[i] = count
+        if visits[i] > 0:
+            total_count += float(visited_count[i])
+            total_weight += float(visited_weight[i])
+            last = max(last, i)
+
+    def f(x):
+        return "%.3f" % x
+
+    def div(a, b):
+        return a / b if b else float("nan")
+
+    out = ["Counts, Weights and Directions\n"]
+    out.append("Counts:\t%d\t%s\t%s\t\n" % (count, f(total_count), f(div(total_count, count))))
+    out.append("Weights:\t%d\t%s\t%s\t%s\n" % (count, f(total_weight), f(div(total_weight, count)), f(div(total_weight, total_count))))
+    out.append("\n")
+    out.append("Bucket\tCumulative\tUnique\t%Unique\tCount\t%Count\tWeight\tQualProb\t%Weight\n")
+    for i in range(1, last + 1):
+        label = i if i <= zoom_max else int(2.0 ** (i + zoom_log_skip - zoom_max))
+        v, c, w = int(visits[i]), int(visited_count[i]), float(visited_weight[i])
+        out.append("%d\t%d\t%d\t%s\t%d\t%s\t\t%s\t%s\t%s\t\n" % (
+            label, cum[i], v, f(div(100.0 * v, count)), c, f(div(100.0 * c, total_count)), f(w), f(div(w, c)), f(div(100.0 * w, total_weight))))
+    return "".join(out)

@@ -157,7 +157,14 @@ def test_count_table_synthetic(K, k, n_reads, kw):
     osp = oracle_table(bases, q, off, k, threads=4)
     assert_tables_equal(ctx.export(), osp.export())
     gh = ctx.histogram()
-    ov, oc, ow = osp.histogram(256)
+    for zm in (255, 256):                # serial apps print Histogram(256), FilterReads-P MPIHistogram(255)
+        ov, oc, ow = osp.histogram(zm)
+        gv, gc = np.zeros(len(ov), np.uint64), np.zeros(len(ov), np.uint64)
+        for c in np.nonzero(gh)[0]:
+            b = oracle.histogram_bin(int(c), zm)
+            gv[b] += gh[c]
+            gc[b] += gh[c] * np.uint64(c)
+        assert (gv == ov).all() and (gc == oc).all()
     exact = np.zeros(65536, np.uint64)
     for c in np.unique(osp.export()["count"]):
         exact[c] = (osp.export()["count"] == c).sum()
@@ -169,6 +176,44 @@ def test_count_table_synthetic(K, k, n_reads, kw):
         ctx.purge_min_depth(md)
         osp.purge_min_depth(md)
         assert_tables_equal(ctx.export(), osp.export())
+    ctx.close()
+
+
+@pytest.mark.parametrize("k", [31, 63])
+def test_histogram_weight_column(K, k):
+    """a9: KmerSpectrum::Histogram (src/KmerSpectrum.h:909-1057) with the weight column -- visits and visitedCount exact,
+    visitedWeight (a sum of fp32 weightedCounts, order-dependent in the reference too) to 1e-5, for both zoomMax values
+    and before / after the singleton purge (singletons report their quantised weight, src/KmerTrackingData.h:641-661)"""
+    bases, q, off = synth.reads_numpy(12000, 150, 25000, seed=21, err=0.004, lowq=0.002, n_rate=0.0005)
+    rng = np.random.default_rng(2)
+    q = q.copy()
+    q[rng.random(len(q)) < 0.3] = 33 + 25          # varied qualities: weights well below 1
+    ctx = K.Context(kmer_size=k, table_slots=1 << 22, value_kind=K.capi.KMN_VALUE_WEIGHTS)
+    ctx.count_batch(bases, q, off)
+    ctx.count_finish(apply_purge=False)
+    osp = oracle_table(bases, q, off, k, threads=4)
+    for purge in (0, 2):
+        if purge:
+            ctx.purge_min_depth(purge)
+            osp.purge_min_depth(purge)
+        gh, gw = ctx.histogram(with_weights=True)
+        for zm in (255, 256):
+            ov, oc, ow = osp.histogram(zm)
+            gv, gc, gws = np.zeros(len(ov), np.uint64), np.zeros(len(ov), np.uint64), np.zeros(len(ov), np.float64)
+            for c in np.nonzero(gh)[0]:
+                b = oracle.histogram_bin(int(c), zm)
+                gv[b] += gh[c]
+                gc[b] += gh[c] * np.uint64(c)
+                gws[b] += gw[c]
+            if purge:                    # the reference keeps counting purged singletons as (1, 1.0) records (:1046-1048)
+                ps = osp.stats()["purged_singletons"]
+                assert ov[1] == ps and gv[1] == 0
+                ov, oc, ow = ov.copy(), oc.copy(), ow.copy()
+                ov[1] = oc[1] = 0
+                ow[1] = 0.0
+            assert (gv == ov).all() and (gc == oc).all()
+            assert np.allclose(gws, ow, rtol=1e-5, atol=1e-6)
+            assert ow[2:].sum() > 0
     ctx.close()
 
 

@@ -49,6 +49,61 @@ def test_filter_reads_p_without_kmers_matches_serial(filter_reads, golden_dir, t
     assert not os.path.exists(str(tmp_path / "comm")) and not os.path.exists(str(tmp_path / "par-1000.fastq.rank1"))
 
 
+def _norm_oracle(golden_dir, seed, depth, minlen=25.0, start=64, both=False):
+    """expected output of `FilterReads --max-kmer-output-depth D ... 0 1000.fastq` (no k-mer work: score = read length after
+    the artifact quality trim) from the oracle's restatement of pickCoverageNormalizedSubset and an MT19937 stream"""
+    from oracle import filter_oracle as F
+    import oracle
+    recs = F.parse_fastq(open(os.path.join(golden_dir, "1000.fastq")).read())
+    F.normalise_quals(recs, start=start)
+    F.artifact_quality_trim(recs, start, 3, minlen)
+    scores = [0 if r["discarded"] else len(r["seq"]) for r in recs]
+    passes = [(not r["discarded"]) and s >= 2 and oracle.passes_length(s, len(r["seq"]), minlen) for r, s in zip(recs, scores)]
+    pairs = F.identify_pairs(recs)
+    rng = F.MT19937(seed)
+    picked = F.pick_coverage_normalized_subset(scores, passes, pairs, depth, True, both, rng)
+    text = "".join(F.format_fastq(recs[i], dict(label="", off=0, len=scores[i]), start) for i in picked)
+    return text, picked, scores
+
+
+@pytest.mark.parametrize("seed,depth,both", [(12345, 50, False), (7, 70, False), (99, 40, True)])
+def test_random_normalisation_decisions_match_oracle(filter_reads, golden_dir, tmp_path, seed, depth, both):
+    """a12: chooseRead / pickCoverageNormalizedSubset (src/ReadSelector.h:661-749) with an injected mt19937 stream make
+    the identical keep / drop decisions as the oracle's restatement -- same picked set, same output bytes.  kmer-size 0
+    keeps the test on the CPU (score = length of the artifact-filtered read)."""
+    out = str(tmp_path / "n")
+    args = ["--max-kmer-output-depth", str(depth), "--fastq-output-base-quality", "64", "--min-read-length", "25"]
+    if both:
+        args += ["--min-passing-in-pair", "2"]
+    env = dict(os.environ, KMN_SEED=str(seed))
+    p = subprocess.run([filter_reads] + args + ["--out", out, "0", "1000.fastq"], capture_output=True, text=True, cwd=golden_dir, env=env, timeout=600)
+    assert p.returncode == 0, p.stderr
+    want, picked, scores = _norm_oracle(golden_dir, seed, depth, both=both)
+    assert 0 < len(picked) < 1000                     # the depth really subsamples
+    assert open("%s-MaxDepth%d-1000.fastq" % (out, depth)).read() == want
+
+
+def test_random_normalisation_kept_fraction(filter_reads, tmp_path):
+    """a12, SURVEY 8: the kept count follows sum min(1, (D+1)/s) -- 20000 unpaired reads of random length, time-seeded
+    RNG as in the reference, |kept - expectation| within 5 sigma"""
+    import numpy as np
+    from oracle import filter_oracle as F
+    rng = np.random.default_rng(3)
+    lens = rng.integers(60, 251, 20000)
+    fq = tmp_path / "len.fastq"
+    with open(fq, "w") as f:
+        for i, L in enumerate(lens):
+            f.write("@r%d\n%s\n+\n%s\n" % (i, "ACGT"[i % 4] * int(L), "I" * int(L)))
+    out = str(tmp_path / "k")
+    depth = 80
+    p = _run(filter_reads, ["--max-kmer-output-depth", str(depth), "--skip-artifact-filter", "1", "--out", out, "0", str(fq)])
+    assert p.returncode == 0, p.stderr
+    kept = sum(1 for l in open("%s-MaxDepth%d-len.fastq" % (out, depth)).read().split("\n")[0::4] if l)
+    exp, var = F.expected_kept_fraction(lens, depth)
+    assert abs(kept - exp) <= 5.0 * var ** 0.5 + 1, (kept, exp, var)
+    assert kept < 20000
+
+
 def test_help_lists_reference_options(filter_reads):
     p = _run(filter_reads, ["--help"])
     assert p.returncode == 1                       # apps/FilterReads.cpp:85: `if (!parseOpts) exit(1)`
