@@ -37,8 +37,9 @@ struct kmn_ctx {
     cudaStream_t stream = nullptr;        // main stream: phase 1 (parse), scans, lookup pass; the one kmn_stream() returns
     cudaStream_t s_insert = nullptr;      // phase 2 (insert) runs here so that it overlaps phase 1 of the next sub-batch
     cudaStream_t s_copy = nullptr;        // H2D staging of host inputs, overlapping the kernels of the previous batch
-    bool pipeline = true;                 // two staging sets + insert stream (KMN_PIPELINE=0: one set, phase 2 follows phase 1 on the main stream)
-    int n_sets = 2;
+    bool pipeline = false;                // KMN_PIPELINE=1: two staging sets + insert stream (phase 2 of one sub-batch overlaps phase 1 of the
+                                          // next; measured slower than one set on one stream on B200: both phases want the same SM resources)
+    int n_sets = 1;
     std::string err;
     uint64_t launches = 0;
     // optional per-kernel timing
@@ -72,6 +73,14 @@ struct kmn_ctx {
     int n_cta = 0;                    // grid of k_kmer_scatter / k_route_records = staging sub-regions per partition
     int scatter_tpb = 512, scatter_ctas = 2;   // phase-1b CTA size and CTAs per SM (KMN_SCATTER_TPB / KMN_SCATTER_CTAS)
     uint32_t ring_R = 0;              // record slots per bin ring in phase 1b (0: no rings, every record stored directly)
+    // phase 2 in shared memory (k <= 31 without extra record word): second split by table slice + counting per slice
+    bool smem_count = false;
+    u64 *l2buf = nullptr;             // [n_groups][S][slices per group][cap2] records, sorted by slice
+    u32 *cnt2 = nullptr;              // [n_groups][S][slices per group]
+    u32 *tickets = nullptr;           // [2] work tickets of k_slice_split / k_count_slices
+    uint32_t split_S = 4, split_cap2 = 0, split_R = 0;
+    int split_tpb = 1024, split_ctas = 1, count_ctas = 3;
+    size_t split_smem = 0;
     uint32_t zero_below = 0;
     size_t scatter_smem = 0, route_smem = 0;
     DevBuf mask, wts;                 // phase 1a -> 1b: "counted" bits (and fp32 weights for KMN_VALUE_WEIGHTS)
@@ -226,8 +235,8 @@ static int alloc_stage_sets(kmn_ctx *c)
     const kmn_opts &o = c->o;
     uint64_t sk = o.stage_keys;
     if (!sk) {
-        sk = (o.est_raw_kmers ? o.est_raw_kmers : (1ull << 22)) / (c->pipeline ? 8 : 1);
-        uint64_t lim = (uint64_t)(0.35 * (double)free_b / (double)(c->RW * 8) / (double)c->n_sets);
+        sk = (o.est_raw_kmers ? o.est_raw_kmers : (1ull << 22)) / (c->pipeline ? 8 : 4);
+        uint64_t lim = (uint64_t)(0.22 * (double)free_b / (double)(c->RW * 8) / (double)c->n_sets);    // the slice-sorted copy is as large again
         if (sk > lim) sk = lim;
     }
     if (sk < (1ull << 16)) sk = 1ull << 16;
@@ -272,6 +281,43 @@ static int alloc_stage_sets(kmn_ctx *c)
         c->ring_R = R;
         c->scatter_smem = hdr + n_bins * R * c->RW * 8;
         c->route_smem = (n_pad + 64) * 4;
+    }
+    // shared-memory phase 2: one more split of every group by slice, then counting with the slice in shared memory
+    if (c->l2buf) { CK(c, cudaFree(c->l2buf)); c->l2buf = nullptr; }
+    if (c->cnt2) { CK(c, cudaFree(c->cnt2)); c->cnt2 = nullptr; }
+    // (phase 1 may insert directly into the table when a sub-region overflows, and k_count_slices holds slices in shared
+    //  memory: the two must never run at the same time, so the single-GPU pipeline is incompatible and the push path
+    //  orders phase 1 behind the drains, see kmn_count_batch)
+    c->smem_count = c->W == 1 && !c->hasx && ((c->nranks == 1 && !c->pipeline) || c->p2p) && c->table.part_slots * 16 <= 64 * 1024;
+    if (const char *e = getenv("KMN_SMEM_COUNT")) c->smem_count = c->smem_count && atoi(e) != 0;
+    if (c->smem_count) {
+        int dev_smem = 0;
+        CK(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+        const size_t nb = (size_t)1 << c->table.group_shift, n_pad = (nb + 31) & ~(size_t)31;
+        if (const char *e = getenv("KMN_SPLIT_S")) c->split_S = (uint32_t)std::min(COUNT_MAX_S, std::max(1, atoi(e)));
+        if (const char *e = getenv("KMN_SPLIT_TPB")) c->split_tpb = std::min(1024, std::max(64, atoi(e) & ~31));
+        if (const char *e = getenv("KMN_SPLIT_CTAS")) c->split_ctas = std::max(1, atoi(e));
+        if (c->split_tpb * c->split_ctas > 2048) c->split_ctas = 2048 / c->split_tpb;
+        const size_t budget = (size_t)dev_smem / (size_t)c->split_ctas - 2048;
+        uint32_t R = 32;
+        while (R >= 4 && 2 * n_pad * 4 + nb * R * 8 > budget) R >>= 1;
+        if (R < 4) c->smem_count = false;
+        c->split_R = R;
+        c->split_smem = 2 * n_pad * 4 + nb * R * 8;
+        // records of one drain per sub-run: stage_keys / (slices * S), plus slack for the spread (a sub-run that fills up
+        // sends its records straight to the table)
+        const uint64_t m2 = sk / c->table.n_parts / c->split_S + 1;
+        c->split_cap2 = (uint32_t)((m2 + m2 / 8 + 8 * (uint64_t)std::sqrt((double)m2) + 32 + 3) & ~3ull);
+        const size_t n_sub2 = (size_t)n_groups * c->split_S * nb;
+        if (c->smem_count) {
+            if (cudaMalloc((void **)&c->l2buf, n_sub2 * c->split_cap2 * 8) != cudaSuccess) { cudaGetLastError(); c->l2buf = nullptr; c->smem_count = false; }
+        }
+        if (c->smem_count) {
+            CK(c, cudaMalloc((void **)&c->cnt2, n_sub2 * 4));
+            if (!c->tickets) CK(c, cudaMalloc((void **)&c->tickets, 64));
+            CK(c, cudaFuncSetAttribute(k_slice_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
+            CK(c, cudaFuncSetAttribute(k_count_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16)));
+        }
     }
     return 0;
 }
@@ -481,7 +527,7 @@ void kmn_destroy(kmn_ctx *c)
 #ifdef KMN_WITH_NCCL
     if (c->comm) ncclCommDestroy(c->comm);
 #endif
-    void *ptrs[] = {c->sets[0].v.ovf_recs, c->sets[0].v.ovf_count, c->sets[1].v.ovf_recs, c->sets[1].v.ovf_count, c->recv_all, c->run_off, c->grp_off, c->flags, c->d_const, c->ent_ptr, c->ent_cnt, c->coarse,c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
+    void *ptrs[] = {c->l2buf, c->cnt2, c->tickets, c->sets[0].v.ovf_recs, c->sets[0].v.ovf_count, c->sets[1].v.ovf_recs, c->sets[1].v.ovf_count, c->recv_all, c->run_off, c->grp_off, c->flags, c->d_const, c->ent_ptr, c->ent_cnt, c->coarse,c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
                     c->chunk_start, c->next_item,
                     c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts, c->seg_recs, c->seg_count,
                     c->in_bases[0].p, c->in_quals[0].p, c->in_off[0].p, c->in_disc[0].p,
@@ -520,14 +566,42 @@ static int launch_insert(kmn_ctx *c, const StageView &v, int rb, uint64_t units,
     const u32 n_entries = v.n_parts * (v.n_cta + (rv.n_src > 1 ? (rv.n_src - 1) * (rv.mode == 1 ? v.n_cta : 1u) : 0)) +
                           (rv.mode == 1 && rv.n_src > 1 ? rv.n_src - 1 : 0u);
     k_build_entries<<<std::min<u32>((n_entries + 255) / 256, (u32)c->n_sms * 4), 256, 0, si>>>(v, rv, (u32)c->RW, c->ent_ptr, c->ent_cnt);
-    k_build_worklist<<<1, 1024, 0, si>>>(c->ent_cnt, n_entries, (u32)INSERT_CHUNK, c->chunk_start, c->next_item, c->coarse);
-    c->launches += 2;
+    c->launches++;
+    const u64 *ent_ptr = c->ent_ptr;
+    const u32 *ent_cnt = c->ent_cnt;
+    u32 n_list = n_entries;
+    if (c->smem_count) {
+        // grouped entries: split every group by slice, then count slice by slice in shared memory; the ungrouped rest
+        // (overflow lists of the peers) goes through the generic insert below, after the slices are back in the table
+        const u32 per_group = v.n_cta + (rv.n_src > 1 ? (rv.n_src - 1) * (rv.mode == 1 ? v.n_cta : 1u) : 0);
+        const u32 n_grouped = v.n_parts * per_group;
+        SplitArgs sa{};
+        sa.table = c->table; sa.ent_ptr = c->ent_ptr; sa.ent_cnt = c->ent_cnt; sa.per_group = per_group; sa.n_groups = v.n_parts;
+        sa.S = std::min<u32>(c->split_S, per_group); sa.epp = (per_group + sa.S - 1) / sa.S;
+        sa.buf = c->l2buf; sa.cnt2 = c->cnt2; sa.cap2 = c->split_cap2; sa.ring_R = c->split_R; sa.ticket = c->tickets; sa.ctr = c->ctr;
+        CK(c, cudaMemsetAsync(c->tickets, 0, 8, si));
+        {
+            ProfScope ps(c, KMN_PROF_SUBPART, units, si);
+            k_slice_split<<<c->n_sms * c->split_ctas, c->split_tpb, c->split_smem, si>>>(sa);
+        }
+        {
+            ProfScope ps(c, KMN_PROF_INSERT, units, si);
+            k_count_slices<<<c->n_sms * c->count_ctas, COUNT_TPB, c->table.part_slots * 16, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, v.n_parts, c->tickets + 1, c->ctr);
+        }
+        c->launches += 2;
+        CK(c, cudaGetLastError());
+        if (n_entries == n_grouped) return 0;
+        ent_ptr += n_grouped; ent_cnt += n_grouped; n_list = n_entries - n_grouped;
+        units = 0;
+    }
+    k_build_worklist<<<1, 1024, 0, si>>>(ent_cnt, n_list, (u32)INSERT_CHUNK, c->chunk_start, c->next_item, c->coarse);
+    c->launches++;
     const int grid = c->n_sms * c->insert_ctas;
     const u32 n_split = rb >= 0 ? (u32)c->round_split : 1u;
     for (u32 sp = 0; sp < n_split; ++sp) {
         ProfScope ps(c, KMN_PROF_INSERT, sp == 0 ? units : 0, si);
         KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
-            k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, si>>>(c->table, c->ent_ptr, c->ent_cnt, n_entries, c->chunk_start, c->coarse, c->next_item, c->ctr, sp, n_split);
+            k_insert_staged<W_, X_><<<grid, INSERT_TPB, 0, si>>>(c->table, ent_ptr, ent_cnt, n_list, c->chunk_start, c->coarse, c->next_item, c->ctr, sp, n_split);
         }));
         c->launches++;
     }
@@ -1126,6 +1200,7 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
 #ifdef KMN_WITH_NCCL
         if (c->p2p) {                                       // one launch = one round: fill a set, push it, insert
             r = push_set_ready(c, c->cur); if (r) return r;
+            if (c->smem_count) { r = wait_drains(c); if (r) return r; }      // phase 1 never overlaps a shared-memory phase 2
             const uint64_t nr = rg.r1 - rg.r0, ns = (uint64_t)std::max(1, c->round_split);
             for (uint64_t sp = 0; sp < ns; ++sp) {            // same set, several launches (see round_split)
                 const uint64_t q0 = rg.r0 + nr * sp / ns, q1 = rg.r0 + nr * (sp + 1) / ns;
@@ -1232,6 +1307,8 @@ int kmn_histogram(kmn_ctx *c, uint64_t *hist, double *wsum)
 {
     if (!c || !hist) return KMN_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    if (c->nranks > 1 && c->p2p && !c->finished)          // the round buffers are still in use by the count pass (header: KMN_ERR_STATE)
+        return fail(c, KMN_ERR_STATE, "%s before kmn_count_finish on a multi-GPU context", __func__);
     int r = drain(c); if (r) return r;
     DevBuf &hb = c->lk_out;
     r = ensure(c, hb, 65536 * 16); if (r) return r;
@@ -1263,6 +1340,8 @@ int kmn_lookup(kmn_ctx *c, const uint8_t *keys, uint64_t n, uint16_t *counts)
 {
     if (!c || (n && (!keys || !counts))) return KMN_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    if (c->nranks > 1 && c->p2p && !c->finished)          // the round buffers are still in use by the count pass (header: KMN_ERR_STATE)
+        return fail(c, KMN_ERR_STATE, "%s before kmn_count_finish on a multi-GPU context", __func__);
     int r = drain(c); if (r) return r;
 #ifdef KMN_WITH_NCCL
     if (c->nranks > 1) {
@@ -1397,6 +1476,8 @@ int kmn_trim_batch(kmn_ctx *c, const uint8_t *bases, const uint64_t *read_off, u
     if (!c) return KMN_ERR_INVALID;
     if (scoring < 0 || scoring > 4) return fail(c, KMN_ERR_INVALID, "Invalid scoring type!");
     CK(c, cudaSetDevice(c->device));
+    if (c->nranks > 1 && c->p2p && !c->finished)          // the round buffers are still in use by the count pass (header: KMN_ERR_STATE)
+        return fail(c, KMN_ERR_STATE, "%s before kmn_count_finish on a multi-GPU context", __func__);
     int r = drain(c); if (r) return r;
 #ifdef KMN_WITH_NCCL
     if (c->nranks > 1 && n_reads == 0) {           // a rank without reads still serves the other ranks' requests
@@ -1493,6 +1574,8 @@ int kmn_export(kmn_ctx *c, uint32_t min_count, uint8_t *keys, uint16_t *count, u
 {
     if (!c || !n_out) return KMN_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
+    if (c->nranks > 1 && c->p2p && !c->finished)          // the round buffers are still in use by the count pass (header: KMN_ERR_STATE)
+        return fail(c, KMN_ERR_STATE, "%s before kmn_count_finish on a multi-GPU context", __func__);
     int r = drain(c); if (r) return r;
     if (min_count < 1) min_count = 1;
     CK(c, cudaMemsetAsync(c->scratch, 0, 16, c->stream));

@@ -1270,6 +1270,238 @@ __global__ void __launch_bounds__(INSERT_TPB, KMN_INSERT_MIN_CTAS) k_insert_stag
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3': phase 2 for single-word keys without an extra record word (k <= 31, the FilterReads value kind): counting in
+// SHARED MEMORY.  A scattered access to L2 costs the SM 1.5 (RED) to 3.5 (load, store) cycles per lane, a shared-memory
+// access a tenth of that (bench/micro/lsu.cu), so the records of a table group are split once more -- by the 64 KB slice
+// of the table their key lives in (k_slice_split, the ring / whole-sector mechanism of phase 1b with the slices of one
+// group as bins) -- and k_count_slices then brings one slice at a time into shared memory, probes and counts there
+// (LDS.128 probe, ATOMS add, ATOMS CAS to claim), and writes the slice back: the table only ever sees coalesced traffic.
+// Same slot layout, same probe sequence (linear from the even slot below the home slot, wrapping inside the slice) and
+// the same saturating count as table_insert, so k_insert_staged / table_find / the scans work on the same table.
+// ------------------------------------------------------------------------------------------------
+struct SplitArgs {
+    TableView table;
+    const u64 *ent_ptr;    // phase-2 work list entries, group-major (k_build_entries)
+    const u32 *ent_cnt;
+    u32 per_group;         // entries per group
+    u32 n_groups;
+    u32 S;                 // a group's entries are cut into S parts; one CTA splits one (group, part) into private sub-runs
+    u32 epp;               // entries per part
+    u64 *buf;              // [n_groups][S][slices per group][cap2] records
+    u32 *cnt2;             // [n_groups][S][slices per group] records of every sub-run
+    u32 cap2;              // multiple of 4
+    u32 ring_R;            // power of two >= 4
+    u32 *ticket;
+    Counters *ctr;
+};
+
+static constexpr int SPLIT_RPT = 4;        // records per thread and round
+
+__global__ void __launch_bounds__(1024, 1) k_slice_split(SplitArgs a)
+{
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    __shared__ u32 s_item;
+    const u32 nb = 1u << a.table.group_shift;                          // bins = slices of one group
+    const u32 n_pad = (nb + 31u) & ~31u;
+    u32 *cnt = reinterpret_cast<u32 *>(smem_raw);
+    u32 *fl = cnt + n_pad;
+    u64 *ring = reinterpret_cast<u64 *>(fl + n_pad);
+    const u32 R = a.ring_R, cap2 = a.cap2;
+    const u32 n_items = a.n_groups * a.S;
+    const u32 T = blockDim.x;
+    LocalCtr lc{0, 0, 0, 0, 0, 0};
+    while (true) {
+        if (threadIdx.x == 0) s_item = atomicAdd(a.ticket, 1u);
+        for (u32 i = threadIdx.x; i < nb; i += T) { cnt[i] = 0; fl[i] = 0; }
+        __syncthreads();
+        const u32 item = s_item;
+        if (item >= n_items) break;
+        const u32 g = item / a.S, part = item - g * a.S;
+        u64 *const obase = a.buf + (size_t)item * nb * cap2;
+        auto flush = [&](bool all) {
+            for (u32 b = threadIdx.x; b < nb; b += T) {
+                u32 c = cnt[b];
+                if (c > cap2) c = cap2;
+                const u32 f = fl[b];
+                if (c <= f) continue;
+                u32 end, nfl;
+                if (c - f > R) { end = f + R; nfl = c; }
+                else { end = all ? c : (c & ~3u); nfl = end; }
+                if (end <= f) continue;
+                u64 *gdst = obase + (size_t)b * cap2;
+                const u64 *rb = ring + (size_t)b * R;
+                u32 pos = f;
+                for (; pos < end && (pos & 3u); ++pos) gdst[pos] = rb[pos & (R - 1u)];
+                for (; pos + 4u <= end; pos += 4u) st_sector(gdst + pos, rb + (pos & (R - 1u)));
+                for (; pos < end; ++pos) gdst[pos] = rb[pos & (R - 1u)];
+                fl[b] = nfl;
+            }
+        };
+        // the records of the item's entries are taken in rounds of T * SPLIT_RPT; the records of the next round are
+        // requested before this round's are binned, so a round never waits for memory
+        const u32 e1 = min(g * a.per_group + (part + 1u) * a.epp, (g + 1u) * a.per_group);
+        u32 e = g * a.per_group + part * a.epp, base = 0, n = 0;
+        const u64 *src = nullptr;
+        auto open_entry = [&]() {                                      // first entry at or after e that has records
+            while (e < e1) {
+                n = __ldg(&a.ent_cnt[e]);
+                if (n) { src = reinterpret_cast<const u64 *>(__ldg(&a.ent_ptr[e])); base = 0; return; }
+                ++e;
+            }
+            n = 0;
+        };
+        auto fetch = [&](u64 (&r)[SPLIT_RPT], u32 &have) {             // this thread's records of the current round, then advance
+            have = 0;
+            if (e >= e1) return;
+#pragma unroll
+            for (int u = 0; u < SPLIT_RPT; ++u) {
+                const u32 idx = base + (u32)u * T + threadIdx.x;
+                if (idx < n) { r[u] = ld_nc64(src + idx); have |= 1u << u; }
+            }
+            base += T * SPLIT_RPT;
+            if (base >= n) { ++e; open_entry(); }
+        };
+        open_entry();
+        u64 cur[SPLIT_RPT], nxt[SPLIT_RPT];
+        u32 hc = 0, hn = 0;
+        bool more = e < e1;                                            // uniform: every thread walks the same (entry, base) sequence
+        fetch(cur, hc);
+        while (more) {
+            more = e < e1;
+            fetch(nxt, hn);
+#pragma unroll
+            for (int u = 0; u < SPLIT_RPT; ++u) {
+                if (!((hc >> u) & 1u)) continue;
+                u64 key[1] = {cur[u] & ~1ull};
+                const u64 ph = place_hash<1>(key);
+                const u32 b = part_of(ph, a.table.n_parts) & (nb - 1u);
+                const u32 p = atomicAdd(&cnt[b], 1u);
+                if (p < cap2) {
+                    if (p - fl[b] < R) ring[(size_t)b * R + (p & (R - 1u))] = cur[u];
+                    else obase[(size_t)b * cap2 + p] = cur[u];
+                } else {                                               // sub-run full (skewed input): straight into the table
+                    Rec<1, false> r; r.w[0] = cur[u];
+                    insert_record<1, false>(a.table, r, lc.unique, lc.full, lc.probes);
+                    lc.direct++;
+                }
+            }
+            __syncthreads();
+            flush(false);
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < SPLIT_RPT; ++u) cur[u] = nxt[u];
+            hc = hn;
+        }
+        flush(true);
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < nb; i += T) a.cnt2[(size_t)item * nb + i] = min(cnt[i], cap2);
+        __syncthreads();
+    }
+    ctr_commit(a.ctr, lc);
+}
+
+static constexpr int COUNT_TPB = 256;
+static constexpr int COUNT_U = 8;          // records per thread and batch
+static constexpr int COUNT_MAX_S = 16;     // sub-runs per slice (SplitArgs::S)
+
+__global__ void __launch_bounds__(COUNT_TPB, 3) k_count_slices(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, u32 n_groups,
+                                                              u32 *ticket, Counters *ctr)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Slot<1> *sl = reinterpret_cast<Slot<1> *>(smem_raw);               // one slice of the table
+    __shared__ u32 s_pre[2][32];                                       // exclusive prefix of the S sub-run sizes of this / the next slice
+    const u32 nb = 1u << t.group_shift;
+    const u32 SL = (u32)t.part_slots;
+    u64 n_unique = 0, n_full = 0;
+    // slices are dealt round-robin (the work per slice is uniform); the sub-run sizes of a CTA's next slice are requested
+    // while it works on the current one (warp 0: one lane per sub-run, prefix by shuffles; s_pre[][S] = total)
+    auto load_pre = [&](u32 pi, u32 *dst) {
+        if (threadIdx.x < 32) {
+            u32 c = (threadIdx.x < S && pi < t.n_parts) ? cnt2[((size_t)(pi >> t.group_shift) * S + threadIdx.x) * nb + (pi & (nb - 1u))] : 0u;
+            u32 v = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(0xffffffffu, v, d); if ((int)threadIdx.x >= d) v += x; }
+            if (threadIdx.x < COUNT_MAX_S + 1u) dst[threadIdx.x] = v - c;
+        }
+    };
+    load_pre(blockIdx.x, s_pre[0]);
+    u32 it = 0;
+    for (u32 pi = blockIdx.x; pi < t.n_parts; pi += gridDim.x, ++it) {
+        __syncthreads();                                               // s_pre[it & 1] is complete; the previous slice has left shared memory
+        load_pre(pi + gridDim.x, s_pre[(it + 1u) & 1u]);
+        const u32 *pre = s_pre[it & 1u];
+        const u32 total = pre[S];
+        if (total == 0) continue;                                      // nothing staged for this slice in this drain
+        const u32 g = pi >> t.group_shift, j = pi & (nb - 1u);
+        const u64 *run0 = buf + (((size_t)g * S) * nb + j) * cap2;     // sub-run p starts at run0 + p * nb * cap2
+        const size_t run_stride = (size_t)nb * cap2;
+        auto fetch = [&](u32 v0, u64 (&r)[COUNT_U], u32 &have) {       // records v0 + u * TPB + tid of the slice's concatenated sub-runs
+            have = 0;
+#pragma unroll
+            for (int u = 0; u < COUNT_U; ++u) {
+                const u32 v = v0 + (u32)u * COUNT_TPB + threadIdx.x;
+                if (v < total) {
+                    u32 p = 0;
+                    for (u32 q = 1; q < S; ++q) p += v >= pre[q] ? 1u : 0u;
+                    r[u] = ld_nc64(run0 + (size_t)p * run_stride + (v - pre[p]));
+                    have |= 1u << u;
+                }
+            }
+        };
+        u64 cur[COUNT_U], nxt[COUNT_U];
+        u32 hc = 0, hn = 0;
+        fetch(0, cur, hc);                                             // in flight while the slice is loaded
+        uint4 *gsl = reinterpret_cast<uint4 *>(reinterpret_cast<Slot<1> *>(t.slots) + (size_t)pi * SL);
+        uint4 *ssl = reinterpret_cast<uint4 *>(sl);
+        for (u32 i = threadIdx.x; i < SL; i += COUNT_TPB) ssl[i] = gsl[i];
+        __syncthreads();
+        for (u32 v0 = 0; v0 < total; v0 += COUNT_TPB * COUNT_U) {
+            if (v0 + COUNT_TPB * COUNT_U < total) fetch(v0 + COUNT_TPB * COUNT_U, nxt, hn); else hn = 0;
+#pragma unroll
+            for (int u = 0; u < COUNT_U; ++u) {
+                if (!((hc >> u) & 1u)) continue;
+                const u64 rec = cur[u];
+                const u64 key1 = rec & ~1ull, want = ~key1, add = 1ull | ((rec & 1ull) << 32);
+                u64 key[1] = {key1};
+                const u64 ph = place_hash<1>(key);
+                u32 s = (u32)home_slot(ph, SL) & ~1u;
+                u32 probes = 0;
+                for (; probes < SL; ++probes) {
+                    const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(&sl[s]);      // {val, key}
+                    u64 k = x.y;
+                    bool sat = (u32)x.x >= MAX_COUNT;
+                    if (k == 0ull) {
+                        k = atomicCAS(&sl[s].k[0], 0ull, want);
+                        if (k == 0ull) { n_unique++; k = want; }
+                        sat = false;
+                    }
+                    if (k == want) {
+                        if (!sat) atomicAdd(&sl[s].val, add);
+                        break;
+                    }
+                    s = s + 1u == SL ? 0u : s + 1u;
+                }
+                if (probes >= SL) n_full++;
+            }
+#pragma unroll
+            for (int u = 0; u < COUNT_U; ++u) cur[u] = nxt[u];
+            hc = hn;
+        }
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < SL; i += COUNT_TPB) gsl[i] = ssl[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_unique) atomicAdd(&ctr->unique, n_unique);
+        if (n_full) atomicAdd(&ctr->table_full, n_full);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // table scans
 // ------------------------------------------------------------------------------------------------
 template <int W>

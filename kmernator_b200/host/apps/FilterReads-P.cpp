@@ -24,7 +24,14 @@ int main(int argc, char *argv[])
         if (!root && !Options::getOptions().getDebug()) Log::verboseLevel() = 0;       // gathered logs: rank 0 speaks
         OptionsBaseInterface::FileListType &inputs = Options::getOptions().getInputFiles();
         LOG_VERBOSE(1, "Reading Input Files (rank " << world.rank() << " of " << world.size() << ")");
+        reads.deferNormalise();
         reads.appendAllFiles(inputs, world.rank(), world.size());
+        {   // every rank must rescale its qualities by the same amount: a rank whose slice shows evidence against the
+            // configured input base (ReadSet::validateFastqStart, src/ReadSet.h:171-194) makes all ranks switch
+            const int dflt = Options::getOptions().getFastqBaseQuality();
+            const unsigned long flipped = world.allMax(reads.detectInputBase() != dflt ? 1ul : 0ul);
+            reads.normaliseQualities(flipped ? (dflt == 33 ? 64 : 33) : dflt);
+        }
         LOG_VERBOSE(1, "loaded " << reads.getSize() << " Reads, " << reads.getBaseCount() << " Bases ");
         long numPairs = reads.identifyPairs();
         LOG_VERBOSE(1, "Pairs + single = " << numPairs);

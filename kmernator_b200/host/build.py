@@ -7,10 +7,11 @@ PKG = os.path.dirname(HERE)
 BIN = os.path.join(HERE, "bin")
 FILTER_READS = os.path.join(BIN, "FilterReads")
 FILTER_READS_P = os.path.join(BIN, "FilterReads-P")
+MERACULOUS_COUNTER = os.path.join(BIN, "MeraculousCounter")
 
 
 def _deps():
-    d = [os.path.join(HERE, "apps", f) for f in ("FilterReads.cpp", "FilterReads-P.cpp", "FilterReads.h")]
+    d = [os.path.join(HERE, "apps", f) for f in ("FilterReads.cpp", "FilterReads-P.cpp", "FilterReads.h", "MeraculousCounter.cpp")]
     d.append(os.path.join(os.path.dirname(PKG), "include", "kmernator_b200.h"))
     kd = os.path.join(HERE, "kmernator")
     return d + [os.path.join(kd, f) for f in os.listdir(kd) if f.endswith(".h")]
@@ -21,7 +22,7 @@ def build(force=False):
     if not os.path.exists(lib):
         raise ImportError("kmernator_b200.host: %s not built (build the CUDA library first)" % lib)
     os.makedirs(BIN, exist_ok=True)
-    for exe, src in ((FILTER_READS, "FilterReads.cpp"), (FILTER_READS_P, "FilterReads-P.cpp")):
+    for exe, src in ((FILTER_READS, "FilterReads.cpp"), (FILTER_READS_P, "FilterReads-P.cpp"), (MERACULOUS_COUNTER, "MeraculousCounter.cpp")):
         if not force and os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in _deps()):
             continue
         cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", exe, os.path.join(HERE, "apps", src),

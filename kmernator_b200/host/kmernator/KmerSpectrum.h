@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <iomanip>
 #include <sstream>
 #include <string>
@@ -186,7 +187,51 @@ public:
     }
     void printHistograms(std::ostream &os, bool solidOnly = false) { os << getHistogram(solidOnly); }
 
+    // MeraculousDistributedKmerSpectrum::dumpCounts / dumpGraphs (src/Meraculous.h:107-133): for every k-mer of this rank's
+    // table with count >= minDepth one line for the k-mer and one for its reverse complement -- "<kmer>\t<count>", and
+    // "<kmer>\t<6 left + 6 right extension counters A C G T N X> 0" (ExtensionTracking::toTextValues,
+    // src/KmerTrackingData.h:153-230; the reverse complement swaps the sides and complements the bases).  The reference
+    // writes in bucket order and its test sorts (test/runMeraculousTests.sh:39-75); here: ascending key order.
+    void dumpCounts(std::ostream &os, int minDepth) { dump(os, minDepth, false); }
+    void dumpGraphs(std::ostream &os, int minDepth) { dump(os, minDepth, true); }
+
 private:
+    void dump(std::ostream &os, int minDepth, bool graph)
+    {
+        if (!weak.ctx) LOG_THROW("dump on an empty KmerSpectrum");
+        const unsigned int k = KmerBaseOptions::getOptions().getKmerSize(), kb = (k + 3) / 4;
+        uint64_t n = 0;
+        const uint32_t md = (uint32_t)std::max(1, minDepth);
+        KMN_CHECK(weak.ctx, kmn_export(weak.ctx, md, NULL, NULL, NULL, NULL, NULL, 0, &n));
+        if (n == 0) return;
+        std::vector<uint8_t> keys((size_t)n * kb);
+        std::vector<uint16_t> count(n);
+        std::vector<uint32_t> ext(graph ? (size_t)n * 12 : 0);
+        uint64_t got = 0;
+        KMN_CHECK(weak.ctx, kmn_export(weak.ctx, md, keys.data(), count.data(), NULL, NULL, graph ? ext.data() : NULL, n, &got));
+        std::vector<size_t> order(got);
+        for (size_t i = 0; i < got; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return memcmp(&keys[a * kb], &keys[b * kb], kb) < 0; });
+        static const char B[] = "ACGT";
+        static const int COMP[6] = {3, 2, 1, 0, 4, 5};                   // A<->T, C<->G, N, X
+        std::string km(k, 'A'), rc(k, 'A');
+        for (size_t q = 0; q < got; ++q) {
+            const size_t i = order[q];
+            for (unsigned int b = 0; b < k; ++b) {
+                const int code = (keys[i * kb + (b >> 2)] >> (6 - 2 * (b & 3))) & 3;
+                km[b] = B[code]; rc[k - 1 - b] = B[3 - code];
+            }
+            if (!graph) { os << km << "\t" << count[i] << "\n" << rc << "\t" << count[i] << "\n"; continue; }
+            const uint32_t *e = &ext[i * 12];
+            uint32_t r[12];
+            for (int c = 0; c < 6; ++c) { r[COMP[c]] = e[6 + c]; r[6 + COMP[c]] = e[c]; }
+            os << km << "\t";
+            for (int c = 0; c < 12; ++c) os << e[c] << " ";
+            os << "0\n" << rc << "\t";
+            for (int c = 0; c < 12; ++c) os << r[c] << " ";
+            os << "0\n";
+        }
+    }
     unsigned long _rawKmers;
 };
 

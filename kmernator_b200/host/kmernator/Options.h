@@ -278,9 +278,17 @@ public:
         _FilterKnownOdditiesOptions::setOptions();
         _FilterReadsBaseOptions::setOptions();
     }
-    static bool parseOpts(int argc, char *argv[])
+    // resetDefaults: an app's own defaults (e.g. MeraculousCounter: min-quality-score 2, min-kmer-quality 0,
+    // apps/MeraculousCounter.cpp:66-80), applied before the command line
+    static void setDefault(const std::string &name, const std::string &v)
+    {
+        kmn_host::OptionSpec &s = kmn_host::OptionRegistry::get().spec(name);
+        s.def = v; s.value = v;
+    }
+    static bool parseOpts(int argc, char *argv[], void (*resetDefaults)() = NULL, bool kmerSizePositional = true)
     {
         registerAll();
+        if (resetDefaults) resetDefaults();
         kmn_host::OptionRegistry &r = kmn_host::OptionRegistry::get();
         try {
             std::vector<std::string> positional;
@@ -302,7 +310,7 @@ public:
                 else positional.push_back(a);
             }
             size_t p = 0;
-            if (!r.spec("kmer-size").isSet && p < positional.size()) r.set("kmer-size", positional[p++]);
+            if (kmerSizePositional && !r.spec("kmer-size").isSet && p < positional.size()) r.set("kmer-size", positional[p++]);
             for (; p < positional.size(); ++p) r.set("input-file", positional[p]);
             Options::getOptions().inputFiles = r.spec("input-file").values;
             Log::verboseLevel() = Options::getOptions().getVerbose();

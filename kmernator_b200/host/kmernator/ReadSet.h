@@ -27,6 +27,7 @@ class Read {
 public:
     static int &FASTQ_START_CHAR() { static int c = 33; return c; }        // Read::FASTQ_START_CHAR, src/Sequence.cpp:543-547
     static const unsigned char REF_QUAL = 0xff;                              // Kmernator::REF_QUAL: FASTA reads carry no qualities
+    static const unsigned char PRINT_REF_QUAL = 33 + 70;                     // Kmernator::PRINT_REF_QUAL = 103 ('g'), src/config.h:140
 
     Read() : discarded(false), fileNum(0) {}
     Read(const std::string &n, const std::string &c, const std::string &s, const std::string &q)
@@ -50,7 +51,7 @@ public:
         if (!label.empty()) hdr += " " + label;
         if (discarded || trimLength <= 1) return hdr + "\nN\n+\n" + std::string(1, (char)(FASTQ_START_CHAR() + 1)) + "\n";
         std::string q = quals.substr(trimOffset, trimLength);
-        if (!q.empty() && (unsigned char)q[0] == REF_QUAL) q.assign(trimLength, 'h');   // PRINT_REF_QUAL for quality-less reads
+        if (!q.empty() && (unsigned char)q[0] == REF_QUAL) q.assign(trimLength, (char)PRINT_REF_QUAL);   // quality-less reads, src/Sequence.cpp:744-747
         return hdr + "\n" + seq.substr(trimOffset, trimLength) + "\n+\n" + q + "\n";
     }
     std::string toFasta(unsigned int trimOffset, unsigned int trimLength, const std::string &label) const
@@ -81,7 +82,7 @@ public:
         bool operator<(const Pair &o) const { return lesser() < o.lesser(); }
     };
 
-    ReadSet() : _baseCount(0), _maxLength(0), _inputBase(0) {}
+    ReadSet() : _baseCount(0), _maxLength(0), _inputBase(0), _deferNormalise(false) {}
 
     // each rank parses byte range [rank, rank+1)/size of every file in the reference (src/ReadFileReader.h:379-398);
     // here one process feeds one GPU and slices by record count instead
@@ -89,8 +90,9 @@ public:
     {
         unsigned int fileNum = 0;
         for (OptionsBaseInterface::FileListType::const_iterator it = files.begin(); it != files.end(); ++it) appendAnyFile(*it, ++fileNum, rank, size);
-        normaliseQualities();
+        if (!_deferNormalise) normaliseQualities();
     }
+    void deferNormalise(bool d = true) { _deferNormalise = d; }       // the distributed driver agrees on the input base first
     void appendAnyFile(const std::string &path, unsigned int fileNum = 1, int rank = 0, int size = 1)
     {
         std::ifstream in(path.c_str());
@@ -225,17 +227,32 @@ private:
         if (cm.size() >= 3 && (cm[0] == '1' || cm[0] == '2') && cm[1] == ':' && (cm[2] == 'Y' || cm[2] == 'N')) return cm[0] - '0';
         return 0;
     }
-    // auto-detect the input Phred base (33 <-> 64) and re-express every quality in FASTQ_START_CHAR
-    void normaliseQualities()
+    // auto-detect the input Phred base (33 <-> 64) and re-express every quality in FASTQ_START_CHAR.  As in the reference
+    // only the first 20000 reads are examined (ReadSet::validateFastqStart, src/ReadSet.h:171-194: `getSize() < 20000`), a
+    // read whose MINIMUM quality lies outside [base, base + 40] flips the assumed base (Read::validateFastqStart tests the
+    // minimum twice, src/Sequence.h:455-480), and a flip far into the file is reported.
+public:
+    int detectInputBase() const
     {
         int base = Options::getOptions().getFastqBaseQuality();
-        for (size_t i = 0; i < _reads.size(); ++i) {
+        const size_t n = std::min<size_t>(_reads.size(), 20000);
+        for (size_t i = 0; i < n; ++i) {
             const std::string &q = _reads[i].quals;
             if (q.empty() || (unsigned char)q[0] == Read::REF_QUAL) continue;
             unsigned char m = 255;
             for (size_t j = 0; j < q.size(); ++j) if ((unsigned char)q[j] < m) m = (unsigned char)q[j];
-            if ((int)m < base || (int)m > base + 40) base = (base == 33) ? 64 : 33;
+            if ((int)m < base || (int)m > base + 40) {
+                if (i > 10000) LOG_WARN(1, "expected base-" << base << " fastq but detected the other base only very far into the file, "
+                                           "please make sure standard fastq and illumina fastq are not mixed");
+                base = (base == 33) ? 64 : 33;
+            }
         }
+        return base;
+    }
+    // base = the agreed input base (FilterReads-P: every rank must rescale by the same amount)
+    void normaliseQualities(int base = 0)
+    {
+        if (base == 0) base = detectInputBase();
         _inputBase = base;
         const int d = Read::FASTQ_START_CHAR() - base;
         if (d == 0) return;
@@ -251,6 +268,7 @@ private:
     unsigned long _baseCount;
     unsigned int _maxLength;
     int _inputBase;
+    bool _deferNormalise;
 };
 
 #endif

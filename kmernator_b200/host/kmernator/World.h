@@ -8,6 +8,7 @@
 #define KMERNATOR_HOST_WORLD_H
 
 #include <chrono>
+#include <ctime>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -16,6 +17,7 @@
 #include <thread>
 #include <vector>
 
+#include <dirent.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -40,7 +42,7 @@ public:
             ss << (t ? t : "/tmp") << "/kmn-comm-" << (id ? id : "run") << "-" << (long)getppid();
         }
         _dir = ss.str();
-        if (_size > 1) mkdir(_dir.c_str(), 0700);
+        if (_size > 1) openRendezvous();
     }
     int rank() const { return _rank; }
     int size() const { return _size; }
@@ -108,17 +110,54 @@ public:
         for (unsigned long q = 0; q < _seq; ++q)
             for (int r = 0; r < _size; ++r) remove(name(q, r).c_str());
         for (int r = 0; r < _size; ++r) remove(doneName(r).c_str());
+        remove((_dir + "/token").c_str());
         rmdir(_dir.c_str());
     }
 
 private:
+    // The rendezvous directory may hold the files of an earlier run that crashed (a fixed KMN_COMM_DIR, a reused parent
+    // pid).  Rank 0 therefore empties it and publishes a per-launch token; every file of this launch carries the token in
+    // its name, and the other ranks only accept a token that is not older than their own start (minus a launch skew of
+    // ten minutes).  The directory must be ours (mode 0700), and for multi-node runs it must be on a shared file system.
+    void openRendezvous()
+    {
+        const long t0 = (long)time(NULL);
+        if (mkdir(_dir.c_str(), 0700) != 0) {
+            struct stat sb;
+            if (stat(_dir.c_str(), &sb) != 0 || !S_ISDIR(sb.st_mode)) LOG_THROW("cannot create the rendezvous directory " << _dir);
+            if (sb.st_uid != geteuid()) LOG_THROW("rendezvous directory " << _dir << " belongs to another user");
+        }
+        const std::string tok = _dir + "/token";
+        if (_rank == 0) {
+            if (DIR *d = opendir(_dir.c_str())) {                         // leftovers of a crashed run
+                while (struct dirent *e = readdir(d)) {
+                    const std::string n = e->d_name;
+                    if (n != "." && n != "..") remove((_dir + "/" + n).c_str());
+                }
+                closedir(d);
+            }
+            std::ostringstream ss;
+            ss << t0 << "-" << (long)getpid();
+            _nonce = ss.str();
+            { std::ofstream of((tok + ".tmp").c_str()); of << _nonce; }
+            if (rename((tok + ".tmp").c_str(), tok.c_str()) != 0) LOG_THROW("could not publish " << tok);
+            return;
+        }
+        for (int waited = 0;; ++waited) {
+            std::ifstream in(tok.c_str());
+            std::string v;
+            if (in.good() && (in >> v) && !v.empty() && atol(v.c_str()) >= t0 - 600) { _nonce = v; return; }
+            std::this_thread::sleep_for(std::chrono::milliseconds(2));
+            if (waited > 300000) LOG_THROW("rank 0 did not open the rendezvous in " << _dir);
+        }
+    }
     static int envInt(const char *n, int dflt) { const char *v = getenv(n); return v && *v ? atoi(v) : dflt; }
     static std::string toStr(unsigned long v) { std::ostringstream ss; ss << v; return ss.str(); }
-    std::string name(unsigned long seq, int r) const { std::ostringstream ss; ss << _dir << "/" << seq << "." << r; return ss.str(); }
-    std::string doneName(int r) const { std::ostringstream ss; ss << _dir << "/done." << r; return ss.str(); }
+    std::string name(unsigned long seq, int r) const { std::ostringstream ss; ss << _dir << "/" << _nonce << "." << seq << "." << r; return ss.str(); }
+    std::string doneName(int r) const { std::ostringstream ss; ss << _dir << "/" << _nonce << ".done." << r; return ss.str(); }
     int _rank, _size, _localRank;
     unsigned long _seq;
-    std::string _dir;
+    std::string _dir, _nonce;
 };
 
 #endif

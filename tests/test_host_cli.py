@@ -188,3 +188,67 @@ def test_filter_reads_normalisation_and_aliases(filter_reads, golden_dir, tmp_pa
     assert 0 < len(hdrs) < len([l for l in full if l])
     p2 = subprocess.run([filter_reads] + args, capture_output=True, text=True, cwd=golden_dir, env=env, timeout=600)
     assert p2.returncode == 0 and open(out + "-MinDepth2-MaxDepth4-1000.fastq").read().split("\n")[0::4][: len(hdrs)] == hdrs
+
+
+def test_fasta_input_prints_ref_quality(filter_reads, tmp_path):
+    """quality-less (FASTA) reads written as FASTQ carry PRINT_REF_QUAL = 33 + 70 = 'g' (src/config.h:140,
+    src/Sequence.cpp:744-747)"""
+    fa = tmp_path / "in.fasta"
+    fa.write_text(">s1\nACGTACGTAC\nGTACGT\n>s2 note\nTTTTGGGGCCCCAAAA\n")
+    out = str(tmp_path / "o")
+    p = _run(filter_reads, ["--skip-artifact-filter", "1", "--out", out, "0", str(fa)])
+    assert p.returncode == 0, p.stderr
+    assert open(out + "-in.fastq").read() == "@s1\nACGTACGTACGTACGT\n+\n" + "g" * 16 + "\n@s2 note\nTTTTGGGGCCCCAAAA\n+\n" + "g" * 16 + "\n"
+
+
+def test_phred_base_detection_examines_first_reads_only(filter_reads, tmp_path):
+    """ReadSet::validateFastqStart (src/ReadSet.h:171-194) looks at the first 20000 reads: a high-quality Phred+33 read
+    (minimum quality above 33 + 40) far into the file must not flip the base of the whole file"""
+    fq = tmp_path / "hq.fastq"
+    with open(fq, "w") as f:
+        for i in range(20050):
+            q = "K" * 20 if i >= 20010 else "I" * 19 + "5"
+            f.write("@r%d\n%s\n+\n%s\n" % (i, "ACGT" * 5, q))
+    out = str(tmp_path / "o")
+    p = _run(filter_reads, ["--skip-artifact-filter", "1", "--out", out, "0", str(fq)])
+    assert p.returncode == 0, p.stderr
+    lines = open(out + "-hq.fastq").read().split("\n")
+    assert lines[3] == "I" * 19 + "5" and lines[4 * 20020 + 3] == "K" * 20
+
+
+MERA_ARGS = ["--fastq-base-quality", "64", "--thread", "2", "--min-kmer-quality=0", "--min-quality-score=2", "--kmer-size", "21"]
+
+
+def _check_meraculous(out, golden_dir):
+    for mine, good in ((out + ".mercount.m21", "phix.mercount.m21"), (out + ".mergraph.m21.D2", "phix.mergraph.m21.D2")):
+        got = sorted(open(mine).read().splitlines())                   # `sort $TEST | diff - $GOOD`
+        assert got == open(os.path.join(golden_dir, good)).read().splitlines(), good
+
+
+@pytest.mark.gpu
+def test_meraculous_counter_goldens(filter_reads, golden_dir, tmp_path):
+    """the reference's own test of MeraculousCounter (test/runMeraculousTests.sh:39-75): k-mer counts and extension
+    counters of test/1000.fastq, sorted, equal phix.mercount.m21 and phix.mergraph.m21.D2 line for line"""
+    exe = os.path.join(os.path.dirname(filter_reads), "MeraculousCounter")
+    out = str(tmp_path / "m")
+    p = _run(exe, MERA_ARGS + ["--out", out, "1000.fastq"], cwd=golden_dir)
+    assert p.returncode == 0, p.stderr
+    _check_meraculous(out, golden_dir)
+
+
+@pytest.mark.gpu
+def test_meraculous_counter_two_ranks(filter_reads, golden_dir, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(os.path.dirname(filter_reads), "MeraculousCounter")
+    out = str(tmp_path / "m")
+    res = _run_ranks(exe, MERA_ARGS + ["--out", out, "1000.fastq"], 2, golden_dir, str(tmp_path / "comm"), gpus=True)
+    assert all(rc == 0 for rc, _ in res), res
+    _check_meraculous(out, golden_dir)
+
+
+def test_meraculous_counter_requires_kmer_size(filter_reads, golden_dir):
+    exe = os.path.join(os.path.dirname(filter_reads), "MeraculousCounter")
+    p = _run(exe, ["--out", "/tmp/never", os.path.join(golden_dir, "10.fastq")])
+    assert p.returncode == 1 and "can not be 0" in p.stderr
