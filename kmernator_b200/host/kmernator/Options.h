@@ -231,9 +231,9 @@ public:
     {
         kmn_host::OptionRegistry &r = kmn_host::OptionRegistry::get();
         r.add("skip-artifact-filter", "0", "skip homo-polymer, primer-dimer and duplicated fragment pair filtering");
-        r.add("artifact-match-length", "24", "kmer match length to known artifact sequences (screen not implemented)");
-        r.add("artifact-edit-distance", "2", "edit distance of the artifact screen (screen not implemented)");
-        r.add("build-artifact-edits-in-filter", "2", "artifact screen tuning (screen not implemented)");
+        r.add("artifact-match-length", "24", "kmer match length to known artifact sequences (a multiple of 4, at most 28)");
+        r.add("artifact-edit-distance", "2", "edit distance to apply to artifact-match-length matches to known artifacts");
+        r.add("build-artifact-edits-in-filter", "2", "0 - edits are searched for at run time, 1 - built into the filter, 2 - built while the filter is small");
         r.add("mask-simple-repeats", "0", "mask simple repeats", false, true);
         r.add("phix-output", "0", "separate PhiX reads", false, false);
         r.add("filter-output", "0", "separate artifact reads", false, false);

@@ -40,7 +40,8 @@ public:
     const std::string &getQuals() const { return quals; }
     bool isDiscarded() const { return discarded; }
     void discard() { discarded = true; }
-    void addComment(const std::string &c) { comment = comment.empty() ? c : comment + " " + c; }
+    // Read::getTrimRead joins an existing comment and the label with a tab (src/Sequence.h:485-496)
+    void addComment(const std::string &c, const char *sep = " ") { comment = comment.empty() ? c : comment + sep + c; }
 
     // Read::toFastq / Sequence::_getFastaString with a trim (src/Sequence.cpp:296-328,729-770): a discarded read, or one
     // trimmed to <= 1 base, is written as "N" with quality START+1

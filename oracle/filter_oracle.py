@@ -311,3 +311,168 @@ def format_histogram(visits, visited_count, visited_weight, zoom_max=256):
         out.append("%d\t%d\t%d\t%s\t%d\t%s\t\t%s\t%s\t%s\t\n" % (
             label, cum[i], v, f(div(100.0 * v, count)), c, f(div(100.0 * c, total_count)), f(w), f(div(w, c)), f(div(100.0 * w, total_weight))))
     return "".join(out)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# f2: FilterKnownOddities with the 24-mer artifact screen (src/FilterKnownOddities.h:190-286,389-541,693-704).
+# numpy restatement on uint64-packed k-mers, independent of the host C++ (kmernator_b200/host/kmernator/FilterKnownOddities.h);
+# only the list of artifact sequences is shared (host/data/artifacts.inc = the reference's getArtifactFasta, :742-795).
+# ---------------------------------------------------------------------------------------------------------
+def artifact_sequences():
+    import os
+    import re
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kmernator_b200", "host", "data", "artifacts.inc")
+    return re.findall(r'\{"([^"]*)", "([^"]*)"\}', open(inc).read())
+
+
+_CODE = np.zeros(256, dtype=np.uint64)
+for _c, _v in ((b"C", 1), (b"G", 2), (b"T", 3), (b"c", 1), (b"g", 2), (b"t", 3)):
+    _CODE[_c[0]] = _v                                                   # everything else packs as A (TwoBitSequence)
+
+
+def _pack_all(seq, L):
+    """uint64 array of every L-mer of seq (first base in the highest used bits)"""
+    c = _CODE[np.frombuffer(seq.encode("latin1"), dtype=np.uint8)]
+    n = len(c) - L + 1
+    if n <= 0:
+        return np.zeros(0, dtype=np.uint64)
+    k = np.zeros(n, dtype=np.uint64)
+    for i in range(L):
+        k = (k << np.uint64(2)) | c[i:i + n]
+    return k
+
+
+def _canonical(k, L):
+    rc = np.zeros_like(k)
+    f = k.copy()
+    for _ in range(L):
+        rc = (rc << np.uint64(2)) | (np.uint64(3) - (f & np.uint64(3)))
+        f >>= np.uint64(2)
+    return np.minimum(k, rc)
+
+
+def _substitutions(k, L):
+    """all single-base substitutions of every k-mer in k (3 * L each)"""
+    out = []
+    for b in range(L):
+        sh = np.uint64(2 * (L - 1 - b))
+        orig = (k >> sh) & np.uint64(3)
+        cleared = k & ~(np.uint64(3) << sh)
+        for d in (1, 2, 3):
+            out.append(cleared | (((orig + np.uint64(d)) & np.uint64(3)) << sh))
+    return np.concatenate(out) if out else k[:0]
+
+
+class ArtifactFilter:
+    def __init__(self, match_length=24, edit_distance=2, build_edits=2):
+        self.L = match_length
+        seqs = [""] + [s for _, s in artifact_sequences()]
+        seqs = [s + s[:match_length] for s in seqs]                      # ReadSet::circularize (src/ReadSet.cpp:120-130)
+        self.n_sequences = len(seqs)
+        ks = [_canonical(_pack_all(s, match_length), match_length) for s in seqs]
+        filt = np.unique(np.concatenate(ks))
+        self.num_errors = edit_distance
+        for _ in range(edit_distance):                                   # prepareMaps :254-283
+            if build_edits == 1 or (build_edits == 2 and len(filt) < 750000):
+                self.num_errors -= 1
+                filt = np.unique(np.concatenate([filt, _canonical(_substitutions(filt, match_length), match_length)]))
+        self.filter = filt
+
+    def _hit(self, k):
+        """k: uint64 array of canonical k-mers -> bool array: within the remaining run-time edit distance of the filter"""
+        def member(x):
+            i = np.searchsorted(self.filter, x)
+            i[i >= len(self.filter)] = 0
+            return self.filter[i] == x
+        hit = member(k)
+        cur = [k]
+        for _ in range(self.num_errors):                                 # superset of the reference's increasing-position walk: same reachable set
+            nxt = _substitutions(np.concatenate(cur), self.L)
+            m = member(_canonical(nxt, self.L)).reshape(3 * self.L, -1) if len(nxt) else np.zeros((0, 0), bool)
+            per = len(np.concatenate(cur))
+            if per:
+                mm = m.reshape(3 * self.L, per).any(axis=0)
+                # fold the hits of the variants back onto the originating k-mers
+                reps = per // len(k)
+                hit |= mm.reshape(reps, len(k)).any(axis=0)
+            cur = [nxt]
+        return hit
+
+    def screen(self, seq, qual, start, min_quality):
+        """applyFilterToRead (:389-541) -> (value, minPass, maxPass, secondBest)"""
+        L = self.L
+        n = len(seq)
+        best, second, test = [0, 0], [0, 0], [0, 0]
+        if qual is not None:
+            for i, c in enumerate(qual):
+                test[1] = i
+                if c < start + min_quality:
+                    if test[1] - test[0] > best[1] - best[0]:
+                        best, test = test, best
+                    if test[1] - test[0] > second[1] - second[0]:
+                        second, test = test, second
+                    test = [i + 1, i + 1]
+        test[1] = n
+        if test[1] - test[0] > best[1] - best[0]:
+            best, test = test, best
+        if test[1] - test[0] > second[1] - second[0]:
+            second, test = test, second
+        min_pass, max_pass = (best[0], best[1]) if best[1] > best[0] else (0, 0)
+        byte_hops = (max_pass + 3) // 4 - L // 4 - (0 if n % 4 == 0 else 1)
+        if byte_hops < 0 or byte_hops > (n + 3) // 4:
+            byte_hops = 0
+        value = 0
+        min_aff, max_aff = max_pass, min_pass
+        hops = list(range(min_pass // 4, byte_hops + 1))
+        if hops:
+            ptrs = np.arange(len(hops)) * 4                              # the scan pointer starts at byte 0 of the read (:466-486)
+            ok = ptrs + L <= n
+            allk = _pack_all(seq, L)
+            if ok.any():
+                ks = _canonical(allk[ptrs[ok]], L)
+                h = self._hit(ks)
+                for hop, hh in zip(np.array(hops)[ok], h):
+                    if hh:
+                        pos = int(hop) * 4
+                        value = 1
+                        min_aff = min(min_aff, pos)
+                        max_aff = max(max_aff, pos + L)
+        if value > 0 and min_aff <= max_aff:
+            if (min_aff - min_pass) >= (max_pass - max_aff):
+                max_pass = min_aff
+            else:
+                min_pass = max_aff
+        if value == 0 and (max_pass - min_pass) != n:
+            value = self.n_sequences
+        return value, min_pass, max_pass, tuple(second)
+
+
+def artifact_filter(recs, start, min_quality, min_read_length, match_length=24, edit_distance=2, build_edits=2, flt=None):
+    """FilterKnownOddities::applyFilter (:663-732): trims / discards in place, appends the rescued "-qtrim" remnants.
+    Returns (trimmed, discarded, remnants)."""
+    flt = flt or ArtifactFilter(match_length, edit_distance, build_edits)
+    n_trim = n_disc = 0
+    remnants = []
+    for r in recs:
+        has_q = bool(r["qual"]) and ord(r["qual"][0]) != 0xFF
+        q = r["qual"].encode("latin1") if has_q else None
+        value, a, b, second = flt.screen(r["seq"], q, start, min_quality)
+        if value == 0:
+            continue
+        L = len(r["seq"])
+        if value == flt.n_sequences and B.passes_length(second[1] - second[0], L, min_read_length):
+            sl = second[1] - second[0]
+            lab = "AFTrim:%d+%d" % (second[0], sl)
+            remnants.append(dict(name=r["name"] + "-qtrim", comment=(r["comment"] + "\t" + lab) if r["comment"] else lab,
+                                 seq=r["seq"][second[0]:second[1]], qual=r["qual"][second[0]:second[1]], discarded=False))
+        n = b - a
+        if n <= 0 or not B.passes_length(n, L, min_read_length):
+            r["discarded"] = True
+            n_disc += 1
+        else:
+            lab = "AFTrim:%d+%d" % (a, n)
+            r["seq"], r["qual"] = r["seq"][a:b], r["qual"][a:b]
+            r["comment"] = (r["comment"] + "\t" + lab) if r["comment"] else lab
+            n_trim += 1
+    recs.extend(remnants)
+    return n_trim, n_disc, len(remnants)

@@ -252,3 +252,64 @@ def test_meraculous_counter_requires_kmer_size(filter_reads, golden_dir):
     exe = os.path.join(os.path.dirname(filter_reads), "MeraculousCounter")
     p = _run(exe, ["--out", "/tmp/never", os.path.join(golden_dir, "10.fastq")])
     assert p.returncode == 1 and "can not be 0" in p.stderr
+
+
+def _contaminated_fastq(path, n=3000, seed=4):
+    """reads with adapter / homopolymer fragments (0-2 substitutions, any offset), low-quality heads (the quality-trimmed
+    head shifts the screen's scan pointer) and low-quality bases in the middle (second stretch rescued as -qtrim)"""
+    import numpy as np
+    from oracle import filter_oracle as F
+    rng = np.random.default_rng(seed)
+    arts = [s for _, s in F.artifact_sequences()]
+    with open(path, "w") as f:
+        for i in range(n):
+            L = int(rng.integers(60, 152))
+            s = list("ACGT"[x] for x in rng.integers(0, 4, L))
+            q = ["I"] * L
+            kind = rng.random()
+            if kind < 0.35:
+                a = arts[int(rng.integers(0, len(arts)))].replace("N", "A")
+                fl = int(rng.integers(24, 41))
+                o = int(rng.integers(0, max(1, len(a) - fl + 1)))
+                frag = list(a[o:o + fl])
+                for _ in range(int(rng.integers(0, 3))):
+                    p = int(rng.integers(0, len(frag)))
+                    frag[p] = "ACGT"[("ACGT".index(frag[p]) + int(rng.integers(1, 4))) % 4]
+                at = int(rng.integers(0, L - len(frag) + 1))
+                if rng.random() < 0.6:
+                    at &= ~3
+                s[at:at + len(frag)] = frag
+            if 0.25 < kind < 0.45:
+                for p in range(int(rng.integers(1, 13))):
+                    q[p] = "#"
+            if 0.4 < kind < 0.5:
+                q[int(rng.integers(20, L - 20))] = "!"
+            if kind > 0.97:
+                q = ["#"] * L
+            f.write("@r%d%s\n%s\n+\n%s\n" % (i, " c%d" % i if i % 5 == 0 else "", "".join(s), "".join(q)))
+
+
+@pytest.mark.parametrize("edit,build,minlen", [(2, 2, "0.4"), (1, 2, "0.4"), (2, 0, "0.4"), (1, 1, "40"), (0, 2, "0.4")])
+def test_artifact_screen_matches_oracle(filter_reads, tmp_path, edit, build, minlen):
+    """f2: FilterKnownOddities with the 24-mer adapter / homopolymer screen (src/FilterKnownOddities.h:190-286,389-541)
+    against the oracle's numpy restatement on contaminated reads: same trims, discards and rescued remnants, byte for byte,
+    for edits built into the filter and edits searched at run time"""
+    from oracle import filter_oracle as F
+    fq = tmp_path / "cont.fastq"
+    _contaminated_fastq(str(fq))
+    out = str(tmp_path / "o")
+    p = _run(filter_reads, ["--artifact-edit-distance", str(edit), "--build-artifact-edits-in-filter", str(build), "--min-read-length", minlen,
+                            "--out", out, "0", str(fq)])
+    assert p.returncode == 0, p.stderr
+    recs = F.parse_fastq(open(fq).read())
+    n_trim, n_disc, n_rem = F.artifact_filter(recs, 33, 3, float(minlen), 24, edit, build)
+    # the rescued "-qtrim" remnants join the read set (and the k-mer count of a k > 0 run) but have no pair entry
+    # (ReadSet::append(const Read&), src/ReadSet.cpp:260-262; pairs are identified before the filter,
+    # apps/FilterReads.cpp:103,114), so the pair-wise selection never writes them -- in the reference and here
+    want = "".join(F.format_fastq(r, dict(label="", off=0, len=len(r["seq"])), 33) for r in recs
+                   if not r["discarded"] and len(r["seq"]) > 1 and not r["name"].endswith("-qtrim"))
+    got = open(out + "-cont.fastq").read()
+    assert got == want
+    assert n_trim > 300 and n_disc > 30 and n_rem > 20             # every branch was exercised
+    if edit == 2:
+        assert ("filter affected (trimmed/removed) %d Reads" % n_trim) in p.stderr
