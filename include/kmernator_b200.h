@@ -134,10 +134,25 @@ int  kmn_trim_batch(kmn_ctx *ctx, const uint8_t *bases, const uint64_t *read_off
 int  kmn_export(kmn_ctx *ctx, uint32_t min_count, uint8_t *keys, uint16_t *count, uint16_t *dir, float *wsum,
                 uint32_t *ext, uint64_t cap, uint64_t *n_out);
 
+/* restore of a saved spectrum: KmerMapByKmerArrayPair(const void *mmap) / KmerSpectrum::restoreMmap
+ * (src/Kmer.h:3124-3191, src/KmerSpectrum.h:489-518).  n entries in the format kmn_export writes (dir / wsum / ext
+ * may be NULL); an entry whose key is already in the table is merged.  HOST or DEVICE arrays.                    */
+int  kmn_import(kmn_ctx *ctx, const uint8_t *keys, const uint16_t *count, const uint16_t *dir, const float *wsum,
+                const uint32_t *ext, uint64_t n);
+
+/* spectrum.subtractReference(other): k-mers present in `other` (count >= 1 after its own purge) are removed from this
+ * spectrum (src/KmerSpectrum.h:472-474,1582-1589; apps/FilterReads-P.cpp:281-308).  Both contexts on one device; with
+ * a communicator both are sharded by the same owner rule, so the call is local.                                   */
+int  kmn_subtract(kmn_ctx *ctx, kmn_ctx *other, uint64_t *removed_entries, uint64_t *removed_instances);
+
 /* per-k-mer records of one batch, for parity tests of steps (1)-(3): canonical key bytes, strand, fp32 weight,
  * KmerHasher hash.  HOST outputs sized sum(max(0,len-k+1)).                      src/KmerReadUtils.h:176-248 */
 int  kmn_debug_kmers(kmn_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *read_off,
                      uint64_t n_reads, uint8_t *keys, uint8_t *is_fwd, float *weight, uint64_t *hash, uint64_t *n_out);
+
+/* the owner rank the device assigns to canonical keys for `nranks` ranks: ((KmerHasher hash >> 24) & 0x7ffff) % nranks,
+ * getDistributedThreadId src/Kmer.h:2284-2295 (parity test of a5 on one GPU).  HOST or DEVICE arrays.               */
+int  kmn_debug_owner(kmn_ctx *ctx, const uint8_t *keys, uint64_t n, uint32_t nranks, uint32_t *owner);
 
 int  kmn_sync(kmn_ctx *ctx);
 

@@ -16,7 +16,7 @@ EXPORTED = [
     "kmn_default_opts", "kmn_last_error", "kmn_version", "kmn_create", "kmn_destroy", "kmn_reset", "kmn_comm_unique_id",
     "kmn_comm_init", "kmn_count_batch", "kmn_count_finish", "kmn_get_stats", "kmn_purge_min_depth", "kmn_histogram",
     "kmn_lookup", "kmn_trim_batch", "kmn_export", "kmn_debug_kmers", "kmn_sync", "kmn_stream", "kmn_launch_count",
-    "kmn_profile_enable", "kmn_profile_read",
+    "kmn_profile_enable", "kmn_profile_read", "kmn_import", "kmn_subtract", "kmn_debug_owner",
 ]
 PROF_KINDS = ["parse", "insert", "route", "lookup", "trim", "scan", "weight", "subpart"]
 
@@ -82,6 +82,9 @@ def load():
     L.kmn_export.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.kmn_debug_kmers.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, vp, vp, vp, C.POINTER(C.c_uint64)]
     L.kmn_sync.argtypes = [vp]
+    L.kmn_debug_owner.argtypes = [vp, vp, C.c_uint64, C.c_uint32, vp]
+    L.kmn_import.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint64]
+    L.kmn_subtract.argtypes = [vp, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.kmn_profile_enable.argtypes = [vp, C.c_int]
     L.kmn_profile_read.argtypes = [vp, C.POINTER(KmnProfile)]
     L.kmn_stream.restype = vp
@@ -223,6 +226,27 @@ class Context:
                 if ext is not None:
                     ext = ext[order]
         return dict(keys=keys, count=cnt, dir=dr, wsum=ws, ext=ext)
+
+    def debug_owner(self, keys, nranks):
+        keys = np.ascontiguousarray(keys, dtype=np.uint8).reshape(-1, self.kb)
+        out = np.zeros(len(keys), dtype=np.uint32)
+        self._ck(self._L.kmn_debug_owner(self._h, keys.ctypes.data, len(keys), nranks, out.ctypes.data))
+        return out
+
+    def import_entries(self, keys, count, dir=None, wsum=None, ext=None):
+        """kmn_import: entries as export() returns them"""
+        keys = np.ascontiguousarray(keys, dtype=np.uint8).reshape(-1, self.kb)
+        count = np.ascontiguousarray(count, dtype=np.uint16)
+        dir_ = np.ascontiguousarray(dir, dtype=np.uint16) if dir is not None else None
+        wsum = np.ascontiguousarray(wsum, dtype=np.float32) if wsum is not None else None
+        ext = np.ascontiguousarray(ext, dtype=np.uint32) if ext is not None else None
+        self._ck(self._L.kmn_import(self._h, _ptr(keys), _ptr(count), _ptr(dir_), _ptr(wsum), _ptr(ext), len(count)))
+
+    def subtract(self, other):
+        """kmn_subtract: -> (entries removed, instances removed)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.kmn_subtract(self._h, other._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def debug_kmers(self, bases, quals, read_off):
         read_off = np.ascontiguousarray(read_off, dtype=np.uint64)

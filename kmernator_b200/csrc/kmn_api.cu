@@ -80,9 +80,10 @@ struct kmn_ctx {
     u32 *tickets = nullptr;           // [2] work tickets of k_slice_split / k_count_slices
     uint32_t split_S = 4, split_cap2 = 0, split_R = 0;
     int split_tpb = 1024, split_ctas = 1, count_ctas = 3;
+    bool count_tma = true;            // k_count_slices_tma (bulk-copy engine) instead of k_count_slices (KMN_COUNT_TMA=0)
     size_t split_smem = 0;
     uint32_t zero_below = 0;
-    size_t scatter_smem = 0, route_smem = 0;
+    size_t scatter_smem = 0;
     DevBuf mask, wts;                 // phase 1a -> 1b: "counted" bits (and fp32 weights for KMN_VALUE_WEIGHTS)
     // input staging (host inputs), double-buffered: the copy of batch b+1 overlaps the kernels of batch b
     DevBuf in_bases[2], in_quals[2], in_off[2], in_disc[2];
@@ -97,11 +98,13 @@ struct kmn_ctx {
     // multi-GPU
     int rank = 0, nranks = 1;
     u64 *send_recs = nullptr, *send_cursor = nullptr, *recv_recs = nullptr, *all_counts = nullptr;
-    u64 *seg_recs = nullptr; u32 *seg_count = nullptr;
-    uint64_t send_cap = 0, recv_cap = 0, seg_cap = 0;
+    uint64_t send_cap = 0, recv_cap = 0;
     // multi-GPU push path: phase 1 bins by (owner, group); the other owners' parts are written into their receive
     // buffers over NVLink (peer pointers from CUDA IPC), sorted by group, and inserted from there
-    bool p2p = false;
+    bool p2p = false;                     // more than one rank: phase 1 bins by (owner, group) and the rounds below move the parts
+    bool ipc = false;                     // the peers' receive buffers are mapped (CUDA IPC): parts travel by copy engine or by
+                                          // k_push_copy over NVLink; otherwise they travel as ncclSend / ncclRecv
+    int pending_set = -1, pending_rb = -1;   // the round whose phase 2 has not been submitted yet (it follows the NEXT phase 1)
     cudaStream_t s_comm = nullptr;        // push kernels + the NCCL barriers of a round
     cudaStream_t s_comm2 = nullptr;       // second copy stream: half of the peers, so two copy engines feed NVLink at once
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -280,7 +283,6 @@ static int alloc_stage_sets(kmn_ctx *c)
         if (hdr > budget) return fail(c, KMN_ERR_INVALID, "too many staging bins (%zu) for the phase-1 shared memory", n_bins);
         c->ring_R = R;
         c->scatter_smem = hdr + n_bins * R * c->RW * 8;
-        c->route_smem = (n_pad + 64) * 4;
     }
     // shared-memory phase 2: one more split of every group by slice, then counting with the slice in shared memory
     if (c->l2buf) { CK(c, cudaFree(c->l2buf)); c->l2buf = nullptr; }
@@ -317,6 +319,9 @@ static int alloc_stage_sets(kmn_ctx *c)
             if (!c->tickets) CK(c, cudaMalloc((void **)&c->tickets, 64));
             CK(c, cudaFuncSetAttribute(k_slice_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
             CK(c, cudaFuncSetAttribute(k_count_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16)));
+            CK(c, cudaFuncSetAttribute(k_count_slices_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + 2 * COUNT_CHUNK * 8)));
+            if (const char *e = getenv("KMN_COUNT_TMA")) c->count_tma = atoi(e) != 0;
+            if ((c->table.part_slots * 16) % 16 != 0) c->count_tma = false;
         }
     }
     return 0;
@@ -410,12 +415,18 @@ static int plan_and_alloc(kmn_ctx *c)
 }
 
 static int wait_drains(kmn_ctx *c);
+#ifdef KMN_WITH_NCCL
+static int flush_pending_insert(kmn_ctx *c);
+#endif
 
 int kmn_reset(kmn_ctx *c)
 {
     if (!c) return KMN_ERR_INVALID;
     CK(c, cudaSetDevice(c->device));
     int r = wait_drains(c); if (r) return r;          // phase-2 work still in flight must not see the cleared table
+#ifdef KMN_WITH_NCCL
+    r = flush_pending_insert(c); if (r) return r;     // a round whose phase 2 was deferred behind the next phase 1
+#endif
     for (int si = 0; si < 2; ++si)                     // nor may a push still read the fill counters cleared below
         if (c->push_pending[si]) { CK(c, cudaStreamWaitEvent(c->stream, c->ev_pushed[si], 0)); c->push_pending[si] = false; }
     CK(c, cudaMemsetAsync(c->table.slots, 0, c->n_slots * c->slot_bytes, c->stream));
@@ -430,7 +441,6 @@ int kmn_reset(kmn_ctx *c)
     if (c->flags) CK(c, cudaMemsetAsync(c->flags, 0, 16, c->stream));
     CK(c, cudaMemsetAsync(c->ctr, 0, sizeof(Counters), c->stream));
     if (c->send_cursor) CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)c->nranks * 8, c->stream));
-    if (c->seg_count) CK(c, cudaMemsetAsync(c->seg_count, 0, (size_t)c->nranks * c->n_cta * 4, c->stream));
     c->purged_depth = 0;
     c->finished = false;
     return 0;
@@ -439,17 +449,14 @@ int kmn_reset(kmn_ctx *c)
 template <int W, bool X>
 static int set_smem_attrs(kmn_ctx *c)
 {
-    const int s = (int)std::max(c->scatter_smem, c->route_smem);
+    const int s = (int)c->scatter_smem;
     if (s <= 48 * 1024) return 0;
     CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
-    CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
     CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
     if (X) {
         CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
-        CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
         CK(c, cudaFuncSetAttribute(k_kmer_scatter<W, X, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
     }
-    CK(c, cudaFuncSetAttribute(k_route_records<W, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, s));
     return 0;
 }
 
@@ -529,7 +536,7 @@ void kmn_destroy(kmn_ctx *c)
 #endif
     void *ptrs[] = {c->l2buf, c->cnt2, c->tickets, c->sets[0].v.ovf_recs, c->sets[0].v.ovf_count, c->sets[1].v.ovf_recs, c->sets[1].v.ovf_count, c->recv_all, c->run_off, c->grp_off, c->flags, c->d_const, c->ent_ptr, c->ent_cnt, c->coarse,c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
                     c->chunk_start, c->next_item,
-                    c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts, c->seg_recs, c->seg_count,
+                    c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts,
                     c->in_bases[0].p, c->in_quals[0].p, c->in_off[0].p, c->in_disc[0].p,
                     c->in_bases[1].p, c->in_quals[1].p, c->in_off[1].p, c->in_disc[1].p, c->vals.p, c->first_nx.p, c->out_off.p,
                     c->lk_origin.p, c->lk_resp_in.p, c->lk_resp_out.p, c->mask.p, c->wts.p,
@@ -586,7 +593,10 @@ static int launch_insert(kmn_ctx *c, const StageView &v, int rb, uint64_t units,
         }
         {
             ProfScope ps(c, KMN_PROF_INSERT, units, si);
-            k_count_slices<<<c->n_sms * c->count_ctas, COUNT_TPB, c->table.part_slots * 16, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, v.n_parts, c->tickets + 1, c->ctr);
+            if (c->count_tma)
+                k_count_slices_tma<<<c->n_sms * 2, COUNT3_TPB, c->table.part_slots * 16 + 2 * COUNT_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr);
+            else
+                k_count_slices<<<c->n_sms * c->count_ctas, COUNT_TPB, c->table.part_slots * 16, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, v.n_parts, c->tickets + 1, c->ctr);
         }
         c->launches += 2;
         CK(c, cudaGetLastError());
@@ -684,7 +694,6 @@ static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, cons
     a.l2_hints = getenv("KMN_NO_L2_HINTS") ? 0 : 1;
     a.table = c->table; a.stage = c->sets[c->cur].v; a.ctr = c->ctr;
     a.send_recs = c->send_recs; a.send_cursor = c->send_cursor; a.send_cap = c->send_cap;
-    a.seg_recs = c->seg_recs; a.seg_count = c->seg_count; a.seg_cap = (u32)c->seg_cap;
     a.flags = c->flags;
     // pieces of 32 reads for large launches; smaller pieces when that would leave CTAs without work (at least 2 per CTA)
     uint32_t ps = 5;
@@ -711,12 +720,10 @@ static int launch_parse(kmn_ctx *c, const ParseArgs &a)
         ProfScope ps(c, KMN_PROF_PARSE, a.n_reads);
         const int grid = c->n_cta;
         const size_t sm = c->scatter_smem;
-        const int mode = !dist ? 0 : (c->p2p ? 2 : 1);
 #define KMN_SCATTER(X_, E_)                                                                          \
         do {                                                                                         \
-            if (mode == 0) k_kmer_scatter<W_, X_, E_, 0><<<grid, c->scatter_tpb, sm, c->stream>>>(a);    \
-            else if (mode == 1) k_kmer_scatter<W_, X_, E_, 1><<<grid, c->scatter_tpb, sm, c->stream>>>(a); \
-            else k_kmer_scatter<W_, X_, E_, 2><<<grid, c->scatter_tpb, sm, c->stream>>>(a);              \
+            if (!dist) k_kmer_scatter<W_, X_, E_, 0><<<grid, c->scatter_tpb, sm, c->stream>>>(a);     \
+            else k_kmer_scatter<W_, X_, E_, 2><<<grid, c->scatter_tpb, sm, c->stream>>>(a);           \
         } while (0)
         KMN_DISPATCH_W(c, {
             if (!c->hasx) KMN_SCATTER(false, false);
@@ -730,86 +737,15 @@ static int launch_parse(kmn_ctx *c, const ParseArgs &a)
     return 0;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// multi-GPU exchange: the k-mer shuffle of _buildKmerSpectrumMPI (src/DistributedFunctions.h:340-458) /
-// MPIAllToAllMessageBuffer::sendReceive (src/MPIBuffer.h:588-600,872-892) as an NCCL all-to-all of 8*RW-byte
-// records, preceded by an all-gather of the per-destination counts.
-// ---------------------------------------------------------------------------------------------------------
-static int exchange(kmn_ctx *c)
-{
-#ifdef KMN_WITH_NCCL
-    if (c->nranks <= 1) return 0;
-    const int R = c->nranks;
-    // pack the per-CTA send segments into one contiguous buffer per destination
-    CK(c, cudaMemsetAsync(c->scratch + 5, 0, 8, c->stream));
-    CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)R * 8, c->stream));
-    {
-        ProfScope ps(c, KMN_PROF_ROUTE, 0);
-        k_compact_send<<<dim3((unsigned)c->n_cta, (unsigned)R), 256, 0, c->stream>>>(c->seg_recs, c->seg_count, (u32)c->seg_cap, (u32)c->n_cta, (u32)c->RW,
-                                                                                   c->send_recs, c->send_cap, c->send_cursor, c->scratch + 5);
-    }
-    c->launches++;
-    CK(c, cudaGetLastError());
-    CK(c, cudaMemsetAsync(c->seg_count, 0, (size_t)R * c->n_cta * 4, c->stream));
-    ncclResult_t nr = ncclAllGather(c->send_cursor, c->all_counts, (size_t)R, ncclUint64, c->comm, c->stream);
-    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclAllGather failed: %s", ncclGetErrorString(nr));
-    std::vector<u64> counts((size_t)R * R);
-    u64 seg_overflow = 0;
-    CK(c, cudaMemcpyAsync(counts.data(), c->all_counts, counts.size() * 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaMemcpyAsync(&seg_overflow, c->scratch + 5, 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
-    if (seg_overflow) return fail(c, KMN_ERR_COMM, "send segment overflow (%llu segments; capacity %llu records each); use smaller batches",
-                                  (unsigned long long)seg_overflow, (unsigned long long)c->seg_cap);
-    // counts[src*R + dst]
-    u64 recv_total = 0;
-    for (int s = 0; s < R; ++s) {
-        if (counts[(size_t)s * R + (s == c->rank ? 0 : 0)] > 0) {}
-        if (s != c->rank) recv_total += counts[(size_t)s * R + c->rank];
-        for (int d = 0; d < R; ++d)
-            if (s == c->rank && counts[(size_t)s * R + d] > c->send_cap)
-                return fail(c, KMN_ERR_COMM, "send region overflow: %llu records for rank %d (capacity %llu); use smaller batches",
-                            (unsigned long long)counts[(size_t)s * R + d], d, (unsigned long long)c->send_cap);
-    }
-    if (recv_total > c->recv_cap) return fail(c, KMN_ERR_COMM, "receive region overflow: %llu > %llu", (unsigned long long)recv_total, (unsigned long long)c->recv_cap);
-    ncclGroupStart();
-    u64 roff = 0;
-    for (int p = 0; p < R; ++p) {
-        if (p == c->rank) continue;
-        u64 ns = counts[(size_t)c->rank * R + p], nrv = counts[(size_t)p * R + c->rank];
-        if (ns) ncclSend(c->send_recs + (size_t)p * c->send_cap * c->RW, ns * c->RW, ncclUint64, p, c->comm, c->stream);
-        if (nrv) ncclRecv(c->recv_recs + roff * c->RW, nrv * c->RW, ncclUint64, p, c->comm, c->stream);
-        roff += nrv;
-    }
-    nr = ncclGroupEnd();
-    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "nccl all-to-all failed: %s", ncclGetErrorString(nr));
-    CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)R * 8, c->stream));
-    if (recv_total) {
-        { int r = stage_room(c, recv_total); if (r) return r; }
-        RouteArgs ra;
-        ra.recs = c->recv_recs; ra.n_recs = recv_total;
-        ra.table = c->table; ra.stage = c->sets[c->cur].v; ra.ctr = c->ctr;
-        {
-            ProfScope ps(c, KMN_PROF_ROUTE, recv_total);
-            KMN_DISPATCH_W(c, KMN_DISPATCH_X(c, {
-                k_route_records<W_, X_><<<c->n_cta, ROUTE_TPB, c->route_smem, c->stream>>>(ra);
-            }));
-        }
-        c->launches++;
-        CK(c, cudaGetLastError());
-        c->sets[c->cur].staged_upper += recv_total;
-    }
-    return 0;
-#else
-    (void)c;
-    return 0;
-#endif
-}
-
 #ifdef KMN_WITH_NCCL
 // ---------------------------------------------------------------------------------------------------------
-// multi-GPU push path.  Set-up: every rank allocates its receive buffers, exports them with CUDA IPC, and the handles
-// travel through the NCCL communicator itself; all ranks switch to the push path only if every rank could map every
-// peer (otherwise the NCCL all-to-all path above stays in charge).
+// multi-GPU count pass.  Phase 1 bins every record by (owner rank, table group) into the staging set; one phase-1 launch
+// is one ROUND: the parts of the other owners travel into their receive buffers, and phase 2 inserts this rank's own part
+// plus what the peers sent.  Transport: the peers' receive buffers mapped with CUDA IPC and written over NVLink by the
+// copy engines (default) or by k_push_copy (KMN_PUSH=kernel); when the buffers cannot be mapped (KMN_P2P=0, another
+// node) the same parts travel as ncclSend / ncclRecv.  Every rank runs the same sequence of rounds whatever its input
+// (a rank without reads takes part with empty parts), so no collective ever depends on a rank's own data.
+// Set-up: every rank allocates its receive buffers, exports them, and the handles travel through the communicator.
 // ---------------------------------------------------------------------------------------------------------
 static int nccl_sum_u64(kmn_ctx *c, u64 mine, u64 *out, cudaStream_t st)
 {
@@ -824,37 +760,38 @@ static int nccl_sum_u64(kmn_ctx *c, u64 mine, u64 *out, cudaStream_t st)
 static int setup_push(kmn_ctx *c)
 {
     const int R = c->nranks;
-    c->p2p = false;
-    bool want = R <= KMN_MAX_PUSH_RANKS;
-    if (const char *e = getenv("KMN_P2P")) want = want && atoi(e) != 0;
-    const uint64_t G = c->n_groups;
-    {   // phase 1 keeps one shared-memory counter per (owner, group) bin
+    bool want_ipc = R <= KMN_MAX_PUSH_RANKS;
+    if (const char *e = getenv("KMN_P2P")) want_ipc = want_ipc && atoi(e) != 0;
+    {   // phase 1 keeps a counter and a flush mark per (owner, group) bin in shared memory: with many ranks the groups
+        // are made coarser (a group is only a binning granularity; the table's slices stay as they are)
         int dev_smem = 0;
         CK(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-        if ((G * (uint64_t)R + 128) * 8 > (uint64_t)dev_smem / c->scatter_ctas - 4096) want = false;
+        const uint64_t budget = (uint64_t)dev_smem / (uint64_t)c->scatter_ctas - 4096;
+        while (c->n_groups > 1 && (c->n_groups * (uint64_t)R + 128) * 8 > budget / 2) {
+            c->table.group_shift++;
+            c->n_groups = c->table.n_groups();
+        }
     }
+    const uint64_t G = c->n_groups;
     c->push_ce = true;
     if (const char *e = getenv("KMN_PUSH")) c->push_ce = strcmp(e, "kernel") != 0;
-    uint64_t cap = c->stage_keys / (uint64_t)R; cap += cap / 4 + 65536;
-    size_t meta_words = (size_t)G + 1;
-    const bool old_pipeline = c->pipeline;
-    const int old_sets = c->n_sets;
-    if (want) { c->pipeline = true; c->n_sets = 2; }
-    if (want && c->push_ce) {
-        // the receive buffer of a source is a verbatim copy of its part of the staging set: size the sets by owner first
-        c->p2p = true;
-        int r = alloc_stage_sets(c); if (r) return r;
-        c->p2p = false;
-        cap = (uint64_t)c->n_cta * G * c->sets[0].v.sub_cap + c->sets[0].v.ovf_cap;
-        meta_words = (size_t)G * c->n_cta + 1;
-    }
+    if (!want_ipc) c->push_ce = true;                       // the NCCL transport ships whole parts like the copy engines do
+    // two staging sets cut by owner; the receive buffer of a source is a verbatim copy of its part of a set
+    c->pipeline = true; c->n_sets = 2;
+    c->p2p = true;
+    { int r = alloc_stage_sets(c); if (r) return r; }
+    uint64_t cap; size_t meta_words;
+    if (c->push_ce) { cap = (uint64_t)c->n_cta * G * c->sets[0].v.sub_cap + c->sets[0].v.ovf_cap; meta_words = (size_t)G * c->n_cta + 1; }
+    else { cap = c->stage_keys / (uint64_t)R; cap += cap / 4 + 65536; meta_words = (size_t)G + 1; }
     const size_t rec_bytes = 2 * (size_t)R * cap * c->RW * 8, meta_bytes = 2 * (size_t)R * meta_words * 4;
-    u64 ok = want ? 1 : 0;
+    if (cudaMalloc(&c->recv_all, rec_bytes + meta_bytes + 256) != cudaSuccess) {
+        cudaGetLastError(); c->recv_all = nullptr;
+        return fail(c, KMN_ERR_NOMEM, "receive buffers of the multi-GPU count pass do not fit (%zu bytes); use a smaller stage_keys", rec_bytes + meta_bytes);
+    }
+    u64 ok = want_ipc ? 1 : 0;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof mine);
-    if (ok && cudaMalloc(&c->recv_all, rec_bytes + meta_bytes + 256) != cudaSuccess) { cudaGetLastError(); c->recv_all = nullptr; ok = 0; }
     if (ok && cudaIpcGetMemHandle(&mine, c->recv_all) != cudaSuccess) { cudaGetLastError(); ok = 0; }
-    // handles of all ranks
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
     std::vector<cudaIpcMemHandle_t> all((size_t)R);
     {
@@ -867,8 +804,8 @@ static int setup_push(kmn_ctx *c)
         CK(c, cudaStreamSynchronize(c->stream));
         CK(c, cudaFree(d));
     }
-    {   // the peers write straight into each other's buffers: the layout (groups, CTAs, sub-region capacity, record
-        // width) must be the same on every rank, otherwise everybody stays on the NCCL path, which re-buckets on arrival
+    {   // the ranks write into each other's buffers: the layout (groups, CTAs, sub-region capacity, record width) must be
+        // the same on every rank (same options and the same kind of GPU); anything else is a configuration error
         u64 geo[6] = {G, (u64)c->n_cta, (u64)c->sets[0].v.sub_cap, (u64)c->RW, cap, (u64)meta_words};
         void *d = nullptr;
         CK(c, cudaMalloc(&d, (size_t)(R + 1) * sizeof geo));
@@ -879,7 +816,10 @@ static int setup_push(kmn_ctx *c)
         CK(c, cudaMemcpyAsync(allgeo.data(), d, (size_t)R * sizeof geo, cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
         CK(c, cudaFree(d));
-        for (int p = 0; p < R; ++p) if (memcmp(&allgeo[(size_t)p * 6], geo, sizeof geo) != 0) ok = 0;
+        for (int p = 0; p < R; ++p)
+            if (memcmp(&allgeo[(size_t)p * 6], geo, sizeof geo) != 0)
+                return fail(c, KMN_ERR_INVALID, "rank %d was created with a different table / staging geometry than rank %d (est_raw_kmers, table_slots, "
+                                                "stage_keys, kmer size and value kind must agree on all ranks)", p, c->rank);
     }
     u64 all_ok = 0;
     { int r = nccl_sum_u64(c, ok, &all_ok, c->stream); if (r) return r; }
@@ -890,25 +830,21 @@ static int setup_push(kmn_ctx *c)
         }
     } else ok = 0;
     { int r = nccl_sum_u64(c, ok, &all_ok, c->stream); if (r) return r; }
-    if (all_ok != (u64)R) {                       // somebody could not: everybody stays on the NCCL path
-        for (int p = 0; p < R; ++p) { if (p != c->rank && c->peer_all[p]) cudaIpcCloseMemHandle(c->peer_all[p]); c->peer_all[p] = nullptr; }
-        if (c->recv_all) { cudaFree(c->recv_all); c->recv_all = nullptr; }
+    c->ipc = all_ok == (u64)R;
+    if (!c->ipc) {                                 // somebody could not map a peer: everybody uses the NCCL transport
+        for (int p = 0; p < KMN_MAX_PUSH_RANKS; ++p) { if (p != c->rank && c->peer_all[p]) cudaIpcCloseMemHandle(c->peer_all[p]); c->peer_all[p] = nullptr; }
         cudaGetLastError();
-        c->pipeline = old_pipeline; c->n_sets = old_sets;
-        if (want && c->push_ce) { int r = alloc_stage_sets(c); if (r) return r; }      // back to sets with a single owner
-        return 0;
+        if (!c->push_ce) return fail(c, KMN_ERR_INVALID, "KMN_PUSH=kernel needs peer-mapped receive buffers");
     }
-    c->p2p = true;
     c->push_cap = cap;
     c->push_meta = meta_words;
-    if (!c->s_insert || c->s_insert == c->stream) CK(c, cudaStreamCreateWithFlags(&c->s_insert, cudaStreamNonBlocking));
+    c->s_insert = c->stream;                       // phase 1 and phase 2 alternate on one stream; only the transfers overlap them
     {   // the barrier kernels of a round are tiny but sit behind long persistent kernels: give them the first free SM
         int lo_pri = 0, hi_pri = 0;
         CK(c, cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
         CK(c, cudaStreamCreateWithPriority(&c->s_comm, cudaStreamNonBlocking, hi_pri));
     }
-    if (const char *e = getenv("KMN_ROUND_SPLIT")) c->round_split = std::min(8, std::max(1, atoi(e)));
-    if (getenv("KMN_TWO_COPY_STREAMS")) {
+    if (getenv("KMN_TWO_COPY_STREAMS") && c->ipc) {
         CK(c, cudaStreamCreateWithFlags(&c->s_comm2, cudaStreamNonBlocking));
         CK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         CK(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -927,33 +863,30 @@ static int setup_push(kmn_ctx *c)
     CK(c, cudaMemcpyAsync(c->d_const, consts, 32, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaMemsetAsync(c->flags, 0, 16, c->stream));
     CK(c, cudaMemsetAsync(c->recv_all, 0, rec_bytes + meta_bytes, c->stream));
-    if (!c->push_ce) { int r = alloc_stage_sets(c); if (r) return r; }      // sets cut by owner
     { int r = apply_smem_attrs(c); if (r) return r; }
     CK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 
-// One round of the push path: the set `si` (filled by phase 1 on the main stream, possibly empty) is pushed to its
-// owners, and phase 2 inserts this rank's own part plus what the peers pushed.  Every rank runs the same sequence of
-// rounds; `done` says this rank has no more input, and the sum of the flags comes back when `done_sum` is given.
-//   comm stream  : plan -> barrier A (peers' round buffer is free; carries the done flags) -> copy over NVLink -> barrier B
-//   insert stream: after barrier B: entries + work list + insert
-static int push_round(kmn_ctx *c, int si, bool done, u64 *done_sum)
+// Transfers of one round: the set `si` (filled by phase 1 on the main stream, possibly empty) is pushed to its owners.
+// `done` says this rank has no more input; the sum of the flags comes back when `done_sum` is given.
+//   comm stream: plan -> barrier A (the peers' round buffer is free; carries the done flags) -> parts over NVLink / NCCL -> barrier B
+static int push_comm(kmn_ctx *c, int si, bool done, u64 *done_sum)
 {
     kmn_ctx::StageSet &st = c->sets[si];
     const int R = c->nranks, rb = (int)(c->round & 1);
     const size_t G = (size_t)c->n_groups;
-    cudaStream_t sc = c->s_comm, sins = c->s_insert;
+    cudaStream_t sc = c->s_comm;
     CK(c, cudaEventRecord(st.ev_parsed, c->stream));
     CK(c, cudaStreamWaitEvent(sc, st.ev_parsed, 0));
     if (c->rb_busy[rb]) { CK(c, cudaStreamWaitEvent(sc, c->ev_rb_free[rb], 0)); c->rb_busy[rb] = false; }
     if (!c->push_ce) { k_push_plan<<<R, 1024, 0, sc>>>(st.v, c->push_cap, c->run_off, c->grp_off, c->flags); c->launches++; }
     ncclResult_t nr = ncclAllReduce(c->d_const + (done ? 1 : 0), c->d_const + 3, 1, ncclUint64, ncclSum, c->comm, sc);
     if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "push barrier failed: %s", ncclGetErrorString(nr));
-    if (c->push_ce) {
+    const size_t n_sub = G * c->n_cta, part = n_sub * st.v.sub_cap * c->RW;          // u64 words per owner part
+    if (c->push_ce && c->ipc) {
         // copy engines: the part of every other owner (whole sub-region capacity) and its fill counters go to that
         // owner's round buffer as they are; no SM takes part in the transfer
-        const size_t n_sub = G * c->n_cta, part = n_sub * st.v.sub_cap * c->RW;          // u64 words per owner part
         ProfScope ps(c, KMN_PROF_ROUTE, (uint64_t)(R - 1) * ((done ? 0 : part * 8) + n_sub * 4), sc);   // units = bytes leaving this GPU
         const bool two = c->s_comm2 != nullptr && R > 2;
         if (two) { CK(c, cudaEventRecord(c->ev_fork, sc)); CK(c, cudaStreamWaitEvent(c->s_comm2, c->ev_fork, 0)); }
@@ -972,6 +905,29 @@ static int push_round(kmn_ctx *c, int si, bool done, u64 *done_sum)
             if (st.v.ovf_cap) CK(c, cudaMemcpyAsync(dmeta + n_sub, st.v.ovf_count + p, 4, cudaMemcpyDeviceToDevice, scp));
         }
         if (two) { CK(c, cudaEventRecord(c->ev_join, c->s_comm2)); CK(c, cudaStreamWaitEvent(sc, c->ev_join, 0)); }
+    } else if (c->push_ce) {
+        // NCCL transport: the same parts and counters as send / receive pairs (MPIAllToAllMessageBuffer::sendReceive,
+        // src/MPIBuffer.h:588-600).  The receiver cannot know whether a sender is in a finishing round, so the parts always travel.
+        ProfScope ps(c, KMN_PROF_ROUTE, (uint64_t)(R - 1) * (part * 8 + n_sub * 4), sc);
+        u64 *mybase = (u64 *)c->recv_all;
+        ncclGroupStart();
+        for (int q = 1; q < R; ++q) {
+            const int p = (c->rank + q) % R;
+            u64 *rrec = mybase + ((size_t)rb * R + p) * c->push_cap * c->RW;
+            u32 *rmeta = (u32 *)(mybase + 2 * (size_t)R * c->push_cap * c->RW) + ((size_t)rb * R + p) * c->push_meta;
+            ncclSend(st.v.recs + (size_t)p * part, part, ncclUint64, p, c->comm, sc);
+            ncclRecv(rrec, part, ncclUint64, p, c->comm, sc);
+            if (st.v.ovf_cap) {
+                ncclSend(st.v.ovf_recs + (size_t)p * st.v.ovf_cap * c->RW, (size_t)st.v.ovf_cap * c->RW, ncclUint64, p, c->comm, sc);
+                ncclRecv(rrec + part, (size_t)st.v.ovf_cap * c->RW, ncclUint64, p, c->comm, sc);
+                ncclSend(st.v.ovf_count + p, 1, ncclUint32, p, c->comm, sc);
+                ncclRecv(rmeta + n_sub, 1, ncclUint32, p, c->comm, sc);
+            }
+            ncclSend(st.v.count + (size_t)p * n_sub, n_sub, ncclUint32, p, c->comm, sc);
+            ncclRecv(rmeta, n_sub, ncclUint32, p, c->comm, sc);
+        }
+        nr = ncclGroupEnd();
+        if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "nccl exchange of the round failed: %s", ncclGetErrorString(nr));
     } else {
         PushPeers pp;
         memset(&pp, 0, sizeof pp);
@@ -986,7 +942,6 @@ static int push_round(kmn_ctx *c, int si, bool done, u64 *done_sum)
     }
     CK(c, cudaGetLastError());
     {   // the other owners' fill counters of this set are consumed
-        const size_t n_sub = G * c->n_cta;
         if (c->rank > 0) CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)c->rank * n_sub * 4, sc));
         if (c->rank + 1 < R) CK(c, cudaMemsetAsync(st.v.count + (size_t)(c->rank + 1) * n_sub, 0, (size_t)(R - 1 - c->rank) * n_sub * 4, sc));
         if (st.v.ovf_count) CK(c, cudaMemsetAsync(st.v.ovf_count, 0, (size_t)R * 4, sc));
@@ -996,14 +951,6 @@ static int push_round(kmn_ctx *c, int si, bool done, u64 *done_sum)
     nr = ncclAllReduce(c->d_const, c->d_const + 2, 1, ncclUint64, ncclSum, c->comm, sc);
     if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "push barrier failed: %s", ncclGetErrorString(nr));
     CK(c, cudaEventRecord(c->ev_recv[rb], sc));
-    CK(c, cudaStreamWaitEvent(sins, st.ev_parsed, 0));
-    CK(c, cudaStreamWaitEvent(sins, c->ev_recv[rb], 0));
-    { int r = launch_insert(c, st.v, rb, c->stage_keys, sins); if (r) return r; }
-    CK(c, cudaMemsetAsync(st.v.count + (size_t)c->rank * G * c->n_cta, 0, G * c->n_cta * 4, sins));
-    CK(c, cudaEventRecord(st.ev_drained, sins));
-    st.drain_pending = true;
-    CK(c, cudaEventRecord(c->ev_rb_free[rb], sins));
-    c->rb_busy[rb] = true;
     c->round++;
     if (done_sum) {
         CK(c, cudaMemcpyAsync(done_sum, c->d_const + 3, 8, cudaMemcpyDeviceToHost, sc));
@@ -1012,12 +959,44 @@ static int push_round(kmn_ctx *c, int si, bool done, u64 *done_sum)
     return 0;
 }
 
-// phase 1 may write into set `si` again: its previous push and its previous insert are complete
-static int push_set_ready(kmn_ctx *c, int si)
+// Phase 2 of a round on the main stream, once the peers' parts have arrived: this rank's own part of set `si` plus round
+// buffer `rb`.  It is submitted AFTER the next round's phase 1, so the main stream runs P1(r+1), I(r), P1(r+2), I(r+1), ...
+// while the transfers of round r+1 overlap I(r): phase 1 and phase 2 never run at the same time (phase 1 may insert
+// directly into the table when a sub-region overflows, and phase 2 holds table slices in shared memory).
+static int push_insert(kmn_ctx *c, int si, int rb)
 {
     kmn_ctx::StageSet &st = c->sets[si];
+    const size_t G = (size_t)c->n_groups;
+    CK(c, cudaStreamWaitEvent(c->stream, c->ev_recv[rb], 0));
+    { int r = launch_insert(c, st.v, rb, c->stage_keys, c->stream); if (r) return r; }
+    CK(c, cudaMemsetAsync(st.v.count + (size_t)c->rank * G * c->n_cta, 0, G * c->n_cta * 4, c->stream));
+    CK(c, cudaEventRecord(c->ev_rb_free[rb], c->stream));
+    c->rb_busy[rb] = true;
+    return 0;
+}
+
+static int flush_pending_insert(kmn_ctx *c)
+{
+    if (c->pending_set < 0) return 0;
+    const int si = c->pending_set, rb = c->pending_rb;
+    c->pending_set = c->pending_rb = -1;
+    return push_insert(c, si, rb);
+}
+
+// one round: phase 1 has been submitted into set `si`; ship it, then run the previous round's phase 2
+static int push_round(kmn_ctx *c, int si, bool done, u64 *done_sum)
+{
+    const int rb = (int)(c->round & 1);
+    int r = push_comm(c, si, done, done_sum); if (r) return r;
+    r = flush_pending_insert(c); if (r) return r;
+    c->pending_set = si; c->pending_rb = rb;
+    return 0;
+}
+
+// phase 1 may write into set `si` again: its previous push is complete (its previous insert precedes on the main stream)
+static int push_set_ready(kmn_ctx *c, int si)
+{
     if (c->push_pending[si]) { CK(c, cudaStreamWaitEvent(c->stream, c->ev_pushed[si], 0)); c->push_pending[si] = false; }
-    if (st.drain_pending) { CK(c, cudaStreamWaitEvent(c->stream, st.ev_drained, 0)); st.drain_pending = false; }
     return 0;
 }
 #endif
@@ -1052,26 +1031,14 @@ int kmn_comm_init(kmn_ctx *c, int rank, int nranks, const void *id128)
     CK(c, cudaMalloc((void **)&c->send_cursor, (size_t)nranks * 8));
     CK(c, cudaMalloc((void **)&c->all_counts, (size_t)nranks * nranks * 8));
     CK(c, cudaMemsetAsync(c->send_cursor, 0, (size_t)nranks * 8, c->stream));
-    // request/answer regions of the lookup pass (and of the NCCL count path): a launch is bounded by stage_keys/2
-    // instances, 1/nranks of which go to each peer on average
-    c->send_cap = c->stage_keys / 2 / (uint64_t)nranks * 3 / 2 + 65536;
-    c->recv_cap = c->send_cap * (uint64_t)(nranks - 1);
     { int r = setup_push(c); if (r) return r; }
-    if (c->p2p) {
-        // the lookup pass runs after the count pass: its request / receive regions reuse the two round buffers
-        const size_t half = (size_t)nranks * c->push_cap * c->RW;
-        if ((size_t)nranks * c->send_cap * c->RW > half) c->send_cap = half / ((size_t)nranks * c->RW);
-        c->recv_cap = c->send_cap * (uint64_t)(nranks - 1);
-        c->send_recs = (u64 *)c->recv_all;
-        c->recv_recs = (u64 *)c->recv_all + half;
-        return 0;
-    }
-    c->seg_cap = c->stage_keys / 2 / (uint64_t)nranks / (uint64_t)c->n_cta * 2 + 4096;
-    CK(c, cudaMalloc((void **)&c->seg_recs, (size_t)nranks * c->n_cta * c->seg_cap * c->RW * 8));
-    CK(c, cudaMalloc((void **)&c->seg_count, (size_t)nranks * c->n_cta * 4));
-    CK(c, cudaMemsetAsync(c->seg_count, 0, (size_t)nranks * c->n_cta * 4, c->stream));
-    CK(c, cudaMalloc((void **)&c->send_recs, (size_t)nranks * c->send_cap * c->RW * 8));
-    CK(c, cudaMalloc((void **)&c->recv_recs, (size_t)c->recv_cap * c->RW * 8));
+    // request / answer regions of the lookup pass: it runs after the count pass, so they reuse the two round buffers
+    c->send_cap = c->stage_keys / 2 / (uint64_t)nranks * 3 / 2 + 65536;
+    const size_t half = (size_t)nranks * c->push_cap * c->RW;
+    if ((size_t)nranks * c->send_cap * c->RW > half) c->send_cap = half / ((size_t)nranks * c->RW);
+    c->recv_cap = c->send_cap * (uint64_t)(nranks - 1);
+    c->send_recs = (u64 *)c->recv_all;
+    c->recv_recs = (u64 *)c->recv_all + half;
     return 0;
 #else
     (void)rank; (void)nranks; (void)id128;
@@ -1158,7 +1125,7 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
     if (n_reads && (!bases || !read_off)) return fail(c, KMN_ERR_INVALID, "null input");
     CK(c, cudaSetDevice(c->device));
     c->finished = false;
-    if (n_reads == 0) return c->nranks > 1 && !c->p2p ? exchange(c) : 0;
+    if (n_reads == 0) return 0;          // a rank without reads still takes part in every round: kmn_count_finish runs empty ones
     BatchPtrs bp;
     int r = stage_inputs(c, bases, quals, read_off, n_reads, discarded, true, bp);
     if (r) return r;
@@ -1170,7 +1137,7 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
     // A launch may stage at most `limit` instances (one staging set; multi-GPU: half of it, the other half takes the
     // records received from the peers and the same bound sizes the send regions).  The exact number of k-mer
     // positions of a read range is computed on the device; ranges that do not fit are halved.
-    const uint64_t limit = std::max<uint64_t>(c->nranks > 1 && !c->p2p ? c->stage_keys / 2 : c->stage_keys, 1);
+    const uint64_t limit = std::max<uint64_t>(c->stage_keys, 1);
     const bool host_sizes = bp.off_on_host && (!discarded || !is_device_ptr(discarded));
     if (!host_sizes && bp.slot >= 0) CK(c, cudaStreamSynchronize(c->s_copy));   // count_positions reads the staged copies
     struct Range { uint64_t r0, r1; };
@@ -1200,7 +1167,6 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
 #ifdef KMN_WITH_NCCL
         if (c->p2p) {                                       // one launch = one round: fill a set, push it, insert
             r = push_set_ready(c, c->cur); if (r) return r;
-            if (c->smem_count) { r = wait_drains(c); if (r) return r; }      // phase 1 never overlaps a shared-memory phase 2
             const uint64_t nr = rg.r1 - rg.r0, ns = (uint64_t)std::max(1, c->round_split);
             for (uint64_t sp = 0; sp < ns; ++sp) {            // same set, several launches (see round_split)
                 const uint64_t q0 = rg.r0 + nr * sp / ns, q1 = rg.r0 + nr * (sp + 1) / ns;
@@ -1219,7 +1185,6 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
         fill_parse_args(c, a, bp.bases, bp.quals, bp.off + rg.r0, bp.disc ? bp.disc + rg.r0 : nullptr, rg.r1 - rg.r0, bp.total_bytes);
         r = launch_parse(c, a); if (r) return r;
         c->sets[c->cur].staged_upper += npos;
-        r = exchange(c); if (r) return r;
     }
     return release_inputs(c, bp);
 }
@@ -1252,7 +1217,7 @@ int kmn_count_finish(kmn_ctx *c, int apply_purge)
             c->cur ^= 1;
             if (n_done == (u64)c->nranks) break;
         }
-        r = wait_drains(c); if (r) return r;
+        r = flush_pending_insert(c); if (r) return r;
         u64 fl[2] = {0, 0};
         CK(c, cudaMemcpyAsync(fl, c->flags, 16, cudaMemcpyDeviceToHost, c->stream));
         CK(c, cudaStreamSynchronize(c->stream));
@@ -1604,6 +1569,69 @@ int kmn_export(kmn_ctx *c, uint32_t min_count, uint8_t *keys, uint16_t *count, u
     if (ext) CK(c, cudaMemcpyAsync(ext, de, n_live * 48, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     cudaFree(dk); cudaFree(dc); cudaFree(dd); cudaFree(dw); cudaFree(de);
+    return 0;
+}
+
+int kmn_import(kmn_ctx *c, const uint8_t *keys, const uint16_t *count, const uint16_t *dir, const float *wsum, const uint32_t *ext, uint64_t n)
+{
+    if (!c || (n && (!keys || !count))) return KMN_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    int r = drain(c); if (r) return r;
+    if (n == 0) { c->finished = true; return 0; }
+    uint8_t *dk = nullptr; uint16_t *dc = nullptr, *dd = nullptr; float *dw = nullptr; u32 *de = nullptr;
+    CK(c, cudaMalloc((void **)&dk, n * c->kb)); CK(c, cudaMalloc((void **)&dc, n * 2));
+    CK(c, cudaMemcpyAsync(dk, keys, n * c->kb, cudaMemcpyDefault, c->stream));
+    CK(c, cudaMemcpyAsync(dc, count, n * 2, cudaMemcpyDefault, c->stream));
+    if (dir) { CK(c, cudaMalloc((void **)&dd, n * 2)); CK(c, cudaMemcpyAsync(dd, dir, n * 2, cudaMemcpyDefault, c->stream)); }
+    if (wsum && c->table.wsum) { CK(c, cudaMalloc((void **)&dw, n * 4)); CK(c, cudaMemcpyAsync(dw, wsum, n * 4, cudaMemcpyDefault, c->stream)); }
+    if (ext && c->table.ext) { CK(c, cudaMalloc((void **)&de, n * 48)); CK(c, cudaMemcpyAsync(de, ext, n * 48, cudaMemcpyDefault, c->stream)); }
+    KMN_DISPATCH_W(c, { k_import<W_><<<c->n_sms * 8, 256, 0, c->stream>>>(c->table, dk, dc, dd, dw, de, n, (u32)c->kb, c->ctr); });
+    c->launches++;
+    CK(c, cudaGetLastError());
+    Counters h;
+    CK(c, cudaMemcpyAsync(&h, c->ctr, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dk); cudaFree(dc); cudaFree(dd); cudaFree(dw); cudaFree(de);
+    if (h.table_full) return fail(c, KMN_ERR_TABLE_FULL, "count table overflow during import: %llu entries did not fit (capacity %llu slots)",
+                                  (unsigned long long)h.table_full, (unsigned long long)c->n_slots);
+    c->finished = true;
+    return 0;
+}
+
+int kmn_subtract(kmn_ctx *c, kmn_ctx *other, uint64_t *removed_entries, uint64_t *removed_instances)
+{
+    if (!c || !other || c == other) return KMN_ERR_INVALID;
+    if (c->device != other->device || c->o.kmer_size != other->o.kmer_size) return fail(c, KMN_ERR_INVALID, "kmn_subtract needs two spectra of the same k on the same device");
+    CK(c, cudaSetDevice(c->device));
+    int r = drain(c); if (r) return r;
+    r = drain(other); if (r) return r;
+    CK(c, cudaStreamSynchronize(other->stream));
+    CK(c, cudaMemsetAsync(c->scratch, 0, 16, c->stream));
+    KMN_DISPATCH_W(c, { k_subtract<W_><<<c->n_sms * 8, 256, 0, c->stream>>>(c->table, c->n_slots, other->table, c->scratch); });
+    c->launches++;
+    CK(c, cudaGetLastError());
+    u64 out[2];
+    CK(c, cudaMemcpyAsync(out, c->scratch, 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (removed_entries) *removed_entries = out[0];
+    if (removed_instances) *removed_instances = out[1];
+    return 0;
+}
+
+int kmn_debug_owner(kmn_ctx *c, const uint8_t *keys, uint64_t n, uint32_t nranks, uint32_t *owner)
+{
+    if (!c || !keys || !owner || nranks == 0) return KMN_ERR_INVALID;
+    CK(c, cudaSetDevice(c->device));
+    if (n == 0) return 0;
+    uint8_t *dk = nullptr; u32 *dout = nullptr;
+    CK(c, cudaMalloc((void **)&dk, n * c->kb)); CK(c, cudaMalloc((void **)&dout, n * 4));
+    CK(c, cudaMemcpyAsync(dk, keys, n * c->kb, cudaMemcpyDefault, c->stream));
+    KMN_DISPATCH_W(c, { k_debug_owner<W_><<<c->n_sms * 4, 256, 0, c->stream>>>(dk, n, (u32)c->kb, nranks, c->o.hash_kind == KMN_HASH_LOOKUP8_HASH2, dout); });
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(owner, dout, n * 4, cudaMemcpyDefault, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dk); cudaFree(dout);
     return 0;
 }
 

@@ -4,7 +4,7 @@
 //               + k_kmer_scatter  (phase 1b: bases -> canonical k-mers -> staging set partitioned by (owner,) table group)
 //               + k_build_entries / k_build_worklist / k_insert_staged (phase 2: group by group into L2-resident slices)
 //   multi-GPU   = k_push_plan / k_push_copy (records to their owners' receive buffers over NVLink; the default transport
-//                 uses copy engines instead), k_compact_send / k_route_records (NCCL fallback path)
+//                 uses copy engines instead, the fallback ncclSend / ncclRecv of the same parts)
 //   lookup pass = k_lookup_vals (+ _dist / k_lookup_words / k_scatter_answers) + k_trim_score
 //   table scans = k_histogram, k_purge, k_export, k_count_live
 //
@@ -21,7 +21,6 @@ namespace kmn {
 
 static constexpr int MASK_TPB = 256;       // phase 1a: one warp per 32 reads
 static constexpr int SCATTER_MAX_TPB = 1024;           // phase 1b: one thread per read; CTA size and CTAs per SM are chosen at run time
-static constexpr int ROUTE_TPB = 1024;
 #ifndef KMN_INSERT_MIN_CTAS
 #define KMN_INSERT_MIN_CTAS 4
 #endif
@@ -61,10 +60,6 @@ struct ParseArgs {
     TableView table;
     StageView stage;
     Counters *ctr;
-    // multi-GPU count pass: records owned by other ranks go to this CTA's segment of the destination's send region
-    u64 *seg_recs;         // [nranks][n_cta][seg_cap][RW]
-    u32 *seg_count;        // [nranks][n_cta]
-    u32 seg_cap;
     // multi-GPU lookup pass: requests are appended to per-destination regions
     u64 *flags;            // [0] += records lost to a full remote-owner sub-region (push path; reported by kmn_count_finish)
     u64 *send_recs;        // [nranks][send_cap][W]
@@ -581,23 +576,6 @@ __device__ __forceinline__ void st_hint64(u64 *p, u64 v, u64 policy)
     asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(policy) : "memory");
 }
 
-// cbase = this CTA's sub-region of group 0 of the local owner (the sub-regions of one CTA and owner are contiguous)
-template <int W, bool HASX>
-__device__ __forceinline__ void stage_put(u64 *cbase, u32 sub_cap, const TableView &tab, u32 *cnt, u32 part, const Rec<W, HASX> &rec, LocalCtr &lc,
-                                          u64 policy)
-{
-    constexpr int RW = Rec<W, HASX>::RW;
-    const u32 pos = atomicAdd(&cnt[part], 1u);
-    if (pos < sub_cap) {
-        u64 *d = cbase + ((size_t)part * sub_cap + pos) * RW;
-#pragma unroll
-        for (int q = 0; q < RW; ++q) st_hint64(d + q, rec.w[q], policy);
-    } else {
-        insert_record<W, HASX>(tab, rec, lc.unique, lc.full, lc.probes);
-        lc.direct++;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // K1+K2b (+K5 partition): phase 1b of the count pass.  One thread walks one read and rolls the canonical k-mer
 // (a1 TwoBitSequence::compressSequence src/TwoBitSequence.cpp:242-269, a2 KmerArrayPair::build src/Kmer.h:1323-1375,
@@ -612,9 +590,8 @@ __device__ __forceinline__ void stage_put(u64 *cbase, u32 sub_cap, const TableVi
 // step of the CTA (a ROUND: at most 8 records per thread) one thread per bin moves the bin's complete, aligned groups of
 // four records to global memory as whole sectors.  A record that finds its ring full (more than R records of one bin in
 // a round: skewed input) is stored directly, which is merely slower.
-// Multi-GPU: DIST 2 bins by (owner, group) (a5: owner = lookup3 hash, src/Kmer.h:2284-2295) into this CTA's sub-region of
-// the owner's part of the staging set (push path); DIST 1 (NCCL all-to-all path) writes records of other owners to
-// per-CTA send segments instead.
+// Multi-GPU (DIST 2): bins are (owner, group) pairs (a5: owner = lookup3 hash, src/Kmer.h:2284-2295), the sub-region
+// belongs to the owner's part of the staging set, which travels to that owner as it is.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void st_sector(u64 *dst, const u64 *src_smem)      // 32 bytes, both 32-byte aligned
 {
@@ -633,8 +610,7 @@ __global__ void __launch_bounds__(1024, 1) k_kmer_scatter(ParseArgs a)
     const u32 lo = a.stage.local_owner();
     u32 *cnt = reinterpret_cast<u32 *>(smem_raw);                      // [n_bins] records given a position so far (may exceed sub_cap)
     u32 *fl = cnt + n_pad;                                             // [n_bins] positions below fl are in global memory
-    u32 *scnt = fl + n_pad;                                            // [32 or nranks] fill level of this CTA's send segments (DIST 1)
-    u64 *ring = reinterpret_cast<u64 *>(scnt + ((DIST == 1 ? a.nranks + 31u : 31u) & ~31u) + 32u);
+    u64 *ring = reinterpret_cast<u64 *>(fl + n_pad + 32u);
     const u32 R = a.ring_R;                                            // power of two >= 4, or 0: every record is stored directly
     const u32 sub_cap = a.stage.sub_cap;
     for (u32 i = threadIdx.x; i < n_bins; i += blockDim.x) {
@@ -643,7 +619,6 @@ __global__ void __launch_bounds__(1024, 1) k_kmer_scatter(ParseArgs a)
         cnt[i] = c0;
         fl[i] = c0 < sub_cap ? c0 : sub_cap;
     }
-    if (DIST == 1) for (u32 i = threadIdx.x; i < a.nranks; i += blockDim.x) scnt[i] = a.seg_count[(size_t)i * gridDim.x + blockIdx.x];
     __syncthreads();
 
     LocalCtr lc{0, 0, 0, 0, 0, 0};
@@ -709,21 +684,6 @@ __global__ void __launch_bounds__(1024, 1) k_kmer_scatter(ParseArgs a)
         if (DIST != 0) {
             const u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
             own = owner_of(h, a.nranks);
-            if (DIST == 1 && own != a.rank) {
-                // one shared atomicAdd per (converged lanes, destination) group
-                namespace cg = cooperative_groups;
-                auto grp = cg::labeled_partition(cg::coalesced_threads(), (int)own);
-                u32 base = 0;
-                if (grp.thread_rank() == 0) base = atomicAdd(&scnt[own], (u32)grp.size());
-                base = grp.shfl(base, 0);
-                const u32 pos = base + grp.thread_rank();
-                if (pos < a.seg_cap) {
-                    u64 *d = a.seg_recs + (((size_t)own * gridDim.x + blockIdx.x) * a.seg_cap + pos) * RW;
-#pragma unroll
-                    for (int q = 0; q < RW; ++q) d[q] = rec.w[q];
-                }
-                return;
-            }
         }
         const u32 bin = DIST == 2 ? own * n_parts + group : group;
         const u32 p = atomicAdd(&cnt[bin], 1u);
@@ -791,7 +751,6 @@ __global__ void __launch_bounds__(1024, 1) k_kmer_scatter(ParseArgs a)
         const u32 o = DIST == 2 ? i / n_parts : lo, g = DIST == 2 ? i - o * n_parts : i;
         a.stage.count[a.stage.cnt_index(o, g, blockIdx.x)] = cnt[i];
     }
-    if (DIST == 1) for (u32 i = threadIdx.x; i < a.nranks; i += blockDim.x) a.seg_count[(size_t)i * gridDim.x + blockIdx.x] = scnt[i];
     if (DIST == 2 && lost) atomicAdd(a.flags, lost);
     ctr_commit(a.ctr, lc);
 }
@@ -884,70 +843,6 @@ __global__ void __launch_bounds__(128, 16) k_push_copy(StageView st, PushPeers p
         if (o == st.me) continue;
         peers.meta[o][i - (u64)o * (st.n_parts + 1)] = grp_off[i];
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// multi-GPU: the per-CTA send segments of every destination are packed into one contiguous send buffer per
-// destination (what the all-to-all ships).  grid = (n_cta, nranks).  send_cursor[d] = records for d; flag != 0 on overflow.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_compact_send(const u64 *seg_recs, const u32 *seg_count, u32 seg_cap, u32 n_cta, u32 rw,
-                                                      u64 *send_recs, u64 send_cap, u64 *send_cursor, u64 *flag)
-{
-    const u32 d = blockIdx.y, c = blockIdx.x;
-    __shared__ u64 part[8];
-    __shared__ u64 s_off;
-    u64 mine = 0;
-    for (u32 i = threadIdx.x; i < c; i += blockDim.x) { const u32 n = seg_count[(size_t)d * n_cta + i]; mine += n < seg_cap ? n : seg_cap; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = mine;
-    __syncthreads();
-    if (threadIdx.x == 0) { u64 t = 0; for (int i = 0; i < 8; ++i) t += part[i]; s_off = t; }
-    __syncthreads();
-    const u64 off = s_off;
-    u32 n = seg_count[(size_t)d * n_cta + c];
-    if (n > seg_cap) { if (threadIdx.x == 0) atomicAdd(flag, 1ull); n = seg_cap; }
-    if (off + n > send_cap) { if (threadIdx.x == 0) atomicAdd(flag, 1ull); n = off < send_cap ? (u32)(send_cap - off) : 0u; }
-    const u64 *src = seg_recs + ((size_t)d * n_cta + c) * seg_cap * rw;
-    u64 *dst = send_recs + ((size_t)d * send_cap + off) * rw;
-    for (u64 i = threadIdx.x; i < (u64)n * rw; i += blockDim.x) dst[i] = src[i];
-    if (c == n_cta - 1 && threadIdx.x == 0) send_cursor[d] = off + n;
-}
-
-// ------------------------------------------------------------------------------------------------
-// multi-GPU: records received from other ranks are routed into the local staging regions the same way
-// (the receiving half of MPIAllToAllMessageBuffer, src/MPIBuffer.h:412-1073).  Same grid as k_kmer_scatter.
-// ------------------------------------------------------------------------------------------------
-struct RouteArgs {
-    const u64 *recs; u64 n_recs;
-    TableView table; StageView stage; Counters *ctr;
-};
-
-template <int W, bool HASX>
-__global__ void __launch_bounds__(ROUTE_TPB, 1) k_route_records(RouteArgs a)
-{
-    constexpr int RW = Rec<W, HASX>::RW;
-    extern __shared__ __align__(16) u32 smem_u32[];
-    const u32 n_parts = a.stage.n_parts;
-    u32 *cnt = smem_u32;
-    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) cnt[i] = a.stage.count[a.stage.cnt_index(a.stage.local_owner(), i, blockIdx.x)];
-    __syncthreads();
-    LocalCtr lc{0, 0, 0, 0, 0, 0};
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    const u64 keep = l2_policy_evict_last();
-    u64 *const cbase = a.stage.recs + a.stage.sub_index(a.stage.local_owner(), 0, blockIdx.x) * a.stage.sub_cap * RW;
-    for (u64 idx = (u64)blockIdx.x * 32u + (threadIdx.x & 31u) + (u64)(threadIdx.x >> 5) * 32u * gridDim.x; idx < a.n_recs; idx += stride) {
-        Rec<W, HASX> rec;
-#pragma unroll
-        for (int q = 0; q < RW; ++q) rec.w[q] = ld_nc64(a.recs + idx * RW + q);
-        u64 key[W]; bool fwd; float wt; u32 eb;
-        rec.unpack(key, fwd, wt, eb);
-        const u64 ph = place_hash<W>(key);
-        stage_put<W, HASX>(cbase, a.stage.sub_cap, a.table, cnt, part_of(ph, a.table.n_parts) >> a.table.group_shift, rec, lc, keep);
-    }
-    __syncthreads();
-    for (u32 i = threadIdx.x; i < n_parts; i += blockDim.x) a.stage.count[a.stage.cnt_index(a.stage.local_owner(), i, blockIdx.x)] = cnt[i];
-    ctr_commit(a.ctr, lc);
 }
 
 // number of k-mer positions in reads [0,n): sum max(0, len-k+1) (discarded reads excluded)
@@ -1401,8 +1296,8 @@ __global__ void __launch_bounds__(1024, 1) k_slice_split(SplitArgs a)
 }
 
 static constexpr int COUNT_TPB = 256;
-static constexpr int COUNT_U = 8;          // records per thread and batch
-static constexpr int COUNT_MAX_S = 16;     // sub-runs per slice (SplitArgs::S)
+static constexpr int COUNT_U = 4;          // records per thread and batch
+static constexpr int COUNT_MAX_S = 8;      // sub-runs per slice (SplitArgs::S)
 
 __global__ void __launch_bounds__(COUNT_TPB, 3) k_count_slices(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, u32 n_groups,
                                                               u32 *ticket, Counters *ctr)
@@ -1429,8 +1324,10 @@ __global__ void __launch_bounds__(COUNT_TPB, 3) k_count_slices(TableView t, cons
     for (u32 pi = blockIdx.x; pi < t.n_parts; pi += gridDim.x, ++it) {
         __syncthreads();                                               // s_pre[it & 1] is complete; the previous slice has left shared memory
         load_pre(pi + gridDim.x, s_pre[(it + 1u) & 1u]);
-        const u32 *pre = s_pre[it & 1u];
-        const u32 total = pre[S];
+        u32 pre[COUNT_MAX_S];                                          // start of sub-run p in the slice's concatenated records
+#pragma unroll
+        for (int p = 0; p < COUNT_MAX_S; ++p) pre[p] = (u32)p < S ? s_pre[it & 1u][p] : 0xffffffffu;
+        const u32 total = s_pre[it & 1u][S];
         if (total == 0) continue;                                      // nothing staged for this slice in this drain
         const u32 g = pi >> t.group_shift, j = pi & (nb - 1u);
         const u64 *run0 = buf + (((size_t)g * S) * nb + j) * cap2;     // sub-run p starts at run0 + p * nb * cap2
@@ -1441,9 +1338,10 @@ __global__ void __launch_bounds__(COUNT_TPB, 3) k_count_slices(TableView t, cons
             for (int u = 0; u < COUNT_U; ++u) {
                 const u32 v = v0 + (u32)u * COUNT_TPB + threadIdx.x;
                 if (v < total) {
-                    u32 p = 0;
-                    for (u32 q = 1; q < S; ++q) p += v >= pre[q] ? 1u : 0u;
-                    r[u] = ld_nc64(run0 + (size_t)p * run_stride + (v - pre[p]));
+                    u32 p = 0, start = 0;
+#pragma unroll
+                    for (int q = 1; q < COUNT_MAX_S; ++q) if (v >= pre[q]) { p = (u32)q; start = pre[q]; }
+                    r[u] = ld_nc64(run0 + (size_t)p * run_stride + (v - start));
                     have |= 1u << u;
                 }
             }
@@ -1461,7 +1359,7 @@ __global__ void __launch_bounds__(COUNT_TPB, 3) k_count_slices(TableView t, cons
             for (int u = 0; u < COUNT_U; ++u) {
                 if (!((hc >> u) & 1u)) continue;
                 const u64 rec = cur[u];
-                const u64 key1 = rec & ~1ull, want = ~key1, add = 1ull | ((rec & 1ull) << 32);
+                const u64 key1 = rec & ~1ull, want = ~key1;
                 u64 key[1] = {key1};
                 const u64 ph = place_hash<1>(key);
                 u32 s = (u32)home_slot(ph, SL) & ~1u;
@@ -1476,7 +1374,13 @@ __global__ void __launch_bounds__(COUNT_TPB, 3) k_count_slices(TableView t, cons
                         sat = false;
                     }
                     if (k == want) {
-                        if (!sat) atomicAdd(&sl[s].val, add);
+                        // count in the low word, directionBias in the high word: two native 32-bit shared atomics (a 64-bit
+                        // shared atomicAdd compiles to a compare-and-swap loop); no carry ever crosses the words
+                        if (!sat) {
+                            u32 *w32 = reinterpret_cast<u32 *>(&sl[s].val);
+                            atomicAdd(w32, 1u);
+                            if (rec & 1ull) atomicAdd(w32 + 1, 1u);
+                        }
                         break;
                     }
                     s = s + 1u == SL ? 0u : s + 1u;
@@ -1490,6 +1394,154 @@ __global__ void __launch_bounds__(COUNT_TPB, 3) k_count_slices(TableView t, cons
         __syncthreads();
         for (u32 i = threadIdx.x; i < SL; i += COUNT_TPB) gsl[i] = ssl[i];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_unique) atomicAdd(&ctr->unique, n_unique);
+        if (n_full) atomicAdd(&ctr->table_full, n_full);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_count_slices with the bulk-copy engine (TMA, cp.async.bulk): the slice, the record chunks and the write-back move
+// between global and shared memory as asynchronous bulk copies tracked by mbarriers, issued by one thread, so no thread
+// holds loads in registers and the next chunk of records streams in while the current one is counted.
+//   shared memory per CTA: the slice (part_slots * 16 B) + two record buffers of COUNT_CHUNK records
+// ------------------------------------------------------------------------------------------------
+static constexpr int COUNT3_TPB = 512;
+static constexpr int COUNT_CHUNK = 2048;   // records per bulk copy (16 KB)
+
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tKMN_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra KMN_DONE_%=;\n\tbra KMN_WAIT_%=;\n\tKMN_DONE_%=:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u32 bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(COUNT3_TPB, 2) k_count_slices_tma(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, Counters *ctr)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const u32 SL = (u32)t.part_slots;
+    Slot<1> *sl = reinterpret_cast<Slot<1> *>(smem_raw);               // one slice of the table
+    u64 *rbuf = reinterpret_cast<u64 *>(smem_raw + (size_t)SL * 16);   // [2][COUNT_CHUNK] record chunks
+    __shared__ __align__(8) u64 bar_slice, bar_rec[2];
+    __shared__ u32 s_pre[2][32];                                       // exclusive prefix of the sub-run sizes of this / the next slice
+    const u32 nb = 1u << t.group_shift;
+    u64 n_unique = 0, n_full = 0;
+    if (threadIdx.x == 0) { mbar_init(&bar_slice, 1); mbar_init(&bar_rec[0], 1); mbar_init(&bar_rec[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    auto load_pre = [&](u32 pi, u32 *dst) {
+        if (threadIdx.x < 32) {
+            u32 c = (threadIdx.x < S && pi < t.n_parts) ? cnt2[((size_t)(pi >> t.group_shift) * S + threadIdx.x) * nb + (pi & (nb - 1u))] : 0u;
+            u32 v = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(0xffffffffu, v, d); if ((int)threadIdx.x >= d) v += x; }
+            if (threadIdx.x < COUNT_MAX_S + 1u) dst[threadIdx.x] = v - c;
+        }
+    };
+    load_pre(blockIdx.x, s_pre[0]);
+    u32 it = 0, ph_slice = 0, ph_rec0 = 0, ph_rec1 = 0;
+    for (u32 pi = blockIdx.x; pi < t.n_parts; pi += gridDim.x, ++it) {
+        __syncthreads();                                               // s_pre[it & 1] complete; every thread has left the previous slice
+        load_pre(pi + gridDim.x, s_pre[(it + 1u) & 1u]);
+        const u32 *pre = s_pre[it & 1u];
+        const u32 total = pre[S];
+        if (total == 0) continue;                                      // nothing staged for this slice in this drain
+        const u32 g = pi >> t.group_shift, j = pi & (nb - 1u);
+        const u64 *run0 = buf + (((size_t)g * S) * nb + j) * cap2;     // sub-run p starts at run0 + p * nb * cap2
+        const size_t run_stride = (size_t)nb * cap2;
+        Slot<1> *gsl = reinterpret_cast<Slot<1> *>(t.slots) + (size_t)pi * SL;
+        // chunk q of the slice = records [q0, q0 + n) of sub-run p: every sub-run is cut into chunks of COUNT_CHUNK
+        u32 n_chunks = 0;
+        for (u32 p = 0; p < S; ++p) n_chunks += (pre[p + 1] - pre[p] + COUNT_CHUNK - 1) / COUNT_CHUNK;
+        auto chunk_of = [&](u32 q, u32 &p, u32 &o, u32 &n) {           // q-th chunk -> (sub-run, offset, records)
+            p = 0;
+            while (true) {
+                const u32 len = pre[p + 1] - pre[p], nc = (len + COUNT_CHUNK - 1) / COUNT_CHUNK;
+                if (q < nc) { o = q * COUNT_CHUNK; n = min((u32)COUNT_CHUNK, len - o); return; }
+                q -= nc; ++p;
+            }
+        };
+        auto issue = [&](u32 q) {                                      // thread 0: chunk q -> record buffer q & 1
+            u32 p, o, n;
+            chunk_of(q, p, o, n);
+            const u32 bytes = ((n + 1u) & ~1u) * 8u;                   // bulk copies move multiples of 16 bytes (cap2 is a multiple of 4)
+            mbar_expect_tx(&bar_rec[q & 1u], bytes);
+            bulk_g2s(rbuf + (size_t)(q & 1u) * COUNT_CHUNK, run0 + (size_t)p * run_stride + o, bytes, &bar_rec[q & 1u]);
+        };
+        if (threadIdx.x == 0) {
+            bulk_wait_read();                                          // the previous slice has been read out of shared memory
+            mbar_expect_tx(&bar_slice, SL * 16u);
+            bulk_g2s(sl, gsl, SL * 16u, &bar_slice);
+            issue(0);
+        }
+        mbar_wait(&bar_slice, ph_slice);
+        ph_slice ^= 1u;
+        for (u32 q = 0; q < n_chunks; ++q) {
+            if (threadIdx.x == 0 && q + 1 < n_chunks) issue(q + 1);    // its buffer was released by the barrier that ended chunk q - 1
+            u32 p, o, n;
+            chunk_of(q, p, o, n);
+            if (q & 1u) { mbar_wait(&bar_rec[1], ph_rec1); ph_rec1 ^= 1u; } else { mbar_wait(&bar_rec[0], ph_rec0); ph_rec0 ^= 1u; }
+            const u64 *recs = rbuf + (size_t)(q & 1u) * COUNT_CHUNK;
+            for (u32 idx = threadIdx.x; idx < n; idx += COUNT3_TPB) {
+                const u64 rec = recs[idx];
+                const u64 key1 = rec & ~1ull, want = ~key1;
+                u64 key[1] = {key1};
+                const u64 ph = place_hash<1>(key);
+                u32 s = (u32)home_slot(ph, SL) & ~1u;
+                u32 probes = 0;
+                for (; probes < SL; ++probes) {
+                    const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(&sl[s]);      // {val, key}
+                    u64 k = x.y;
+                    bool sat = (u32)x.x >= MAX_COUNT;
+                    if (k == 0ull) {
+                        k = atomicCAS(&sl[s].k[0], 0ull, want);
+                        if (k == 0ull) { n_unique++; k = want; }
+                        sat = false;
+                    }
+                    if (k == want) {
+                        if (!sat) {
+                            u32 *w32 = reinterpret_cast<u32 *>(&sl[s].val);
+                            atomicAdd(w32, 1u);
+                            if (rec & 1ull) atomicAdd(w32 + 1, 1u);
+                        }
+                        break;
+                    }
+                    s = s + 1u == SL ? 0u : s + 1u;
+                }
+                if (probes >= SL) n_full++;
+            }
+            __syncthreads();                                           // buffer q & 1 is free; after the last chunk: the slice is final
+        }
+        if (threadIdx.x == 0) {
+            fence_async_smem();                                        // the counts written by all threads are visible to the bulk store
+            bulk_s2g(gsl, sl, SL * 16u);
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
@@ -1601,6 +1653,76 @@ __global__ void __launch_bounds__(256) k_export(TableView t, u64 n_slots, u32 mi
         if (dir) dir[o] = (uint16_t)(c == 1 ? 0 : clamp_dir(s.val));
         if (wsum) wsum[o] = t.wsum ? report_wsum(c, t.wsum[i]) : 0.f;
         if (ext) for (int q = 0; q < 12; ++q) ext[o * 12 + q] = t.ext ? t.ext[i * 12 + q] : 0u;
+    }
+}
+
+// kmn_import: entries of a saved spectrum (reference-format key bytes, count, directionBias, weightedCount, extension
+// counters) go into the table; an entry whose key is already present is merged (counts add up, saturating)
+template <int W>
+__global__ void __launch_bounds__(256) k_import(TableView t, const uint8_t *keys, const uint16_t *count, const uint16_t *dir, const float *wsum,
+                                                const u32 *ext, u64 n, u32 kb, Counters *ctr)
+{
+    u64 n_unique = 0, n_full = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 key[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) key[q] = 0;
+        for (u32 b = 0; b < kb; ++b) key[b >> 3] |= (u64)keys[i * kb + b] << (56 - 8 * (b & 7));
+        const u32 c = count[i];
+        if (c == 0) continue;
+        const u64 ph = place_hash<W>(key);
+        u64 slot; u32 probes = 0;
+        const int r = table_insert<W>(t, part_of(ph, t.n_parts), home_slot(ph, t.part_slots), key, (u64)c | ((u64)(dir ? dir[i] : 0) << 32), &slot, &probes);
+        if (r < 0) { n_full++; continue; }
+        n_unique += (u64)r;
+        // a count-1 entry reports its weight quantised to n/254 (report_wsum); a quarter quantum keeps floor(w * 254) = n
+        if (t.wsum && wsum) atomicAdd(&t.wsum[slot], c == 1 ? wsum[i] + 0.25f / 254.f : wsum[i]);
+        if (t.ext && ext) for (int q = 0; q < 12; ++q) if (ext[i * 12 + q]) atomicAdd(&t.ext[slot * 12 + q], ext[i * 12 + q]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o); n_full += __shfl_xor_sync(0xffffffffu, n_full, o); }
+    if ((threadIdx.x & 31) == 0) { if (n_unique) atomicAdd(&ctr->unique, n_unique); if (n_full) atomicAdd(&ctr->table_full, n_full); }
+}
+
+// kmn_subtract: every live entry whose key is present (count >= 1) in the other table loses its value, like a purge:
+// KmerSpectrum::append skips k-mers of the subtracting spectrum (src/KmerSpectrum.h:1582-1589); removing them after the
+// build leaves the same table.  out[0] += entries removed, out[1] += their counts
+template <int W>
+__global__ void __launch_bounds__(256) k_subtract(TableView t, u64 n_slots, TableView other, u64 *out)
+{
+    Slot<W> *sl = reinterpret_cast<Slot<W> *>(t.slots);
+    u64 removed = 0, inst = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += (u64)gridDim.x * blockDim.x) {
+        Slot<W> s = sl[i];
+        if (!slot_live<W>(s)) continue;
+        u64 key[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) key[q] = (W == 1) ? ~s.k[q] : s.k[q];
+        const u64 ph = place_hash<W>(key);
+        const u64 v = table_find<W>(other, part_of(ph, other.n_parts), home_slot(ph, other.part_slots), key, nullptr);
+        if ((u32)v == 0) continue;
+        removed++; inst += clamp_count(s.val);
+        sl[i].val = s.val & VAL_READY;
+        if (t.wsum) t.wsum[i] = 0.f;
+        if (t.ext) for (int q = 0; q < 12; ++q) t.ext[i * 12 + q] = 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { removed += __shfl_xor_sync(0xffffffffu, removed, o); inst += __shfl_xor_sync(0xffffffffu, inst, o); }
+    if ((threadIdx.x & 31) == 0 && removed) { atomicAdd(out, removed); atomicAdd(out + 1, inst); }
+}
+
+// debug / parity of a5: the owner rank the device assigns to reference-format keys for a given number of ranks -- the same
+// hash + owner_of the multi-GPU scatter and lookup kernels use (src/Kmer.h:2284-2295)
+template <int W>
+__global__ void __launch_bounds__(256) k_debug_owner(const uint8_t *keys, u64 n, u32 kb, u32 nranks, u32 use_lookup8, u32 *owner)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 key[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) key[q] = 0;
+        for (u32 b = 0; b < kb; ++b) key[b >> 3] |= (u64)keys[i * kb + b] << (56 - 8 * (b & 7));
+        const u64 h = use_lookup8 ? hash_lookup8<W>(key, (int)kb) : hash_lookup3<W>(key, (int)kb);
+        owner[i] = owner_of(h, nranks);
     }
 }
 

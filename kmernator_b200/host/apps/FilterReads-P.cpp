@@ -50,8 +50,37 @@ int main(int argc, char *argv[])
         if (k > 0) {
             unsigned long rawKmers = KS::estimateRawKmers(world, reads);
             LOG_DEBUG(1, "targeting " << rawKmers << " raw kmers per rank");
+            // --reference-file / --subtract-file: a second spectrum whose k-mers leave the main one
+            // (apps/FilterReads-P.cpp:281-308, src/KmerSpectrum.h:1582-1589).  reference files are counted as they are,
+            // subtract files go through the artifact filter and the min-depth purge like the input
+            KS subtracting(0);
+            OptionsBaseInterface::FileListType referenceFiles = FilterReadsBaseOptions::getOptions().getReferenceFiles();
+            OptionsBaseInterface::FileListType subtractFiles = FilterReadsBaseOptions::getOptions().getSubtractFiles();
+            if (!referenceFiles.empty() || !subtractFiles.empty()) {
+                subtracting = KS(world, rawKmers);
+                if (!referenceFiles.empty()) {
+                    LOG_VERBOSE(1, "Subtracting reference-file set");
+                    ReadSet refReads;
+                    refReads.appendAllFiles(referenceFiles, world.rank(), world.size());
+                    subtracting.buildKmerSpectrum(refReads, false);
+                }
+                if (!subtractFiles.empty()) {
+                    LOG_VERBOSE(1, "Subtracting abundant kmers in subtract-file set");
+                    ReadSet subReads;
+                    subReads.appendAllFiles(subtractFiles, world.rank(), world.size());
+                    subReads.identifyPairs();
+                    if (!FilterKnownOdditiesOptions::getOptions().getSkipArtifactFilter()) { FilterKnownOddities f; f.applyFilter(subReads); }
+                    subtracting.buildKmerSpectrum(subReads, false);
+                }
+                subtracting.finishBuild();
+                if (!subtractFiles.empty() && KmerSpectrumOptions::getOptions().getMinDepth() > 1)
+                    subtracting.purgeMinDepth(KmerSpectrumOptions::getOptions().getMinDepth(), true);
+            }
             spectrum = KS(world, rawKmers);
-            spectrum.buildKmerSpectrumInParts(reads, KmerSpectrumOptions::getOptions().getBuildPartitions());
+            spectrum.buildKmerSpectrum(reads);
+            if (subtracting.weak.ctx) spectrum.subtractReference(subtracting);
+            subtracting.reset();
+            spectrum.purgeMinDepth(KmerSpectrumOptions::getOptions().getMinDepth());
             // the histogram is all-reduced inside the library: every rank asks, rank 0 prints / writes
             const std::string hist = spectrum.getHistogram(false, 255);               // MPIHistogram(255), src/DistributedFunctions.h:575
             if (root) {

@@ -29,13 +29,24 @@ int main(int argc, char *argv[])
 
         KS spectrum(0);
         const unsigned int k = KmerBaseOptions::getOptions().getKmerSize();
-        if (k > 0) {
+        const std::string loadMmap = KmerSpectrumOptions::getOptions().getLoadKmerMmap();
+        if (k > 0 && !loadMmap.empty()) {                                   // apps/FilterReads.cpp:129-130
+            spectrum = KS(KS::estimateRawKmers(reads));
+            spectrum.restoreMmap(loadMmap);
+        } else if (k > 0) {
             long rawKmers = KS::estimateRawKmers(reads);
             LOG_DEBUG(1, "targeting " << rawKmers << " raw kmers for reads ");
             spectrum = KS(rawKmers);
+            const std::string sizeHistoryFile = FilterReadsBaseOptions::getOptions().getSizeHistoryFile();
+            spectrum.enableSizeTracking(!sizeHistoryFile.empty());
             spectrum.buildKmerSpectrumInParts(reads, KmerSpectrumOptions::getOptions().getBuildPartitions(), outputFilename.empty() ? "" : outputFilename + "-mmap");
             spectrum.optimize();
             spectrum.trackSpectrum(true);
+            if (!sizeHistoryFile.empty()) {                                 // apps/FilterReads.cpp:142-146
+                LOG_VERBOSE(1, "Writing size history file to: " << sizeHistoryFile);
+                std::ofstream of(sizeHistoryFile.c_str());
+                of << spectrum.getSizeTracker().toString();
+            }
             if (Log::isVerbose(1)) {
                 kmn_stats st = spectrum.getStats();
                 LOG_VERBOSE(1, "Kmer counters: raw " << st.raw_kmers << ", rawGood " << st.raw_good_kmers << ", unique " << st.unique_kmers

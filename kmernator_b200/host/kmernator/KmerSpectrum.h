@@ -18,7 +18,10 @@
 #include <string>
 #include <vector>
 
+#include <fstream>
+
 #include "../../../include/kmernator_b200.h"
+#include "KmerHasher.h"
 #include "Log.h"
 #include "Options.h"
 #include "ReadSet.h"
@@ -95,13 +98,14 @@ public:
     KmerSpectrum &operator=(const KmerSpectrum &) = delete;
     KmerSpectrum &operator=(KmerSpectrum &&o)                            // spectrum = KS(rawKmers)  apps/FilterReads.cpp:138
     {
-        if (this != &o) { reset(); weak = o.weak; _rawKmers = o._rawKmers; o.weak.ctx = NULL; }
+        if (this != &o) { reset(); weak = o.weak; _rawKmers = o._rawKmers; _sizeTracker = o._sizeTracker; _trackSizes = o._trackSizes; o.weak.ctx = NULL; }
         return *this;
     }
     KmerSpectrum(KmerSpectrum &&o) : weak(o.weak), _rawKmers(o._rawKmers) { o.weak.ctx = NULL; }
 
     // count pass over the whole ReadSet in --batch-size batches           src/KmerSpectrum.h:2081-2115
-    void buildKmerSpectrum(const ReadSet &reads)
+    // finish = false: more read sets follow into the same spectrum (reference files, then subtract files); finishBuild() ends it
+    void buildKmerSpectrum(const ReadSet &reads, bool finish = true)
     {
         if (!weak.ctx) LOG_THROW("buildKmerSpectrum on an empty KmerSpectrum");
         const ReadSet::ReadSetSizeType n = reads.getSize();
@@ -118,17 +122,19 @@ public:
             const ReadSet::ReadSetSizeType r0 = std::min<ReadSet::ReadSetSizeType>(n, b * batch), r1 = std::min<ReadSet::ReadSetSizeType>(n, r0 + batch);
             reads.concat(r0, r1, bases, quals, off, disc);
             KMN_CHECK(weak.ctx, kmn_count_batch(weak.ctx, (const uint8_t *)bases.data(), (const uint8_t *)quals.data(), off.data(), r1 - r0, disc.data()));
+            if (_trackSizes) { for (ReadSet::ReadSetSizeType q = r0; q < r1; ++q) { unsigned long l = reads.getRead(q).getLength(); if (l >= _k()) _rawSubmitted += l - _k() + 1; } trackSpectrum(false); }
         }
-        KMN_CHECK(weak.ctx, kmn_count_finish(weak.ctx, 0));
+        if (finish) finishBuild();
     }
-    // build + post-build purge (src/KmerSpectrum.h:1818-1831); more than one part is never needed in HBM
-    void buildKmerSpectrumInParts(const ReadSet &reads, unsigned int /*numParts*/, const std::string & /*mmapPrefix*/ = "")
+    void finishBuild() { KMN_CHECK(weak.ctx, kmn_count_finish(weak.ctx, 0)); }
+    // build + post-build purge (+ --save-kmer-mmap) (src/KmerSpectrum.h:1818-1831); more than one part is never needed in HBM
+    void buildKmerSpectrumInParts(const ReadSet &reads, unsigned int /*numParts*/, const std::string &mmapPrefix = "")
     {
         buildKmerSpectrum(reads);
         purgeMinDepth(KmerSpectrumOptions::getOptions().getMinDepth());
+        if (KmerSpectrumOptions::getOptions().getSaveKmerMmap() && !mmapPrefix.empty()) storeMmap(mmapPrefix);
     }
     void optimize(bool = false) {}
-    void trackSpectrum(bool = true) {}
     void purgeMinDepth(long minimumCount, bool = false)
     {
         if (weak.ctx && minimumCount > 1) KMN_CHECK(weak.ctx, kmn_purge_min_depth(weak.ctx, (uint32_t)minimumCount));
@@ -187,6 +193,76 @@ public:
     }
     void printHistograms(std::ostream &os, bool solidOnly = false) { os << getHistogram(solidOnly); }
 
+    // ---- persistence: --save-kmer-mmap / --load-kmer-mmap ---------------------------------------------------------
+    // The reference writes one file per map (src/KmerSpectrum.h:476-518): "<name>" for the weak map and, when min-depth
+    // <= 1, "<name>-singleton".  Layout of a map file (KmerMapByKmerArrayPair::store src/Kmer.h:3138-3155, KmerArrayPair::store
+    // :960-969): u64 numBuckets, u64 bucketMask, u64 byte offset of every bucket; then per bucket u32 n, n keys of (k+3)/4
+    // bytes, n values.  A key lives in bucket hash & mask (KmerHasher, :2329-2333), keys inside a bucket ascend in memcmp
+    // order (:3076-3088).  Values: TrackingDataWithDirection = {u16 count, f32 weightedCount @4, u16 directionBias @8}, 12
+    // bytes (src/KmerTrackingData.h:406-407,508); TrackingDataSingleton = one byte (u8)(weight * 254) + 1 (:623,641-661).
+    // numBuckets = the next power of two >= estimatedRawKmers / estimated-depth / kmers-per-bucket + 1 (:2837,2224-2229).
+    void storeMmap(const std::string &filename)
+    {
+        if (!weak.ctx) LOG_THROW("storeMmap on an empty KmerSpectrum");
+        LOG_VERBOSE(1, "Saving weak kmer spectrum");
+        std::vector<uint8_t> keys; std::vector<uint16_t> count, dir; std::vector<float> wsum;
+        exportAll(keys, count, dir, wsum);
+        writeMapFile(filename, keys, count, dir, wsum, false);
+        if (KmerSpectrumOptions::getOptions().getMinDepth() <= 1) {
+            LOG_VERBOSE(1, "Saving singleton kmer spectrum");
+            writeMapFile(filename + "-singleton", keys, count, dir, wsum, true);
+        }
+    }
+    void restoreMmap(const std::string &filename)
+    {
+        if (!weak.ctx) LOG_THROW("restoreMmap on an empty KmerSpectrum");
+        LOG_VERBOSE(1, "Loading kmer spectrum from saved mmaps: " + filename);
+        const bool a = readMapFile(filename, false), b = readMapFile(filename + "-singleton", true);
+        if (!a && !b) LOG_THROW("Terribly sorry but there were no kmer spectrum mmap files at: " << filename << "*\n\tCan not continue");
+    }
+    // k-mers of the subtracting spectrum leave this one (src/KmerSpectrum.h:472-474,1582-1589)
+    unsigned long subtractReference(KmerSpectrum &subtracting)
+    {
+        uint64_t entries = 0, instances = 0;
+        KMN_CHECK(weak.ctx, kmn_subtract(weak.ctx, subtracting.weak.ctx, &entries, &instances));
+        LOG_VERBOSE(1, "Subtracted " << entries << " kmers (" << instances << " instances) present in the subtracting spectrum");
+        return (unsigned long)entries;
+    }
+
+    // SizeTracker (src/KmerSpectrum.h:812-900): (rawKmers, rawGoodKmers, uniqueKmers, singletonKmers) whenever rawKmers has
+    // grown by 5% since the last sample -- here at batch granularity (the counters are exact after every batch)
+    struct SizeTracker {
+        struct Element { unsigned long rawKmers, rawGoodKmers, uniqueKmers, singletonKmers; };
+        double nextToTrack;
+        std::vector<Element> elements;
+        SizeTracker() { reset(); }
+        void reset() { nextToTrack = 128; elements.clear(); track(0, 0, 0, 0); }
+        void track(unsigned long raw, unsigned long rawGood, unsigned long unique, unsigned long single, bool force = false)
+        {
+            if ((double)raw < nextToTrack && !force) return;
+            Element e = {raw, rawGood, unique, single};
+            elements.push_back(e);
+            while ((double)raw >= nextToTrack) nextToTrack *= 1.05;
+        }
+        std::string toString() const
+        {
+            std::ostringstream ss;
+            ss << "rawKmers\trawGoodKmers\tuniqueKmers\tsingletonKmers" << std::endl;
+            for (size_t i = 0; i < elements.size(); ++i)
+                ss << elements[i].rawKmers << "\t" << elements[i].rawGoodKmers << "\t" << elements[i].uniqueKmers << "\t" << elements[i].singletonKmers << std::endl;
+            return ss.str();
+        }
+    };
+    SizeTracker &getSizeTracker() { return _sizeTracker; }
+    void trackSpectrum(bool force = true)
+    {
+        if (!weak.ctx || !_trackSizes) return;
+        if (!force && (double)_rawSubmitted < _sizeTracker.nextToTrack) return;      // the counters cost a drain and a table scan
+        kmn_stats st = getStats();
+        _sizeTracker.track(st.raw_kmers, st.raw_good_kmers, st.unique_kmers, st.singleton_kmers, force);
+    }
+    void enableSizeTracking(bool on = true) { _trackSizes = on; }
+
     // MeraculousDistributedKmerSpectrum::dumpCounts / dumpGraphs (src/Meraculous.h:107-133): for every k-mer of this rank's
     // table with count >= minDepth one line for the k-mer and one for its reverse complement -- "<kmer>\t<count>", and
     // "<kmer>\t<6 left + 6 right extension counters A C G T N X> 0" (ExtensionTracking::toTextValues,
@@ -196,6 +272,91 @@ public:
     void dumpGraphs(std::ostream &os, int minDepth) { dump(os, minDepth, true); }
 
 private:
+    void exportAll(std::vector<uint8_t> &keys, std::vector<uint16_t> &count, std::vector<uint16_t> &dir, std::vector<float> &wsum)
+    {
+        const unsigned int kb = (KmerBaseOptions::getOptions().getKmerSize() + 3) / 4;
+        uint64_t n = 0, got = 0;
+        KMN_CHECK(weak.ctx, kmn_export(weak.ctx, 1, NULL, NULL, NULL, NULL, NULL, 0, &n));
+        keys.resize((size_t)n * kb); count.resize(n); dir.resize(n); wsum.resize(n);
+        if (n) KMN_CHECK(weak.ctx, kmn_export(weak.ctx, 1, keys.data(), count.data(), dir.data(), wsum.data(), NULL, n, &got));
+    }
+    unsigned long numBuckets() const
+    {
+        unsigned long want = (unsigned long)((int)((double)_rawKmers / KmerSpectrumOptions::getOptions().getEstimatedDepth())) / (unsigned long)kmn_host::asLong("kmers-per-bucket") + 1;
+        if (want > (1ul << 26)) want = 1ul << 26;
+        unsigned long p = 1;
+        while (p < want) p <<= 1;
+        return p;
+    }
+    void writeMapFile(const std::string &fn, const std::vector<uint8_t> &keys, const std::vector<uint16_t> &count, const std::vector<uint16_t> &dir,
+                      const std::vector<float> &wsum, bool singletons) const
+    {
+        const unsigned int kb = (KmerBaseOptions::getOptions().getKmerSize() + 3) / 4;
+        const uint64_t nb = numBuckets(), mask = nb - 1;
+        std::vector<std::pair<uint64_t, size_t> > order;                  // (bucket, entry)
+        for (size_t i = 0; i < count.size(); ++i)
+            if ((count[i] == 1) == singletons) order.push_back(std::make_pair(kmn_host::kmerHash(&keys[i * kb], kb) & mask, i));
+        std::sort(order.begin(), order.end(), [&](const std::pair<uint64_t, size_t> &a, const std::pair<uint64_t, size_t> &b) {
+            if (a.first != b.first) return a.first < b.first;
+            return memcmp(&keys[a.second * kb], &keys[b.second * kb], kb) < 0;
+        });
+        const size_t vsz = singletons ? 1 : 12;
+        std::vector<uint64_t> head(2 + nb);
+        head[0] = nb; head[1] = mask;
+        std::string body;
+        size_t q = 0;
+        for (uint64_t b = 0; b < nb; ++b) {
+            head[2 + b] = 8 * (2 + nb) + body.size();
+            size_t e = q;
+            while (e < order.size() && order[e].first == b) ++e;
+            const uint32_t n = (uint32_t)(e - q);
+            body.append((const char *)&n, 4);
+            for (size_t i = q; i < e; ++i) body.append((const char *)&keys[order[i].second * kb], kb);
+            for (size_t i = q; i < e; ++i) {
+                const size_t x = order[i].second;
+                char v[12] = {0};
+                if (singletons) v[0] = (char)((unsigned char)((double)wsum[x] * 254.0 + 0.5) + 1);      // the table reports (w8 - 1) / 254
+                else { memcpy(v, &count[x], 2); memcpy(v + 4, &wsum[x], 4); memcpy(v + 8, &dir[x], 2); }
+                body.append(v, vsz);
+            }
+            q = e;
+        }
+        std::ofstream of(fn.c_str(), std::ios::binary);
+        if (!of.good()) LOG_THROW("Could not open " << fn << " for writing");
+        of.write((const char *)head.data(), (std::streamsize)(head.size() * 8));
+        of.write(body.data(), (std::streamsize)body.size());
+    }
+    bool readMapFile(const std::string &fn, bool singletons)
+    {
+        std::ifstream in(fn.c_str(), std::ios::binary);
+        if (!in.good()) return false;
+        std::string data((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        if (data.size() < 16) return false;
+        const unsigned int kb = (KmerBaseOptions::getOptions().getKmerSize() + 3) / 4;
+        uint64_t nb, mask;
+        memcpy(&nb, &data[0], 8); memcpy(&mask, &data[8], 8);
+        if (nb == 0 || mask != nb - 1 || data.size() < 8 * (2 + nb)) LOG_THROW("not a kmer spectrum map file: " << fn);
+        const size_t vsz = singletons ? 1 : 12;
+        std::vector<uint8_t> keys; std::vector<uint16_t> count, dir; std::vector<float> wsum;
+        for (uint64_t b = 0; b < nb; ++b) {
+            uint64_t off; memcpy(&off, &data[8 * (2 + b)], 8);
+            if (off + 4 > data.size()) LOG_THROW("truncated kmer spectrum map file: " << fn);
+            uint32_t n; memcpy(&n, &data[off], 4);
+            const size_t k0 = off + 4, v0 = k0 + (size_t)n * kb;
+            if (v0 + (size_t)n * vsz > data.size()) LOG_THROW("truncated kmer spectrum map file: " << fn);
+            keys.insert(keys.end(), data.begin() + k0, data.begin() + v0);
+            for (uint32_t i = 0; i < n; ++i) {
+                const char *v = &data[v0 + (size_t)i * vsz];
+                uint16_t c = 1, d = 0; float w;
+                if (singletons) w = (float)(((int)(unsigned char)v[0] - 1 + 0.5) / 254.0);   // mid-quantum: re-quantises to the same byte
+                else { memcpy(&c, v, 2); memcpy(&w, v + 4, 4); memcpy(&d, v + 8, 2); }
+                count.push_back(c); dir.push_back(d); wsum.push_back(w);
+            }
+        }
+        KMN_CHECK(weak.ctx, kmn_import(weak.ctx, keys.data(), count.data(), dir.data(), wsum.data(), NULL, count.size()));
+        LOG_VERBOSE(1, "Loaded " << count.size() << " kmers from " << fn);
+        return true;
+    }
     void dump(std::ostream &os, int minDepth, bool graph)
     {
         if (!weak.ctx) LOG_THROW("dump on an empty KmerSpectrum");
@@ -232,7 +393,10 @@ private:
             os << "0\n";
         }
     }
-    unsigned long _rawKmers;
+    static unsigned long _k() { return KmerBaseOptions::getOptions().getKmerSize(); }
+    unsigned long _rawKmers, _rawSubmitted = 0;
+    SizeTracker _sizeTracker;
+    bool _trackSizes = false;
 };
 
 #endif

@@ -176,8 +176,8 @@ public:
         r.alias("min-kmer-depth", "min-depth");
         r.add("estimated-depth", "20", "sizing hint", false, true);
         r.add("estimated-error-rate", "0.35", "sizing hint", false, true);
-        r.add("save-kmer-mmap", "0", "save the kmer spectrum", false, false);
-        r.add("load-kmer-mmap", "", "load a saved kmer spectrum", false, false);
+        r.add("save-kmer-mmap", "0", "If set, creates a memory map of the kmer spectrum for later use");
+        r.add("load-kmer-mmap", "", "Instead of generating kmer spectrum, load an existing one named by this option");
         r.add("build-partitions", "0", "build the spectrum in this many hash partitions (one pass suffices in HBM)");
         r.add("kmer-subsample", "1", "subsample kmers", false, false);
         r.add("variant-sigmas", "-1", "purge variants", false, false);
@@ -189,6 +189,8 @@ public:
     double getMinKmerQuality() { return kmn_host::asDouble("min-kmer-quality"); }
     unsigned int getMinDepth() { return (unsigned int)kmn_host::asLong("min-depth"); }
     unsigned int getBuildPartitions() { return (unsigned int)kmn_host::asLong("build-partitions"); }
+    bool getSaveKmerMmap() { return kmn_host::asLong("save-kmer-mmap") != 0; }
+    std::string getLoadKmerMmap() { return kmn_host::asString("load-kmer-mmap"); }
     double getEstimatedDepth() { return kmn_host::asDouble("estimated-depth"); }
     double getEstimatedErrorRate() { return kmn_host::asDouble("estimated-error-rate"); }
 };
@@ -249,9 +251,9 @@ public:
     {
         kmn_host::OptionRegistry &r = kmn_host::OptionRegistry::get();
         r.add("histogram-file", "", "if set, the kmer histogram is written to this file");
-        r.add("size-history-file", "", "size-history file", false, false);
-        r.add("subtract-file", "", "subtract-file(s)", true, false);
-        r.add("reference-file", "", "reference-file(s)", true, false);
+        r.add("size-history-file", "", "if set, the kmer spectrum size history (for EstimateSize.R) is written here");
+        r.add("subtract-file", "", "file(s) whose abundant kmers (>= min-depth) are subtracted from the spectrum", true);
+        r.add("reference-file", "", "reference file(s) whose kmers are subtracted from the spectrum", true);
         // MPIOptions / DuplicateFragmentFilterOptions: accepted so reference command lines parse
         r.add("mpi-buffer-size", "33554432", "accepted; the exchange is an NCCL all-to-all here");
         r.add("mpi-min-transmit-size", "2048", "accepted; unused");
@@ -263,6 +265,9 @@ public:
         r.add("dedup-length", "24", "dedup", false, false);
     }
     std::string getHistogramFile() { return kmn_host::asString("histogram-file"); }
+    std::string getSizeHistoryFile() { return kmn_host::asString("size-history-file"); }
+    OptionsBaseInterface::FileListType getSubtractFiles() { return kmn_host::OptionRegistry::get().spec("subtract-file").values; }
+    OptionsBaseInterface::FileListType getReferenceFiles() { return kmn_host::OptionRegistry::get().spec("reference-file").values; }
 };
 class FilterReadsBaseOptions { public: static _FilterReadsBaseOptions &getOptions() { static _FilterReadsBaseOptions o; return o; } };
 

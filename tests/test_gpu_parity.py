@@ -361,3 +361,63 @@ def test_filter_goldens_gpu(K, golden_dir, fn, minlen, both, start):
             out += [F.format_fastq(recs[i], res[i], start), F.format_fastq(recs[j], res[j], start)]
     assert "".join(out) == open(os.path.join(golden_dir, fn)).read()
     ctx.close()
+
+
+@pytest.mark.parametrize("k", [21, 31, 63])
+def test_owner_rule_on_device(K, k):
+    """a5 on one GPU: the device's owner_of(hash) for 1..16 ranks equals getDistributedThreadId
+    ((hashlittle2 >> 24) & 0x7ffff) % R (src/Kmer.h:2284-2295) computed by the oracle -- the rule every multi-GPU kernel
+    bins by"""
+    bases, q, off = synth.reads_numpy(400, 150, 20000, seed=31)
+    keys = oracle_table(bases, q, off, k).export()["keys"]
+    ctx = K.Context(kmer_size=k, table_slots=4096)
+    for nranks in (1, 2, 3, 4, 5, 8, 16):
+        got = ctx.debug_owner(keys, nranks)
+        want = np.array([oracle.owner(oracle.kmer_hash(x.tobytes()), nranks) for x in keys], dtype=np.uint32)
+        assert (got == want).all(), nranks
+        assert nranks == 1 or len(np.unique(got)) == nranks
+    ctx.close()
+    ctx8 = K.Context(kmer_size=k, table_slots=4096, hash_kind=K.capi.KMN_HASH_LOOKUP8)
+    got = ctx8.debug_owner(keys[:500], 8)
+    assert (got == np.array([oracle.owner(oracle.kmer_hash_lookup8(x.tobytes()), 8) for x in keys[:500]], dtype=np.uint32)).all()
+    ctx8.close()
+
+
+@pytest.mark.parametrize("k,vk", [(31, 0), (31, 2), (63, 0), (21, 1)])
+def test_import_and_subtract(K, k, vk):
+    """f4: kmn_import restores exported entries (the --load-kmer-mmap path) and merges duplicates; kmn_subtract removes the
+    k-mers of a second spectrum (--subtract-file / --reference-file, src/KmerSpectrum.h:1582-1589)"""
+    bases, q, off = synth.reads_numpy(6000, 150, 30000, seed=12, err=0.003, lowq=0.001)
+    a = K.Context(kmer_size=k, table_slots=1 << 21, value_kind=vk)
+    a.count_batch(bases, q, off)
+    a.count_finish(apply_purge=False)
+    ea = a.export()
+    b = K.Context(kmer_size=k, table_slots=1 << 21, value_kind=vk)
+    half = len(ea["count"]) // 2
+    for sl in (slice(0, half), slice(half, None)):
+        b.import_entries(ea["keys"][sl], ea["count"][sl], ea["dir"][sl], ea["wsum"][sl], ea["ext"][sl] if ea["ext"] is not None else None)
+    eb = b.export()
+    assert (eb["keys"] == ea["keys"]).all() and (eb["count"] == ea["count"]).all() and (eb["dir"] == ea["dir"]).all()
+    if vk == 2:
+        assert np.allclose(eb["wsum"], ea["wsum"], rtol=1e-6)
+    if vk == 1:
+        assert (eb["ext"] == ea["ext"]).all()
+    assert b.stats()["unique_kmers"] == len(ea["count"])
+    assert (b.lookup(ea["keys"][:1000]) == ea["count"][:1000]).all()
+    b.import_entries(ea["keys"][:100], ea["count"][:100])                    # merge: counts add up
+    assert (b.lookup(ea["keys"][:100]).astype(np.int64) == np.minimum(2 * ea["count"][:100].astype(np.int64), 65535)).all()
+    # subtract the spectrum of the first 2000 reads (min depth 2) from the full one
+    n_sub = 2000
+    cut = int(off[n_sub])
+    s = K.Context(kmer_size=k, table_slots=1 << 21)
+    s.count_batch(bases[:cut], q[:cut], np.ascontiguousarray(off[:n_sub + 1]))
+    s.count_finish(apply_purge=True)
+    es = s.export()
+    removed, inst = a.subtract(s)
+    drop = set(x.tobytes() for x in es["keys"])
+    keep = np.array([x.tobytes() not in drop for x in ea["keys"]])
+    assert removed == int((~keep).sum()) and inst == int(ea["count"][~keep].astype(np.int64).sum())
+    e2 = a.export()
+    assert (e2["keys"] == ea["keys"][keep]).all() and (e2["count"] == ea["count"][keep]).all()
+    for c in (a, b, s):
+        c.close()

@@ -313,3 +313,113 @@ def test_artifact_screen_matches_oracle(filter_reads, tmp_path, edit, build, min
     assert n_trim > 300 and n_disc > 30 and n_rem > 20             # every branch was exercised
     if edit == 2:
         assert ("filter affected (trimmed/removed) %d Reads" % n_trim) in p.stderr
+
+
+def _parse_map_file(path, kb, singletons=False):
+    """reader of the reference's map-file layout (KmerMapByKmerArrayPair::store src/Kmer.h:3138-3155, KmerArrayPair::store
+    :960-969): -> (numBuckets, mask, [(bucket, key bytes, value bytes)])"""
+    import struct
+    data = open(path, "rb").read()
+    nb, mask = struct.unpack_from("<QQ", data, 0)
+    offs = struct.unpack_from("<%dQ" % nb, data, 16)
+    vsz = 1 if singletons else 12
+    out = []
+    for b in range(nb):
+        (n,) = struct.unpack_from("<I", data, offs[b])
+        k0 = offs[b] + 4
+        v0 = k0 + n * kb
+        for i in range(n):
+            out.append((b, data[k0 + i * kb: k0 + (i + 1) * kb], data[v0 + i * vsz: v0 + (i + 1) * vsz]))
+        if b + 1 < nb:
+            assert offs[b + 1] == v0 + n * vsz                          # buckets are contiguous, in index order
+    return nb, mask, out
+
+
+@pytest.mark.gpu
+def test_save_and_load_kmer_mmap(filter_reads, golden_dir, tmp_path):
+    """f4: --save-kmer-mmap writes the weak map in the reference's file layout (bucket = KmerHasher hash & mask, keys of a
+    bucket ascending, TrackingDataWithDirection values); --load-kmer-mmap on that file reproduces the filtered output"""
+    import struct
+    import numpy as np
+    import oracle
+    from oracle import filter_oracle as F
+    opts = ["--fastq-output-base-quality", "64", "--min-read-length", "25", "--kmer-scoring-type", "MEDIAN"]
+    out1, out2 = str(tmp_path / "a"), str(tmp_path / "b")
+    p = _run(filter_reads, opts + ["--save-kmer-mmap", "1", "--out", out1, "31", "1000.fastq"], cwd=golden_dir)
+    assert p.returncode == 0, p.stderr
+    nb, mask, ents = _parse_map_file(out1 + "-mmap", 8)
+    assert nb & (nb - 1) == 0 and mask == nb - 1
+    recs = F.parse_fastq(open(os.path.join(golden_dir, "1000.fastq")).read())
+    F.normalise_quals(recs, start=64)
+    F.artifact_quality_trim(recs, 64, 3, 25.0)
+    bases, q, off, disc = F.to_buffers(recs)
+    osp = oracle.OracleSpectrum(31, start=64, est_distinct=1 << 17)
+    osp.add_reads(bases, q, off, disc)
+    osp.purge_min_depth(2)
+    o = osp.export()
+    # the reference's sizing: next power of two >= (int)(rawKmers / estimated-depth) / kmers-per-bucket + 1 (src/Kmer.h:2837)
+    raw = oracle.estimate_raw_kmers(len(recs), sum(len(r["seq"]) for r in recs), 31)
+    want_nb = 1
+    while want_nb < int(raw / 20.0) // 32 + 1:
+        want_nb *= 2
+    assert nb == want_nb
+    assert len(ents) == len(o["count"])
+    lut = {bytes(k): (int(c), int(d)) for k, c, d in zip(o["keys"], o["count"], o["dir"])}
+    last = (-1, b"")
+    for b, key, val in ents:
+        assert oracle.kmer_hash(key) & mask == b
+        assert (b, key) > last                                          # bucket order, then memcmp order inside a bucket
+        last = (b, key)
+        cnt, w, dr = struct.unpack("<HxxfHxx", val)
+        assert cnt == lut[key][0] and dr - lut[key][1] in (0, 1) and 0.0 < w <= cnt
+    p = _run(filter_reads, opts + ["--load-kmer-mmap", out1 + "-mmap", "--out", out2, "31", "1000.fastq"], cwd=golden_dir)
+    assert p.returncode == 0, p.stderr
+    assert open(out2 + "-MinDepth2-1000.fastq").read() == open(out1 + "-MinDepth2-1000.fastq").read()
+    assert open(out2 + "-MinDepth2-1000.fastq").read().split() == open(os.path.join(golden_dir, "1000-Filtered.fastq")).read().split()
+
+
+@pytest.mark.gpu
+def test_size_history_file(filter_reads, golden_dir, tmp_path):
+    """f4: --size-history-file (SizeTracker, src/KmerSpectrum.h:812-900): one (rawKmers, rawGoodKmers, uniqueKmers,
+    singletonKmers) sample per 5% growth at batch granularity; the last one is the final state of the spectrum"""
+    import oracle
+    from oracle import filter_oracle as F
+    hist = str(tmp_path / "size.txt")
+    p = _run(filter_reads, ["--fastq-output-base-quality", "64", "--batch-size", "100", "--size-history-file", hist, "--out", str(tmp_path / "o"),
+                            "31", "1000.fastq"], cwd=golden_dir)
+    assert p.returncode == 0, p.stderr
+    lines = open(hist).read().strip().split("\n")
+    assert lines[0] == "rawKmers\trawGoodKmers\tuniqueKmers\tsingletonKmers"
+    rows = [tuple(int(x) for x in l.split("\t")) for l in lines[1:]]
+    assert len(rows) >= 8            # (SizeTracker::reset's track(0,0,0,0) is below nextToTrack and records nothing, :890-894)
+    assert all(a[0] <= b[0] and a[2] <= b[2] for a, b in zip(rows, rows[1:]))
+    recs = F.parse_fastq(open(os.path.join(golden_dir, "1000.fastq")).read())
+    F.normalise_quals(recs, start=64)
+    F.artifact_quality_trim(recs, 64, 3, 0.40)
+    bases, q, off, disc = F.to_buffers(recs)
+    osp = oracle.OracleSpectrum(31, start=64, est_distinct=1 << 17)
+    osp.add_reads(bases, q, off, disc)
+    st = osp.stats()
+    # the post-build purge has removed the singletons by the time of the final forced sample (apps/FilterReads.cpp:139-141)
+    assert rows[-1][:3] == (st["raw"], st["raw_good"], st["unique"]) and rows[-1][3] == 0
+    assert any(r[3] > 0 for r in rows[1:-1])
+
+
+@pytest.mark.gpu
+def test_reference_file_subtraction(filter_reads, golden_dir, tmp_path):
+    """f4: --reference-file (apps/FilterReads-P.cpp:281-308): k-mers of the reference spectrum leave the main spectrum.
+    Subtracting the input from itself empties the spectrum; subtracting an unrelated sequence changes nothing."""
+    exe_p = filter_reads + "-P"
+    opts = ["--fastq-output-base-quality", "64", "--min-read-length", "25", "--kmer-scoring-type", "MEDIAN"]
+    out = str(tmp_path / "s")
+    p = _run(exe_p, opts + ["--reference-file", "1000.fastq", "--out", out, "31", "1000.fastq"], cwd=golden_dir)
+    assert p.returncode == 0, p.stderr
+    assert "Subtracted" in p.stderr
+    kept = open(out + "-MinDepth2-1000.fastq").read() if os.path.exists(out + "-MinDepth2-1000.fastq") else ""
+    assert kept == ""
+    other = tmp_path / "other.fasta"
+    other.write_text(">x\n" + "ACGTTGCA" * 40 + "\n")
+    out2 = str(tmp_path / "t")
+    p = _run(exe_p, opts + ["--reference-file", str(other), "--out", out2, "31", "1000.fastq"], cwd=golden_dir)
+    assert p.returncode == 0, p.stderr
+    assert open(out2 + "-MinDepth2-1000.fastq").read().split() == open(os.path.join(golden_dir, "1000-Filtered.fastq")).read().split()
