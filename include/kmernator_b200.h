@@ -100,6 +100,14 @@ int  kmn_comm_init(kmn_ctx *ctx, int rank, int nranks, const void *id128);
  * (Read::isDiscarded, src/KmerReadUtils.h:177-180).  Asynchronous: returns once the batch is staged. */
 int  kmn_count_batch(kmn_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *read_off,
                      uint64_t n_reads, const uint8_t *discarded);
+/* The same batch in the reference's in-memory form (Read::_data, src/Sequence.h:372-380): per read (len+3)/4
+ * TwoBitSequence bytes, 4 bases per byte, first base in bits 7..6 (src/TwoBitSequence.cpp:242-269), the reads' byte
+ * strings concatenated (packed_off: n_reads+1 byte offsets), plus the markups of the non-ACGT bases as (position in the
+ * concatenated batch, character) pairs -- a packed non-ACGT base reads as 'A' until its markup is applied.  A quarter of
+ * the bases' bytes cross PCIe; the library unpacks on the device.  packed_off / read_off: HOST arrays.                  */
+int  kmn_count_batch_2na(kmn_ctx *ctx, const uint8_t *packed, const uint64_t *packed_off, const uint8_t *quals,
+                         const uint64_t *read_off, uint64_t n_reads, const uint8_t *discarded,
+                         const uint64_t *markup_pos, const uint8_t *markup_chr, uint64_t n_markups);
 /* end of buildKmerSpectrum: drain staging (+ exchange), then the post-build purge per min_depth
  * (src/KmerSpectrum.h:1825, src/DistributedFunctions.h:559-569) when apply_purge != 0                     */
 int  kmn_count_finish(kmn_ctx *ctx, int apply_purge);

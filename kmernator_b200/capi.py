@@ -16,7 +16,7 @@ EXPORTED = [
     "kmn_default_opts", "kmn_last_error", "kmn_version", "kmn_create", "kmn_destroy", "kmn_reset", "kmn_comm_unique_id",
     "kmn_comm_init", "kmn_count_batch", "kmn_count_finish", "kmn_get_stats", "kmn_purge_min_depth", "kmn_histogram",
     "kmn_lookup", "kmn_trim_batch", "kmn_export", "kmn_debug_kmers", "kmn_sync", "kmn_stream", "kmn_launch_count",
-    "kmn_profile_enable", "kmn_profile_read", "kmn_import", "kmn_subtract", "kmn_debug_owner",
+    "kmn_profile_enable", "kmn_profile_read", "kmn_import", "kmn_subtract", "kmn_debug_owner", "kmn_count_batch_2na",
 ]
 PROF_KINDS = ["parse", "insert", "route", "lookup", "trim", "scan", "weight", "subpart"]
 
@@ -73,6 +73,7 @@ def load():
     L.kmn_comm_unique_id.argtypes = [vp]
     L.kmn_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.kmn_count_batch.argtypes = [vp, vp, vp, vp, C.c_uint64, vp]
+    L.kmn_count_batch_2na.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, vp, vp, vp, C.c_uint64]
     L.kmn_count_finish.argtypes = [vp, C.c_int]
     L.kmn_get_stats.argtypes = [vp, C.POINTER(KmnStats)]
     L.kmn_purge_min_depth.argtypes = [vp, C.c_uint32]
@@ -107,6 +108,34 @@ def _ptr(x):
     if hasattr(x, "data_ptr"):
         return x.data_ptr()
     raise TypeError(type(x))
+
+
+def pack_2na(bases, read_off):
+    """ASCII bases + offsets -> (packed u8, packed_off u64, markup_pos u64, markup_chr u8): the reference's TwoBitSequence
+    bytes per read (src/TwoBitSequence.cpp:242-269; non-ACGT packs as A and becomes a markup, '.' counts as N :253-260,
+    lower case is upper-cased by the reader before packing)."""
+    b = np.frombuffer(bases, dtype=np.uint8) if isinstance(bases, (bytes, bytearray)) else np.asarray(bases, dtype=np.uint8)
+    off = np.asarray(read_off, dtype=np.uint64)
+    n = len(off) - 1
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    nb = (lens + 3) // 4
+    poff = np.zeros(n + 1, dtype=np.uint64)
+    poff[1:] = np.cumsum(nb)
+    up = b & 0xDF
+    code = np.zeros(len(b), dtype=np.uint8)
+    code[up == ord("C")] = 1
+    code[up == ord("G")] = 2
+    code[up == ord("T")] = 3
+    valid = (up == ord("A")) | (up == ord("C")) | (up == ord("G")) | (up == ord("T"))
+    packed = np.zeros(int(poff[-1]), dtype=np.uint8)
+    read_of = np.repeat(np.arange(n), lens)
+    pos_in = np.arange(len(b)) - np.repeat(off[:-1].astype(np.int64), lens)
+    byte_idx = poff[read_of].astype(np.int64) + pos_in // 4
+    np.add.at(packed, byte_idx, (code << (6 - 2 * (pos_in % 4)).astype(np.uint8)).astype(np.uint8))
+    mpos = np.nonzero(~valid)[0].astype(np.uint64)
+    mchr = b[~valid].copy()
+    mchr[mchr == ord(".")] = ord("N")
+    return packed, poff, mpos, mchr
 
 
 class Context:
@@ -170,6 +199,15 @@ class Context:
             n_reads = len(read_off) - 1
         self._keep = (bases, quals, read_off, discarded)
         self._ck(self._L.kmn_count_batch(self._h, _ptr(bases), _ptr(quals), _ptr(read_off), n_reads, _ptr(discarded)))
+
+    def count_batch_2na(self, packed, packed_off, quals, read_off, n_reads=None, discarded=None, markup_pos=None, markup_chr=None):
+        """kmn_count_batch_2na: TwoBitSequence-packed bases + markups (see pack_2na)"""
+        if n_reads is None:
+            n_reads = len(read_off) - 1
+        n_mk = 0 if markup_pos is None else len(markup_pos)
+        self._keep = (packed, packed_off, quals, read_off, discarded, markup_pos, markup_chr)
+        self._ck(self._L.kmn_count_batch_2na(self._h, _ptr(packed), _ptr(packed_off), _ptr(quals), _ptr(read_off), n_reads, _ptr(discarded),
+                                             _ptr(markup_pos), _ptr(markup_chr), n_mk))
 
     def count_finish(self, apply_purge=True):
         self._ck(self._L.kmn_count_finish(self._h, int(apply_purge)))

@@ -86,10 +86,13 @@ struct kmn_ctx {
     size_t scatter_smem = 0;
     DevBuf mask, wts;                 // phase 1a -> 1b: "counted" bits (and fp32 weights for KMN_VALUE_WEIGHTS)
     // input staging (host inputs), double-buffered: the copy of batch b+1 overlaps the kernels of batch b
-    DevBuf in_bases[2], in_quals[2], in_off[2], in_disc[2];
-    cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
-    bool in_used[2] = {false, false};
+    static constexpr int IN_SLOTS = 4;    // host batches in flight: copies run ahead of the kernels by up to three batches
+    DevBuf in_bases[IN_SLOTS], in_quals[IN_SLOTS], in_off[IN_SLOTS], in_disc[IN_SLOTS];
+    DevBuf in_packed[IN_SLOTS], in_poff[IN_SLOTS], in_mpos[IN_SLOTS], in_mchr[IN_SLOTS];     // kmn_count_batch_2na
+    cudaEvent_t ev_in_ready[IN_SLOTS] = {}, ev_in_ready2[IN_SLOTS] = {}, ev_in_free[IN_SLOTS] = {};
+    bool in_used[IN_SLOTS] = {};
     int in_cur = 0;
+    cudaStream_t s_copy2 = nullptr;       // the qualities travel on a second copy stream (two DMA engines feed PCIe)
     // lookup pass scratch
     DevBuf vals, first_nx, out_off, out_len, out_score, out_trim, lk_keys, lk_out;
     DevBuf lk_origin, lk_resp_in, lk_resp_out;   // multi-GPU lookup pass: request origins, answers in / out
@@ -300,12 +303,14 @@ static int alloc_stage_sets(kmn_ctx *c)
         if (const char *e = getenv("KMN_SPLIT_TPB")) c->split_tpb = std::min(1024, std::max(64, atoi(e) & ~31));
         if (const char *e = getenv("KMN_SPLIT_CTAS")) c->split_ctas = std::max(1, atoi(e));
         if (c->split_tpb * c->split_ctas > 2048) c->split_ctas = 2048 / c->split_tpb;
-        const size_t budget = (size_t)dev_smem / (size_t)c->split_ctas - 2048;
+        c->split_tpb = SPLIT_TPB; c->split_ctas = 1;
+        const size_t in_bytes = 2 * (size_t)SPLIT_CHUNK * 8;              // two input buffers of one round each
+        const size_t budget = (size_t)dev_smem - 2048;
         uint32_t R = 32;
-        while (R >= 4 && 2 * n_pad * 4 + nb * R * 8 > budget) R >>= 1;
+        while (R >= 4 && in_bytes + 2 * n_pad * 4 + nb * R * 8 > budget) R >>= 1;
         if (R < 4) c->smem_count = false;
         c->split_R = R;
-        c->split_smem = 2 * n_pad * 4 + nb * R * 8;
+        c->split_smem = in_bytes + 2 * n_pad * 4 + nb * R * 8;
         // records of one drain per sub-run: stage_keys / (slices * S), plus slack for the spread (a sub-run that fills up
         // sends its records straight to the table)
         const uint64_t m2 = sk / c->table.n_parts / c->split_S + 1;
@@ -319,7 +324,7 @@ static int alloc_stage_sets(kmn_ctx *c)
             if (!c->tickets) CK(c, cudaMalloc((void **)&c->tickets, 64));
             CK(c, cudaFuncSetAttribute(k_slice_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
             CK(c, cudaFuncSetAttribute(k_count_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16)));
-            CK(c, cudaFuncSetAttribute(k_count_slices_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + 2 * COUNT_CHUNK * 8)));
+            CK(c, cudaFuncSetAttribute(k_count_slices_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNT_NBUF * COUNT_CHUNK * 8)));
             if (const char *e = getenv("KMN_COUNT_TMA")) c->count_tma = atoi(e) != 0;
             if ((c->table.part_slots * 16) % 16 != 0) c->count_tma = false;
         }
@@ -497,8 +502,10 @@ int kmn_create(kmn_ctx **out, const kmn_opts *opts)
             if (cudaStreamCreateWithFlags(&c->s_insert, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "stream create failed"); break; }
         } else c->s_insert = c->stream;
         if (cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "stream create failed"); break; }
-        for (int i = 0; i < 2; ++i) {
+        if (cudaStreamCreateWithFlags(&c->s_copy2, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(nullptr, KMN_ERR_CUDA, "stream create failed"); break; }
+        for (int i = 0; i < kmn_ctx::IN_SLOTS; ++i) {
             cudaEventCreateWithFlags(&c->ev_in_ready[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&c->ev_in_ready2[i], cudaEventDisableTiming);
             cudaEventCreateWithFlags(&c->ev_in_free[i], cudaEventDisableTiming);
         }
         rc = plan_and_alloc(c);
@@ -523,6 +530,7 @@ void kmn_destroy(kmn_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    if (c->s_copy2) cudaStreamSynchronize(c->s_copy2);
     if (c->s_insert) cudaStreamSynchronize(c->s_insert);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->s_comm) cudaStreamSynchronize(c->s_comm);
@@ -537,13 +545,20 @@ void kmn_destroy(kmn_ctx *c)
     void *ptrs[] = {c->l2buf, c->cnt2, c->tickets, c->sets[0].v.ovf_recs, c->sets[0].v.ovf_count, c->sets[1].v.ovf_recs, c->sets[1].v.ovf_count, c->recv_all, c->run_off, c->grp_off, c->flags, c->d_const, c->ent_ptr, c->ent_cnt, c->coarse,c->table.slots, c->table.wsum, c->table.ext, c->sets[0].v.recs, c->sets[0].v.count, c->sets[1].v.recs, c->sets[1].v.count,
                     c->chunk_start, c->next_item,
                     c->ctr, c->scratch, c->ptab, c->send_recs, c->send_cursor, c->recv_recs, c->all_counts,
-                    c->in_bases[0].p, c->in_quals[0].p, c->in_off[0].p, c->in_disc[0].p,
-                    c->in_bases[1].p, c->in_quals[1].p, c->in_off[1].p, c->in_disc[1].p, c->vals.p, c->first_nx.p, c->out_off.p,
+                    c->vals.p, c->first_nx.p, c->out_off.p,
                     c->lk_origin.p, c->lk_resp_in.p, c->lk_resp_out.p, c->mask.p, c->wts.p,
                     c->out_len.p, c->out_score.p, c->out_trim.p, c->lk_keys.p, c->lk_out.p};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < kmn_ctx::IN_SLOTS; ++i)
+        for (DevBuf *b : {&c->in_bases[i], &c->in_quals[i], &c->in_off[i], &c->in_disc[i], &c->in_packed[i], &c->in_poff[i], &c->in_mpos[i], &c->in_mchr[i]})
+            if (b->p) cudaFree(b->p);
     for (auto &st : c->sets) { if (st.ev_parsed) cudaEventDestroy(st.ev_parsed); if (st.ev_drained) cudaEventDestroy(st.ev_drained); }
-    for (int i = 0; i < 2; ++i) { if (c->ev_in_ready[i]) cudaEventDestroy(c->ev_in_ready[i]); if (c->ev_in_free[i]) cudaEventDestroy(c->ev_in_free[i]); }
+    for (int i = 0; i < kmn_ctx::IN_SLOTS; ++i) {
+        if (c->ev_in_ready[i]) cudaEventDestroy(c->ev_in_ready[i]);
+        if (c->ev_in_ready2[i]) cudaEventDestroy(c->ev_in_ready2[i]);
+        if (c->ev_in_free[i]) cudaEventDestroy(c->ev_in_free[i]);
+    }
+    if (c->s_copy2) cudaStreamDestroy(c->s_copy2);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_pushed[i]) cudaEventDestroy(c->ev_pushed[i]);
         if (c->ev_rb_free[i]) cudaEventDestroy(c->ev_rb_free[i]);
@@ -594,7 +609,7 @@ static int launch_insert(kmn_ctx *c, const StageView &v, int rb, uint64_t units,
         {
             ProfScope ps(c, KMN_PROF_INSERT, units, si);
             if (c->count_tma)
-                k_count_slices_tma<<<c->n_sms * 2, COUNT3_TPB, c->table.part_slots * 16 + 2 * COUNT_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr);
+                k_count_slices_tma<<<c->n_sms * 2, COUNT3_TPB, c->table.part_slots * 16 + COUNT_NBUF * COUNT_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr);
             else
                 k_count_slices<<<c->n_sms * c->count_ctas, COUNT_TPB, c->table.part_slots * 16, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, v.n_parts, c->tickets + 1, c->ctr);
         }
@@ -1078,9 +1093,9 @@ static int stage_inputs(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, 
     bp.off = reinterpret_cast<const u64 *>(read_off); bp.bases = bases; bp.quals = need_quals ? quals : nullptr; bp.disc = discarded;
     if (!(bp.off_on_host || h_bases || h_quals || h_disc)) return 0;
     const int j = c->in_cur;
-    c->in_cur ^= 1;
+    c->in_cur = (c->in_cur + 1) % kmn_ctx::IN_SLOTS;
     bp.slot = j;
-    if (c->in_used[j]) CK(c, cudaStreamWaitEvent(c->s_copy, c->ev_in_free[j], 0));
+    if (c->in_used[j]) { CK(c, cudaStreamWaitEvent(c->s_copy, c->ev_in_free[j], 0)); CK(c, cudaStreamWaitEvent(c->s_copy2, c->ev_in_free[j], 0)); }
     cudaStream_t sc = c->s_copy;
     if (bp.off_on_host) {
         int r = ensure(c, c->in_off[j], (n_reads + 1) * 8); if (r) return r;
@@ -1094,7 +1109,7 @@ static int stage_inputs(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, 
     }
     if (h_quals) {
         int r = ensure(c, c->in_quals[j], last + 16); if (r) return r;
-        CK(c, cudaMemcpyAsync(c->in_quals[j].p, quals, last, cudaMemcpyHostToDevice, sc));
+        CK(c, cudaMemcpyAsync(c->in_quals[j].p, quals, last, cudaMemcpyHostToDevice, c->s_copy2));
         bp.quals = (const uint8_t *)c->in_quals[j].p;
     }
     if (h_disc) {
@@ -1103,7 +1118,9 @@ static int stage_inputs(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, 
         bp.disc = (const uint8_t *)c->in_disc[j].p;
     }
     CK(c, cudaEventRecord(c->ev_in_ready[j], sc));
+    CK(c, cudaEventRecord(c->ev_in_ready2[j], c->s_copy2));
     CK(c, cudaStreamWaitEvent(c->stream, c->ev_in_ready[j], 0));
+    CK(c, cudaStreamWaitEvent(c->stream, c->ev_in_ready2[j], 0));
     return 0;
 }
 
@@ -1115,8 +1132,11 @@ static int release_inputs(kmn_ctx *c, const BatchPtrs &bp)
     CK(c, cudaEventRecord(c->ev_in_free[bp.slot], c->stream));
     c->in_used[bp.slot] = true;
     CK(c, cudaEventSynchronize(c->ev_in_ready[bp.slot]));
+    CK(c, cudaEventSynchronize(c->ev_in_ready2[bp.slot]));
     return 0;
 }
+
+static int count_staged(kmn_ctx *c, BatchPtrs &bp, const uint64_t *read_off, uint64_t n_reads, const uint8_t *discarded);
 
 int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, const uint64_t *read_off, uint64_t n_reads,
                     const uint8_t *discarded)
@@ -1129,6 +1149,64 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
     BatchPtrs bp;
     int r = stage_inputs(c, bases, quals, read_off, n_reads, discarded, true, bp);
     if (r) return r;
+    return count_staged(c, bp, read_off, n_reads, discarded);
+}
+
+int kmn_count_batch_2na(kmn_ctx *c, const uint8_t *packed, const uint64_t *packed_off, const uint8_t *quals, const uint64_t *read_off,
+                        uint64_t n_reads, const uint8_t *discarded, const uint64_t *markup_pos, const uint8_t *markup_chr, uint64_t n_markups)
+{
+    if (!c) return KMN_ERR_INVALID;
+    if (n_reads && (!packed || !packed_off || !read_off || !quals)) return fail(c, KMN_ERR_INVALID, "null input");
+    if (n_markups && (!markup_pos || !markup_chr)) return fail(c, KMN_ERR_INVALID, "null markup arrays");
+    if (is_device_ptr(read_off) || is_device_ptr(packed_off)) return fail(c, KMN_ERR_INVALID, "kmn_count_batch_2na takes host offset arrays");
+    CK(c, cudaSetDevice(c->device));
+    c->finished = false;
+    if (n_reads == 0) return 0;
+    if (read_off[0] != 0 || packed_off[0] != 0) return fail(c, KMN_ERR_INVALID, "read_off[0] and packed_off[0] must be 0");
+    const u64 total = read_off[n_reads], ptotal = packed_off[n_reads];
+    const int j = c->in_cur;
+    c->in_cur = (c->in_cur + 1) % kmn_ctx::IN_SLOTS;
+    if (c->in_used[j]) { CK(c, cudaStreamWaitEvent(c->s_copy, c->ev_in_free[j], 0)); CK(c, cudaStreamWaitEvent(c->s_copy2, c->ev_in_free[j], 0)); }
+    int r;
+    if ((r = ensure(c, c->in_off[j], (n_reads + 1) * 8)) || (r = ensure(c, c->in_poff[j], (n_reads + 1) * 8)) || (r = ensure(c, c->in_packed[j], ptotal + 16)) ||
+        (r = ensure(c, c->in_bases[j], total + 16)) || (r = ensure(c, c->in_quals[j], total + 16))) return r;
+    cudaStream_t sc = c->s_copy;
+    CK(c, cudaMemcpyAsync(c->in_off[j].p, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, sc));
+    CK(c, cudaMemcpyAsync(c->in_poff[j].p, packed_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, sc));
+    CK(c, cudaMemcpyAsync(c->in_packed[j].p, packed, ptotal, cudaMemcpyDefault, sc));
+    CK(c, cudaMemcpyAsync(c->in_quals[j].p, quals, total, cudaMemcpyDefault, c->s_copy2));
+    if (discarded) {
+        if ((r = ensure(c, c->in_disc[j], n_reads + 16))) return r;
+        CK(c, cudaMemcpyAsync(c->in_disc[j].p, discarded, n_reads, cudaMemcpyDefault, sc));
+    }
+    if (n_markups) {
+        if ((r = ensure(c, c->in_mpos[j], n_markups * 8)) || (r = ensure(c, c->in_mchr[j], n_markups + 16))) return r;
+        CK(c, cudaMemcpyAsync(c->in_mpos[j].p, markup_pos, n_markups * 8, cudaMemcpyDefault, sc));
+        CK(c, cudaMemcpyAsync(c->in_mchr[j].p, markup_chr, n_markups, cudaMemcpyDefault, sc));
+    }
+    CK(c, cudaEventRecord(c->ev_in_ready[j], sc));
+    CK(c, cudaEventRecord(c->ev_in_ready2[j], c->s_copy2));
+    CK(c, cudaStreamWaitEvent(c->stream, c->ev_in_ready[j], 0));
+    CK(c, cudaStreamWaitEvent(c->stream, c->ev_in_ready2[j], 0));
+    // packed bases -> ASCII in the slot's base buffer, markups on top
+    k_unpack_2na<<<c->n_sms * 8, 256, 0, c->stream>>>((const uint8_t *)c->in_packed[j].p, (const u64 *)c->in_poff[j].p, (const u64 *)c->in_off[j].p, n_reads, (uint8_t *)c->in_bases[j].p);
+    c->launches++;
+    if (n_markups) {
+        k_apply_markups<<<(unsigned)std::min<u64>((n_markups + 255) / 256, (u64)c->n_sms * 4), 256, 0, c->stream>>>((const u64 *)c->in_mpos[j].p, (const uint8_t *)c->in_mchr[j].p, n_markups, total, (uint8_t *)c->in_bases[j].p);
+        c->launches++;
+    }
+    CK(c, cudaGetLastError());
+    BatchPtrs bp;
+    bp.bases = (const uint8_t *)c->in_bases[j].p; bp.quals = (const uint8_t *)c->in_quals[j].p; bp.off = (const u64 *)c->in_off[j].p;
+    bp.disc = discarded ? (const uint8_t *)c->in_disc[j].p : nullptr;
+    bp.total_bytes = total; bp.off_on_host = true; bp.slot = j;
+    return count_staged(c, bp, read_off, n_reads, is_device_ptr(discarded) ? nullptr : discarded);
+}
+
+// phase 1 of a staged batch (inputs on the device; read_off / discarded: the host copies when there are any)
+static int count_staged(kmn_ctx *c, BatchPtrs &bp, const uint64_t *read_off, uint64_t n_reads, const uint8_t *discarded)
+{
+    int r;
     // phase 1a -> 1b scratch: one bit per base position of the batch (+ one fp32 per position for KMN_VALUE_WEIGHTS)
     const size_t mask_bytes = (bp.total_bytes / 32 + 4) * 4;
     r = ensure(c, c->mask, mask_bytes); if (r) return r;
@@ -1139,7 +1217,7 @@ int kmn_count_batch(kmn_ctx *c, const uint8_t *bases, const uint8_t *quals, cons
     // positions of a read range is computed on the device; ranges that do not fit are halved.
     const uint64_t limit = std::max<uint64_t>(c->stage_keys, 1);
     const bool host_sizes = bp.off_on_host && (!discarded || !is_device_ptr(discarded));
-    if (!host_sizes && bp.slot >= 0) CK(c, cudaStreamSynchronize(c->s_copy));   // count_positions reads the staged copies
+    if (!host_sizes && bp.slot >= 0) { CK(c, cudaStreamSynchronize(c->s_copy)); CK(c, cudaStreamSynchronize(c->s_copy2)); }   // count_positions reads the staged copies
     struct Range { uint64_t r0, r1; };
     std::vector<Range> todo;
     todo.push_back({0, n_reads});

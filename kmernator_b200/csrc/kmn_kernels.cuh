@@ -845,6 +845,35 @@ __global__ void __launch_bounds__(128, 16) k_push_copy(StageView st, PushPeers p
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// kmn_count_batch_2na: the reference keeps a read in memory as TwoBitSequence bytes (4 bases per byte, first base in the
+// top two bits, src/TwoBitSequence.cpp:242-269) plus a list of markups for its non-ACGT bases (src/Sequence.h:372-380).
+// A batch in that form crosses PCIe at a quarter of the ASCII size; these two kernels turn it back into the ASCII the
+// walkers read.  One warp per read, a lane per packed byte.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_unpack_2na(const uint8_t *packed, const u64 *packed_off, const u64 *read_off, u64 n_reads, uint8_t *bases)
+{
+    const u32 lane = threadIdx.x & 31u;
+    const u64 n_warps = (u64)gridDim.x * (blockDim.x >> 5);
+    for (u64 r = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_reads; r += n_warps) {
+        const u64 o0 = read_off[r], len = read_off[r + 1] - o0, p0 = packed_off[r];
+        const u64 nbytes = (len + 3) >> 2;
+        for (u64 j = lane; j < nbytes; j += 32) {
+            const u32 b = packed[p0 + j];
+            const u64 at = o0 + 4 * j;
+#pragma unroll
+            for (u32 q = 0; q < 4; ++q)
+                if (4 * j + q < len) bases[at + q] = (uint8_t)((0x54474341u >> (8u * ((b >> (6u - 2u * q)) & 3u))) & 0xffu);   // "ACGT"
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_apply_markups(const u64 *pos, const uint8_t *chr, u64 n, u64 total, uint8_t *bases)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        if (pos[i] < total) bases[pos[i]] = chr[i];
+}
+
 // number of k-mer positions in reads [0,n): sum max(0, len-k+1) (discarded reads excluded)
 __global__ void __launch_bounds__(256) k_count_positions(const u64 *read_off, const uint8_t *discarded, u64 n_reads, u32 k, u64 *total)
 {
@@ -1174,6 +1203,39 @@ __global__ void __launch_bounds__(INSERT_TPB, KMN_INSERT_MIN_CTAS) k_insert_stag
 // Same slot layout, same probe sequence (linear from the even slot below the home slot, wrapping inside the slice) and
 // the same saturating count as table_insert, so k_insert_staged / table_find / the scans work on the same table.
 // ------------------------------------------------------------------------------------------------
+// ---- bulk asynchronous copies (TMA, cp.async.bulk) and the mbarriers that track them ----
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tKMN_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra KMN_DONE_%=;\n\tbra KMN_WAIT_%=;\n\tKMN_DONE_%=:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u32 bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(u64 *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+
 struct SplitArgs {
     TableView table;
     const u64 *ent_ptr;    // phase-2 work list entries, group-major (k_build_entries)
@@ -1191,30 +1253,39 @@ struct SplitArgs {
 };
 
 static constexpr int SPLIT_RPT = 4;        // records per thread and round
+static constexpr int SPLIT_TPB = 1024;
+static constexpr int SPLIT_CHUNK = SPLIT_TPB * SPLIT_RPT;              // records per round = per bulk copy (32 KB)
 
-__global__ void __launch_bounds__(1024, 1) k_slice_split(SplitArgs a)
+// The records of the item's entries come into shared memory as bulk copies of one round each (two buffers, the copy of
+// the next round runs while this round is binned); threads take their records from there, so the kernel waits for memory
+// only at the start of an item.
+__global__ void __launch_bounds__(SPLIT_TPB, 1) k_slice_split(SplitArgs a)
 {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ u32 s_item;
+    __shared__ __align__(8) u64 bar_full[2];
     const u32 nb = 1u << a.table.group_shift;                          // bins = slices of one group
     const u32 n_pad = (nb + 31u) & ~31u;
-    u32 *cnt = reinterpret_cast<u32 *>(smem_raw);
+    u64 *inbuf = reinterpret_cast<u64 *>(smem_raw);                    // [2][SPLIT_CHUNK] input records
+    u32 *cnt = reinterpret_cast<u32 *>(inbuf + 2 * SPLIT_CHUNK);
     u32 *fl = cnt + n_pad;
     u64 *ring = reinterpret_cast<u64 *>(fl + n_pad);
     const u32 R = a.ring_R, cap2 = a.cap2;
     const u32 n_items = a.n_groups * a.S;
-    const u32 T = blockDim.x;
     LocalCtr lc{0, 0, 0, 0, 0, 0};
+    if (threadIdx.x == 0) { mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    u32 ph0 = 0, ph1 = 0, q = 0;                                       // chunks are numbered through all items (buffer = number & 1)
     while (true) {
         if (threadIdx.x == 0) s_item = atomicAdd(a.ticket, 1u);
-        for (u32 i = threadIdx.x; i < nb; i += T) { cnt[i] = 0; fl[i] = 0; }
+        for (u32 i = threadIdx.x; i < nb; i += SPLIT_TPB) { cnt[i] = 0; fl[i] = 0; }
         __syncthreads();
         const u32 item = s_item;
         if (item >= n_items) break;
         const u32 g = item / a.S, part = item - g * a.S;
         u64 *const obase = a.buf + (size_t)item * nb * cap2;
         auto flush = [&](bool all) {
-            for (u32 b = threadIdx.x; b < nb; b += T) {
+            for (u32 b = threadIdx.x; b < nb; b += SPLIT_TPB) {
                 u32 c = cnt[b];
                 if (c > cap2) c = cap2;
                 const u32 f = fl[b];
@@ -1232,64 +1303,66 @@ __global__ void __launch_bounds__(1024, 1) k_slice_split(SplitArgs a)
                 fl[b] = nfl;
             }
         };
-        // the records of the item's entries are taken in rounds of T * SPLIT_RPT; the records of the next round are
-        // requested before this round's are binned, so a round never waits for memory
+        // the item's records = the records of its entries, one after the other, in chunks of SPLIT_CHUNK that do not
+        // cross an entry; every thread steps the consumer position (ce, co), thread 0 also the producer's (pe, po)
         const u32 e1 = min(g * a.per_group + (part + 1u) * a.epp, (g + 1u) * a.per_group);
-        u32 e = g * a.per_group + part * a.epp, base = 0, n = 0;
-        const u64 *src = nullptr;
-        auto open_entry = [&]() {                                      // first entry at or after e that has records
-            while (e < e1) {
-                n = __ldg(&a.ent_cnt[e]);
-                if (n) { src = reinterpret_cast<const u64 *>(__ldg(&a.ent_ptr[e])); base = 0; return; }
-                ++e;
-            }
+        const u32 e0 = g * a.per_group + part * a.epp;
+        u32 ce = e0, co = 0, cn = 0, pe = e0, po = 0, pn = 0;
+        auto skip = [&](u32 &e, u32 &o, u32 &n) {                      // first entry at or after e with records left
+            while (e < e1) { n = __ldg(&a.ent_cnt[e]); if (o < n) return; ++e; o = 0; }
             n = 0;
         };
-        auto fetch = [&](u64 (&r)[SPLIT_RPT], u32 &have) {             // this thread's records of the current round, then advance
-            have = 0;
-            if (e >= e1) return;
-#pragma unroll
-            for (int u = 0; u < SPLIT_RPT; ++u) {
-                const u32 idx = base + (u32)u * T + threadIdx.x;
-                if (idx < n) { r[u] = ld_nc64(src + idx); have |= 1u << u; }
-            }
-            base += T * SPLIT_RPT;
-            if (base >= n) { ++e; open_entry(); }
+        auto produce = [&](u32 qq) {                                   // thread 0: the chunk at (pe, po) -> buffer qq & 1
+            skip(pe, po, pn);
+            if (pe >= e1) return false;
+            const u32 n = min((u32)SPLIT_CHUNK, pn - po);
+            // entries start on 32-byte boundaries (sub-regions hold multiples of 4 records); a bulk copy moves a multiple of 16 bytes
+            const u32 bytes = ((n + 1u) & ~1u) * 8u;
+            const u64 *src = reinterpret_cast<const u64 *>(__ldg(&a.ent_ptr[pe])) + po;
+            mbar_expect_tx(&bar_full[qq & 1u], bytes);
+            bulk_g2s(inbuf + (size_t)(qq & 1u) * SPLIT_CHUNK, src, bytes, &bar_full[qq & 1u]);
+            po += n;
+            return true;
         };
-        open_entry();
-        u64 cur[SPLIT_RPT], nxt[SPLIT_RPT];
-        u32 hc = 0, hn = 0;
-        bool more = e < e1;                                            // uniform: every thread walks the same (entry, base) sequence
-        fetch(cur, hc);
-        while (more) {
-            more = e < e1;
-            fetch(nxt, hn);
+        u32 q_issue = q;
+        if (threadIdx.x == 0) { if (produce(q_issue)) ++q_issue; if (produce(q_issue)) ++q_issue; }
+        skip(ce, co, cn);
+        while (ce < e1) {
+            const u32 n = min((u32)SPLIT_CHUNK, cn - co);
+            if (q & 1u) { mbar_wait(&bar_full[1], ph1); ph1 ^= 1u; } else { mbar_wait(&bar_full[0], ph0); ph0 ^= 1u; }
+            const u64 *in = inbuf + (size_t)(q & 1u) * SPLIT_CHUNK;
+            u64 rec[SPLIT_RPT];
 #pragma unroll
             for (int u = 0; u < SPLIT_RPT; ++u) {
-                if (!((hc >> u) & 1u)) continue;
-                u64 key[1] = {cur[u] & ~1ull};
-                const u64 ph = place_hash<1>(key);
+                const u32 idx = (u32)u * SPLIT_TPB + threadIdx.x;
+                rec[u] = idx < n ? in[idx] : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < SPLIT_RPT; ++u) {
+                const u32 idx = (u32)u * SPLIT_TPB + threadIdx.x;
+                if (idx >= n) continue;
+                const u64 ph = mix64(rec[u] & ~1ull);
                 const u32 b = part_of(ph, a.table.n_parts) & (nb - 1u);
                 const u32 p = atomicAdd(&cnt[b], 1u);
                 if (p < cap2) {
-                    if (p - fl[b] < R) ring[(size_t)b * R + (p & (R - 1u))] = cur[u];
-                    else obase[(size_t)b * cap2 + p] = cur[u];
+                    if (p - fl[b] < R) ring[(size_t)b * R + (p & (R - 1u))] = rec[u];
+                    else obase[(size_t)b * cap2 + p] = rec[u];
                 } else {                                               // sub-run full (skewed input): straight into the table
-                    Rec<1, false> r; r.w[0] = cur[u];
+                    Rec<1, false> r; r.w[0] = rec[u];
                     insert_record<1, false>(a.table, r, lc.unique, lc.full, lc.probes);
                     lc.direct++;
                 }
             }
-            __syncthreads();
+            __syncthreads();                                           // the round's records are in the rings; its input buffer is free
+            if (threadIdx.x == 0 && produce(q_issue)) ++q_issue;       // (the chunk after next, into the buffer just read)
             flush(false);
             __syncthreads();
-#pragma unroll
-            for (int u = 0; u < SPLIT_RPT; ++u) cur[u] = nxt[u];
-            hc = hn;
+            co += n; ++q;
+            skip(ce, co, cn);
         }
         flush(true);
         __syncthreads();
-        for (u32 i = threadIdx.x; i < nb; i += T) a.cnt2[(size_t)item * nb + i] = min(cnt[i], cap2);
+        for (u32 i = threadIdx.x; i < nb; i += SPLIT_TPB) a.cnt2[(size_t)item * nb + i] = min(cnt[i], cap2);
         __syncthreads();
     }
     ctr_commit(a.ctr, lc);
@@ -1412,46 +1485,28 @@ __global__ void __launch_bounds__(COUNT_TPB, 3) k_count_slices(TableView t, cons
 //   shared memory per CTA: the slice (part_slots * 16 B) + two record buffers of COUNT_CHUNK records
 // ------------------------------------------------------------------------------------------------
 static constexpr int COUNT3_TPB = 512;
-static constexpr int COUNT_CHUNK = 2048;   // records per bulk copy (16 KB)
+static constexpr int COUNT_CHUNK = 1024;   // records per bulk copy (8 KB)
+static constexpr int COUNT_NBUF = 4;       // record buffers: a chunk is requested COUNT_NBUF chunks before it is counted
 
-__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tKMN_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra KMN_DONE_%=;\n\tbra KMN_WAIT_%=;\n\tKMN_DONE_%=:\n\t}"
-                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u32 bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __global__ void __launch_bounds__(COUNT3_TPB, 2) k_count_slices_tma(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, Counters *ctr)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const u32 SL = (u32)t.part_slots;
     Slot<1> *sl = reinterpret_cast<Slot<1> *>(smem_raw);               // one slice of the table
-    u64 *rbuf = reinterpret_cast<u64 *>(smem_raw + (size_t)SL * 16);   // [2][COUNT_CHUNK] record chunks
-    __shared__ __align__(8) u64 bar_slice, bar_rec[2];
+    u64 *rbuf = reinterpret_cast<u64 *>(smem_raw + (size_t)SL * 16);   // [COUNT_NBUF][COUNT_CHUNK] record chunks
+    __shared__ __align__(8) u64 bar_slice, bar_full[COUNT_NBUF], bar_empty[COUNT_NBUF];
     __shared__ u32 s_pre[2][32];                                       // exclusive prefix of the sub-run sizes of this / the next slice
     const u32 nb = 1u << t.group_shift;
+    const u32 lane = threadIdx.x & 31u;
     u64 n_unique = 0, n_full = 0;
-    if (threadIdx.x == 0) { mbar_init(&bar_slice, 1); mbar_init(&bar_rec[0], 1); mbar_init(&bar_rec[1], 1); }
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_slice, 1);
+        for (int b = 0; b < COUNT_NBUF; ++b) {
+            mbar_init(&bar_full[b], 1);                                // completed by the bulk copy's bytes
+            mbar_init(&bar_empty[b], COUNT3_TPB / 32);                 // one arrival per warp
+        }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     auto load_pre = [&](u32 pi, u32 *dst) {
         if (threadIdx.x < 32) {
@@ -1463,7 +1518,10 @@ __global__ void __launch_bounds__(COUNT3_TPB, 2) k_count_slices_tma(TableView t,
         }
     };
     load_pre(blockIdx.x, s_pre[0]);
-    u32 it = 0, ph_slice = 0, ph_rec0 = 0, ph_rec1 = 0;
+    // parities of the next completion to wait for (one bit per buffer); the chunks of all slices are numbered through
+    // (buffer = number % COUNT_NBUF)
+    u32 it = 0, ph_slice = 0, ph_full = 0, ph_empty = 0, qn = 0;
+    const u32 sl_addr = smem_u32(sl), sl_end = sl_addr + SL * 16u;
     for (u32 pi = blockIdx.x; pi < t.n_parts; pi += gridDim.x, ++it) {
         __syncthreads();                                               // s_pre[it & 1] complete; every thread has left the previous slice
         load_pre(pi + gridDim.x, s_pre[(it + 1u) & 1u]);
@@ -1474,68 +1532,81 @@ __global__ void __launch_bounds__(COUNT3_TPB, 2) k_count_slices_tma(TableView t,
         const u64 *run0 = buf + (((size_t)g * S) * nb + j) * cap2;     // sub-run p starts at run0 + p * nb * cap2
         const size_t run_stride = (size_t)nb * cap2;
         Slot<1> *gsl = reinterpret_cast<Slot<1> *>(t.slots) + (size_t)pi * SL;
-        // chunk q of the slice = records [q0, q0 + n) of sub-run p: every sub-run is cut into chunks of COUNT_CHUNK
-        u32 n_chunks = 0;
-        for (u32 p = 0; p < S; ++p) n_chunks += (pre[p + 1] - pre[p] + COUNT_CHUNK - 1) / COUNT_CHUNK;
-        auto chunk_of = [&](u32 q, u32 &p, u32 &o, u32 &n) {           // q-th chunk -> (sub-run, offset, records)
-            p = 0;
-            while (true) {
-                const u32 len = pre[p + 1] - pre[p], nc = (len + COUNT_CHUNK - 1) / COUNT_CHUNK;
-                if (q < nc) { o = q * COUNT_CHUNK; n = min((u32)COUNT_CHUNK, len - o); return; }
-                q -= nc; ++p;
-            }
-        };
-        auto issue = [&](u32 q) {                                      // thread 0: chunk q -> record buffer q & 1
-            u32 p, o, n;
-            chunk_of(q, p, o, n);
+        // the slice's records as chunks of at most COUNT_CHUNK records that do not cross a sub-run: an iterator every thread
+        // advances in step (sub-run p, offset o)
+        u32 cp = 0, co = 0;                                            // consumer position
+        u32 pp = 0, po = 0;                                            // producer position (thread 0), one chunk ahead
+        auto skip_empty = [&](u32 &p, u32 &o) { while (p < S && o >= pre[p + 1] - pre[p]) { ++p; o = 0; } };
+        skip_empty(cp, co);
+        pp = cp; po = co;
+        u32 q_issue = qn;                                              // number of the next chunk to issue (thread 0; == qn between slices)
+        auto produce = [&]() {                                         // thread 0 only
+            skip_empty(pp, po);
+            if (pp >= S) return;
+            const u32 b = q_issue % COUNT_NBUF;
+            // the buffer's previous chunk (COUNT_NBUF numbers back) has been consumed by every warp
+            if (q_issue >= COUNT_NBUF) { mbar_wait(&bar_empty[b], (ph_empty >> b) & 1u); ph_empty ^= 1u << b; }
+            const u32 n = min((u32)COUNT_CHUNK, pre[pp + 1] - pre[pp] - po);
             const u32 bytes = ((n + 1u) & ~1u) * 8u;                   // bulk copies move multiples of 16 bytes (cap2 is a multiple of 4)
-            mbar_expect_tx(&bar_rec[q & 1u], bytes);
-            bulk_g2s(rbuf + (size_t)(q & 1u) * COUNT_CHUNK, run0 + (size_t)p * run_stride + o, bytes, &bar_rec[q & 1u]);
+            mbar_expect_tx(&bar_full[b], bytes);
+            bulk_g2s(rbuf + (size_t)b * COUNT_CHUNK, run0 + (size_t)pp * run_stride + po, bytes, &bar_full[b]);
+            po += n;
+            ++q_issue;
         };
         if (threadIdx.x == 0) {
             bulk_wait_read();                                          // the previous slice has been read out of shared memory
             mbar_expect_tx(&bar_slice, SL * 16u);
             bulk_g2s(sl, gsl, SL * 16u, &bar_slice);
-            issue(0);
+            for (int b = 0; b < COUNT_NBUF; ++b) produce();
         }
         mbar_wait(&bar_slice, ph_slice);
         ph_slice ^= 1u;
-        for (u32 q = 0; q < n_chunks; ++q) {
-            if (threadIdx.x == 0 && q + 1 < n_chunks) issue(q + 1);    // its buffer was released by the barrier that ended chunk q - 1
-            u32 p, o, n;
-            chunk_of(q, p, o, n);
-            if (q & 1u) { mbar_wait(&bar_rec[1], ph_rec1); ph_rec1 ^= 1u; } else { mbar_wait(&bar_rec[0], ph_rec0); ph_rec0 ^= 1u; }
-            const u64 *recs = rbuf + (size_t)(q & 1u) * COUNT_CHUNK;
+        while (cp < S) {
+            const u32 n = min((u32)COUNT_CHUNK, pre[cp + 1] - pre[cp] - co);
+            const u32 b = qn % COUNT_NBUF;
+            mbar_wait(&bar_full[b], (ph_full >> b) & 1u);
+            ph_full ^= 1u << b;
+            const u64 *recs = rbuf + (size_t)b * COUNT_CHUNK;
             for (u32 idx = threadIdx.x; idx < n; idx += COUNT3_TPB) {
                 const u64 rec = recs[idx];
-                const u64 key1 = rec & ~1ull, want = ~key1;
-                u64 key[1] = {key1};
-                const u64 ph = place_hash<1>(key);
-                u32 s = (u32)home_slot(ph, SL) & ~1u;
-                u32 probes = 0;
-                for (; probes < SL; ++probes) {
-                    const ulonglong2 x = *reinterpret_cast<const ulonglong2 *>(&sl[s]);      // {val, key}
-                    u64 k = x.y;
-                    bool sat = (u32)x.x >= MAX_COUNT;
-                    if (k == 0ull) {
-                        k = atomicCAS(&sl[s].k[0], 0ull, want);
-                        if (k == 0ull) { n_unique++; k = want; }
-                        sat = false;
+                const u64 want = ~(rec & ~1ull);
+                const u64 ph = mix64(rec & ~1ull);
+                u32 addr = sl_addr + (((u32)(((u64)(u32)ph * SL) >> 32)) & ~1u) * 16u;
+                u32 left = SL;
+                while (true) {
+                    u64 v, k;
+                    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(v), "=l"(k) : "r"(addr));      // {val, key}
+                    bool hit = k == want;
+                    if (!hit && k == 0ull) {
+                        u64 old;
+                        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr + 8u), "l"(0ull), "l"(want) : "memory");
+                        if (old == 0ull) n_unique++;
+                        hit = old == 0ull || old == want;
+                        v = 0;
                     }
-                    if (k == want) {
-                        if (!sat) {
-                            u32 *w32 = reinterpret_cast<u32 *>(&sl[s].val);
-                            atomicAdd(w32, 1u);
-                            if (rec & 1ull) atomicAdd(w32 + 1, 1u);
+                    if (hit) {
+                        // count in the low word, directionBias in the high word: two native 32-bit shared atomics (a 64-bit
+                        // shared atomicAdd compiles to a compare-and-swap loop); no carry ever crosses the words
+                        if ((u32)v < MAX_COUNT) {
+                            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+                            if (rec & 1ull) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr + 4u) : "memory");
                         }
                         break;
                     }
-                    s = s + 1u == SL ? 0u : s + 1u;
+                    addr += 16u;
+                    if (addr == sl_end) addr = sl_addr;
+                    if (--left == 0u) { n_full++; break; }
                 }
-                if (probes >= SL) n_full++;
             }
-            __syncthreads();                                           // buffer q & 1 is free; after the last chunk: the slice is final
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[b]);                 // this warp is done with buffer b
+            co += n; ++qn;
+            skip_empty(cp, co);
+            if (threadIdx.x == 0) produce();                           // refill the buffer just read, COUNT_NBUF chunks ahead (waits for its release)
         }
+        // (the releases of the slice's last chunks are waited for by the first chunks of the next slice: chunk q always
+        //  waits for the release of chunk q - COUNT_NBUF, across slices)
+        __syncthreads();                                               // every warp has counted its records: the slice is final
         if (threadIdx.x == 0) {
             fence_async_smem();                                        // the counts written by all threads are visible to the bulk store
             bulk_s2g(gsl, sl, SL * 16u);

@@ -421,3 +421,33 @@ def test_import_and_subtract(K, k, vk):
     assert (e2["keys"] == ea["keys"][keep]).all() and (e2["count"] == ea["count"][keep]).all()
     for c in (a, b, s):
         c.close()
+
+
+@pytest.mark.parametrize("k", [31, 63])
+def test_count_batch_2na_equals_ascii(K, k):
+    """kmn_count_batch_2na (the reference's in-memory read: TwoBitSequence bytes + markups, src/Sequence.h:372-380) counts
+    exactly what kmn_count_batch counts on the ASCII form of the same reads -- N / X / '.' markups, ragged lengths, reads
+    shorter than k, an empty read, several batches through the staging slots"""
+    bases, q, off = synth.reads_numpy(5000, 150, 30000, seed=41, err=0.003, lowq=0.002, n_rate=0.004, var_len=True)
+    bases = bases.copy()
+    bases[::997] = ord("X")
+    bases[5::1201] = ord(".")
+    off = off.copy()
+    a = K.Context(kmer_size=k, table_slots=1 << 21)
+    b = K.Context(kmer_size=k, table_slots=1 << 21)
+    a.count_batch(bases, q, off)
+    a.count_finish(apply_purge=False)
+    step = 700
+    for r0 in range(0, 5000, step):
+        r1 = min(5000, r0 + step)
+        b0, b1 = int(off[r0]), int(off[r1])
+        o = np.ascontiguousarray(off[r0:r1 + 1] - off[r0])
+        packed, poff, mpos, mchr = K.capi.pack_2na(bases[b0:b1], o)
+        b.count_batch_2na(packed, poff, np.ascontiguousarray(q[b0:b1]), o, markup_pos=mpos if len(mpos) else None, markup_chr=mchr if len(mpos) else None)
+    b.count_finish(apply_purge=False)
+    assert_tables_equal(a.export(), b.export())
+    sa, sb = a.stats(), b.stats()
+    assert (sa["raw_kmers"], sa["raw_good_kmers"], sa["unique_kmers"]) == (sb["raw_kmers"], sb["raw_good_kmers"], sb["unique_kmers"])
+    assert_tables_equal(b.export(), oracle_table(bases, q, off, k, threads=4).export())
+    a.close()
+    b.close()
