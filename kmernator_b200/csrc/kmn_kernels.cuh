@@ -1033,6 +1033,24 @@ __global__ void __launch_bounds__(INSERT_TPB, KMN_INSERT_MIN_CTAS) k_insert_stag
     constexpr int U = INSERT_UNROLL;
     __shared__ u64 s_item;
     __shared__ u32 s_entry;
+    // pre-aggregation of hot k-mers (single-word keys): when the records of a ticket repeat few keys (a tiny genome at
+    // enormous depth, a repeat, an adapter) every record would fight for the same L2 atomic unit -- the L2 serialises
+    // atomics per address.  Such tickets are first counted into a small shared-memory table, and only one update per
+    // distinct key and chunk goes to the table in HBM, carrying the whole multiplicity (count, directionBias, weight,
+    // extension counters); the count still saturates at 65535 (src/KmerTrackingData.h:427-448).
+    constexpr int AGG = 512;                                           // slots of the shared table; a chunk holds INSERT_CHUNK records
+    constexpr bool CAN_AGG = W == 1;
+    __shared__ u64 agg_key[CAN_AGG ? AGG : 1];                         // ~key, 0 = empty
+    __shared__ u32 agg_cnt[CAN_AGG ? AGG : 1], agg_dir[CAN_AGG ? AGG : 1];
+    __shared__ float agg_w[CAN_AGG && HASX ? AGG : 1];
+    __shared__ u32 agg_ext[CAN_AGG && HASX ? AGG * 12 : 1];
+    __shared__ u32 s_hot;
+    if (CAN_AGG) {
+        for (u32 i = threadIdx.x; i < (u32)AGG; i += INSERT_TPB) {
+            agg_key[i] = 0; agg_cnt[i] = 0; agg_dir[i] = 0;
+            if (HASX) { agg_w[i] = 0.f; for (int q = 0; q < 12; ++q) agg_ext[i * 12 + q] = 0; }
+        }
+    }
     u64 n_unique = 0, n_full = 0, n_probes = 0;
     // this launch covers the items [item_lo, total_items) of the work list's `split`-th part (the multi-GPU rounds cut
     // phase 2 into several launches so that the small barrier kernels of the next round are not stuck behind it)
@@ -1084,6 +1102,20 @@ __global__ void __launch_bounds__(INSERT_TPB, KMN_INSERT_MIN_CTAS) k_insert_stag
         const u64 *src; u32 cnt;
         locate(item0, entry, src, cnt);
         load(src, cnt, rec);
+        bool hot = false;
+        if constexpr (CAN_AGG) {
+            // a sample of 32 records of the ticket: hot when at least a quarter of them share their key with another one
+            if (threadIdx.x < 32) {
+                const bool have = threadIdx.x < cnt;
+                const u32 act = __ballot_sync(0xffffffffu, have);
+                u32 dup = 0;
+                if (have) { const u32 peers = __match_any_sync(act, rec[0].w[0] & ~1ull); dup = __popc(peers) > 1 ? 1u : 0u; }
+                const u32 n_dup = __popc(__ballot_sync(0xffffffffu, dup != 0));
+                if (threadIdx.x == 0) s_hot = (n_dup >= 8u) ? 1u : 0u;
+            }
+            __syncthreads();
+            hot = s_hot != 0;
+        }
 #pragma unroll 1
         for (u32 g = 0; g < (u32)INSERT_GROUP; ++g) {
             const u64 item = item0 + g;
@@ -1092,7 +1124,57 @@ __global__ void __launch_bounds__(INSERT_TPB, KMN_INSERT_MIN_CTAS) k_insert_stag
             u32 cnt_n = 0;
             if (g + 1 < (u32)INSERT_GROUP && item + 1 < total_items) { locate(item + 1, entry, src, cnt_n); load(src, cnt_n, rec_n); }
 
-            if constexpr (W == 1) {
+            if (CAN_AGG && hot) {
+                if constexpr (CAN_AGG) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if ((u32)u * INSERT_TPB + threadIdx.x >= cnt) continue;
+                        u64 key[1]; bool fwd; float weight; u32 eb;
+                        rec[u].unpack(key, fwd, weight, eb);
+                        const u64 want = ~key[0];
+                        u32 h = (u32)(mix64(key[0]) >> 40) & (AGG - 1);
+                        bool placed = false;
+                        for (int pr = 0; pr < 8 && !placed; ++pr) {
+                            u64 k = agg_key[h];
+                            if (k == 0ull) k = atomicCAS(&agg_key[h], 0ull, want);
+                            if (k == 0ull || k == want) placed = true; else h = (h + 1) & (AGG - 1);
+                        }
+                        if (placed) {
+                            atomicAdd(&agg_cnt[h], 1u);
+                            if (fwd) atomicAdd(&agg_dir[h], 1u);
+                            if (HASX) {
+                                if (t.wsum) atomicAdd(&agg_w[h], weight);
+                                if (t.ext) {
+                                    const u32 l = eb & 7u, rr = (eb >> 3) & 7u;
+                                    if (l < 6) atomicAdd(&agg_ext[h * 12 + l], 1u);
+                                    if (rr < 6) atomicAdd(&agg_ext[h * 12 + 6 + rr], 1u);
+                                }
+                            }
+                        } else insert_record<W, HASX>(t, rec[u], n_unique, n_full, n_probes);      // too many distinct keys for the shared table
+                    }
+                    __syncthreads();
+                    for (u32 i = threadIdx.x; i < (u32)AGG; i += INSERT_TPB) {
+                        const u64 kk = agg_key[i];
+                        if (kk == 0ull) continue;
+                        u64 key[1] = {~kk};
+                        const u64 ph = place_hash<1>(key);
+                        u64 slot; u32 probes = 0;
+                        const int r = table_insert<1>(t, part_of(ph, t.n_parts), home_slot(ph, t.part_slots), key,
+                                                      (u64)agg_cnt[i] | ((u64)agg_dir[i] << 32), &slot, &probes);
+                        if (r < 0) n_full += agg_cnt[i];
+                        else {
+                            n_unique += (u64)r;
+                            if (HASX) {
+                                if (t.wsum) atomicAdd(&t.wsum[slot], agg_w[i]);
+                                if (t.ext) for (int q = 0; q < 12; ++q) if (agg_ext[i * 12 + q]) atomicAdd(&t.ext[slot * 12 + q], agg_ext[i * 12 + q]);
+                            }
+                        }
+                        agg_key[i] = 0; agg_cnt[i] = 0; agg_dir[i] = 0;
+                        if (HASX) { agg_w[i] = 0.f; for (int q = 0; q < 12; ++q) agg_ext[i * 12 + q] = 0; }
+                    }
+                    __syncthreads();
+                }
+            } else if constexpr (W == 1) {
                 // lockstep probing.  state: 0 done, 1 pair load in flight, 2/3 CAS on slot 0/1 of the pair in flight
                 u64 want[U], k0[U], k1[U], add[U];
                 Slot<1> *sbase[U];

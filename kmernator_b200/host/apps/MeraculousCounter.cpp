@@ -44,6 +44,7 @@ int main(int argc, char *argv[])
         if (k == 0) LOG_THROW("The Kmer size can not be 0");
         World world;
         World::instance() = &world;
+        const bool showHistogram = Log::isVerbose(1);                    // decided before the other ranks go quiet: the histogram is collective
         if (world.rank() != 0 && !Options::getOptions().getDebug()) Log::verboseLevel() = 0;
         LOG_VERBOSE(1, "Reading Input Files");
         ReadSet reads;
@@ -57,7 +58,7 @@ int main(int argc, char *argv[])
         KmerSpectrum spectrum(world, KmerSpectrum::estimateRawKmers(world, reads), KMN_VALUE_DIR_EXT);
         spectrum.buildKmerSpectrum(reads);
         const int minDepth = (int)KmerSpectrumOptions::getOptions().getMinDepth();
-        if (Log::isVerbose(1)) {
+        if (showHistogram) {
             const std::string hist = spectrum.getHistogram(false, 255);
             if (world.rank() == 0) std::cerr << "Collective Kmer Histogram" << std::endl << hist;
         }

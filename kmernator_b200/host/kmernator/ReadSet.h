@@ -94,56 +94,102 @@ public:
         if (!_deferNormalise) normaliseQualities();
     }
     void deferNormalise(bool d = true) { _deferNormalise = d; }       // the distributed driver agrees on the input base first
+    // Rank `rank` of `size` parses only its BYTE RANGE of the file: the range starts at the first record boundary at or
+    // after fileSize / size * rank and ends at the one at or after fileSize / size * (rank + 1), so the ranks' ranges tile
+    // the file without reading each other's part (ReadFileReader::seekToPartition src/ReadFileReader.h:379-398,
+    // SequenceStreamParser::seekToNextRecord :657-760).
     void appendAnyFile(const std::string &path, unsigned int fileNum = 1, int rank = 0, int size = 1)
     {
-        std::ifstream in(path.c_str());
+        std::ifstream in(path.c_str(), std::ios::binary);
         if (!in.good()) LOG_THROW("Could not open : " << path);
-        std::vector<Read> tmp;
-        std::string l1, l2, l3, l4;
-        int first = in.peek();
-        if (first == '@') {
-            while (std::getline(in, l1)) {
-                if (l1.empty()) continue;
-                if (l1[0] != '@') LOG_THROW("Missing '@' in header of " << path << ": " << l1);
-                if (!std::getline(in, l2) || !std::getline(in, l3) || !std::getline(in, l4)) LOG_THROW("Truncated FASTQ record in " << path << ": " << l1);
-                stripCR(l1); stripCR(l2); stripCR(l4);
-                if (l2.size() != l4.size()) LOG_THROW("Number of bases and quals do not match in " << path << ": " << l1);
-                tmp.push_back(makeRead(l1.substr(1), l2, l4, fileNum));
-            }
-        } else if (first == '>') {
-            std::string hdr, seq;
-            while (std::getline(in, l1)) {
-                stripCR(l1);
-                if (!l1.empty() && l1[0] == '>') {
-                    if (!hdr.empty()) tmp.push_back(makeRead(hdr, seq, std::string(seq.size(), (char)Read::REF_QUAL), fileNum));
-                    hdr = l1.substr(1); seq.clear();
-                } else seq += l1;
-            }
-            if (!hdr.empty()) tmp.push_back(makeRead(hdr, seq, std::string(seq.size(), (char)Read::REF_QUAL), fileNum));
-        } else if (first != EOF) LOG_THROW("Unrecognised sequence file format: " << path);
-        // contiguous slice of the records; a cut never separates two mates (the reference's readers re-synchronise on
-        // record and pair boundaries after seeking, src/ReadFileReader.h:379-398)
-        const size_t n = tmp.size();
-        size_t a = n * (size_t)rank / (size_t)size, b = n * (size_t)(rank + 1) / (size_t)size;
-        if (size > 1) { a = pairAlignedCut(tmp, a); b = pairAlignedCut(tmp, b); }
-        for (size_t i = a; i < b; ++i) append(tmp[i]);
-    }
-    // first index >= cut that does not separate record cut-1 from its mate at cut.  Mates are adjacent records, so the
-    // records before the cut are paired off from the start of the file exactly as identifyPairs() does
-    static size_t pairAlignedCut(const std::vector<Read> &v, size_t cut)
-    {
-        if (cut == 0 || cut >= v.size()) return cut;
-        size_t i = 0;
-        while (i < cut) {
-            if (i + 1 < v.size()) {
-                std::string c1, c2;
-                const int n1 = readNum(v[i], c1), n2 = readNum(v[i + 1], c2);
-                if (n1 && n2 && n1 != n2 && c1 == c2) { i += 2; continue; }
-            }
-            ++i;
+        const int first = in.peek();
+        if (first == EOF) return;
+        if (first != '@' && first != '>') LOG_THROW("Unrecognised sequence file format: " << path);
+        const char marker = (char)first;
+        in.seekg(0, std::ios::end);
+        const unsigned long fileSize = (unsigned long)in.tellg();
+        unsigned long firstPos = 0, lastPos = fileSize;
+        if (size > 1) {
+            const unsigned long blockSize = fileSize / (unsigned long)size;
+            if (rank + 1 != size) seekToNextRecord(in, blockSize * (unsigned long)(rank + 1), fileSize, marker, lastPos);
+            if (!seekToNextRecord(in, blockSize * (unsigned long)rank, fileSize, marker, firstPos)) firstPos = lastPos;
         }
-        return i;
+        in.clear();
+        in.seekg((std::streamoff)firstPos);
+        unsigned long pos = firstPos;
+        std::string hdr, seq, qual;
+        while (pos < lastPos && readRecord(in, marker, pos, fileSize, hdr, seq, qual, path)) append(makeRead(hdr, seq, qual, fileNum));
     }
+
+private:
+    static bool getLine(std::ifstream &in, std::string &l, unsigned long &pos)
+    {
+        if (!std::getline(in, l)) return false;
+        pos += l.size() + (in.eof() ? 0 : 1);
+        stripCR(l);
+        return true;
+    }
+    // one record starting at `pos` (a marker line); FASTA sequences may span lines.  false at the end of the file.
+    static bool readRecord(std::ifstream &in, char marker, unsigned long &pos, unsigned long fileSize, std::string &hdr, std::string &seq, std::string &qual,
+                           const std::string &path)
+    {
+        std::string l;
+        do { if (pos >= fileSize || !getLine(in, l, pos)) return false; } while (l.empty());
+        if (l[0] != marker) LOG_THROW("Missing '" << marker << "' in header of " << path << ": " << l);
+        hdr = l.substr(1);
+        seq.clear(); qual.clear();
+        if (marker == '@') {
+            std::string plus;
+            if (!getLine(in, seq, pos) || !getLine(in, plus, pos) || !getLine(in, qual, pos)) LOG_THROW("Truncated FASTQ record in " << path << ": " << hdr);
+            if (seq.size() != qual.size()) LOG_THROW("Number of bases and quals do not match in " << path << ": " << hdr);
+        } else {
+            while (pos < fileSize && in.peek() != marker && in.peek() != EOF) { if (!getLine(in, l, pos)) break; seq += l; }
+            qual.assign(seq.size(), (char)Read::REF_QUAL);
+        }
+        return true;
+    }
+    // SequenceStreamParser::seekToNextRecord(minimumPos, byPair = true): the first record boundary at or after minimumPos
+    // that does not split two adjacent mates.  false (pos = end of file) when there is none.
+    static bool seekToNextRecord(std::ifstream &in, unsigned long minimumPos, unsigned long fileSize, char marker, unsigned long &out)
+    {
+        out = fileSize;
+        in.clear();
+        unsigned long pos = 0;
+        std::string l;
+        if (minimumPos > 0) {
+            if (minimumPos - 1 >= fileSize) return false;
+            in.seekg((std::streamoff)(minimumPos - 1));
+            pos = minimumPos - 1;
+            if (in.peek() == '\n') { in.seekg((std::streamoff)minimumPos); pos = minimumPos; }
+            else if (!getLine(in, l, pos)) return false;               // the rest of the line minimumPos falls into
+        } else { in.seekg(0); out = 0; return true; }
+        while (pos < fileSize && in.peek() != EOF && in.peek() != marker) if (!getLine(in, l, pos)) return false;
+        if (pos >= fileSize || in.peek() == EOF) return false;
+        if (marker == '@') {
+            // '@' is a valid quality character: when the NEXT line starts with '@' too, this one was a quality line and the
+            // record starts there (:688-707)
+            const unsigned long here = pos;
+            if (!getLine(in, l, pos)) return false;
+            if (pos >= fileSize || in.peek() != marker) { in.clear(); in.seekg((std::streamoff)here); pos = here; }
+        }
+        if (pos >= fileSize) return false;
+        // do not split a pair of adjacent mates (:712-757)
+        const unsigned long here1 = pos;
+        std::string h1, h2, h3, sq, ql;
+        if (!readRecord(in, marker, pos, fileSize, h1, sq, ql, "") || pos >= fileSize) return false;
+        const unsigned long here2 = pos;
+        if (!readRecord(in, marker, pos, fileSize, h2, sq, ql, "") || pos >= fileSize) return false;
+        if (!readRecord(in, marker, pos, fileSize, h3, sq, ql, "")) { out = here1; return true; }
+        const Read r1 = makeRead(h1, "", "", 0), r2 = makeRead(h2, "", "", 0), r3 = makeRead(h3, "", "", 0);
+        std::string c1, c2, c3;
+        const int n1 = readNum(r1, c1), n2 = readNum(r2, c2), n3 = readNum(r3, c3);
+        if (n1 && n2 && n1 != n2 && c1 == c2) out = here1;             // a natural pair starts here
+        else if (n2 && n3 && n2 != n3 && c2 == c3) out = here2;        // the boundary fell between two mates: one record further
+        else out = here1;
+        return true;
+    }
+
+public:
     void append(const Read &r)
     {
         _reads.push_back(r);

@@ -451,3 +451,38 @@ def test_count_batch_2na_equals_ascii(K, k):
     assert_tables_equal(b.export(), oracle_table(bases, q, off, k, threads=4).export())
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("k,vk,n_reads", [(21, 1, 60000), (31, 2, 40000), (21, 0, 60000), (32, 0, 30000)])
+def test_hot_kmers_tiny_genome(K, k, vk, n_reads):
+    """N1 / config C5b scaled down: a 5386-bp genome at enormous depth -- every staged chunk repeats a handful of keys, the
+    shared-memory pre-aggregation path of the insert kernel (and the sub-region / sub-run overflow paths around it) must
+    give the oracle's table: counts, directionBias, weights, extension counters"""
+    bases, q, off = synth.reads_numpy(n_reads, 150, 5386, seed=0x50, err=0.001, lowq=0.0005)
+    kw = dict(min_quality_score=2, min_kmer_quality=0.0) if vk == 1 else {}
+    ctx = K.Context(kmer_size=k, table_slots=1 << 20, value_kind=vk, stage_keys=1 << 21, **kw)
+    ctx.count_batch(bases, q, off)
+    ctx.count_finish(apply_purge=False)
+    osp = oracle_table(bases, q, off, k, threads=4, track_ext=(vk == 1), min_quality=kw.get("min_quality_score", 3),
+                       min_kmer_quality=kw.get("min_kmer_quality", 0.10))
+    g, o = ctx.export(), osp.export()
+    assert_tables_equal(g, o, check_wsum=(vk == 2), check_ext=(vk == 1))
+    assert int(g["count"].max()) > 500
+    st, ost = ctx.stats(), osp.stats()
+    assert (st["raw_kmers"], st["raw_good_kmers"], st["unique_kmers"]) == (ost["raw"], ost["raw_good"], ost["unique"])
+    ctx.close()
+
+
+def test_hot_kmers_saturate_with_extensions(K):
+    """70000 copies of one read through the pre-aggregated path with extension tracking: every count saturates at 65535
+    (src/KmerTrackingData.h:427-448)"""
+    seq = b"ACGTTGCAAGGCTTAACCGGATATCGCGATTACGGATCCA"
+    n = 70000
+    bases, q, off = oracle.concat_reads([seq] * n)
+    ctx = K.Context(kmer_size=21, table_slots=1 << 12, value_kind=K.capi.KMN_VALUE_DIR_EXT)
+    ctx.count_batch(np.frombuffer(bases, np.uint8), q, off)
+    ctx.count_finish(apply_purge=False)
+    g = ctx.export()
+    assert len(g["count"]) == 20 and (g["count"] == 65535).all()
+    assert ctx.stats()["raw_kmers"] == n * 20
+    ctx.close()

@@ -22,7 +22,7 @@ def filter_reads():
 
 
 def _run(exe, args, cwd=None):
-    return subprocess.run([exe] + args, capture_output=True, text=True, cwd=cwd, timeout=600)
+    return subprocess.run([exe] + args, capture_output=True, text=True, cwd=cwd, timeout=300)
 
 
 def _run_ranks(exe, args, world, cwd, comm_dir, gpus=False):
@@ -31,7 +31,7 @@ def _run_ranks(exe, args, world, cwd, comm_dir, gpus=False):
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r if gpus else 0), KMN_COMM_DIR=comm_dir)
         procs.append(subprocess.Popen([exe] + args, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
-    outs = [p.communicate(timeout=600) for p in procs]
+    outs = [p.communicate(timeout=180) for p in procs]
     return [(p.returncode, o[1]) for p, o in zip(procs, outs)]
 
 
@@ -423,3 +423,32 @@ def test_reference_file_subtraction(filter_reads, golden_dir, tmp_path):
     p = _run(exe_p, opts + ["--reference-file", str(other), "--out", out2, "31", "1000.fastq"], cwd=golden_dir)
     assert p.returncode == 0, p.stderr
     assert open(out2 + "-MinDepth2-1000.fastq").read().split() == open(os.path.join(golden_dir, "1000-Filtered.fastq")).read().split()
+
+
+@pytest.mark.parametrize("paired", [True, False])
+def test_byte_range_slicing_tiles_the_file(filter_reads, tmp_path, paired):
+    """f1: every rank of FilterReads-P parses only its byte range of the input, cut at record boundaries that never
+    split two mates and never mistake a quality line starting with '@' for a header (src/ReadFileReader.h:379-398,
+    657-760): for any number of ranks the joined output equals the serial run's"""
+    import numpy as np
+    rng = np.random.default_rng(8 + paired)
+    fq = tmp_path / "in.fastq"
+    with open(fq, "w") as f:
+        for i in range(700):
+            L = int(rng.integers(30, 90))
+            s = "".join("ACGT"[x] for x in rng.integers(0, 4, L))
+            q = "".join(chr(int(x)) for x in rng.integers(64, 74, L))          # '@' (64) is a frequent quality character here
+            if i % 3 == 0:
+                q = "@" + q[1:]
+            name = ("p%d/%d" % (i // 2, 1 + i % 2)) if paired else ("s%d" % i)
+            f.write("@%s\n%s\n+\n%s\n" % (name, s, q))
+    args = ["--skip-artifact-filter", "1", "--fastq-base-quality", "33", "--min-read-length", "1"]
+    p = _run(filter_reads, args + ["--out", str(tmp_path / "serial"), "0", str(fq)])
+    assert p.returncode == 0, p.stderr
+    want = open(str(tmp_path / "serial-in.fastq")).read()
+    assert want.count("\n") == 4 * 700
+    for world in (2, 3, 5, 8):
+        out = str(tmp_path / ("par%d" % world))
+        res = _run_ranks(filter_reads + "-P", args + ["--out", out, "0", str(fq)], world, str(tmp_path), str(tmp_path / ("comm%d" % world)))
+        assert all(rc == 0 for rc, _ in res), res
+        assert open(out + "-in.fastq").read() == want, world

@@ -33,6 +33,6 @@ def test_owner_sharded_count_and_lookup(world, env):
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900, env=dict(os.environ, **env))
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=420, env=dict(os.environ, **env))
     assert p.returncode == 0, p.stdout[-3000:] + "\n" + p.stderr[-6000:]
     assert p.stdout.count("mgpu ok") == 4
