@@ -81,6 +81,7 @@ struct kmn_ctx {
     uint32_t split_S = 4, split_cap2 = 0, split_R = 0;
     int split_tpb = 1024, split_ctas = 1, count_ctas = 3;
     bool count_tma = true;            // k_count_slices_tma (bulk-copy engine) instead of k_count_slices (KMN_COUNT_TMA=0)
+    bool count_ws = false;            // KMN_COUNT_WS=1: k_count_slices_ws (producer warp + lane-persistent consumers) instead of k_count_slices_tma
     size_t split_smem = 0;
     uint32_t zero_below = 0;
     size_t scatter_smem = 0;
@@ -325,7 +326,9 @@ static int alloc_stage_sets(kmn_ctx *c)
             CK(c, cudaFuncSetAttribute(k_slice_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
             CK(c, cudaFuncSetAttribute(k_count_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16)));
             CK(c, cudaFuncSetAttribute(k_count_slices_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNT_NBUF * COUNT_CHUNK * 8)));
+            CK(c, cudaFuncSetAttribute(k_count_slices_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8)));
             if (const char *e = getenv("KMN_COUNT_TMA")) c->count_tma = atoi(e) != 0;
+            if (const char *e = getenv("KMN_COUNT_WS")) c->count_ws = atoi(e) != 0;
             if ((c->table.part_slots * 16) % 16 != 0) c->count_tma = false;
         }
     }
@@ -608,7 +611,9 @@ static int launch_insert(kmn_ctx *c, const StageView &v, int rb, uint64_t units,
         }
         {
             ProfScope ps(c, KMN_PROF_INSERT, units, si);
-            if (c->count_tma)
+            if (c->count_tma && c->count_ws)
+                k_count_slices_ws<<<c->n_sms * 2, COUNTW_TPB, c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr);
+            else if (c->count_tma)
                 k_count_slices_tma<<<c->n_sms * 2, COUNT3_TPB, c->table.part_slots * 16 + COUNT_NBUF * COUNT_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr);
             else
                 k_count_slices<<<c->n_sms * c->count_ctas, COUNT_TPB, c->table.part_slots * 16, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, v.n_parts, c->tickets + 1, c->ctr);
@@ -707,6 +712,8 @@ static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, cons
     a.nranks = (u32)c->nranks; a.rank = (u32)c->rank;
     a.use_lookup8 = c->o.hash_kind == KMN_HASH_LOOKUP8_HASH2;
     a.l2_hints = getenv("KMN_NO_L2_HINTS") ? 0 : 1;
+    a.fast_bound = getenv("KMN_NO_WEIGHT_BOUND") ? 0 : 1;
+    a.scatter_steps = getenv("KMN_SCATTER_STEPS") ? (u32)std::max(1, atoi(getenv("KMN_SCATTER_STEPS"))) : 1u;
     a.table = c->table; a.stage = c->sets[c->cur].v; a.ctr = c->ctr;
     a.send_recs = c->send_recs; a.send_cursor = c->send_cursor; a.send_cap = c->send_cap;
     a.flags = c->flags;
@@ -1236,9 +1243,10 @@ static int count_staged(kmn_ctx *c, BatchPtrs &bp, const uint64_t *read_off, uin
             if (r) return r;
         }
         if (npos > limit && rg.r1 - rg.r0 > 1) {
-            uint64_t mid = rg.r0 + (rg.r1 - rg.r0) / 2;
-            todo.push_back({mid, rg.r1});          // processed after the first half (stack order)
-            todo.push_back({rg.r0, mid});
+            // ceil(npos / limit) pieces of equal read count (every piece is measured again: read lengths may be uneven)
+            const uint64_t nr = rg.r1 - rg.r0, parts = std::min<uint64_t>(nr, (npos + limit - 1) / limit);
+            for (uint64_t q = parts; q-- > 0;)      // stack order: the first piece is processed first
+                todo.push_back({rg.r0 + nr * q / parts, rg.r0 + nr * (q + 1) / parts});
             continue;
         }
         if (npos == 0) continue;

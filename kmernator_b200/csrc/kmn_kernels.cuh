@@ -57,6 +57,8 @@ struct ParseArgs {
     u32 piece_shift;       // log2(reads per piece), 5 for large launches; small launches use smaller pieces so that they
                            // still spread over all CTAs (the sub-region capacities assume an even spread)
     u32 ring_R;            // phase 1b: record slots of one bin's shared-memory ring (power of two >= 4; 0 = no rings)
+    u32 fast_bound;        // phase 1a: non-uniform reads whose weights are bounded away from min_weight skip the recurrence
+    u32 scatter_steps;     // phase 1b: walker steps per round (between two flushes of the rings)
     TableView table;
     StageView stage;
     Counters *ctr;
@@ -347,7 +349,8 @@ __device__ __forceinline__ void walker_step(Walker<W> &s, const ParseArgs &a, co
                     const u32 re = ((rq & 0xffu) >= 20u || rc >= 4) ? rc : 7u;
                     eb = le | (re << 3);
                 }
-                emit(i, fwd ? s.roll.f : s.roll.r, fwd, NEED_W ? s.wf : 1.0f, NEED_W ? s.good : true, eb);
+                // without weights `good` = no markup inside the window (the k-mer's weight would be 0, KmerReadUtils.h:207-217)
+                emit(i, fwd ? s.roll.f : s.roll.r, fwd, NEED_W ? s.wf : 1.0f, NEED_W ? s.good : s.last_bad < (int)i, eb);
             }
         }
     };
@@ -389,7 +392,7 @@ __device__ __forceinline__ void weight_walk_read(const ParseArgs &a, const doubl
     auto emit = [&](u32 i, const u64 (&)[1], bool, float wf, bool good, u32) {
         const u64 gb = o0 + i, w = gb >> 5;
         if (w != curw) { if (acc) atomicOr(&a.mask[curw], acc); acc = 0; curw = w; }
-        if (good) { acc |= 1u << (u32)(gb & 31ull); lc.good++; }
+        if (good) { acc |= 1u << (u32)(gb & 31ull); if (WTS) lc.good++; }
         if (WTS) a.wts[gb] = wf;
         lc.raw++;
     };
@@ -410,18 +413,90 @@ __device__ __forceinline__ void mask_set_range(u32 *mask, u64 b0, u32 n)
     }
 }
 
+// clears bits [b0, b0+n) of the mask
+__device__ __forceinline__ void mask_clear_range(u32 *mask, u64 b0, u32 n)
+{
+    u64 w = b0 >> 5;
+    u32 sh = (u32)(b0 & 31ull);
+    while (n) {
+        const u32 take = min(n, 32u - sh);
+        const u32 bits = (take == 32u ? 0xffffffffu : ((1u << take) - 1u)) << sh;
+        atomicAnd(&mask[w], ~bits);
+        n -= take; sh = 0; ++w;
+    }
+}
+// k-mers [max(0, b-k+1), min(b, n-1)] of a read contain position b: their "counted" bits are cleared
+__device__ __forceinline__ void mask_clear_around(u32 *mask, u64 o0, u32 b, u32 k, u32 n)
+{
+    const u32 lo = b + 1u >= k ? b + 1u - k : 0u;
+    const u32 hi = b < n ? b : n - 1u;
+    if (hi >= lo) mask_clear_range(mask, o0 + lo, hi - lo + 1u);
+}
+
+// lower bound of p^n for 0 < p <= 1 (square-and-multiply rounds differently from a chain of n multiplications)
+__device__ __forceinline__ double pow_bound(double p, u32 n)
+{
+    double r = 1.0, sq = p;
+    for (u32 e = n; e; e >>= 1) { if (e & 1u) r *= sq; sq *= sq; }
+    return r * (1.0 - 1e-12);
+}
+// true when a weight >= lb (1 - 3e-13) is certainly counted: (float)w > min_weight
+__device__ __forceinline__ bool bound_passes(double lb, float min_weight)
+{
+    return lb > 1e-30 && lb * (1.0 - 9.5367431640625e-07) > (double)min_weight;
+}
+
+// calls f(j, x, m) for the lane's read [pos, pos+len) in the shared buffer: x = bytes j..j+7, m = byte mask of the valid ones
+template <typename F>
+__device__ __forceinline__ void smem_each_word(const u64 *buf64, u32 pos, u32 len, F &&f)
+{
+    u32 wi = pos >> 3;
+    const u32 sh = (pos & 7u) * 8u;
+    u64 w0 = buf64[wi];
+    for (u32 j = 0; j < len; j += 8) {
+        const u64 w1 = buf64[++wi];
+        const u64 x = sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0;
+        w0 = w1;
+        const u32 nb = len - j;
+        f(j, x, nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1ull));
+    }
+}
+
 static constexpr u32 MASK_WBUF = 8192 + 64;      // bytes of one warp's staging buffer: 32 reads of up to 256 bases
 
-// coalesced copy of the 16-byte blocks that hold bytes [b0, b1) of buf into a warp's shared buffer; returns the offset of
-// byte b0 inside the buffer.  Only blocks containing at least one valid byte are touched.
-__device__ __forceinline__ u32 warp_stage_bytes(const uint8_t *buf, u64 b0, u64 b1, uint4 *dst, u32 lane)
-{
-    const unsigned long long a0 = (unsigned long long)buf + b0, a1 = (unsigned long long)buf + b1;
-    const unsigned long long blk0 = a0 & ~15ull;
-    const u32 n_blk = (u32)((a1 - blk0 + 15ull) >> 4);
-    for (u32 i = lane; i < n_blk; i += 32) dst[i] = __ldg(reinterpret_cast<const uint4 *>(blk0) + i);
-    return (u32)(a0 - blk0);
-}
+// coalesced copy of the 16-byte blocks that hold bytes [b0, b1) of buf into a warp's shared buffer, in two halves: load()
+// requests up to STAGE_U blocks per lane at once and keeps them in registers (ten independent 16-byte loads per lane in
+// flight -- with one load in flight per lane and 768 threads per SM the kernel ran at the latency of 20 dependent memory
+// round trips per round), store() writes them to the buffer (and copies what did not fit into the registers).  Between
+// the two the warp works on the buffer's previous contents.  sh0 = offset of byte b0 inside the buffer.
+static constexpr int STAGE_U = 10;
+struct StageRegs {
+    uint4 v[STAGE_U];
+    const uint4 *src;
+    u32 n_blk, sh0;
+    __device__ __forceinline__ void load(const uint8_t *buf, u64 b0, u64 b1, u32 lane)
+    {
+        const unsigned long long a0 = (unsigned long long)buf + b0, a1 = (unsigned long long)buf + b1;
+        const unsigned long long blk0 = a0 & ~15ull;
+        src = reinterpret_cast<const uint4 *>(blk0);
+        n_blk = (u32)((a1 - blk0 + 15ull) >> 4);
+        sh0 = (u32)(a0 - blk0);
+#pragma unroll
+        for (int u = 0; u < STAGE_U; ++u) {
+            const u32 i = (u32)u * 32u + lane;
+            if (i < n_blk) v[u] = __ldg(src + i);
+        }
+    }
+    __device__ __forceinline__ void store(uint4 *dst, u32 lane) const
+    {
+#pragma unroll
+        for (int u = 0; u < STAGE_U; ++u) {
+            const u32 i = (u32)u * 32u + lane;
+            if (i < n_blk) dst[i] = v[u];
+        }
+        for (u32 i = (u32)STAGE_U * 32u + lane; i < n_blk; i += 32) dst[i] = __ldg(src + i);
+    }
+};
 
 // true iff some byte of the lane's read [pos, pos+len) in the shared buffer differs from pat (pat_valid: ACGT test instead)
 template <bool BASES>
@@ -448,7 +523,7 @@ __device__ __forceinline__ bool smem_scan_read(const u64 *buf64, u32 pos, u32 le
 }
 
 template <bool WTS>
-__global__ void __launch_bounds__(MASK_TPB) k_weight_mask(ParseArgs a)
+__global__ void __launch_bounds__(MASK_TPB, 3) k_weight_mask(ParseArgs a)
 {
     __shared__ double ptab[256];
     __shared__ float powk[256];                       // (float)(p[q] * p[q] * ... ), k factors, left to right
@@ -470,15 +545,24 @@ __global__ void __launch_bounds__(MASK_TPB) k_weight_mask(ParseArgs a)
     const u64 *wbuf64 = reinterpret_cast<const u64 *>(wbuf);
     u32 qn = 0;
     u64 base = ((u64)blockIdx.x * (MASK_TPB / 32) + warp) * 32u;
+    // offsets of a round's reads: lane l holds read_off[b + l], e = end of the last read; requested one round ahead
+    u64 pre_o0 = 0, pre_B1 = 0;
+    auto request_offsets = [&](u64 b, u64 &o, u64 &e) {
+        if (b < a.n_reads) {
+            const u32 n = (u32)min((u64)32, a.n_reads - b);
+            o = lane < n ? __ldg(&a.read_off[b + lane]) : 0ull;
+            e = __ldg(&a.read_off[b + n]);
+        }
+    };
+    request_offsets(base, pre_o0, pre_B1);
     while (true) {
         const bool more = base < a.n_reads;             // warp-uniform
         if (more) {
         const u64 r = base + lane;
         const u32 nr = (u32)min((u64)32, a.n_reads - base);
-        // offsets of the round's reads: lane l holds read_off[base + l], B1 = end of the last read
-        const u64 o0 = lane < nr ? a.read_off[r] : 0ull;
+        const u64 o0 = pre_o0;
         const u64 B0 = __shfl_sync(0xffffffffu, o0, 0);
-        const u64 B1 = a.read_off[base + nr];
+        const u64 B1 = pre_B1;
         const u64 nxt = __shfl_down_sync(0xffffffffu, o0, 1);
         const u64 o1 = lane + 1 < nr ? nxt : B1;
         const u32 len = lane < nr ? (u32)(o1 - o0) : 0u;
@@ -487,19 +571,73 @@ __global__ void __launch_bounds__(MASK_TPB) k_weight_mask(ParseArgs a)
         u64 q0 = 0;
         if (B1 - B0 + 32 <= MASK_WBUF) {
             // the round's bytes go through shared memory with coalesced 16-byte loads: qualities first, then bases
+            StageRegs sr;
+            sr.load(a.quals, B0, B1, lane);
+            request_offsets(base + n_warps * 32u, pre_o0, pre_B1);
             __syncwarp();
-            u32 sh0 = warp_stage_bytes(a.quals, B0, B1, wbuf, lane);
+            sr.store(wbuf, lane);
             __syncwarp();
+            bool bounded = false;
+            const u32 n_kmers = live ? len - a.k + 1u : 0u;
             if (live) {
-                const u32 pos = sh0 + (u32)(o0 - B0);
+                const u32 pos = sr.sh0 + (u32)(o0 - B0);
                 q0 = (wbuf64[pos >> 3] >> ((pos & 7u) * 8u)) & 0xffull;
-                slow = smem_scan_read<false>(wbuf64, pos, len, q0 * 0x0101010101010101ull);
+                const u64 qpat = q0 * 0x0101010101010101ull;
+                slow = smem_scan_read<false>(wbuf64, pos, len, qpat);
+                if (!WTS && slow && a.fast_bound) {
+                    // BOUNDED read: every probability is <= 1, so the weight of a window without a zero-probability quality
+                    // is at least LB = the product of ALL non-zero probabilities of the read; the recurrence (a chain of at
+                    // most 1024 multiplications and divisions between two re-seeds, relative error < 3e-13) cannot bring
+                    // (float)w down to min_weight when LB (1 - 2^-20) > min_weight.  A window WITH a zero-probability
+                    // quality has weight exactly 0 (walker_step: zero factor).  So the "counted" bits of such a read are:
+                    // no zero-probability quality in [i, i+k) -- no recurrence needed.  (Markups are phase 1b's business.)
+                    const double p0 = ptab[q0];
+                    if (p0 > 0.0 && p0 <= 1.0) {
+                        double lb = pow_bound(p0, len);                // p0^len <= p0^(bytes equal to q0)
+                        bool ok = true;
+                        u32 nz = 0, z0 = 0, z1 = 0;                    // zero-probability positions (the first two are remembered)
+                        smem_each_word(wbuf64, pos, len, [&](u32 j, u64 x, u64 m) {
+                            u64 d = ~bytes_eq(x, qpat) & 0x8080808080808080ull & m;
+                            while (d) {
+                                const u32 bi = (u32)(__ffsll((long long)d) - 1) >> 3;
+                                d &= d - 1ull;
+                                const double p = ptab[(u32)(x >> (8u * bi)) & 0xffu];
+                                if (p == 0.0) { if (nz == 0) z0 = j + bi; else if (nz == 1) z1 = j + bi; ++nz; }
+                                else if (p <= 1.0) lb *= p;
+                                else ok = false;
+                            }
+                        });
+                        bounded = ok && bound_passes(lb, a.min_weight);
+                        if (bounded) {
+                            mask_set_range(a.mask, o0, n_kmers);
+                            if (nz > 0) mask_clear_around(a.mask, o0, z0, a.k, n_kmers);
+                            if (nz > 1) mask_clear_around(a.mask, o0, z1, a.k, n_kmers);
+                            if (nz > 2) smem_each_word(wbuf64, pos, len, [&](u32 j, u64 x, u64 m) {
+                                u64 d = ~bytes_eq(x, qpat) & 0x8080808080808080ull & m;
+                                while (d) {
+                                    const u32 bi = (u32)(__ffsll((long long)d) - 1) >> 3;
+                                    d &= d - 1ull;
+                                    if (j + bi > z1 && ptab[(u32)(x >> (8u * bi)) & 0xffu] == 0.0) mask_clear_around(a.mask, o0, j + bi, a.k, n_kmers);
+                                }
+                            });
+                            lc.raw += n_kmers;
+                            slow = false;
+                            q0 = 256;                                  // not a uniform read either
+                        }
+                    }
+                }
             }
-            __syncwarp();
-            sh0 = warp_stage_bytes(a.bases, B0, B1, wbuf, lane);
-            __syncwarp();
-            if (live && !slow) slow = smem_scan_read<true>(wbuf64, sh0 + (u32)(o0 - B0), len, 0);
-        } else if (live) {
+            if (WTS) {
+                // the weight of every k-mer is stored: a markup among the bases zeroes it, the walker has to see the read
+                sr.load(a.bases, B0, B1, lane);
+                __syncwarp();
+                sr.store(wbuf, lane);
+                __syncwarp();
+                if (live && !slow && smem_scan_read<true>(wbuf64, sr.sh0 + (u32)(o0 - B0), len, 0)) slow = true;
+            }
+        } else {
+            request_offsets(base + n_warps * 32u, pre_o0, pre_B1);
+            if (live) {
             // long reads: per-lane streams over global memory
             Stream sb, sq;
             sb.init(a.bases, (long long)o0, a.total_bytes);
@@ -508,25 +646,27 @@ __global__ void __launch_bounds__(MASK_TPB) k_weight_mask(ParseArgs a)
             const u64 qpat = q0 * 0x0101010101010101ull;
             u64 bad = 0;
             for (u32 j = 0; j < len && !bad; j += 8) {
-                sb.prefetch(a.bases, a.total_bytes);
+                if (WTS) sb.prefetch(a.bases, a.total_bytes);
                 sq.prefetch(a.quals, a.total_bytes);
-                const u64 bw = sb.get(), qw = sq.get();
+                const u64 bw = WTS ? sb.get() : 0x4141414141414141ull, qw = sq.get();
                 const u32 nb = len - j;
                 const u64 m = nb >= 8 ? ~0ull : ((1ull << (8 * nb)) - 1ull);
                 const u64 up = bw & 0xDFDFDFDFDFDFDFDFull;
                 const u64 valid = bytes_eq(up, 0x4141414141414141ull) | bytes_eq(up, 0x4343434343434343ull) |
                                   bytes_eq(up, 0x4747474747474747ull) | bytes_eq(up, 0x5454545454545454ull);
                 bad = ((qw ^ qpat) | (~valid & 0x8080808080808080ull)) & m;
-                sb.advance(); sq.advance();
+                if (WTS) sb.advance();
+                sq.advance();
             }
             slow = bad != 0;
+            }
         }
-        if (live && !slow) {
+        if (live && !slow && q0 < 256) {
             // uniform read: every k-mer has the weight p[q]^k (evaluated left to right)
             const u32 n = len - a.k + 1;
             const float wf = powk[q0];
             lc.raw += n;
-            if (wf > a.min_weight) { lc.good += n; mask_set_range(a.mask, o0, n); }
+            if (wf > a.min_weight) { if (WTS) lc.good += n; mask_set_range(a.mask, o0, n); }
             if (WTS) for (u32 i = 0; i < n; ++i) a.wts[o0 + i] = wf;
         }
         const u32 bal = __ballot_sync(0xffffffffu, slow);
@@ -674,8 +814,12 @@ __global__ void __launch_bounds__(1024, 1) k_kmer_scatter(ParseArgs a)
     bool active = false, exhausted = false;
     u64 curw = 0, mbits = 0;
     u32 pend = 0, bits8 = 0, ifirst = 0;                               // bits of k-mers ifirst .. ifirst+7 (this step's)
-    auto emit = [&](u32 i, const u64 (&key)[W], bool fwd, float, bool, u32 eb) {
-        if (!((bits8 >> (i - ifirst)) & 1u)) return;
+    u32 good32 = 0;                                                    // records emitted by this thread
+    auto emit = [&](u32 i, const u64 (&key)[W], bool fwd, float, bool no_markup, u32 eb) {
+        // phase 1a's bit speaks for the qualities; without weights it has not looked at the bases, and a markup inside the
+        // window makes the weight 0 (KmerReadUtils.h:207-217)
+        if (!((bits8 >> (i - ifirst)) & 1u) || !no_markup) return;
+        good32++;
         Rec<W, HASX> rec;
         rec.pack(key, fwd, (HASX && a.wts) ? a.wts[o0 + i] : 1.0f, eb);
         const u64 ph = place_hash<W>(key);
@@ -710,7 +854,11 @@ __global__ void __launch_bounds__(1024, 1) k_kmer_scatter(ParseArgs a)
         }
     };
 
+    const u32 steps_per_round = a.ring_R ? max(1u, a.scatter_steps) : 1u;
     while (true) {
+      // a ROUND = steps_per_round walker steps between two flushes (fewer block-wide barriers per record; the rings have to
+      // hold a round's records of a bin)
+      for (u32 sub = 0; sub < steps_per_round; ++sub) {
         if (!active && !exhausted) {                                   // next read of this thread
             while (sweep0 < a.n_reads) {
                 const u64 r = sweep0 + in_sweep;
@@ -741,6 +889,7 @@ __global__ void __launch_bounds__(1024, 1) k_kmer_scatter(ParseArgs a)
             pend = nxt;
             if (st.j >= st.len) active = false;
         }
+      }
         __syncthreads();
         if (R) flush(false);
         if (!__syncthreads_or((active || !exhausted) ? 1 : 0)) break;
@@ -752,6 +901,7 @@ __global__ void __launch_bounds__(1024, 1) k_kmer_scatter(ParseArgs a)
         a.stage.count[a.stage.cnt_index(o, g, blockIdx.x)] = cnt[i];
     }
     if (DIST == 2 && lost) atomicAdd(a.flags, lost);
+    if (a.wts == nullptr) lc.good += good32;                           // (with weights phase 1a has seen the bases and counted)
     ctr_commit(a.ctr, lc);
 }
 
@@ -1312,6 +1462,14 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait_a(u32 bar_addr, u32 parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tKMN_WAITA_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra KMN_DONEA_%=;\n\tbra KMN_WAITA_%=;\n\tKMN_DONEA_%=:\n\t}"
+                 ::"r"(bar_addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(u32 bar_addr) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory"); }
+__device__ __forceinline__ u32 lds32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ u64 lds64(u32 a) { u64 v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void mbar_arrive(u64 *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -1389,18 +1547,33 @@ __global__ void __launch_bounds__(SPLIT_TPB, 1) k_slice_split(SplitArgs a)
         // cross an entry; every thread steps the consumer position (ce, co), thread 0 also the producer's (pe, po)
         const u32 e1 = min(g * a.per_group + (part + 1u) * a.epp, (g + 1u) * a.per_group);
         const u32 e0 = g * a.per_group + part * a.epp;
-        u32 ce = e0, co = 0, cn = 0, pe = e0, po = 0, pn = 0;
-        auto skip = [&](u32 &e, u32 &o, u32 &n) {                      // first entry at or after e with records left
-            while (e < e1) { n = __ldg(&a.ent_cnt[e]); if (o < n) return; ++e; o = 0; }
+        // (the size of the entry after the current one is requested when the current one is entered, so that stepping to
+        //  it never waits for memory between two block-wide barriers)
+        u32 ce = e0, co = 0, cn = e0 < e1 ? __ldg(&a.ent_cnt[e0]) : 0u, cnn = e0 + 1u < e1 ? __ldg(&a.ent_cnt[e0 + 1u]) : 0u;
+        u32 pe = e0, po = 0, pn = cn, pnn = cnn;
+        auto skip = [&](u32 &e, u32 &o, u32 &n, u32 &nn) {             // first entry at or after e with records left
+            while (e < e1) {
+                if (o < n) return;
+                ++e; o = 0; n = nn;
+                nn = e + 1u < e1 ? __ldg(&a.ent_cnt[e + 1u]) : 0u;
+            }
             n = 0;
         };
+        u64 pptr = 0, pptr_n = 0;                                      // thread 0: address of entry pe / pe + 1
+        if (threadIdx.x == 0) {
+            pptr = e0 < e1 ? __ldg(&a.ent_ptr[e0]) : 0ull;
+            pptr_n = e0 + 1u < e1 ? __ldg(&a.ent_ptr[e0 + 1u]) : 0ull;
+        }
         auto produce = [&](u32 qq) {                                   // thread 0: the chunk at (pe, po) -> buffer qq & 1
-            skip(pe, po, pn);
+            while (pe < e1 && po >= pn) {
+                ++pe; po = 0; pn = pnn; pptr = pptr_n;
+                if (pe + 1u < e1) { pnn = __ldg(&a.ent_cnt[pe + 1u]); pptr_n = __ldg(&a.ent_ptr[pe + 1u]); } else { pnn = 0; pptr_n = 0; }
+            }
             if (pe >= e1) return false;
             const u32 n = min((u32)SPLIT_CHUNK, pn - po);
             // entries start on 32-byte boundaries (sub-regions hold multiples of 4 records); a bulk copy moves a multiple of 16 bytes
             const u32 bytes = ((n + 1u) & ~1u) * 8u;
-            const u64 *src = reinterpret_cast<const u64 *>(__ldg(&a.ent_ptr[pe])) + po;
+            const u64 *src = reinterpret_cast<const u64 *>(pptr) + po;
             mbar_expect_tx(&bar_full[qq & 1u], bytes);
             bulk_g2s(inbuf + (size_t)(qq & 1u) * SPLIT_CHUNK, src, bytes, &bar_full[qq & 1u]);
             po += n;
@@ -1408,7 +1581,7 @@ __global__ void __launch_bounds__(SPLIT_TPB, 1) k_slice_split(SplitArgs a)
         };
         u32 q_issue = q;
         if (threadIdx.x == 0) { if (produce(q_issue)) ++q_issue; if (produce(q_issue)) ++q_issue; }
-        skip(ce, co, cn);
+        skip(ce, co, cn, cnn);
         while (ce < e1) {
             const u32 n = min((u32)SPLIT_CHUNK, cn - co);
             if (q & 1u) { mbar_wait(&bar_full[1], ph1); ph1 ^= 1u; } else { mbar_wait(&bar_full[0], ph0); ph0 ^= 1u; }
@@ -1440,7 +1613,7 @@ __global__ void __launch_bounds__(SPLIT_TPB, 1) k_slice_split(SplitArgs a)
             flush(false);
             __syncthreads();
             co += n; ++q;
-            skip(ce, co, cn);
+            skip(ce, co, cn, cnn);
         }
         flush(true);
         __syncthreads();
@@ -1695,6 +1868,196 @@ __global__ void __launch_bounds__(COUNT3_TPB, 2) k_count_slices_tma(TableView t,
         }
     }
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_unique) atomicAdd(&ctr->unique, n_unique);
+        if (n_full) atomicAdd(&ctr->table_full, n_full);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_count_slices_ws: the same bulk-copy pipeline with a PRODUCER warp (one lane issues the slice load, the record chunks
+// and the write-back) and 16 CONSUMER warps whose lanes never wait for each other's probe sequences: a lane that has
+// counted its record takes the next unclaimed record of its warp's share of the current chunk (ballot + popc give the
+// idle lanes consecutive records), so a warp-wide probe step always works on 32 live records instead of on the few
+// stragglers of a batch (ncu on k_count_slices_tma: 150 warp instructions per 32 records, most of them issued for
+// partially finished batches; the probe loop runs E[max of 32 probe lengths] ~ 5.5 times per batch against 1.85 per record).
+//   chunk q of a CTA (numbered through all its slices) lives in buffer q % NBUF; its `full` barrier completes for the
+//   (q / NBUF)-th time when its bytes have arrived, its `empty` barrier when every consumer warp has taken its share.
+// ------------------------------------------------------------------------------------------------
+static constexpr int COUNTW_CONSUMERS = 16;                            // consumer warps
+static constexpr int COUNTW_TPB = (COUNTW_CONSUMERS + 1) * 32;
+#ifndef KMN_COUNTW_CHUNK
+#define KMN_COUNTW_CHUNK 1024
+#endif
+#ifndef KMN_COUNTW_NBUF
+#define KMN_COUNTW_NBUF 4
+#endif
+static constexpr int COUNTW_CHUNK = KMN_COUNTW_CHUNK;                  // records per bulk copy
+static constexpr int COUNTW_NBUF = KMN_COUNTW_NBUF;
+static constexpr int COUNTW_SHARE = COUNTW_CHUNK / COUNTW_CONSUMERS;   // records of a chunk that belong to one consumer warp
+
+__global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_ws(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, Counters *ctr)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const u32 SL = (u32)t.part_slots;
+    Slot<1> *sl = reinterpret_cast<Slot<1> *>(smem_raw);               // one slice of the table
+    u64 *rbuf = reinterpret_cast<u64 *>(smem_raw + (size_t)SL * 16);   // [COUNTW_NBUF][COUNTW_CHUNK] record chunks
+    __shared__ __align__(8) u64 bar_slice, bar_full[COUNTW_NBUF], bar_empty[COUNTW_NBUF];
+    __shared__ u32 s_pre[2][32];                                       // exclusive prefix of the sub-run sizes of this / the next slice
+    __shared__ u32 buf_n[COUNTW_NBUF];                                 // records of the chunk in every buffer
+    const u32 nb = 1u << t.group_shift;
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const bool producer = warp == COUNTW_CONSUMERS;
+    const u32 lt = (1u << lane) - 1u;
+    u64 n_unique = 0, n_full = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_slice, 1);
+        for (int b = 0; b < COUNTW_NBUF; ++b) {
+            mbar_init(&bar_full[b], 1);                                // completed by the bulk copy's bytes
+            mbar_init(&bar_empty[b], COUNTW_CONSUMERS);                // one arrival per consumer warp
+        }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    auto load_pre = [&](u32 pi, u32 *dst) {                            // warp 0
+        u32 c = (lane < S && pi < t.n_parts) ? cnt2[((size_t)(pi >> t.group_shift) * S + lane) * nb + (pi & (nb - 1u))] : 0u;
+        u32 v = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(0xffffffffu, v, d); if ((int)lane >= d) v += x; }
+        if (lane < COUNT_MAX_S + 1u) dst[lane] = v - c;
+    };
+    if (warp == 0) load_pre(blockIdx.x, s_pre[0]);
+    u32 it = 0, ph_slice = 0, qn = 0;                                  // qn: number of the slice's first chunk
+    // shared-window addresses once, as opaque integers (otherwise the generic-to-shared conversion -- a read of the CTA-id
+    // special register -- is rematerialised inside the probe loop)
+    auto opaque = [](u32 x) { u32 y; asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x)); return y; };
+    const u32 sl_addr = opaque(smem_u32(sl)), sl_end = opaque(sl_addr + SL * 16u);
+    const u32 rbuf_a = opaque(smem_u32(rbuf)), full_a = opaque(smem_u32(&bar_full[0])), empty_a = opaque(smem_u32(&bar_empty[0])),
+              bufn_a = opaque(smem_u32(&buf_n[0])), slice_bar_a = opaque(smem_u32(&bar_slice));
+    u32 n_unique32 = 0, n_full32 = 0;
+    Slot<1> *prev_gsl = nullptr;                                       // producer: slice waiting for its write-back
+    for (u32 pi = blockIdx.x; pi < t.n_parts; pi += gridDim.x, ++it) {
+        __syncthreads();                                               // s_pre[it & 1] complete; every consumer has left the previous slice
+        if (warp == 0) load_pre(pi + gridDim.x, s_pre[(it + 1u) & 1u]);
+        const u32 *pre = s_pre[it & 1u];
+        const u32 total = pre[S];
+        if (total == 0) continue;                                      // nothing staged for this slice in this drain
+        u32 n_chunks = 0;
+        for (u32 p = 0; p < S; ++p) n_chunks += (pre[p + 1] - pre[p] + COUNTW_CHUNK - 1u) / COUNTW_CHUNK;
+        Slot<1> *gsl = reinterpret_cast<Slot<1> *>(t.slots) + (size_t)pi * SL;
+        if (producer) {
+            if (lane == 0) {
+                const u32 g = pi >> t.group_shift, j = pi & (nb - 1u);
+                const u64 *run0 = buf + (((size_t)g * S) * nb + j) * cap2;     // sub-run p starts at run0 + p * nb * cap2
+                const size_t run_stride = (size_t)nb * cap2;
+                if (prev_gsl) bulk_s2g(prev_gsl, sl, SL * 16u);        // (the consumers fenced their counts before the barrier)
+                prev_gsl = gsl;
+                u32 pp = 0, po = 0, q = qn;
+                auto issue = [&]() {
+                    while (pp < S && po >= pre[pp + 1] - pre[pp]) { ++pp; po = 0; }
+                    const u32 b = q % COUNTW_NBUF;
+                    if (q >= COUNTW_NBUF) mbar_wait(&bar_empty[b], ((q / COUNTW_NBUF) - 1u) & 1u);   // chunk q - NBUF has been taken by every warp
+                    const u32 n = min((u32)COUNTW_CHUNK, pre[pp + 1] - pre[pp] - po);
+                    const u32 bytes = ((n + 1u) & ~1u) * 8u;           // bulk copies move multiples of 16 bytes (cap2 is a multiple of 4)
+                    buf_n[b] = n;
+                    mbar_expect_tx(&bar_full[b], bytes);
+                    bulk_g2s(rbuf + (size_t)b * COUNTW_CHUNK, run0 + (size_t)pp * run_stride + po, bytes, &bar_full[b]);
+                    po += n; ++q;
+                };
+                // the first chunks need no free slice; then the old slice has to be out of shared memory before the new one lands
+                const u32 first = min(n_chunks, (u32)COUNTW_NBUF);
+                for (u32 i = 0; i < first; ++i) issue();
+                bulk_wait_read();
+                mbar_expect_tx(&bar_slice, SL * 16u);
+                bulk_g2s(sl, gsl, SL * 16u, &bar_slice);
+                for (u32 i = first; i < n_chunks; ++i) issue();
+            }
+        } else {
+            // consumer warp: chunk c of the slice is current, records [wo, wn) of it are this warp's and not yet taken
+            u32 c = 0, wo = 0, wn = 0, cur_b = 0, recs_a = rbuf_a;
+            auto open_chunk = [&]() -> bool {
+                while (c < n_chunks) {
+                    const u32 q = qn + c;
+                    cur_b = q % COUNTW_NBUF;
+                    mbar_wait_a(full_a + cur_b * 8u, (q / COUNTW_NBUF) & 1u);
+                    const u32 n = lds32(bufn_a + cur_b * 4u), lo = warp * COUNTW_SHARE;
+                    if (lo < n) { wo = lo; wn = min(n, lo + (u32)COUNTW_SHARE); recs_a = rbuf_a + cur_b * (COUNTW_CHUNK * 8u); return true; }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(empty_a + cur_b * 8u);     // nothing of this chunk is ours
+                    ++c;
+                }
+                return false;
+            };
+            bool more = open_chunk();
+            mbar_wait_a(slice_bar_a, ph_slice);
+            u32 busy = 0, addr = sl_addr, left = 0;
+            u64 rec = 0, want = 0;
+            while (true) {
+                const u32 bm = __ballot_sync(0xffffffffu, busy != 0u);
+                u32 took = 0;
+                if (more && bm != 0xffffffffu) {
+                    const u32 idle = ~bm, n_idle = __popc(idle);
+                    const u32 idx = wo + __popc(idle & lt);
+                    if (busy == 0u && idx < wn) {
+                        rec = lds64(recs_a + idx * 8u);
+                        const u64 key = rec & ~1ull;
+                        want = ~key;
+                        addr = sl_addr + (((u32)(((u64)(u32)mix64(key) * SL) >> 32)) & ~1u) * 16u;
+                        left = SL;
+                        busy = 1u;
+                    }
+                    took = min(n_idle, wn - wo);
+                    wo += n_idle;
+                    if (wo >= wn) {                                    // the warp's share is in registers: the buffer may be refilled
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_a(empty_a + cur_b * 8u);
+                        ++c;
+                        more = open_chunk();
+                    }
+                }
+                if ((bm | took) == 0u) break;                          // nothing in flight and nothing left to take
+                // one probe step of every live record, without divergent paths: the slot is loaded by all lanes (an idle lane
+                // re-reads its last slot), the rare claim of an empty slot sits behind a warp-uniform branch, and the two
+                // counter updates are predicated instructions
+                u64 v, k;
+                asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(v), "=l"(k) : "r"(addr));          // {val, key}
+                bool hit = busy != 0u && k == want;
+                const bool emp = busy != 0u && k == 0ull;
+                if (__any_sync(0xffffffffu, emp)) {
+                    if (emp) {
+                        u64 old;
+                        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr + 8u), "l"(0ull), "l"(want) : "memory");
+                        if (old == 0ull) n_unique32++;
+                        hit = old == 0ull || old == want;
+                        v = 0;
+                    }
+                }
+                // count in the low word, directionBias in the high word: two native 32-bit shared atomics; no carry ever
+                // crosses the words
+                const u32 pc = (hit && (u32)v < MAX_COUNT) ? 1u : 0u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(addr), "r"(pc) : "memory");
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(addr + 4u), "r"(pc & (u32)rec) : "memory");
+                addr += 16u;
+                if (addr == sl_end) addr = sl_addr;
+                --left;
+                if (hit) busy = 0u;
+                else if (busy != 0u && left == 0u) { n_full32++; busy = 0u; }
+            }
+            fence_async_smem();                                        // this thread's counts are visible to the bulk store of the slice
+        }
+        ph_slice ^= 1u;
+        qn += n_chunks;
+    }
+    __syncthreads();
+    if (producer && lane == 0) {
+        if (prev_gsl) bulk_s2g(prev_gsl, sl, SL * 16u);
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    n_unique = n_unique32; n_full = n_full32;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);

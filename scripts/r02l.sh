@@ -1,0 +1,10 @@
+set -x
+timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -40 > gpurun_out/r02l_pytest.log
+B="timeout 600 python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-lookup --no-checks"
+$B > gpurun_out/r02l_def.json 2> gpurun_out/r02l_def.err
+KMN_COUNT_WS=0 $B > gpurun_out/r02l_nows.json 2> gpurun_out/r02l_nows.err
+KMN_NO_WEIGHT_BOUND=1 $B > gpurun_out/r02l_nobound.json 2> gpurun_out/r02l_nobound.err
+$B --pipe-batches 2 > gpurun_out/r02l_pb2.json 2> gpurun_out/r02l_pb2.err
+$B --pipe-batches 3 > gpurun_out/r02l_pb3.json 2> gpurun_out/r02l_pb3.err
+timeout 600 compute-sanitizer --tool memcheck python -m pytest "tests/test_gpu_parity.py::test_weight_bound_mixed_qualities" -m gpu -q -x 2>&1 | tail -30 > gpurun_out/r02l_memcheck.log
+for f in gpurun_out/r02l_*.err; do tail -c 4000 $f > $f.tail; rm -f $f; done

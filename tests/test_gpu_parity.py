@@ -486,3 +486,46 @@ def test_hot_kmers_saturate_with_extensions(K):
     assert len(g["count"]) == 20 and (g["count"] == 65535).all()
     assert ctx.stats()["raw_kmers"] == n * 20
     ctx.close()
+
+
+@pytest.mark.parametrize("k,mkq,mq", [(31, 0.10, 3), (21, 0.0, 2), (31, 0.5, 3), (31, 0.9, 3), (63, 0.10, 3), (31, 0.05, 10)])
+def test_weight_bound_mixed_qualities(K, k, mkq, mq):
+    """phase 1a's bounded reads (a3): reads whose product of all non-zero base probabilities stays above
+    min-kmer-quality get their "counted" bits without the recurrence, every other read walks it -- the table and the
+    raw/rawGood counters must equal the oracle's for quality mixes on both sides of the bound, with zero-probability
+    qualities and markups inside"""
+    rng = np.random.default_rng(1000 + k)
+    genome = synth.ACGT[rng.integers(0, 4, 3000)]
+    seqs, quals = [], []
+    for i in range(6000):
+        L = int(rng.integers(20, 200))
+        st = int(rng.integers(0, len(genome) - L))
+        s = bytearray(genome[st:st + L].tobytes())
+        kind = i % 6
+        q = np.full(L, 33 + 40, np.uint8)
+        if kind == 1:                                       # a few mediocre bases: bounded
+            for p in rng.integers(0, L, 3):
+                q[p] = 33 + int(rng.integers(8, 30))
+        elif kind == 2:                                     # many mediocre bases: the bound fails, recurrence decides
+            q = rng.integers(33 + mq, 33 + 25, L).astype(np.uint8)
+        elif kind == 3:                                     # zero-probability qualities and markups
+            for p in rng.integers(0, L, 2):
+                q[p] = 33 + int(rng.integers(0, mq + 1))
+            s[int(rng.integers(0, L))] = rng.choice(list(b"NnX.acgt"))
+        elif kind == 4:                                     # one quality value, markups among the bases
+            q[:] = 33 + int(rng.integers(mq, 41))
+            s[int(rng.integers(0, L))] = ord("N")
+        elif kind == 5:                                     # starts with a zero-probability quality
+            q[0] = 33
+            q[L // 2] = 33 + 12
+        seqs.append(bytes(s))
+        quals.append(q.tobytes())
+    bases, q, off = oracle.concat_reads(seqs, quals)
+    ctx = K.Context(kmer_size=k, table_slots=1 << 16, min_quality_score=mq, min_kmer_quality=mkq)
+    ctx.count_batch(np.frombuffer(bases, np.uint8), q, off)
+    ctx.count_finish(apply_purge=False)
+    osp = oracle_table(bases, q, off, k, min_quality=mq, min_kmer_quality=mkq, threads=4)
+    assert_tables_equal(ctx.export(), osp.export())
+    st, ost = ctx.stats(), osp.stats()
+    assert (st["raw_kmers"], st["raw_good_kmers"], st["unique_kmers"]) == (ost["raw"], ost["raw_good"], ost["unique"])
+    ctx.close()
