@@ -57,9 +57,10 @@ def parse_args():
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--stage-keys", type=int, default=0)
     ap.add_argument("--slice-mb", type=int, default=64)
-    ap.add_argument("--pipe-batches", type=int, default=0, help="drains (multi-GPU: rounds) per step: a staging set holds 1/N of the input; 0 = 4 on one GPU, 8 on several")
+    ap.add_argument("--pipe-batches", type=int, default=0, help="drains (multi-GPU: rounds) per step: a staging set holds 1/N of the input; 0 = 2 on one GPU, 8 on several")
     ap.add_argument("--e2e-reads", type=int, default=0, help="reads per e2e step (0 = same as --reads)")
     ap.add_argument("--e2e-batch", type=int, default=4_000_000)
+    ap.add_argument("--e2e-pipe-batches", type=int, default=8, help="staging sets per step of the end-to-end run on one GPU")
     ap.add_argument("--cpu-reads", type=int, default=400_000)
     ap.add_argument("--parity-reads", type=int, default=240_000, help="reads of the untimed exact oracle comparison (all ranks together)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -322,7 +323,7 @@ def main():
     est_distinct = int((genomic * 1.02 + err_kmers * 1.05) / world) + (1 << 16)
     table_slots = args.table_slots or int(est_distinct / 0.5)
     # staging: one set = 1/pipe_batches of the input
-    pipe_batches = args.pipe_batches or (4 if world == 1 else 8)
+    pipe_batches = args.pipe_batches or (2 if world == 1 else 8)
     stage_keys = args.stage_keys or int(inst_per_rank * 1.02 / pipe_batches)
     vk = KM.capi.KMN_VALUE_DIR_EXT if ext else KM.capi.KMN_VALUE_DIR
     ctx = KM.Context(kmer_size=k, est_raw_kmers=inst_per_rank, table_slots=table_slots, stage_keys=stage_keys, value_kind=vk,
@@ -550,6 +551,17 @@ def main():
         hpoff_t.copy_(torch.arange(bsz + 1, dtype=torch.int64) * pb)
         hpoff = hpoff_t.numpy()
 
+        # batches arrive over PCIe while earlier ones are counted: what is left when the last batch has landed is the drain of
+        # the last staging set, so the end-to-end run wants SMALLER sets than the device-resident one (more drains, each a
+        # sweep of the table, but hidden behind the copies).  One GPU: a fresh context with 1/8 of the input per set.
+        e2e_pipe = pipe_batches
+        if world == 1 and not args.stage_keys and args.e2e_pipe_batches > pipe_batches:
+            e2e_pipe = args.e2e_pipe_batches
+            ctx.close()
+            ctx = KM.Context(kmer_size=k, est_raw_kmers=inst_per_rank, table_slots=table_slots, stage_keys=int(inst_per_rank * 1.02 / e2e_pipe),
+                             value_kind=vk, min_quality_score=wl.get("min_quality_score", 3), min_kmer_quality=wl.get("min_kmer_quality", 0.10),
+                             slice_bytes=args.slice_mb << 20, device=local_rank)
+
         def step_e2e(packed):
             ctx.reset()
             for r0 in range(0, n_e, bsz):
@@ -581,7 +593,7 @@ def main():
         dt, st_e = time_e2e(True)
         e2e = {"value": n_e * kpr * world / dt, "unit": "kmers/s", "h2d_bytes_per_step": n_e * (READ_LEN + pb) + 2 * n_off,
                "d2h_bytes_per_step": 64 + 48, "reads_per_step": n_e, "batch_reads": bsz, "ms_per_step": dt * 1e3,
-               "raw_good_kmers": st_e["raw_good_kmers"], "entry": "kmn_count_batch_2na", "workload_note": note,
+               "raw_good_kmers": st_e["raw_good_kmers"], "entry": "kmn_count_batch_2na", "workload_note": note, "drains_per_step": e2e_pipe,
                "input_format": "host reads as the reference holds them in memory: TwoBitSequence bytes (4 bases per byte) + one quality byte per base"}
         dt, st_a = time_e2e(False)
         e2e["ascii"] = {"value": n_e * kpr * world / dt, "unit": "kmers/s", "h2d_bytes_per_step": 2 * n_e * READ_LEN + n_off, "ms_per_step": dt * 1e3,

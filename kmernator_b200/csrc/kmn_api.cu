@@ -78,10 +78,11 @@ struct kmn_ctx {
     u64 *l2buf = nullptr;             // [n_groups][S][slices per group][cap2] records, sorted by slice
     u32 *cnt2 = nullptr;              // [n_groups][S][slices per group]
     u32 *tickets = nullptr;           // [2] work tickets of k_slice_split / k_count_slices
-    uint32_t split_S = 4, split_cap2 = 0, split_R = 0;
+    uint32_t split_S = 4, split_cap2 = 0, split_R = 0, split_batches = 1, split_gpb = 0;
     int split_tpb = 1024, split_ctas = 1, count_ctas = 3;
     bool count_tma = true;            // k_count_slices_tma (bulk-copy engine) instead of k_count_slices (KMN_COUNT_TMA=0)
-    bool count_ws = false;            // KMN_COUNT_WS=1: k_count_slices_ws (producer warp + lane-persistent consumers) instead of k_count_slices_tma
+    int count_db = 0;                 // KMN_COUNT_DB=1: k_count_slices_db (one CTA per SM, two slice buffers) instead of k_count_slices_tma
+    int count_ws = 2;                 // k_count_slices_ws: 2 = producer warp + plain consumers (default), 1 = lane-persistent consumers, 0 = k_count_slices_tma
     size_t split_smem = 0;
     uint32_t zero_below = 0;
     size_t scatter_smem = 0;
@@ -316,7 +317,13 @@ static int alloc_stage_sets(kmn_ctx *c)
         // sends its records straight to the table)
         const uint64_t m2 = sk / c->table.n_parts / c->split_S + 1;
         c->split_cap2 = (uint32_t)((m2 + m2 / 8 + 8 * (uint64_t)std::sqrt((double)m2) + 32 + 3) & ~3ull);
-        const size_t n_sub2 = (size_t)n_groups * c->split_S * nb;
+        // the slice-sorted copy holds one BATCH of groups at a time (split, count, next batch): 1/split_batches of a drain
+        c->split_batches = 2;
+        if (const char *e = getenv("KMN_SPLIT_BATCHES")) c->split_batches = (uint32_t)std::max(1, atoi(e));
+        if (const char *e = getenv("KMN_COUNT_TMA")) { if (atoi(e) == 0) c->split_batches = 1; }     // (k_count_slices walks the whole table)
+        c->split_batches = (uint32_t)std::min<uint64_t>(c->split_batches, n_groups);
+        c->split_gpb = (uint32_t)((n_groups + c->split_batches - 1) / c->split_batches);
+        const size_t n_sub2 = (size_t)c->split_gpb * c->split_S * nb;
         if (c->smem_count) {
             if (cudaMalloc((void **)&c->l2buf, n_sub2 * c->split_cap2 * 8) != cudaSuccess) { cudaGetLastError(); c->l2buf = nullptr; c->smem_count = false; }
         }
@@ -326,9 +333,16 @@ static int alloc_stage_sets(kmn_ctx *c)
             CK(c, cudaFuncSetAttribute(k_slice_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
             CK(c, cudaFuncSetAttribute(k_count_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16)));
             CK(c, cudaFuncSetAttribute(k_count_slices_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNT_NBUF * COUNT_CHUNK * 8)));
-            CK(c, cudaFuncSetAttribute(k_count_slices_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8)));
+            CK(c, cudaFuncSetAttribute(k_count_slices_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8)));
+            CK(c, cudaFuncSetAttribute(k_count_slices_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8)));
             if (const char *e = getenv("KMN_COUNT_TMA")) c->count_tma = atoi(e) != 0;
-            if (const char *e = getenv("KMN_COUNT_WS")) c->count_ws = atoi(e) != 0;
+            if (const char *e = getenv("KMN_COUNT_WS")) c->count_ws = atoi(e);
+            if (const char *e = getenv("KMN_COUNT_DB")) c->count_db = atoi(e);
+            {
+                const size_t need = c->table.part_slots * 32 + (size_t)COUNTD_NBUF * COUNTD_CHUNK * 8;
+                if (need + 1024 > (size_t)dev_smem) c->count_db = 0;
+                else CK(c, cudaFuncSetAttribute(k_count_slices_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            }
             if ((c->table.part_slots * 16) % 16 != 0) c->count_tma = false;
         }
     }
@@ -601,22 +615,34 @@ static int launch_insert(kmn_ctx *c, const StageView &v, int rb, uint64_t units,
         const u32 per_group = v.n_cta + (rv.n_src > 1 ? (rv.n_src - 1) * (rv.mode == 1 ? v.n_cta : 1u) : 0);
         const u32 n_grouped = v.n_parts * per_group;
         SplitArgs sa{};
-        sa.table = c->table; sa.ent_ptr = c->ent_ptr; sa.ent_cnt = c->ent_cnt; sa.per_group = per_group; sa.n_groups = v.n_parts;
+        sa.table = c->table; sa.ent_ptr = c->ent_ptr; sa.ent_cnt = c->ent_cnt; sa.per_group = per_group;
         sa.S = std::min<u32>(c->split_S, per_group); sa.epp = (per_group + sa.S - 1) / sa.S;
         sa.buf = c->l2buf; sa.cnt2 = c->cnt2; sa.cap2 = c->split_cap2; sa.ring_R = c->split_R; sa.ticket = c->tickets; sa.ctr = c->ctr;
-        CK(c, cudaMemsetAsync(c->tickets, 0, 8, si));
-        {
-            ProfScope ps(c, KMN_PROF_SUBPART, units, si);
-            k_slice_split<<<c->n_sms * c->split_ctas, c->split_tpb, c->split_smem, si>>>(sa);
-        }
-        {
-            ProfScope ps(c, KMN_PROF_INSERT, units, si);
-            if (c->count_tma && c->count_ws)
-                k_count_slices_ws<<<c->n_sms * 2, COUNTW_TPB, c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr);
-            else if (c->count_tma)
-                k_count_slices_tma<<<c->n_sms * 2, COUNT3_TPB, c->table.part_slots * 16 + COUNT_NBUF * COUNT_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr);
-            else
-                k_count_slices<<<c->n_sms * c->count_ctas, COUNT_TPB, c->table.part_slots * 16, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, v.n_parts, c->tickets + 1, c->ctr);
+        const u32 nbs = 1u << c->table.group_shift;
+        for (u32 g0 = 0; g0 < v.n_parts; g0 += c->split_gpb) {
+            // one batch of groups: split its records by slice into the slice-sorted copy, then count slice by slice
+            sa.g0 = g0; sa.n_groups = std::min<u32>(c->split_gpb, v.n_parts - g0);
+            const u32 slice0 = g0 * nbs, n_sl = std::min<u32>(sa.n_groups * nbs, c->table.n_parts - slice0);
+            CK(c, cudaMemsetAsync(c->tickets, 0, 8, si));
+            {
+                ProfScope ps(c, KMN_PROF_SUBPART, g0 == 0 ? units : 0, si);
+                k_slice_split<<<c->n_sms * c->split_ctas, c->split_tpb, c->split_smem, si>>>(sa);
+            }
+            {
+                ProfScope ps(c, KMN_PROF_INSERT, g0 == 0 ? units : 0, si);
+                const size_t sm_w = c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8;
+                if (c->count_tma && c->count_db)
+                    k_count_slices_db<<<c->n_sms, COUNTD_TPB, c->table.part_slots * 32 + (size_t)COUNTD_NBUF * COUNTD_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
+                else if (c->count_tma && c->count_ws == 2)
+                    k_count_slices_ws<false><<<c->n_sms * 2, COUNTW_TPB, sm_w, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
+                else if (c->count_tma && c->count_ws)
+                    k_count_slices_ws<true><<<c->n_sms * 2, COUNTW_TPB, sm_w, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
+                else if (c->count_tma)
+                    k_count_slices_tma<<<c->n_sms * 2, COUNT3_TPB, c->table.part_slots * 16 + COUNT_NBUF * COUNT_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
+                else
+                    k_count_slices<<<c->n_sms * c->count_ctas, COUNT_TPB, c->table.part_slots * 16, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, v.n_parts, c->tickets + 1, c->ctr);
+            }
+            c->launches += 2;
         }
         c->launches += 2;
         CK(c, cudaGetLastError());

@@ -1481,7 +1481,8 @@ struct SplitArgs {
     const u64 *ent_ptr;    // phase-2 work list entries, group-major (k_build_entries)
     const u32 *ent_cnt;
     u32 per_group;         // entries per group
-    u32 n_groups;
+    u32 n_groups;          // groups of this launch: [g0, g0 + n_groups); buf and cnt2 are indexed relative to g0
+    u32 g0;
     u32 S;                 // a group's entries are cut into S parts; one CTA splits one (group, part) into private sub-runs
     u32 epp;               // entries per part
     u64 *buf;              // [n_groups][S][slices per group][cap2] records
@@ -1522,7 +1523,7 @@ __global__ void __launch_bounds__(SPLIT_TPB, 1) k_slice_split(SplitArgs a)
         __syncthreads();
         const u32 item = s_item;
         if (item >= n_items) break;
-        const u32 g = item / a.S, part = item - g * a.S;
+        const u32 g = a.g0 + item / a.S, part = item % a.S;
         u64 *const obase = a.buf + (size_t)item * nb * cap2;
         auto flush = [&](bool all) {
             for (u32 b = threadIdx.x; b < nb; b += SPLIT_TPB) {
@@ -1744,7 +1745,7 @@ static constexpr int COUNT_CHUNK = 1024;   // records per bulk copy (8 KB)
 static constexpr int COUNT_NBUF = 4;       // record buffers: a chunk is requested COUNT_NBUF chunks before it is counted
 
 
-__global__ void __launch_bounds__(COUNT3_TPB, 2) k_count_slices_tma(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, Counters *ctr)
+__global__ void __launch_bounds__(COUNT3_TPB, 2) k_count_slices_tma(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, Counters *ctr, u32 slice0, u32 n_sl)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const u32 SL = (u32)t.part_slots;
@@ -1765,7 +1766,7 @@ __global__ void __launch_bounds__(COUNT3_TPB, 2) k_count_slices_tma(TableView t,
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     auto load_pre = [&](u32 pi, u32 *dst) {
         if (threadIdx.x < 32) {
-            u32 c = (threadIdx.x < S && pi < t.n_parts) ? cnt2[((size_t)(pi >> t.group_shift) * S + threadIdx.x) * nb + (pi & (nb - 1u))] : 0u;
+            u32 c = (threadIdx.x < S && pi < n_sl) ? cnt2[((size_t)(pi >> t.group_shift) * S + threadIdx.x) * nb + (pi & (nb - 1u))] : 0u;
             u32 v = c;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(0xffffffffu, v, d); if ((int)threadIdx.x >= d) v += x; }
@@ -1777,7 +1778,7 @@ __global__ void __launch_bounds__(COUNT3_TPB, 2) k_count_slices_tma(TableView t,
     // (buffer = number % COUNT_NBUF)
     u32 it = 0, ph_slice = 0, ph_full = 0, ph_empty = 0, qn = 0;
     const u32 sl_addr = smem_u32(sl), sl_end = sl_addr + SL * 16u;
-    for (u32 pi = blockIdx.x; pi < t.n_parts; pi += gridDim.x, ++it) {
+    for (u32 pi = blockIdx.x; pi < n_sl; pi += gridDim.x, ++it) {
         __syncthreads();                                               // s_pre[it & 1] complete; every thread has left the previous slice
         load_pre(pi + gridDim.x, s_pre[(it + 1u) & 1u]);
         const u32 *pre = s_pre[it & 1u];
@@ -1786,7 +1787,7 @@ __global__ void __launch_bounds__(COUNT3_TPB, 2) k_count_slices_tma(TableView t,
         const u32 g = pi >> t.group_shift, j = pi & (nb - 1u);
         const u64 *run0 = buf + (((size_t)g * S) * nb + j) * cap2;     // sub-run p starts at run0 + p * nb * cap2
         const size_t run_stride = (size_t)nb * cap2;
-        Slot<1> *gsl = reinterpret_cast<Slot<1> *>(t.slots) + (size_t)pi * SL;
+        Slot<1> *gsl = reinterpret_cast<Slot<1> *>(t.slots) + (size_t)(slice0 + pi) * SL;
         // the slice's records as chunks of at most COUNT_CHUNK records that do not cross a sub-run: an iterator every thread
         // advances in step (sub-run p, offset o)
         u32 cp = 0, co = 0;                                            // consumer position
@@ -1901,7 +1902,12 @@ static constexpr int COUNTW_CHUNK = KMN_COUNTW_CHUNK;                  // record
 static constexpr int COUNTW_NBUF = KMN_COUNTW_NBUF;
 static constexpr int COUNTW_SHARE = COUNTW_CHUNK / COUNTW_CONSUMERS;   // records of a chunk that belong to one consumer warp
 
-__global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_ws(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, Counters *ctr)
+// BALLOT: lane-persistent consumers (a lane that has counted its record takes the warp's next one); otherwise every lane
+// counts the records idx = lane, lane + 32, .. of its warp's share one after the other (fewer instructions per record
+// although the warp idles on the longest probe sequence of every batch of 32: ncu, 166 -> 204 warp instructions per 32
+// records with the ballot loop)
+template <bool BALLOT>
+__global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_ws(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, Counters *ctr, u32 slice0, u32 n_sl)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const u32 SL = (u32)t.part_slots;
@@ -1924,7 +1930,7 @@ __global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_ws(TableView t, 
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     auto load_pre = [&](u32 pi, u32 *dst) {                            // warp 0
-        u32 c = (lane < S && pi < t.n_parts) ? cnt2[((size_t)(pi >> t.group_shift) * S + lane) * nb + (pi & (nb - 1u))] : 0u;
+        u32 c = (lane < S && pi < n_sl) ? cnt2[((size_t)(pi >> t.group_shift) * S + lane) * nb + (pi & (nb - 1u))] : 0u;
         u32 v = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(0xffffffffu, v, d); if ((int)lane >= d) v += x; }
@@ -1940,7 +1946,7 @@ __global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_ws(TableView t, 
               bufn_a = opaque(smem_u32(&buf_n[0])), slice_bar_a = opaque(smem_u32(&bar_slice));
     u32 n_unique32 = 0, n_full32 = 0;
     Slot<1> *prev_gsl = nullptr;                                       // producer: slice waiting for its write-back
-    for (u32 pi = blockIdx.x; pi < t.n_parts; pi += gridDim.x, ++it) {
+    for (u32 pi = blockIdx.x; pi < n_sl; pi += gridDim.x, ++it) {
         __syncthreads();                                               // s_pre[it & 1] complete; every consumer has left the previous slice
         if (warp == 0) load_pre(pi + gridDim.x, s_pre[(it + 1u) & 1u]);
         const u32 *pre = s_pre[it & 1u];
@@ -1948,7 +1954,7 @@ __global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_ws(TableView t, 
         if (total == 0) continue;                                      // nothing staged for this slice in this drain
         u32 n_chunks = 0;
         for (u32 p = 0; p < S; ++p) n_chunks += (pre[p + 1] - pre[p] + COUNTW_CHUNK - 1u) / COUNTW_CHUNK;
-        Slot<1> *gsl = reinterpret_cast<Slot<1> *>(t.slots) + (size_t)pi * SL;
+        Slot<1> *gsl = reinterpret_cast<Slot<1> *>(t.slots) + (size_t)(slice0 + pi) * SL;
         if (producer) {
             if (lane == 0) {
                 const u32 g = pi >> t.group_shift, j = pi & (nb - 1u);
@@ -1976,6 +1982,45 @@ __global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_ws(TableView t, 
                 bulk_g2s(sl, gsl, SL * 16u, &bar_slice);
                 for (u32 i = first; i < n_chunks; ++i) issue();
             }
+        } else if (!BALLOT) {
+            mbar_wait_a(slice_bar_a, ph_slice);
+            for (u32 c = 0; c < n_chunks; ++c) {
+                const u32 q = qn + c, cb = q % COUNTW_NBUF;
+                mbar_wait_a(full_a + cb * 8u, (q / COUNTW_NBUF) & 1u);
+                const u32 n = lds32(bufn_a + cb * 4u), lo = warp * COUNTW_SHARE, hi = min(n, lo + (u32)COUNTW_SHARE);
+                const u32 recs_a = rbuf_a + cb * (COUNTW_CHUNK * 8u);
+                for (u32 idx = lo + lane; idx < hi; idx += 32u) {
+                    const u64 rec = lds64(recs_a + idx * 8u);
+                    const u64 key = rec & ~1ull, want = ~key;
+                    u32 addr = sl_addr + (((u32)(((u64)(u32)mix64(key) * SL) >> 32)) & ~1u) * 16u;
+                    u32 left = SL;
+                    while (true) {
+                        u64 v, k;
+                        asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(v), "=l"(k) : "r"(addr));      // {val, key}
+                        bool hit = k == want;
+                        if (!hit && k == 0ull) {
+                            u64 old;
+                            asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr + 8u), "l"(0ull), "l"(want) : "memory");
+                            if (old == 0ull) n_unique32++;
+                            hit = old == 0ull || old == want;
+                            v = 0;
+                        }
+                        if (hit) {
+                            if ((u32)v < MAX_COUNT) {
+                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+                                if (rec & 1ull) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr + 4u) : "memory");
+                            }
+                            break;
+                        }
+                        addr += 16u;
+                        if (addr == sl_end) addr = sl_addr;
+                        if (--left == 0u) { n_full32++; break; }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(empty_a + cb * 8u);       // this warp's share of the chunk is counted
+            }
+            fence_async_smem();                                        // this thread's counts are visible to the bulk store of the slice
         } else {
             // consumer warp: chunk c of the slice is current, records [wo, wn) of it are this warp's and not yet taken
             u32 c = 0, wo = 0, wn = 0, cur_b = 0, recs_a = rbuf_a;
@@ -2058,6 +2103,203 @@ __global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_ws(TableView t, 
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     n_unique = n_unique32; n_full = n_full32;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_unique) atomicAdd(&ctr->unique, n_unique);
+        if (n_full) atomicAdd(&ctr->table_full, n_full);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_count_slices_db: one CTA per SM, TWO slice buffers.  k_count_slices_tma / _ws spend about half of every slice visit
+// waiting -- the slice is loaded, counted and written back one after the other, and only the other CTA of the SM fills
+// the gaps (both variants take 95 ms on C2 although one issues a third more instructions than the other).  Here the
+// producer warp loads slice j+1 and writes slice j-1 back while the 31 consumer warps count slice j, and there is no
+// block-wide barrier at all: a consumer warp that has taken its share of slice j goes on to slice j+1.
+//   published slice j (empty slices are skipped by the producer) lives in buffer j & 1:
+//     bar_ready[j & 1]  completes for the (j >> 1)-th time when the slice has landed (its chunk count is in s_nchunks)
+//     bar_done[j & 1]   completes for the (j >> 1)-th time when every consumer warp has counted its share of it
+//   record chunks are numbered through all slices of the CTA and live in ring buffer q % NBUF (bar_full / bar_empty as in
+//   k_count_slices_ws).  A chunk count of 0xffffffff ends the stream.
+// ------------------------------------------------------------------------------------------------
+static constexpr int COUNTD_CONSUMERS = 31;
+static constexpr int COUNTD_TPB = (COUNTD_CONSUMERS + 1) * 32;
+static constexpr int COUNTD_SHARE = 64;                                // records of a chunk that belong to one consumer warp
+static constexpr int COUNTD_CHUNK = COUNTD_CONSUMERS * COUNTD_SHARE;   // 1984 records = 15872 bytes per bulk copy
+static constexpr int COUNTD_NBUF = 3;
+
+__global__ void __launch_bounds__(COUNTD_TPB, 1) k_count_slices_db(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, Counters *ctr, u32 slice0, u32 n_sl)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const u32 SL = (u32)t.part_slots;
+    u64 *rbuf = reinterpret_cast<u64 *>(smem_raw + (size_t)SL * 32);   // behind the two slice buffers: [NBUF][CHUNK] record chunks
+    __shared__ __align__(8) u64 bar_ready[2], bar_done[2], bar_full[COUNTD_NBUF], bar_empty[COUNTD_NBUF];
+    __shared__ u32 s_pre[2][32];                                       // producer: exclusive prefix of the sub-run sizes of this / the next slice
+    __shared__ u32 buf_n[COUNTD_NBUF];                                 // records of the chunk in every ring buffer
+    __shared__ u32 s_nchunks[2];                                       // chunks of the slice in every slice buffer
+    const u32 nb = 1u << t.group_shift;
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const u32 lt = (1u << lane) - 1u;
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < 2; ++b) { mbar_init(&bar_ready[b], 1); mbar_init(&bar_done[b], COUNTD_CONSUMERS); }
+        for (int b = 0; b < COUNTD_NBUF; ++b) { mbar_init(&bar_full[b], 1); mbar_init(&bar_empty[b], COUNTD_CONSUMERS); }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    auto opaque = [](u32 x) { u32 y; asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x)); return y; };
+    const u32 sl_a0 = opaque(smem_u32(smem_raw)), sl_bytes = SL * 16u;
+    const u32 rbuf_a = opaque(smem_u32(rbuf)), full_a = opaque(smem_u32(&bar_full[0])), empty_a = opaque(smem_u32(&bar_empty[0])),
+              bufn_a = opaque(smem_u32(&buf_n[0])), ready_a = opaque(smem_u32(&bar_ready[0])), done_a = opaque(smem_u32(&bar_done[0])),
+              nch_a = opaque(smem_u32(&s_nchunks[0]));
+    u32 n_unique32 = 0, n_full32 = 0;
+    if (warp == COUNTD_CONSUMERS) {
+        // ---------------- producer warp ----------------
+        auto load_pre = [&](u32 pi, u32 *dst) {
+            u32 c = (lane < S && pi < n_sl) ? cnt2[((size_t)(pi >> t.group_shift) * S + lane) * nb + (pi & (nb - 1u))] : 0u;
+            u32 v = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(0xffffffffu, v, d); if ((int)lane >= d) v += x; }
+            if (lane < COUNT_MAX_S + 1u) dst[lane] = v - c;
+        };
+        load_pre(blockIdx.x, s_pre[0]);
+        u32 it = 0, j = 0, q = 0;                                      // slices visited, slices published, chunks issued
+        Slot<1> *wb[2] = {nullptr, nullptr};                           // global home of the slice in every buffer
+        auto retire = [&](u32 b, u32 jj) {                             // lane 0: buffer b holds published slice jj, finished or about to be
+            mbar_wait_a(done_a + b * 8u, (jj >> 1) & 1u);
+            bulk_s2g(wb[b], smem_raw + (size_t)b * sl_bytes, sl_bytes);    // (the consumers fenced their counts before arriving)
+            wb[b] = nullptr;
+        };
+        for (u32 pi = blockIdx.x; pi < n_sl; pi += gridDim.x, ++it) {
+            __syncwarp();
+            load_pre(pi + gridDim.x, s_pre[(it + 1u) & 1u]);           // requested one slice ahead
+            __syncwarp();
+            const u32 *pre = s_pre[it & 1u];
+            const u32 total = pre[S];
+            if (total == 0) continue;                                  // nothing staged for this slice in this drain
+            if (lane == 0) {
+                u32 n_chunks = 0;
+                for (u32 p = 0; p < S; ++p) n_chunks += (pre[p + 1] - pre[p] + COUNTD_CHUNK - 1u) / COUNTD_CHUNK;
+                const u32 b = j & 1u;
+                if (wb[b]) { retire(b, j - 2u); bulk_wait_read(); }    // slice j - 2 has left the buffer
+                Slot<1> *gsl = reinterpret_cast<Slot<1> *>(t.slots) + (size_t)(slice0 + pi) * SL;
+                wb[b] = gsl;
+                s_nchunks[b] = n_chunks;
+                mbar_expect_tx(&bar_ready[b], sl_bytes);
+                bulk_g2s(smem_raw + (size_t)b * sl_bytes, gsl, sl_bytes, &bar_ready[b]);
+                const u32 g = pi >> t.group_shift, jn = pi & (nb - 1u);
+                const u64 *run0 = buf + (((size_t)g * S) * nb + jn) * cap2;    // sub-run p starts at run0 + p * nb * cap2
+                const size_t run_stride = (size_t)nb * cap2;
+                u32 pp = 0, po = 0;
+                for (u32 i = 0; i < n_chunks; ++i, ++q) {
+                    while (pp < S && po >= pre[pp + 1] - pre[pp]) { ++pp; po = 0; }
+                    const u32 rb = q % COUNTD_NBUF;
+                    if (q >= COUNTD_NBUF) mbar_wait_a(empty_a + rb * 8u, ((q / COUNTD_NBUF) - 1u) & 1u);   // chunk q - NBUF has been taken by every warp
+                    const u32 n = min((u32)COUNTD_CHUNK, pre[pp + 1] - pre[pp] - po);
+                    const u32 bytes = ((n + 1u) & ~1u) * 8u;           // bulk copies move multiples of 16 bytes (cap2 is a multiple of 4)
+                    buf_n[rb] = n;
+                    mbar_expect_tx(&bar_full[rb], bytes);
+                    bulk_g2s(rbuf + (size_t)rb * COUNTD_CHUNK, run0 + (size_t)pp * run_stride + po, bytes, &bar_full[rb]);
+                    po += n;
+                }
+            }
+            ++j;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            // end of the stream in the next buffer (once its previous slice is out), then the last slice
+            const u32 b = j & 1u;
+            if (wb[b]) retire(b, j - 2u);
+            s_nchunks[b] = 0xffffffffu;
+            mbar_arrive(&bar_ready[b]);
+            if (wb[b ^ 1u]) retire(b ^ 1u, j - 1u);
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else {
+        // ---------------- consumer warps ----------------
+        u32 qn = 0;                                                    // number of the current slice's first chunk
+        for (u32 j = 0;; ++j) {
+            const u32 b = j & 1u;
+            mbar_wait_a(ready_a + b * 8u, (j >> 1) & 1u);
+            const u32 n_chunks = lds32(nch_a + b * 4u);
+            if (n_chunks == 0xffffffffu) break;
+            const u32 sl_addr = sl_a0 + b * sl_bytes, sl_end = sl_addr + sl_bytes;
+            // chunk c of the slice is current, records [wo, wn) of it are this warp's and not yet taken
+            u32 c = 0, wo = 0, wn = 0, cur_b = 0, recs_a = rbuf_a;
+            auto open_chunk = [&]() -> bool {
+                while (c < n_chunks) {
+                    const u32 q = qn + c;
+                    cur_b = q % COUNTD_NBUF;
+                    mbar_wait_a(full_a + cur_b * 8u, (q / COUNTD_NBUF) & 1u);
+                    const u32 n = lds32(bufn_a + cur_b * 4u), lo = warp * COUNTD_SHARE;
+                    if (lo < n) { wo = lo; wn = min(n, lo + (u32)COUNTD_SHARE); recs_a = rbuf_a + cur_b * (COUNTD_CHUNK * 8u); return true; }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_a(empty_a + cur_b * 8u);     // nothing of this chunk is ours
+                    ++c;
+                }
+                return false;
+            };
+            bool more = open_chunk();
+            u32 busy = 0, addr = sl_addr, left = 0;
+            u64 rec = 0, want = 0;
+            while (true) {
+                const u32 bm = __ballot_sync(0xffffffffu, busy != 0u);
+                u32 took = 0;
+                if (more && bm != 0xffffffffu) {
+                    const u32 idle = ~bm, n_idle = __popc(idle);
+                    const u32 idx = wo + __popc(idle & lt);
+                    if (busy == 0u && idx < wn) {
+                        rec = lds64(recs_a + idx * 8u);
+                        const u64 key = rec & ~1ull;
+                        want = ~key;
+                        addr = sl_addr + (((u32)(((u64)(u32)mix64(key) * SL) >> 32)) & ~1u) * 16u;
+                        left = SL;
+                        busy = 1u;
+                    }
+                    took = min(n_idle, wn - wo);
+                    wo += n_idle;
+                    if (wo >= wn) {                                    // the warp's share is in registers: the buffer may be refilled
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_a(empty_a + cur_b * 8u);
+                        ++c;
+                        more = open_chunk();
+                    }
+                }
+                if ((bm | took) == 0u) break;                          // nothing in flight and nothing left to take
+                u64 v, k;
+                asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(v), "=l"(k) : "r"(addr));          // {val, key}
+                bool hit = busy != 0u && k == want;
+                const bool emp = busy != 0u && k == 0ull;
+                if (__any_sync(0xffffffffu, emp)) {
+                    if (emp) {
+                        u64 old;
+                        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr + 8u), "l"(0ull), "l"(want) : "memory");
+                        if (old == 0ull) n_unique32++;
+                        hit = old == 0ull || old == want;
+                        v = 0;
+                    }
+                }
+                // count in the low word, directionBias in the high word: two native 32-bit shared atomics; no carry ever
+                // crosses the words
+                const u32 pc = (hit && (u32)v < MAX_COUNT) ? 1u : 0u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(addr), "r"(pc) : "memory");
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(addr + 4u), "r"(pc & (u32)rec) : "memory");
+                addr += 16u;
+                if (addr == sl_end) addr = sl_addr;
+                --left;
+                if (hit) busy = 0u;
+                else if (busy != 0u && left == 0u) { n_full32++; busy = 0u; }
+            }
+            fence_async_smem();                                        // this thread's counts are visible to the bulk store of the slice
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(done_a + b * 8u);
+            qn += n_chunks;
+        }
+    }
+    u64 n_unique = n_unique32, n_full = n_full32;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
