@@ -115,6 +115,9 @@ struct kmn_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     void *recv_all = nullptr;             // [2 round buffers][nranks sources][push_cap records] + [2][nranks][n_groups+1] offsets
     void *peer_all[KMN_MAX_PUSH_RANKS] = {nullptr};   // recv_all of every peer (cudaIpcOpenMemHandle)
+    void *peer_table[KMN_MAX_PUSH_RANKS] = {};   // count tables of all ranks (own pointer at [rank]), mapped with CUDA IPC
+    u64 *bar_buf = nullptr;               // [2] operands of the stream-ordered barriers around a peer-memory lookup pass
+    bool peer_lookup = false;             // the lookup pass probes the owners' tables over NVLink (no request/response rounds)
     uint64_t push_cap = 0;                // records per (round buffer, source)
     size_t push_meta = 0;                 // u32 words of meta per (round buffer, source)
     bool push_ce = true;                  // transport: copy engines move whole parts (default) / k_push_copy writes sorted runs
@@ -263,7 +266,7 @@ static int alloc_stage_sets(kmn_ctx *c)
         CK(c, cudaMemsetAsync(st.v.count, 0, (size_t)n_own * n_groups * n_cta * 4, c->stream));
         if (n_own > 1 && c->push_ce) {
             // overflow list per owner: records of other owners whose sub-region was full travel ungrouped behind the part
-            st.v.ovf_cap = (u32)std::min<uint64_t>(65536 + sk / n_own / 256, 1u << 30);
+            st.v.ovf_cap = (u32)(std::min<uint64_t>(65536 + sk / n_own / 256, 1u << 30) & ~3ull);   // whole sectors: what follows stays 32-byte aligned
             CK(c, cudaMalloc((void **)&st.v.ovf_recs, (size_t)n_own * st.v.ovf_cap * c->RW * 8));
             CK(c, cudaMalloc((void **)&st.v.ovf_count, (size_t)n_own * 4));
             CK(c, cudaMemsetAsync(st.v.ovf_count, 0, (size_t)n_own * 4, c->stream));
@@ -555,6 +558,8 @@ void kmn_destroy(kmn_ctx *c)
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (int p = 0; p < KMN_MAX_PUSH_RANKS; ++p) if (c->peer_all[p] && p != c->rank) cudaIpcCloseMemHandle(c->peer_all[p]);
+    for (int p = 0; p < KMN_MAX_PUSH_RANKS; ++p) if (c->peer_table[p] && p != c->rank) cudaIpcCloseMemHandle(c->peer_table[p]);
+    if (c->bar_buf) cudaFree(c->bar_buf);
     if (c->p2p) { c->send_recs = nullptr; c->recv_recs = nullptr; }     // aliases of recv_all
 #ifdef KMN_WITH_NCCL
     if (c->comm) ncclCommDestroy(c->comm);
@@ -831,6 +836,7 @@ static int setup_push(kmn_ctx *c)
     uint64_t cap; size_t meta_words;
     if (c->push_ce) { cap = (uint64_t)c->n_cta * G * c->sets[0].v.sub_cap + c->sets[0].v.ovf_cap; meta_words = (size_t)G * c->n_cta + 1; }
     else { cap = c->stage_keys / (uint64_t)R; cap += cap / 4 + 65536; meta_words = (size_t)G + 1; }
+    cap = (cap + 3) & ~3ull;                                // every source's buffer starts on a 32-byte boundary (bulk copies, sector stores)
     const size_t rec_bytes = 2 * (size_t)R * cap * c->RW * 8, meta_bytes = 2 * (size_t)R * meta_words * 4;
     if (cudaMalloc(&c->recv_all, rec_bytes + meta_bytes + 256) != cudaSuccess) {
         cudaGetLastError(); c->recv_all = nullptr;
@@ -883,6 +889,40 @@ static int setup_push(kmn_ctx *c)
         for (int p = 0; p < KMN_MAX_PUSH_RANKS; ++p) { if (p != c->rank && c->peer_all[p]) cudaIpcCloseMemHandle(c->peer_all[p]); c->peer_all[p] = nullptr; }
         cudaGetLastError();
         if (!c->push_ce) return fail(c, KMN_ERR_INVALID, "KMN_PUSH=kernel needs peer-mapped receive buffers");
+    }
+    // lookup pass over peer memory: the tables are mapped like the receive buffers (all ranks or none)
+    {
+        // (opt-in, KMN_PEER_LOOKUP=1: measured on 2 x B200, dependent 32-byte reads of a peer's table run at 0.2 G/s per GPU
+        //  against 2.4 G/s for the request / response rounds -- profiles/r02_summary.md)
+        u64 tok = 0;
+        if (const char *e = getenv("KMN_PEER_LOOKUP")) tok = c->ipc && atoi(e) != 0;
+        cudaIpcMemHandle_t th;
+        memset(&th, 0, sizeof th);
+        if (tok && cudaIpcGetMemHandle(&th, c->table.slots) != cudaSuccess) { cudaGetLastError(); tok = 0; }
+        std::vector<cudaIpcMemHandle_t> tall((size_t)R);
+        void *d = nullptr;
+        CK(c, cudaMalloc(&d, (size_t)(R + 1) * 64));
+        CK(c, cudaMemcpyAsync((char *)d + (size_t)R * 64, &th, 64, cudaMemcpyHostToDevice, c->stream));
+        ncclResult_t nr = ncclAllGather((char *)d + (size_t)R * 64, d, 64, ncclUint8, c->comm, c->stream);
+        if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclAllGather failed: %s", ncclGetErrorString(nr));
+        CK(c, cudaMemcpyAsync(tall.data(), d, (size_t)R * 64, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, cudaFree(d));
+        u64 all_tok = 0;
+        { int r = nccl_sum_u64(c, tok, &all_tok, c->stream); if (r) return r; }
+        if (all_tok == (u64)R) {
+            for (int p = 0; p < R && tok; ++p) {
+                if (p == c->rank) { c->peer_table[p] = c->table.slots; continue; }
+                if (cudaIpcOpenMemHandle(&c->peer_table[p], tall[(size_t)p], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); c->peer_table[p] = nullptr; tok = 0; }
+            }
+        } else tok = 0;
+        { int r = nccl_sum_u64(c, tok, &all_tok, c->stream); if (r) return r; }
+        c->peer_lookup = all_tok == (u64)R;
+        if (c->peer_lookup && !c->bar_buf) { CK(c, cudaMalloc((void **)&c->bar_buf, 16)); CK(c, cudaMemsetAsync(c->bar_buf, 0, 16, c->stream)); }
+        if (!c->peer_lookup) {
+            for (int p = 0; p < R; ++p) { if (p != c->rank && c->peer_table[p]) cudaIpcCloseMemHandle(c->peer_table[p]); c->peer_table[p] = nullptr; }
+            cudaGetLastError();
+        }
     }
     c->push_cap = cap;
     c->push_meta = meta_words;
@@ -1411,6 +1451,23 @@ int kmn_histogram(kmn_ctx *c, uint64_t *hist, double *wsum)
 #ifdef KMN_WITH_NCCL
 static int allreduce_max_u64(kmn_ctx *c, u64 mine, u64 *out);
 static int lookup_exchange(kmn_ctx *c, uint32_t min_depth, uint16_t *vals);
+// Barrier in stream order (no host synchronisation): what follows on c->stream starts when every rank's stream has reached
+// its own call.  A peer-memory lookup pass sits between two of them: the first says "every table is final" (the count pass
+// and purges of all ranks precede it on their streams), the second "nobody reads my table any more" (so a reset, purge or
+// the next count pass behind it on the stream is safe).
+static int stream_barrier(kmn_ctx *c)
+{
+    ncclResult_t nr = ncclAllReduce(c->bar_buf, c->bar_buf + 1, 1, ncclUint64, ncclSum, c->comm, c->stream);
+    if (nr != ncclSuccess) return fail(c, KMN_ERR_COMM, "ncclAllReduce failed: %s", ncclGetErrorString(nr));
+    return 0;
+}
+static PeerTables peer_tables(const kmn_ctx *c)
+{
+    PeerTables pt;
+    memset(&pt, 0, sizeof pt);
+    for (int p = 0; p < c->nranks && p < KMN_MAX_PUSH_RANKS; ++p) pt.slots[p] = c->peer_table[p];
+    return pt;
+}
 #endif
 
 int kmn_lookup(kmn_ctx *c, const uint8_t *keys, uint64_t n, uint16_t *counts)
@@ -1421,6 +1478,31 @@ int kmn_lookup(kmn_ctx *c, const uint8_t *keys, uint64_t n, uint16_t *counts)
         return fail(c, KMN_ERR_STATE, "%s before kmn_count_finish on a multi-GPU context", __func__);
     int r = drain(c); if (r) return r;
 #ifdef KMN_WITH_NCCL
+    if (c->nranks > 1 && c->peer_lookup) {
+        // collective (n may be 0): the owners' tables are probed over peer memory between two stream-ordered barriers
+        r = stream_barrier(c); if (r) return r;
+        if (n) {
+            const uint8_t *dk = keys;
+            if (!is_device_ptr(keys)) {
+                r = ensure(c, c->lk_keys, n * c->kb); if (r) return r;
+                CK(c, cudaMemcpyAsync(c->lk_keys.p, keys, n * c->kb, cudaMemcpyHostToDevice, c->stream));
+                dk = (const uint8_t *)c->lk_keys.p;
+            }
+            uint16_t *dout = counts;
+            const bool out_host = !is_device_ptr(counts);
+            if (out_host) { r = ensure(c, c->lk_out, n * 2); if (r) return r; dout = (uint16_t *)c->lk_out.p; }
+            ParseArgs a;
+            fill_parse_args(c, a, nullptr, nullptr, nullptr, nullptr, 0, 0);
+            const PeerTables pt = peer_tables(c);
+            KMN_DISPATCH_W(c, { k_lookup_keys_peer<W_><<<c->n_sms * 8, 256, 0, c->stream>>>(a, pt, dk, n, dout); });
+            c->launches++;
+            CK(c, cudaGetLastError());
+            if (out_host) CK(c, cudaMemcpyAsync(counts, dout, n * 2, cudaMemcpyDeviceToHost, c->stream));
+        }
+        r = stream_barrier(c); if (r) return r;
+        CK(c, cudaStreamSynchronize(c->stream));
+        return 0;
+    }
     if (c->nranks > 1) {
         // collective: every rank calls it (n may be 0); keys go to their owners in rounds of at most send_cap keys,
         // as DistributedReadSelector::_batchKmerLookup does per batch (src/DistributedFunctions.h:877-902)
@@ -1557,6 +1639,8 @@ int kmn_trim_batch(kmn_ctx *c, const uint8_t *bases, const uint64_t *read_off, u
         return fail(c, KMN_ERR_STATE, "%s before kmn_count_finish on a multi-GPU context", __func__);
     int r = drain(c); if (r) return r;
 #ifdef KMN_WITH_NCCL
+    if (c->nranks > 1 && c->peer_lookup) { r = stream_barrier(c); if (r) return r; }       // every rank's table is final
+    if (c->nranks > 1 && c->peer_lookup && n_reads == 0) return stream_barrier(c);         // (nothing to look up here)
     if (c->nranks > 1 && n_reads == 0) {           // a rank without reads still serves the other ranks' requests
         u64 rounds = 0;
         r = allreduce_max_u64(c, 0, &rounds); if (r) return r;
@@ -1574,7 +1658,18 @@ int kmn_trim_batch(kmn_ctx *c, const uint8_t *bases, const uint64_t *read_off, u
     ParseArgs a;
     fill_parse_args(c, a, bp.bases, nullptr, bp.off, bp.disc, n_reads, bp.total_bytes);
     const int grid = c->n_sms * 8;
-    if (c->nranks > 1) {
+    if (c->nranks > 1 && c->peer_lookup) {
+#ifdef KMN_WITH_NCCL
+        {
+            ProfScope ps(c, KMN_PROF_LOOKUP, bp.total_bytes);
+            const PeerTables pt = peer_tables(c);
+            KMN_DISPATCH_W(c, { k_lookup_vals_peer<W_><<<grid, 256, 0, c->stream>>>(a, pt, min_depth, (uint16_t *)c->vals.p, (u32 *)c->first_nx.p); });
+            c->launches++;
+            CK(c, cudaGetLastError());
+        }
+        r = stream_barrier(c); if (r) return r;                                            // nobody reads this rank's table any more
+#endif
+    } else if (c->nranks > 1) {
 #ifdef KMN_WITH_NCCL
         // rounds: read ranges whose k-mer positions fit one request region even if every k-mer had the same owner
         r = ensure(c, c->lk_origin, (size_t)c->nranks * c->send_cap * 8); if (r) return r;

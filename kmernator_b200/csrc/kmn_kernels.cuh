@@ -2565,6 +2565,59 @@ __global__ void __launch_bounds__(256) k_lookup_vals(ParseArgs a, u32 min_depth,
 // answers travel as two all-to-alls in the same order, so no request id is needed (the reference sends
 // {requestId, k-mer} out and {requestId, score} back, :809-874).
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// multi-GPU lookup pass over peer memory: every rank has the count tables of all ranks mapped (CUDA IPC, NVLink), so a
+// k-mer owned by another rank (a5, ((hashlittle2 >> 24) & 0x7ffff) % R) is probed in that rank's table directly: the
+// same 32-byte pair loads, travelling over NVLink instead of to local HBM.  This replaces the request/response rounds of
+// DistributedReadSelector::_batchKmerLookup (src/DistributedFunctions.h:877-902: 16 B out + 12 B back per k-mer, four
+// all-to-all rounds per batch) -- no request buffers, no counts on the host, no collective inside the pass.
+// ------------------------------------------------------------------------------------------------
+struct PeerTables { void *slots[KMN_MAX_PUSH_RANKS]; };
+
+template <int W>
+__global__ void __launch_bounds__(256) k_lookup_vals_peer(ParseArgs a, PeerTables pt, u32 min_depth, uint16_t *vals, u32 *first_nx)
+{
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += stride) {
+        u64 o0 = a.read_off[r], o1 = a.read_off[r + 1];
+        u32 len = (u32)(o1 - o0);
+        bool disc = a.discarded && a.discarded[r];
+        Walker<W> st;
+        st.clear();
+        if (!disc && len >= a.k) {
+            st.template begin<false>(a, o0, len);
+            auto emit = [&](u32 i, const u64 (&key)[W], bool, float, bool, u32) {
+                const u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
+                TableView t = a.table;
+                t.slots = pt.slots[owner_of(h, a.nranks)];
+                const u64 ph = place_hash<W>(key);
+                const u32 c = clamp_count(table_find<W>(t, part_of(ph, t.n_parts), home_slot(ph, t.part_slots), key, nullptr));
+                vals[o0 + i] = (uint16_t)(c >= min_depth ? c : 0u);
+            };
+            while (st.j < st.len) walker_step<W, false, false>(st, a, nullptr, emit);
+        } else if (!disc) {
+            for (u32 j = 0; j < len; ++j) { u32 c = base_code(a.bases[o0 + j]); if (c == 4 && st.first_nx == 0) st.first_nx = j + 1; }
+        }
+        first_nx[r] = st.first_nx;
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) k_lookup_keys_peer(ParseArgs a, PeerTables pt, const uint8_t *keys, u64 n, uint16_t *out)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+        u64 key[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) key[q] = 0;
+        for (u32 b = 0; b < a.kb; ++b) key[b >> 3] |= (u64)keys[i * a.kb + b] << (56 - 8 * (b & 7));
+        const u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
+        TableView t = a.table;
+        t.slots = pt.slots[owner_of(h, a.nranks)];
+        const u64 ph = place_hash<W>(key);
+        out[i] = (uint16_t)clamp_count(table_find<W>(t, part_of(ph, t.n_parts), home_slot(ph, t.part_slots), key, nullptr));
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(256) k_lookup_vals_dist(ParseArgs a, u32 min_depth, uint16_t *vals, u32 *first_nx, u64 *origin)
 {

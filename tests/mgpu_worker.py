@@ -46,7 +46,9 @@ def main():
         my_off = np.ascontiguousarray(off[r0:r1 + 1] - off[r0])
         my_disc = np.ascontiguousarray(disc[r0:r1])
 
-        ctx = make_ctx(k, table_slots=1 << 21, stage_keys=1 << 20)
+        # (a staging size that makes the per-owner overflow list an odd number of records before rounding: the receive
+        #  buffers of the peers must still start on sector boundaries)
+        ctx = make_ctx(k, table_slots=1 << 21, stage_keys=(1 << 20) + 768 * world)
         # two batches per rank (a rank without reads still has to take part in the collectives)
         n_my = r1 - r0
         half = n_my // 2

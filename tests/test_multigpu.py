@@ -26,7 +26,8 @@ def _n_gpus():
 # transports of the round exchange: peer-mapped receive buffers written by the copy engines (default) or by k_push_copy,
 # and ncclSend / ncclRecv of the same parts when the buffers cannot be mapped (KMN_P2P=0); with and without the
 # shared-memory phase 2
-@pytest.mark.parametrize("world,env", [(2, {}), (2, {"KMN_P2P": "0"}), (2, {"KMN_PUSH": "kernel"}), (2, {"KMN_SMEM_COUNT": "0"}),
+# lookup pass: request / response rounds (default) or the owners' tables probed over peer memory (KMN_PEER_LOOKUP=1)
+@pytest.mark.parametrize("world,env", [(2, {}), (2, {"KMN_P2P": "0"}), (2, {"KMN_PUSH": "kernel"}), (2, {"KMN_SMEM_COUNT": "0"}), (2, {"KMN_PEER_LOOKUP": "1"}),
                                        (4, {}), (4, {"KMN_P2P": "0"}), (8, {})])
 def test_owner_sharded_count_and_lookup(world, env):
     if _n_gpus() < world:
