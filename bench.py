@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("--e2e-reads", type=int, default=0, help="reads per e2e step (0 = same as --reads)")
     ap.add_argument("--e2e-batch", type=int, default=4_000_000)
     ap.add_argument("--e2e-pipe-batches", type=int, default=8, help="staging sets per step of the end-to-end run on one GPU")
-    ap.add_argument("--cpu-reads", type=int, default=400_000)
+    ap.add_argument("--cpu-reads", type=int, default=2_000_000, help="reads of the bounded CPU sample (about 10 s of work for 16 host threads)")
     ap.add_argument("--parity-reads", type=int, default=240_000, help="reads of the untimed exact oracle comparison (all ranks together)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -423,7 +423,7 @@ def main():
     try:                                                 # dram bytes per launch of that kernel from the committed ncu capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         ent = tj.get("%s:%s" % (args.workload, dname))
-        if ent and world == 1 and n_reads == wl["reads"]:
+        if ent and world == 1 and n_reads == wl["reads"] and not args.pipe_batches and not args.stage_keys:
             traffic, traffic_src = float(ent["dram_bytes_per_launch"]), ent["source"]
     except Exception:
         pass

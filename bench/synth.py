@@ -29,12 +29,22 @@ def reads_numpy(n_reads, read_len=150, genome_len=100_000, seed=1, err=0.001, lo
         starts = rng.integers(0, G - read_len, n_reads)
     strand = rng.integers(0, 2, n_reads)
     codes = np.empty(total, dtype=np.uint8)
-    for i in range(n_reads):
-        L = int(lens[i])
-        seg = g[starts[i]: starts[i] + L]
-        if strand[i]:
-            seg = (3 - seg)[::-1]
-        codes[int(off[i]): int(off[i]) + L] = seg
+    if not var_len:
+        # fixed length: gather whole blocks of reads at once (same bytes as the per-read loop below)
+        ar = np.arange(read_len, dtype=np.int64)
+        for c0 in range(0, n_reads, 200_000):
+            c1 = min(n_reads, c0 + 200_000)
+            seg = g[np.asarray(starts[c0:c1], dtype=np.int64)[:, None] + ar]
+            rev = strand[c0:c1].astype(bool)
+            seg[rev] = (3 - seg[rev])[:, ::-1]
+            codes[c0 * read_len: c1 * read_len] = seg.reshape(-1)
+    else:
+        for i in range(n_reads):
+            L = int(lens[i])
+            seg = g[starts[i]: starts[i] + L]
+            if strand[i]:
+                seg = (3 - seg)[::-1]
+            codes[int(off[i]): int(off[i]) + L] = seg
     quals = np.full(total, ord("I"), dtype=np.uint8)
     e = rng.random(total) < err
     codes[e] = (codes[e] + rng.integers(1, 4, int(e.sum()), dtype=np.uint8)) & 3
