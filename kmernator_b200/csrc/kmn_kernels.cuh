@@ -1,18 +1,21 @@
 // kmn_kernels.cuh -- sm_100a kernels of the k-mer spectrum path.
 //
-//   count pass  = k_weight_mask   (phase 1a: quality weights along each read -> one "counted" bit per k-mer position)
-//               + k_kmer_scatter  (phase 1b: bases -> canonical k-mers -> staging set partitioned by (owner,) table group)
-//               + k_build_entries / k_build_worklist / k_insert_staged (phase 2: group by group into L2-resident slices)
-//   multi-GPU   = k_push_plan / k_push_copy (records to their owners' receive buffers over NVLink; the default transport
-//                 uses copy engines instead, the fallback ncclSend / ncclRecv of the same parts)
-//   lookup pass = k_lookup_vals (+ _dist / k_lookup_words / k_scatter_answers) + k_trim_score
-//   table scans = k_histogram, k_purge, k_export, k_count_live
+//   count pass  = k_weight_mask     (phase 1a: quality weights along each read -> one "counted" bit per k-mer position)
+//               + k_kmer_scatter    (phase 1b: bases -> canonical k-mers -> staging set binned by (owner,) table group;
+//                                    records are write-combined in shared-memory rings and leave as whole 32-byte sectors)
+//               + k_build_entries / k_slice_split / k_count_slices_ws   (phase 2, k <= 31 without weights or extension
+//                                    counters: a second radix pass sorts every group's records by table slice, then each
+//                                    64 KB slice is brought into shared memory, counted there and written back)
+//               + k_build_worklist / k_insert_staged   (phase 2 of every other flavour, overflow lists: group by group
+//                                    into L2-resident slices with global atomics, hot k-mers merged in shared memory first)
+//   multi-GPU   = copy engines / k_push_plan + k_push_copy / ncclSend+Recv (records to their owners' receive buffers)
+//   lookup pass = k_lookup_vals (+ _dist / _peer / k_lookup_words / k_scatter_answers) + k_trim_score
+//   table scans = k_histogram, k_purge, k_export, k_import, k_subtract, k_count_live
 //
-// Why two phases: on B200 a 64-bit atomic to an HBM-resident table runs at ~20 G/s while the same
-// atomic to a <=64 MB (L2-resident) region runs at 60-190 G/s (profiles/r01_randacc_microbench.csv).
-// Phase 1 therefore scatters every k-mer into one of n_parts staging regions (each phase-1 CTA owns a private
-// sub-region of every partition, addressed by shared-memory counters), and phase 2 walks the regions in order
-// so that only one table group is hot.
+// Why: on B200 a 64-bit atomic to an HBM-resident table runs at ~20 G/s, the same atomic to a <= 64 MB (L2-resident)
+// region at 60-190 G/s (profiles/r01_randacc_microbench.csv), and a 16-byte slot update in shared memory at the rate the
+// SM issues it.  So the records are sorted until a slice's worth of them meets its slice in shared memory; every byte of
+// HBM traffic on the way is streamed (profiles/r02_summary.md: DRAM bytes = algorithmic bytes for every kernel).
 #pragma once
 #include "kmn_device.cuh"
 #include <cooperative_groups.h>
