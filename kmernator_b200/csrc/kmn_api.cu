@@ -741,6 +741,7 @@ static void fill_parse_args(kmn_ctx *c, ParseArgs &a, const uint8_t *bases, cons
     a.min_weight = c->o.min_kmer_quality; a.start_char = c->o.fastq_start_char;
     a.zero_below = c->zero_below; a.mask = (u32 *)c->mask.p; a.wts = c->weights ? (float *)c->wts.p : nullptr;
     a.nranks = (u32)c->nranks; a.rank = (u32)c->rank;
+    a.owner_magic = c->nranks > 1 ? 0xFFFFFFFFu / (u32)c->nranks + 1u : 0u;
     a.use_lookup8 = c->o.hash_kind == KMN_HASH_LOOKUP8_HASH2;
     a.l2_hints = getenv("KMN_NO_L2_HINTS") ? 0 : 1;
     a.fast_bound = getenv("KMN_NO_WEIGHT_BOUND") ? 0 : 1;

@@ -162,6 +162,14 @@ __device__ __forceinline__ u64 hash_lookup8(const u64 (&w)[W], int kb)
 
 // a5. owner rank: ((hash >> 24) & 0x7ffff) % nranks      src/Kmer.h:187-188,2284-2295
 __device__ __forceinline__ u32 owner_of(u64 h, u32 nranks) { return (u32)((h >> 24) & 0x7ffffu) % nranks; }
+// the same without a division: x < 2^19 and nranks < 8192, so floor(x / nranks) == umulhi(x, floor((2^32 - 1) / nranks) + 1)
+// exactly (the multiplier's excess adds less than 2^-13 to a quotient whose fractional part is at most 1 - 1/nranks).
+// magic is computed on the host (owner_magic); nranks >= 2.
+__device__ __forceinline__ u32 owner_of_fast(u64 h, u32 nranks, u32 magic)
+{
+    const u32 x = (u32)(h >> 24) & 0x7ffffu;
+    return x - __umulhi(x, magic) * nranks;
+}
 
 // ------------------------------------------------------------------------------------------------
 // placement inside one GPU (ours, not the reference's: the reference's growable sorted buckets are

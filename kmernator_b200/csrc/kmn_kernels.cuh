@@ -53,6 +53,7 @@ struct ParseArgs {
     u32 *mask;             // phase 1a -> 1b: bit (read_off[r] + i) set iff k-mer i of read r is counted
     float *wts;            // optional (KMN_VALUE_WEIGHTS): fp32 weight of k-mer i of read r at [read_off[r] + i]
     u32 nranks, rank;
+    u32 owner_magic;       // floor((2^32 - 1) / nranks) + 1 (owner_of_fast); nranks >= 2
     u32 use_lookup8;
     u32 l2_hints;          // staging stores carry an L2 evict_last policy
     u32 cta_rot;           // phase 1b: the pieces of this launch are dealt to CTAs starting at this CTA, so that a
@@ -830,7 +831,7 @@ __global__ void __launch_bounds__(1024, 1) k_kmer_scatter(ParseArgs a)
         u32 own = lo;
         if (DIST != 0) {
             const u64 h = a.use_lookup8 ? hash_lookup8<W>(key, (int)a.kb) : hash_lookup3<W>(key, (int)a.kb);
-            own = owner_of(h, a.nranks);
+            own = owner_of_fast(h, a.nranks, a.owner_magic);
         }
         const u32 bin = DIST == 2 ? own * n_parts + group : group;
         const u32 p = atomicAdd(&cnt[bin], 1u);
