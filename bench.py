@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--stage-keys", type=int, default=0)
     ap.add_argument("--slice-mb", type=int, default=64)
-    ap.add_argument("--pipe-batches", type=int, default=0, help="drains (multi-GPU: rounds) per step: a staging set holds 1/N of the input; 0 = 2 on one GPU, 6 on several")
+    ap.add_argument("--pipe-batches", type=int, default=0, help="drains (multi-GPU: rounds) per step: a staging set holds 1/N of the input; 0 = 2 on one GPU, 8 on several")
     ap.add_argument("--e2e-reads", type=int, default=0, help="reads per e2e step (0 = same as --reads)")
     ap.add_argument("--e2e-batch", type=int, default=4_000_000)
     ap.add_argument("--e2e-pipe-batches", type=int, default=8, help="staging sets per step of the end-to-end run on one GPU")
@@ -323,7 +323,7 @@ def main():
     est_distinct = int((genomic * 1.02 + err_kmers * 1.05) / world) + (1 << 16)
     table_slots = args.table_slots or int(est_distinct / 0.5)
     # staging: one set = 1/pipe_batches of the input
-    pipe_batches = args.pipe_batches or (2 if world == 1 else 6)
+    pipe_batches = args.pipe_batches or (2 if world == 1 else 8)
     stage_keys = args.stage_keys or int(inst_per_rank * 1.02 / pipe_batches)
     vk = KM.capi.KMN_VALUE_DIR_EXT if ext else KM.capi.KMN_VALUE_DIR
     ctx = KM.Context(kmer_size=k, est_raw_kmers=inst_per_rank, table_slots=table_slots, stage_keys=stage_keys, value_kind=vk,

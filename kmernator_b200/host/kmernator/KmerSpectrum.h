@@ -61,16 +61,13 @@ public:
     // NCCL id that rank 0 creates and the world hands round      src/DistributedFunctions.h:126-131, src/MPIUtils.h:256-391
     KmerSpectrum(World &world, unsigned long rawKmers, unsigned int valueKind = KMN_VALUE_DIR) : KmerSpectrum(rawKmers, world.localRank(), valueKind)
     {
-        if (!weak.ctx || world.size() == 1) return;
-        std::string id(128, '\0');
-        if (world.rank() == 0 && kmn_comm_unique_id(&id[0]) != 0) LOG_THROW("kmn_comm_unique_id failed");
-        id = world.broadcast(id);
-        if (id.size() != 128) LOG_THROW("bad communicator id from rank 0");
-        KMN_CHECK(weak.ctx, kmn_comm_init(weak.ctx, world.rank(), world.size(), id.data()));
+        _world = &world;
+        _joinWorld();
     }
 
     explicit KmerSpectrum(unsigned long rawKmers = 0, int device = 0, unsigned int valueKind = KMN_VALUE_DIR) : _rawKmers(rawKmers)
     {
+        kmn_default_opts(&_opts);
         if (rawKmers == 0) return;                                       // KS spectrum(0): placeholder (apps/FilterReads.cpp:128)
         kmn_opts o;
         kmn_default_opts(&o);
@@ -88,20 +85,18 @@ public:
         o.table_slots = (uint64_t)(distinct / 0.5) + 4096;
         o.ignore_quality = Options::getOptions().getIgnoreQual() ? 1 : 0;
         o.device = (uint32_t)device;
-        kmn_ctx *c = NULL;
-        int rc = kmn_create(&c, &o);
-        if (rc != 0) LOG_THROW("kmn_create failed (" << rc << "): " << kmn_last_error(NULL));
-        weak.ctx = c;
+        _opts = o;
+        _create();
     }
     ~KmerSpectrum() { reset(); }
     KmerSpectrum(const KmerSpectrum &) = delete;
     KmerSpectrum &operator=(const KmerSpectrum &) = delete;
     KmerSpectrum &operator=(KmerSpectrum &&o)                            // spectrum = KS(rawKmers)  apps/FilterReads.cpp:138
     {
-        if (this != &o) { reset(); weak = o.weak; _rawKmers = o._rawKmers; _sizeTracker = o._sizeTracker; _trackSizes = o._trackSizes; o.weak.ctx = NULL; }
+        if (this != &o) { reset(); weak = o.weak; _rawKmers = o._rawKmers; _sizeTracker = o._sizeTracker; _trackSizes = o._trackSizes; _opts = o._opts; _world = o._world; _openBuilds = o._openBuilds; o.weak.ctx = NULL; }
         return *this;
     }
-    KmerSpectrum(KmerSpectrum &&o) : weak(o.weak), _rawKmers(o._rawKmers) { o.weak.ctx = NULL; }
+    KmerSpectrum(KmerSpectrum &&o) : weak(o.weak), _opts(o._opts), _world(o._world), _openBuilds(o._openBuilds), _rawKmers(o._rawKmers) { o.weak.ctx = NULL; }
 
     // count pass over the whole ReadSet in --batch-size batches           src/KmerSpectrum.h:2081-2115
     // finish = false: more read sets follow into the same spectrum (reference files, then subtract files); finishBuild() ends it
@@ -118,15 +113,35 @@ public:
         // as every MPI rank must keep calling sendReceive in the reference (src/DistributedFunctions.h:436-447)
         unsigned long nBatches = (n + batch - 1) / batch;
         if (World::instance()) nBatches = World::instance()->allMax(nBatches);
-        for (unsigned long b = 0; b < nBatches; ++b) {
-            const ReadSet::ReadSetSizeType r0 = std::min<ReadSet::ReadSetSizeType>(n, b * batch), r1 = std::min<ReadSet::ReadSetSizeType>(n, r0 + batch);
-            reads.concat(r0, r1, bases, quals, off, disc);
-            KMN_CHECK(weak.ctx, kmn_count_batch(weak.ctx, (const uint8_t *)bases.data(), (const uint8_t *)quals.data(), off.data(), r1 - r0, disc.data()));
-            if (_trackSizes) { for (ReadSet::ReadSetSizeType q = r0; q < r1; ++q) { unsigned long l = reads.getRead(q).getLength(); if (l >= _k()) _rawSubmitted += l - _k() + 1; } trackSpectrum(false); }
+        for (int attempt = 0;; ++attempt) {
+            for (unsigned long b = 0; b < nBatches; ++b) {
+                const ReadSet::ReadSetSizeType r0 = std::min<ReadSet::ReadSetSizeType>(n, b * batch), r1 = std::min<ReadSet::ReadSetSizeType>(n, r0 + batch);
+                reads.concat(r0, r1, bases, quals, off, disc);
+                KMN_CHECK(weak.ctx, kmn_count_batch(weak.ctx, (const uint8_t *)bases.data(), (const uint8_t *)quals.data(), off.data(), r1 - r0, disc.data()));
+                if (_trackSizes) { for (ReadSet::ReadSetSizeType q = r0; q < r1; ++q) { unsigned long l = reads.getRead(q).getLength(); if (l >= _k()) _rawSubmitted += l - _k() + 1; } trackSpectrum(false); }
+            }
+            if (!finish) { _openBuilds++; return; }
+            // The reference's buckets grow as they fill (KmerMapByKmerArrayPair::insert, src/Kmer.h:3095-3110); the table here has a
+            // fixed capacity sized from --estimated-depth / --estimated-error-rate.  When that guess was too small (low coverage:
+            // nearly every k-mer distinct) the build is repeated into a table four times as large -- the reads are still in
+            // memory -- up to the provable bound of one slot pair per k-mer instance.  All ranks decide together.
+            const int rc = kmn_count_finish(weak.ctx, 0);
+            unsigned long full = rc == KMN_ERR_TABLE_FULL ? 1 : 0;
+            if (_world && _world->size() > 1) full = _world->allMax(full);
+            if (!full) { if (rc != 0) LOG_THROW("kmn_count_finish failed (" << rc << "): " << kmn_last_error(weak.ctx)); return; }
+            const uint64_t bound = 2 * (uint64_t)_rawKmers + 8192;
+            if (_openBuilds > 0 || attempt >= 6 || _opts.table_slots >= bound)
+                LOG_THROW("count table overflow (" << _opts.table_slots << " slots): " << kmn_last_error(weak.ctx));
+            LOG_VERBOSE(1, "count table of " << _opts.table_slots << " slots overflowed; rebuilding with " << std::min<uint64_t>(bound, _opts.table_slots * 4));
+            _opts.table_slots = std::min<uint64_t>(bound, _opts.table_slots * 4);
+            reset();
+            _create();
+            _joinWorld();
+            _rawSubmitted = 0;
+            _sizeTracker = SizeTracker();
         }
-        if (finish) finishBuild();
     }
-    void finishBuild() { KMN_CHECK(weak.ctx, kmn_count_finish(weak.ctx, 0)); }
+    void finishBuild() { KMN_CHECK(weak.ctx, kmn_count_finish(weak.ctx, 0)); _openBuilds = 0; }
     // build + post-build purge (+ --save-kmer-mmap) (src/KmerSpectrum.h:1818-1831); more than one part is never needed in HBM
     void buildKmerSpectrumInParts(const ReadSet &reads, unsigned int /*numParts*/, const std::string &mmapPrefix = "")
     {
@@ -394,6 +409,25 @@ private:
         }
     }
     static unsigned long _k() { return KmerBaseOptions::getOptions().getKmerSize(); }
+    void _create()
+    {
+        kmn_ctx *c = NULL;
+        int rc = kmn_create(&c, &_opts);
+        if (rc != 0) LOG_THROW("kmn_create failed (" << rc << "): " << kmn_last_error(NULL));
+        weak.ctx = c;
+    }
+    void _joinWorld()
+    {
+        if (!weak.ctx || !_world || _world->size() == 1) return;
+        std::string id(128, '\0');
+        if (_world->rank() == 0 && kmn_comm_unique_id(&id[0]) != 0) LOG_THROW("kmn_comm_unique_id failed");
+        id = _world->broadcast(id);
+        if (id.size() != 128) LOG_THROW("bad communicator id from rank 0");
+        KMN_CHECK(weak.ctx, kmn_comm_init(weak.ctx, _world->rank(), _world->size(), id.data()));
+    }
+    kmn_opts _opts;
+    World *_world = NULL;
+    int _openBuilds = 0;                 // buildKmerSpectrum(reads, finish = false) calls since the last finishBuild
     unsigned long _rawKmers, _rawSubmitted = 0;
     SizeTracker _sizeTracker;
     bool _trackSizes = false;

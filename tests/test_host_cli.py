@@ -452,3 +452,18 @@ def test_byte_range_slicing_tiles_the_file(filter_reads, tmp_path, paired):
         res = _run_ranks(filter_reads + "-P", args + ["--out", out, "0", str(fq)], world, str(tmp_path), str(tmp_path / ("comm%d" % world)))
         assert all(rc == 0 for rc, _ in res), res
         assert open(out + "-in.fastq").read() == want, world
+
+
+@pytest.mark.gpu
+def test_table_overflow_rebuilds_into_a_larger_table(filter_reads, golden_dir, tmp_path):
+    """the reference's buckets grow as they fill (src/Kmer.h:3095-3110); here a table sized from a hopeless
+    --estimated-depth guess overflows, and the adaptor repeats the build into tables four times as large until the
+    spectrum fits: same golden output as with the default sizing, and the log says what happened"""
+    out = str(tmp_path / "out")
+    args = ["--estimated-depth", "1000000", "--estimated-error-rate", "0", "--fastq-output-base-quality", "64", "--min-read-length", "25",
+            "--kmer-scoring-type", "MEDIAN", "--mask-simple-repeats", "0", "--artifact-edit-distance", "1", "--out", out, "31", "1000.fastq"]
+    p = _run(filter_reads, args, cwd=golden_dir)
+    assert p.returncode == 0, p.stderr
+    assert "overflowed; rebuilding" in p.stderr
+    got = open("%s-MinDepth2-1000.fastq" % out).read().split()
+    assert got == open(os.path.join(golden_dir, "1000-Filtered.fastq")).read().split()
