@@ -2484,7 +2484,9 @@ __global__ void __launch_bounds__(256) k_debug_owner(const uint8_t *keys, u64 n,
         for (int q = 0; q < W; ++q) key[q] = 0;
         for (u32 b = 0; b < kb; ++b) key[b >> 3] |= (u64)keys[i * kb + b] << (56 - 8 * (b & 7));
         const u64 h = use_lookup8 ? hash_lookup8<W>(key, (int)kb) : hash_lookup3<W>(key, (int)kb);
-        owner[i] = owner_of(h, nranks);
+        // the function phase 1b bins by (division-free); the lookup kernels use the plain remainder -- they must agree
+        const u32 fast = nranks > 1 ? owner_of_fast(h, nranks, 0xFFFFFFFFu / nranks + 1u) : 0u;
+        owner[i] = fast == owner_of(h, nranks) ? fast : 0xFFFFFFFFu;
     }
 }
 

@@ -371,11 +371,11 @@ def test_owner_rule_on_device(K, k):
     bases, q, off = synth.reads_numpy(400, 150, 20000, seed=31)
     keys = oracle_table(bases, q, off, k).export()["keys"]
     ctx = K.Context(kmer_size=k, table_slots=4096)
-    for nranks in (1, 2, 3, 4, 5, 8, 16):
+    for nranks in (1, 2, 3, 4, 5, 6, 7, 8, 12, 16, 100, 1000):       # (kmn_debug_owner answers 0xffffffff when its two evaluations differ)
         got = ctx.debug_owner(keys, nranks)
         want = np.array([oracle.owner(oracle.kmer_hash(x.tobytes()), nranks) for x in keys], dtype=np.uint32)
         assert (got == want).all(), nranks
-        assert nranks == 1 or len(np.unique(got)) == nranks
+        assert nranks == 1 or nranks > 16 or len(np.unique(got)) == nranks
     ctx.close()
     ctx8 = K.Context(kmer_size=k, table_slots=4096, hash_kind=K.capi.KMN_HASH_LOOKUP8)
     got = ctx8.debug_owner(keys[:500], 8)
