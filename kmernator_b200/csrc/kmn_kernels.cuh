@@ -2507,6 +2507,20 @@ __global__ void __launch_bounds__(256) k_lookup_keys(TableView t, const uint8_t 
 
 // kmn_lookup with a communicator: a key owned by this rank is answered locally, any other key becomes a request in its
 // owner's send region (same protocol as k_lookup_vals_dist: key words out, u16 counts back in request order)
+// position of a lookup request in the region of its owner: the lanes of a warp that ask the same owner take their
+// positions with ONE atomic (every k-mer of a batch used to add 1 to one of R counters: R addresses serialise in L2 at
+// ~2 G atomics/s, which was the whole cost of the multi-GPU lookup pass)
+__device__ __forceinline__ u64 request_slot(u64 *cursor, u32 own)
+{
+    const u32 act = __activemask();
+    const u32 grp = __match_any_sync(act, own);
+    const u32 lane = threadIdx.x & 31u, leader = (u32)__ffs((int)grp) - 1u;
+    u64 base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[own], (u64)__popc(grp));
+    base = __shfl_sync(grp, base, (int)leader);
+    return base + (u64)__popc(grp & ((1u << lane) - 1u));
+}
+
 template <int W>
 __global__ void __launch_bounds__(256) k_lookup_keys_dist(ParseArgs a, const uint8_t *keys, u64 n, uint16_t *out, u64 *origin)
 {
@@ -2521,7 +2535,7 @@ __global__ void __launch_bounds__(256) k_lookup_keys_dist(ParseArgs a, const uin
             const u64 ph = place_hash<W>(key);
             out[i] = (uint16_t)clamp_count(table_find<W>(a.table, part_of(ph, a.table.n_parts), home_slot(ph, a.table.part_slots), key, nullptr));
         } else {
-            const u64 pos = atomicAdd(&a.send_cursor[own], 1ull);
+            const u64 pos = request_slot(a.send_cursor, own);
             if (pos < a.send_cap) {
                 u64 *d = a.send_recs + ((size_t)own * a.send_cap + pos) * W;
 #pragma unroll
@@ -2645,7 +2659,7 @@ __global__ void __launch_bounds__(256) k_lookup_vals_dist(ParseArgs a, u32 min_d
                     u32 c = clamp_count(v);
                     vals[o0 + i] = (uint16_t)(c >= min_depth ? c : 0u);
                 } else {
-                    const u64 pos = atomicAdd(&a.send_cursor[own], 1ull);
+                    const u64 pos = request_slot(a.send_cursor, own);
                     if (pos < a.send_cap) {
                         u64 *d = a.send_recs + ((size_t)own * a.send_cap + pos) * W;
 #pragma unroll
