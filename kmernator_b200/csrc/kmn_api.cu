@@ -309,8 +309,11 @@ static int alloc_stage_sets(kmn_ctx *c)
         if (const char *e = getenv("KMN_SPLIT_CTAS")) c->split_ctas = std::max(1, atoi(e));
         if (c->split_tpb * c->split_ctas > 2048) c->split_ctas = 2048 / c->split_tpb;
         c->split_tpb = SPLIT_TPB; c->split_ctas = 1;
-        const size_t in_bytes = 2 * (size_t)SPLIT_CHUNK * 8;              // two input buffers of one round each
-        const size_t budget = (size_t)dev_smem - 2048;
+        if (const char *e = getenv("KMN_SPLIT_TPB")) { if (atoi(e) == SPLIT_TPB2) { c->split_tpb = SPLIT_TPB2; c->split_ctas = 2; } }
+        const size_t in_bytes = 2 * (size_t)c->split_tpb * SPLIT_RPT * 8;  // two input buffers of one round each
+        int sm_smem2 = 0;
+        CK(c, cudaDeviceGetAttribute(&sm_smem2, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
+        const size_t budget = std::min<size_t>((size_t)dev_smem, ((size_t)sm_smem2 - 1024u * (size_t)c->split_ctas) / (size_t)c->split_ctas) - 2048;
         uint32_t R = 32;
         while (R >= 4 && in_bytes + 2 * n_pad * 4 + nb * R * 8 > budget) R >>= 1;
         if (R < 4) c->smem_count = false;
@@ -333,11 +336,13 @@ static int alloc_stage_sets(kmn_ctx *c)
         if (c->smem_count) {
             CK(c, cudaMalloc((void **)&c->cnt2, n_sub2 * 4));
             if (!c->tickets) CK(c, cudaMalloc((void **)&c->tickets, 64));
-            CK(c, cudaFuncSetAttribute(k_slice_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
+            CK(c, cudaFuncSetAttribute(k_slice_split<SPLIT_TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
+            CK(c, cudaFuncSetAttribute(k_slice_split<SPLIT_TPB2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
             CK(c, cudaFuncSetAttribute(k_count_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16)));
             CK(c, cudaFuncSetAttribute(k_count_slices_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNT_NBUF * COUNT_CHUNK * 8)));
-            CK(c, cudaFuncSetAttribute(k_count_slices_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8)));
-            CK(c, cudaFuncSetAttribute(k_count_slices_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8)));
+            CK(c, cudaFuncSetAttribute(k_count_slices_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8)));
+            CK(c, cudaFuncSetAttribute(k_count_slices_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8)));
+            CK(c, cudaFuncSetAttribute(k_count_slices_ws<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8)));
             if (const char *e = getenv("KMN_COUNT_TMA")) c->count_tma = atoi(e) != 0;
             if (const char *e = getenv("KMN_COUNT_WS")) c->count_ws = atoi(e);
             if (const char *e = getenv("KMN_COUNT_DB")) c->count_db = atoi(e);
@@ -631,17 +636,20 @@ static int launch_insert(kmn_ctx *c, const StageView &v, int rb, uint64_t units,
             CK(c, cudaMemsetAsync(c->tickets, 0, 8, si));
             {
                 ProfScope ps(c, KMN_PROF_SUBPART, g0 == 0 ? units : 0, si);
-                k_slice_split<<<c->n_sms * c->split_ctas, c->split_tpb, c->split_smem, si>>>(sa);
+                if (c->split_tpb == SPLIT_TPB2) k_slice_split<SPLIT_TPB2><<<c->n_sms * c->split_ctas, SPLIT_TPB2, c->split_smem, si>>>(sa);
+                else k_slice_split<SPLIT_TPB><<<c->n_sms * c->split_ctas, SPLIT_TPB, c->split_smem, si>>>(sa);
             }
             {
                 ProfScope ps(c, KMN_PROF_INSERT, g0 == 0 ? units : 0, si);
                 const size_t sm_w = c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8;
                 if (c->count_tma && c->count_db)
                     k_count_slices_db<<<c->n_sms, COUNTD_TPB, c->table.part_slots * 32 + (size_t)COUNTD_NBUF * COUNTD_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
+                else if (c->count_tma && c->count_ws == 3)
+                    k_count_slices_ws<2><<<c->n_sms * 2, COUNTW_TPB, sm_w, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
                 else if (c->count_tma && c->count_ws == 2)
-                    k_count_slices_ws<false><<<c->n_sms * 2, COUNTW_TPB, sm_w, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
+                    k_count_slices_ws<0><<<c->n_sms * 2, COUNTW_TPB, sm_w, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
                 else if (c->count_tma && c->count_ws)
-                    k_count_slices_ws<true><<<c->n_sms * 2, COUNTW_TPB, sm_w, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
+                    k_count_slices_ws<1><<<c->n_sms * 2, COUNTW_TPB, sm_w, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
                 else if (c->count_tma)
                     k_count_slices_tma<<<c->n_sms * 2, COUNT3_TPB, c->table.part_slots * 16 + COUNT_NBUF * COUNT_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
                 else

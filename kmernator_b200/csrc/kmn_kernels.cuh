@@ -1498,14 +1498,16 @@ struct SplitArgs {
 };
 
 static constexpr int SPLIT_RPT = 4;        // records per thread and round
-static constexpr int SPLIT_TPB = 1024;
-static constexpr int SPLIT_CHUNK = SPLIT_TPB * SPLIT_RPT;              // records per round = per bulk copy (32 KB)
+static constexpr int SPLIT_TPB = 1024;   // one CTA of 1024 threads per SM, or (SPLIT_TPB2) two CTAs of 512: while one waits at its
+static constexpr int SPLIT_TPB2 = 512;   // round barriers the other bins
 
 // The records of the item's entries come into shared memory as bulk copies of one round each (two buffers, the copy of
 // the next round runs while this round is binned); threads take their records from there, so the kernel waits for memory
 // only at the start of an item.
-__global__ void __launch_bounds__(SPLIT_TPB, 1) k_slice_split(SplitArgs a)
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 2048 / TPB / 2) k_slice_split(SplitArgs a)
 {
+    constexpr int SPLIT_CHUNK = TPB * SPLIT_RPT;                       // records per round = per bulk copy
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ u32 s_item;
     __shared__ __align__(8) u64 bar_full[2];
@@ -1523,14 +1525,14 @@ __global__ void __launch_bounds__(SPLIT_TPB, 1) k_slice_split(SplitArgs a)
     u32 ph0 = 0, ph1 = 0, q = 0;                                       // chunks are numbered through all items (buffer = number & 1)
     while (true) {
         if (threadIdx.x == 0) s_item = atomicAdd(a.ticket, 1u);
-        for (u32 i = threadIdx.x; i < nb; i += SPLIT_TPB) { cnt[i] = 0; fl[i] = 0; }
+        for (u32 i = threadIdx.x; i < nb; i += TPB) { cnt[i] = 0; fl[i] = 0; }
         __syncthreads();
         const u32 item = s_item;
         if (item >= n_items) break;
         const u32 g = a.g0 + item / a.S, part = item % a.S;
         u64 *const obase = a.buf + (size_t)item * nb * cap2;
         auto flush = [&](bool all) {
-            for (u32 b = threadIdx.x; b < nb; b += SPLIT_TPB) {
+            for (u32 b = threadIdx.x; b < nb; b += TPB) {
                 u32 c = cnt[b];
                 if (c > cap2) c = cap2;
                 const u32 f = fl[b];
@@ -1594,12 +1596,12 @@ __global__ void __launch_bounds__(SPLIT_TPB, 1) k_slice_split(SplitArgs a)
             u64 rec[SPLIT_RPT];
 #pragma unroll
             for (int u = 0; u < SPLIT_RPT; ++u) {
-                const u32 idx = (u32)u * SPLIT_TPB + threadIdx.x;
+                const u32 idx = (u32)u * TPB + threadIdx.x;
                 rec[u] = idx < n ? in[idx] : 0ull;
             }
 #pragma unroll
             for (int u = 0; u < SPLIT_RPT; ++u) {
-                const u32 idx = (u32)u * SPLIT_TPB + threadIdx.x;
+                const u32 idx = (u32)u * TPB + threadIdx.x;
                 if (idx >= n) continue;
                 const u64 ph = mix64(rec[u] & ~1ull);
                 const u32 b = part_of(ph, a.table.n_parts) & (nb - 1u);
@@ -1622,7 +1624,7 @@ __global__ void __launch_bounds__(SPLIT_TPB, 1) k_slice_split(SplitArgs a)
         }
         flush(true);
         __syncthreads();
-        for (u32 i = threadIdx.x; i < nb; i += SPLIT_TPB) a.cnt2[(size_t)item * nb + i] = min(cnt[i], cap2);
+        for (u32 i = threadIdx.x; i < nb; i += TPB) a.cnt2[(size_t)item * nb + i] = min(cnt[i], cap2);
         __syncthreads();
     }
     ctr_commit(a.ctr, lc);
@@ -1910,7 +1912,7 @@ static constexpr int COUNTW_SHARE = COUNTW_CHUNK / COUNTW_CONSUMERS;   // record
 // counts the records idx = lane, lane + 32, .. of its warp's share one after the other (fewer instructions per record
 // although the warp idles on the longest probe sequence of every batch of 32: ncu, 166 -> 204 warp instructions per 32
 // records with the ballot loop)
-template <bool BALLOT>
+template <int BALLOT>
 __global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_ws(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, Counters *ctr, u32 slice0, u32 n_sl)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1986,6 +1988,55 @@ __global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_ws(TableView t, 
                 bulk_g2s(sl, gsl, SL * 16u, &bar_slice);
                 for (u32 i = first; i < n_chunks; ++i) issue();
             }
+        } else if (BALLOT == 2) {
+            // plain consumers, two records of a lane in flight at once: their probe loads are issued back to back, and the
+            // warp leaves the loop after the longest of 64 probe sequences instead of twice the longest of 32
+            mbar_wait_a(slice_bar_a, ph_slice);
+            for (u32 c = 0; c < n_chunks; ++c) {
+                const u32 q = qn + c, cb = q % COUNTW_NBUF;
+                mbar_wait_a(full_a + cb * 8u, (q / COUNTW_NBUF) & 1u);
+                const u32 n = lds32(bufn_a + cb * 4u), lo = warp * COUNTW_SHARE, hi = min(n, lo + (u32)COUNTW_SHARE);
+                const u32 recs_a = rbuf_a + cb * (COUNTW_CHUNK * 8u);
+                for (u32 idx = lo + lane; idx < hi; idx += 64u) {
+                    bool bA = true, bB = idx + 32u < hi;
+                    const u64 recA = lds64(recs_a + idx * 8u), recB = bB ? lds64(recs_a + (idx + 32u) * 8u) : 0ull;
+                    const u64 wantA = ~(recA & ~1ull), wantB = ~(recB & ~1ull);
+                    u32 addrA = sl_addr + (((u32)(((u64)(u32)mix64(recA & ~1ull) * SL) >> 32)) & ~1u) * 16u;
+                    u32 addrB = sl_addr + (((u32)(((u64)(u32)mix64(recB & ~1ull) * SL) >> 32)) & ~1u) * 16u;
+                    u32 leftA = SL, leftB = SL;
+                    auto step = [&](u64 v, u64 k, u64 rec, u64 want, u32 &addr, u32 &left, bool &busy) {
+                        bool hit = k == want;
+                        if (!hit && k == 0ull) {
+                            u64 old;
+                            asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr + 8u), "l"(0ull), "l"(want) : "memory");
+                            if (old == 0ull) n_unique32++;
+                            hit = old == 0ull || old == want;
+                            v = 0;
+                        }
+                        if (hit) {
+                            if ((u32)v < MAX_COUNT) {
+                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+                                if (rec & 1ull) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr + 4u) : "memory");
+                            }
+                            busy = false;
+                            return;
+                        }
+                        addr += 16u;
+                        if (addr == sl_end) addr = sl_addr;
+                        if (--left == 0u) { n_full32++; busy = false; }
+                    };
+                    while (bA || bB) {
+                        u64 vA, kA, vB, kB;
+                        asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(vA), "=l"(kA) : "r"(addrA));
+                        asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(vB), "=l"(kB) : "r"(addrB));
+                        if (bA) step(vA, kA, recA, wantA, addrA, leftA, bA);
+                        if (bB) step(vB, kB, recB, wantB, addrB, leftB, bB);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(empty_a + cb * 8u);       // this warp's share of the chunk is counted
+            }
+            fence_async_smem();
         } else if (!BALLOT) {
             mbar_wait_a(slice_bar_a, ph_slice);
             for (u32 c = 0; c < n_chunks; ++c) {

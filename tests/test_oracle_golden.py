@@ -227,3 +227,21 @@ def test_oracle_counts_vs_independent_bruteforce_on_skewed_input():
             got["".join("ACGT"[int(bits[2 * j:2 * j + 2], 2)] for j in range(k))] = int(cnt)
         assert got == want
         assert max(want.values()) > 150          # the skew is real: some k-mers are two orders deeper than others
+
+
+def test_synthetic_read_generator_block_gather_equals_per_read_loop():
+    """bench/synth.reads_numpy gathers fixed-length reads in blocks; the bytes must be those of the per-read loop the
+    variable-length path still uses (the CPU sample of bench.py and the parity tests share this generator)"""
+    import numpy as np
+    from bench import synth
+    n, L, G, seed = 3000, 150, 100_000, 5
+    rng = np.random.default_rng(seed + 77)
+    g = synth.genome_codes(G, seed)
+    starts = rng.integers(0, G - L, n)
+    strand = rng.integers(0, 2, n)
+    want = np.empty(n * L, np.uint8)
+    for i in range(n):
+        seg = g[starts[i]: starts[i] + L]
+        want[i * L: (i + 1) * L] = (3 - seg)[::-1] if strand[i] else seg
+    bases, quals, off = synth.reads_numpy(n, L, G, seed=seed, err=0.0, lowq=0.0)
+    assert (bases == synth.ACGT[want]).all() and (quals == ord("I")).all() and int(off[-1]) == n * L
