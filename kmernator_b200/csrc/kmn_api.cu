@@ -81,6 +81,7 @@ struct kmn_ctx {
     uint32_t split_S = 4, split_cap2 = 0, split_R = 0, split_batches = 1, split_gpb = 0;
     int split_tpb = 1024, split_ctas = 1, count_ctas = 3;
     bool count_tma = true;            // k_count_slices_tma (bulk-copy engine) instead of k_count_slices (KMN_COUNT_TMA=0)
+    bool smem_w2 = false;             // shared-memory slices for two-word keys on one GPU (k_slice_split2 + k_count_slices_w2; KMN_SMEM_COUNT_W2=0: off)
     int count_db = 0;                 // KMN_COUNT_DB=1: k_count_slices_db (one CTA per SM, two slice buffers) instead of k_count_slices_tma
     int count_ws = 2;                 // k_count_slices_ws: 2 = producer warp + plain consumers (default), 1 = lane-persistent consumers, 0 = k_count_slices_tma
     size_t split_smem = 0;
@@ -299,6 +300,8 @@ static int alloc_stage_sets(kmn_ctx *c)
     //  memory: the two must never run at the same time, so the single-GPU pipeline is incompatible and the push path
     //  orders phase 1 behind the drains, see kmn_count_batch)
     c->smem_count = c->W == 1 && !c->hasx && ((c->nranks == 1 && !c->pipeline) || c->p2p) && c->table.part_slots * 16 <= 64 * 1024;
+    if (c->smem_w2 && c->nranks == 1 && !c->pipeline && c->table.part_slots * 24 <= 48 * 1024) c->smem_count = true;
+    const bool w2 = c->smem_count && c->W == 2;
     if (const char *e = getenv("KMN_SMEM_COUNT")) c->smem_count = c->smem_count && atoi(e) != 0;
     if (c->smem_count) {
         int dev_smem = 0;
@@ -310,15 +313,16 @@ static int alloc_stage_sets(kmn_ctx *c)
         if (c->split_tpb * c->split_ctas > 2048) c->split_ctas = 2048 / c->split_tpb;
         c->split_tpb = SPLIT_TPB; c->split_ctas = 1;
         if (const char *e = getenv("KMN_SPLIT_TPB")) { if (atoi(e) == SPLIT_TPB2) { c->split_tpb = SPLIT_TPB2; c->split_ctas = 2; } }
-        const size_t in_bytes = 2 * (size_t)c->split_tpb * SPLIT_RPT * 8;  // two input buffers of one round each
+        const size_t rec_b = w2 ? 16 : 8;
+        const size_t in_bytes = 2 * (size_t)c->split_tpb * (w2 ? SPLIT2_RPT : SPLIT_RPT) * rec_b;  // two input buffers of one round each
         int sm_smem2 = 0;
         CK(c, cudaDeviceGetAttribute(&sm_smem2, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
         const size_t budget = std::min<size_t>((size_t)dev_smem, ((size_t)sm_smem2 - 1024u * (size_t)c->split_ctas) / (size_t)c->split_ctas) - 2048;
         uint32_t R = 32;
-        while (R >= 4 && in_bytes + 2 * n_pad * 4 + nb * R * 8 > budget) R >>= 1;
+        while (R >= 4 && in_bytes + 2 * n_pad * 4 + nb * R * rec_b > budget) R >>= 1;
         if (R < 4) c->smem_count = false;
         c->split_R = R;
-        c->split_smem = in_bytes + 2 * n_pad * 4 + nb * R * 8;
+        c->split_smem = in_bytes + 2 * n_pad * 4 + nb * R * rec_b;
         // records of one drain per sub-run: stage_keys / (slices * S), plus slack for the spread (a sub-run that fills up
         // sends its records straight to the table)
         const uint64_t m2 = sk / c->table.n_parts / c->split_S + 1;
@@ -331,11 +335,15 @@ static int alloc_stage_sets(kmn_ctx *c)
         c->split_gpb = (uint32_t)((n_groups + c->split_batches - 1) / c->split_batches);
         const size_t n_sub2 = (size_t)c->split_gpb * c->split_S * nb;
         if (c->smem_count) {
-            if (cudaMalloc((void **)&c->l2buf, n_sub2 * c->split_cap2 * 8) != cudaSuccess) { cudaGetLastError(); c->l2buf = nullptr; c->smem_count = false; }
+            if (cudaMalloc((void **)&c->l2buf, n_sub2 * c->split_cap2 * rec_b) != cudaSuccess) { cudaGetLastError(); c->l2buf = nullptr; c->smem_count = false; }
         }
         if (c->smem_count) {
             CK(c, cudaMalloc((void **)&c->cnt2, n_sub2 * 4));
             if (!c->tickets) CK(c, cudaMalloc((void **)&c->tickets, 64));
+            if (w2) {
+                CK(c, cudaFuncSetAttribute(k_slice_split2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
+                CK(c, cudaFuncSetAttribute(k_count_slices_w2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((c->table.part_slots * 24 + 127) & ~(size_t)127) + COUNT2_NBUF * COUNT2_CHUNK * 16)));
+            }
             CK(c, cudaFuncSetAttribute(k_slice_split<SPLIT_TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
             CK(c, cudaFuncSetAttribute(k_slice_split<SPLIT_TPB2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
             CK(c, cudaFuncSetAttribute(k_count_slices, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16)));
@@ -391,7 +399,9 @@ static int plan_and_alloc(kmn_ctx *c)
     int dev_smem = 0;
     CK(c, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     const uint32_t gbytes = o.slice_bytes ? o.slice_bytes : (64u << 20);
-    uint64_t part_slots = std::min<uint64_t>(SLICE_SLOTS, slots) & ~1ull;   // even: W == 1 probes aligned pairs of slots
+    // (two-word keys: slices of 2048 slots = 48 KB so that a slice fits in shared memory twice per SM; KMN_SMEM_COUNT_W2=0: 4096 slots, L2-resident path)
+    c->smem_w2 = c->W == 2 && !c->hasx && !(getenv("KMN_SMEM_COUNT_W2") && atoi(getenv("KMN_SMEM_COUNT_W2")) == 0);
+    uint64_t part_slots = std::min<uint64_t>(c->smem_w2 ? SLICE_SLOTS / 2 : SLICE_SLOTS, slots) & ~1ull;   // even: W == 1 probes aligned pairs of slots
     uint64_t n_parts = (slots + part_slots - 1) / part_slots;
     if (n_parts >= (1ull << 31)) return fail(c, KMN_ERR_INVALID, "table too large (%llu slices)", (unsigned long long)n_parts);
     slots = part_slots * n_parts;
@@ -636,13 +646,16 @@ static int launch_insert(kmn_ctx *c, const StageView &v, int rb, uint64_t units,
             CK(c, cudaMemsetAsync(c->tickets, 0, 8, si));
             {
                 ProfScope ps(c, KMN_PROF_SUBPART, g0 == 0 ? units : 0, si);
-                if (c->split_tpb == SPLIT_TPB2) k_slice_split<SPLIT_TPB2><<<c->n_sms * c->split_ctas, SPLIT_TPB2, c->split_smem, si>>>(sa);
+                if (c->W == 2) k_slice_split2<<<c->n_sms, SPLIT_TPB, c->split_smem, si>>>(sa);
+                else if (c->split_tpb == SPLIT_TPB2) k_slice_split<SPLIT_TPB2><<<c->n_sms * c->split_ctas, SPLIT_TPB2, c->split_smem, si>>>(sa);
                 else k_slice_split<SPLIT_TPB><<<c->n_sms * c->split_ctas, SPLIT_TPB, c->split_smem, si>>>(sa);
             }
             {
                 ProfScope ps(c, KMN_PROF_INSERT, g0 == 0 ? units : 0, si);
                 const size_t sm_w = c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8;
-                if (c->count_tma && c->count_db)
+                if (c->W == 2)
+                    k_count_slices_w2<<<c->n_sms * 2, COUNTW_TPB, ((c->table.part_slots * 24 + 127) & ~(size_t)127) + COUNT2_NBUF * COUNT2_CHUNK * 16, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
+                else if (c->count_tma && c->count_db)
                     k_count_slices_db<<<c->n_sms, COUNTD_TPB, c->table.part_slots * 32 + (size_t)COUNTD_NBUF * COUNTD_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
                 else if (c->count_tma && c->count_ws == 3)
                     k_count_slices_ws<2><<<c->n_sms * 2, COUNTW_TPB, sm_w, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);

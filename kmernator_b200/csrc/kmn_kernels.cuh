@@ -1630,6 +1630,127 @@ __global__ void __launch_bounds__(TPB, 2048 / TPB / 2) k_slice_split(SplitArgs a
     ctr_commit(a.ctr, lc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_slice_split2: the same second radix pass for two-word keys (33 <= k <= 63: records of two words, the strand flag in
+// bit 0 of the second); counted by k_count_slices_w2.  One GPU (KMN_SMEM_COUNT_W2=0 turns both off).
+// ------------------------------------------------------------------------------------------------
+static constexpr int SPLIT2_RPT = 2;       // records per thread and round: 2048 records = 32 KB per bulk copy
+__global__ void __launch_bounds__(SPLIT_TPB, 1) k_slice_split2(SplitArgs a)
+{
+    constexpr int TPB = SPLIT_TPB, CHUNK = TPB * SPLIT2_RPT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ u32 s_item;
+    __shared__ __align__(8) u64 bar_full[2];
+    const u32 nb = 1u << a.table.group_shift;
+    const u32 n_pad = (nb + 31u) & ~31u;
+    u64 *inbuf = reinterpret_cast<u64 *>(smem_raw);                    // [2][CHUNK][2] input records
+    u32 *cnt = reinterpret_cast<u32 *>(inbuf + 2 * CHUNK * 2);
+    u32 *fl = cnt + n_pad;
+    u64 *ring = reinterpret_cast<u64 *>(fl + n_pad);                   // [nb][R][2]
+    const u32 R = a.ring_R, cap2 = a.cap2;
+    const u32 n_items = a.n_groups * a.S;
+    LocalCtr lc{0, 0, 0, 0, 0, 0};
+    if (threadIdx.x == 0) { mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    u32 ph0 = 0, ph1 = 0, q = 0;
+    while (true) {
+        if (threadIdx.x == 0) s_item = atomicAdd(a.ticket, 1u);
+        for (u32 i = threadIdx.x; i < nb; i += TPB) { cnt[i] = 0; fl[i] = 0; }
+        __syncthreads();
+        const u32 item = s_item;
+        if (item >= n_items) break;
+        const u32 g = a.g0 + item / a.S, part = item % a.S;
+        u64 *const obase = a.buf + (size_t)item * nb * cap2 * 2;
+        auto flush = [&](bool all) {
+            for (u32 b = threadIdx.x; b < nb; b += TPB) {
+                u32 c = cnt[b];
+                if (c > cap2) c = cap2;
+                const u32 f = fl[b];
+                if (c <= f) continue;
+                u32 end, nfl;
+                if (c - f > R) { end = f + R; nfl = c; }
+                else { end = all ? c : (c & ~1u); nfl = end; }         // whole sectors = pairs of records
+                if (end <= f) continue;
+                u64 *gdst = obase + (size_t)b * cap2 * 2;
+                const u64 *rb = ring + (size_t)b * R * 2;
+                u32 pos = f;
+                for (; pos < end && (pos & 1u); ++pos) { gdst[(size_t)pos * 2] = rb[(size_t)(pos & (R - 1u)) * 2]; gdst[(size_t)pos * 2 + 1] = rb[(size_t)(pos & (R - 1u)) * 2 + 1]; }
+                for (; pos + 2u <= end; pos += 2u) st_sector(gdst + (size_t)pos * 2, rb + (size_t)(pos & (R - 1u)) * 2);
+                for (; pos < end; ++pos) { gdst[(size_t)pos * 2] = rb[(size_t)(pos & (R - 1u)) * 2]; gdst[(size_t)pos * 2 + 1] = rb[(size_t)(pos & (R - 1u)) * 2 + 1]; }
+                fl[b] = nfl;
+            }
+        };
+        const u32 e1 = min(g * a.per_group + (part + 1u) * a.epp, (g + 1u) * a.per_group);
+        const u32 e0 = g * a.per_group + part * a.epp;
+        u32 ce = e0, co = 0, cn = e0 < e1 ? __ldg(&a.ent_cnt[e0]) : 0u, cnn = e0 + 1u < e1 ? __ldg(&a.ent_cnt[e0 + 1u]) : 0u;
+        u32 pe = e0, po = 0, pn = cn, pnn = cnn;
+        auto skip = [&](u32 &e, u32 &o, u32 &n, u32 &nn) {
+            while (e < e1) {
+                if (o < n) return;
+                ++e; o = 0; n = nn;
+                nn = e + 1u < e1 ? __ldg(&a.ent_cnt[e + 1u]) : 0u;
+            }
+            n = 0;
+        };
+        u64 pptr = 0, pptr_n = 0;
+        if (threadIdx.x == 0) {
+            pptr = e0 < e1 ? __ldg(&a.ent_ptr[e0]) : 0ull;
+            pptr_n = e0 + 1u < e1 ? __ldg(&a.ent_ptr[e0 + 1u]) : 0ull;
+        }
+        auto produce = [&](u32 qq) {
+            while (pe < e1 && po >= pn) {
+                ++pe; po = 0; pn = pnn; pptr = pptr_n;
+                if (pe + 1u < e1) { pnn = __ldg(&a.ent_cnt[pe + 1u]); pptr_n = __ldg(&a.ent_ptr[pe + 1u]); } else { pnn = 0; pptr_n = 0; }
+            }
+            if (pe >= e1) return false;
+            const u32 n = min((u32)CHUNK, pn - po);
+            const u32 bytes = n * 16u;                                 // (records of 16 bytes: always a multiple of 16)
+            const u64 *src = reinterpret_cast<const u64 *>(pptr) + (size_t)po * 2;
+            mbar_expect_tx(&bar_full[qq & 1u], bytes);
+            bulk_g2s(inbuf + (size_t)(qq & 1u) * CHUNK * 2, src, bytes, &bar_full[qq & 1u]);
+            po += n;
+            return true;
+        };
+        u32 q_issue = q;
+        if (threadIdx.x == 0) { if (produce(q_issue)) ++q_issue; if (produce(q_issue)) ++q_issue; }
+        skip(ce, co, cn, cnn);
+        while (ce < e1) {
+            const u32 n = min((u32)CHUNK, cn - co);
+            if (q & 1u) { mbar_wait(&bar_full[1], ph1); ph1 ^= 1u; } else { mbar_wait(&bar_full[0], ph0); ph0 ^= 1u; }
+            const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(inbuf + (size_t)(q & 1u) * CHUNK * 2);
+#pragma unroll
+            for (int u = 0; u < SPLIT2_RPT; ++u) {
+                const u32 idx = (u32)u * TPB + threadIdx.x;
+                if (idx >= n) continue;
+                const ulonglong2 rec = in[idx];
+                u64 key[2] = {rec.x, rec.y & ~1ull};
+                const u64 ph = place_hash<2>(key);
+                const u32 b = part_of(ph, a.table.n_parts) & (nb - 1u);
+                const u32 p = atomicAdd(&cnt[b], 1u);
+                if (p < cap2) {
+                    u64 *d = (p - fl[b] < R) ? ring + ((size_t)b * R + (p & (R - 1u))) * 2 : obase + ((size_t)b * cap2 + p) * 2;
+                    d[0] = rec.x; d[1] = rec.y;
+                } else {                                               // sub-run full (skewed input): straight into the table
+                    Rec<2, false> r; r.w[0] = rec.x; r.w[1] = rec.y;
+                    insert_record<2, false>(a.table, r, lc.unique, lc.full, lc.probes);
+                    lc.direct++;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0 && produce(q_issue)) ++q_issue;
+            flush(false);
+            __syncthreads();
+            co += n; ++q;
+            skip(ce, co, cn, cnn);
+        }
+        flush(true);
+        __syncthreads();
+        for (u32 i = threadIdx.x; i < nb; i += TPB) a.cnt2[(size_t)item * nb + i] = min(cnt[i], cap2);
+        __syncthreads();
+    }
+    ctr_commit(a.ctr, lc);
+}
+
 static constexpr int COUNT_TPB = 256;
 static constexpr int COUNT_U = 4;          // records per thread and batch
 static constexpr int COUNT_MAX_S = 8;      // sub-runs per slice (SplitArgs::S)
@@ -2155,6 +2276,154 @@ __global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_ws(TableView t, 
     __syncthreads();
     if (producer && lane == 0) {
         if (prev_gsl) bulk_s2g(prev_gsl, sl, SL * 16u);
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    n_unique = n_unique32; n_full = n_full32;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_unique) atomicAdd(&ctr->unique, n_unique);
+        if (n_full) atomicAdd(&ctr->table_full, n_full);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_count_slices_w2: k_count_slices_ws<0> for two-word keys.  Slot = {val, key[2]} = 24 bytes, so a slice of the (smaller,
+// 2048-slot) W = 2 table is 48 KB; records are 16 bytes.  A new key is published as in the global table: CAS val 0 ->
+// LOCK, write the key words, exchange val -> READY | first count; a reader that finds LOCK waits for READY.
+// ------------------------------------------------------------------------------------------------
+static constexpr int COUNT2_CHUNK = 1024, COUNT2_NBUF = 3;             // 16 KB per chunk
+static constexpr int COUNT2_SHARE = COUNT2_CHUNK / COUNTW_CONSUMERS;
+
+__global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_w2(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, Counters *ctr, u32 slice0, u32 n_sl)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const u32 SL = (u32)t.part_slots;
+    const u32 sl_bytes = SL * 24u;
+    u64 *rbuf = reinterpret_cast<u64 *>(smem_raw + (size_t)((sl_bytes + 127u) & ~127u));
+    __shared__ __align__(8) u64 bar_slice, bar_full[COUNT2_NBUF], bar_empty[COUNT2_NBUF];
+    __shared__ u32 s_pre[2][32];
+    __shared__ u32 buf_n[COUNT2_NBUF];
+    const u32 nb = 1u << t.group_shift;
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const bool producer = warp == COUNTW_CONSUMERS;
+    u64 n_unique = 0, n_full = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_slice, 1);
+        for (int b = 0; b < COUNT2_NBUF; ++b) { mbar_init(&bar_full[b], 1); mbar_init(&bar_empty[b], COUNTW_CONSUMERS); }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    auto load_pre = [&](u32 pi, u32 *dst) {                            // warp 0
+        u32 c = (lane < S && pi < n_sl) ? cnt2[((size_t)(pi >> t.group_shift) * S + lane) * nb + (pi & (nb - 1u))] : 0u;
+        u32 v = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(0xffffffffu, v, d); if ((int)lane >= d) v += x; }
+        if (lane < COUNT_MAX_S + 1u) dst[lane] = v - c;
+    };
+    if (warp == 0) load_pre(blockIdx.x, s_pre[0]);
+    u32 it = 0, ph_slice = 0, qn = 0;
+    auto opaque = [](u32 x) { u32 y; asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x)); return y; };
+    const u32 sl_addr = opaque(smem_u32(smem_raw)), sl_end = opaque(sl_addr + sl_bytes);
+    const u32 rbuf_a = opaque(smem_u32(rbuf)), full_a = opaque(smem_u32(&bar_full[0])), empty_a = opaque(smem_u32(&bar_empty[0])),
+              bufn_a = opaque(smem_u32(&buf_n[0])), slice_bar_a = opaque(smem_u32(&bar_slice));
+    u32 n_unique32 = 0, n_full32 = 0;
+    unsigned char *prev_gsl = nullptr;
+    for (u32 pi = blockIdx.x; pi < n_sl; pi += gridDim.x, ++it) {
+        __syncthreads();
+        if (warp == 0) load_pre(pi + gridDim.x, s_pre[(it + 1u) & 1u]);
+        const u32 *pre = s_pre[it & 1u];
+        const u32 total = pre[S];
+        if (total == 0) continue;
+        u32 n_chunks = 0;
+        for (u32 p = 0; p < S; ++p) n_chunks += (pre[p + 1] - pre[p] + COUNT2_CHUNK - 1u) / COUNT2_CHUNK;
+        unsigned char *gsl = reinterpret_cast<unsigned char *>(t.slots) + (size_t)(slice0 + pi) * sl_bytes;
+        if (producer) {
+            if (lane == 0) {
+                const u32 g = pi >> t.group_shift, j = pi & (nb - 1u);
+                const u64 *run0 = buf + (((size_t)g * S) * nb + j) * cap2 * 2;
+                const size_t run_stride = (size_t)nb * cap2 * 2;
+                if (prev_gsl) bulk_s2g(prev_gsl, smem_raw, sl_bytes);
+                prev_gsl = gsl;
+                u32 pp = 0, po = 0, q = qn;
+                auto issue = [&]() {
+                    while (pp < S && po >= pre[pp + 1] - pre[pp]) { ++pp; po = 0; }
+                    const u32 b = q % COUNT2_NBUF;
+                    if (q >= COUNT2_NBUF) mbar_wait(&bar_empty[b], ((q / COUNT2_NBUF) - 1u) & 1u);
+                    const u32 n = min((u32)COUNT2_CHUNK, pre[pp + 1] - pre[pp] - po);
+                    buf_n[b] = n;
+                    mbar_expect_tx(&bar_full[b], n * 16u);
+                    bulk_g2s(rbuf + (size_t)b * COUNT2_CHUNK * 2, run0 + (size_t)pp * run_stride + (size_t)po * 2, n * 16u, &bar_full[b]);
+                    po += n; ++q;
+                };
+                const u32 first = min(n_chunks, (u32)COUNT2_NBUF);
+                for (u32 i = 0; i < first; ++i) issue();
+                bulk_wait_read();
+                mbar_expect_tx(&bar_slice, sl_bytes);
+                bulk_g2s(smem_raw, gsl, sl_bytes, &bar_slice);
+                for (u32 i = first; i < n_chunks; ++i) issue();
+            }
+        } else {
+            mbar_wait_a(slice_bar_a, ph_slice);
+            for (u32 c = 0; c < n_chunks; ++c) {
+                const u32 q = qn + c, cb = q % COUNT2_NBUF;
+                mbar_wait_a(full_a + cb * 8u, (q / COUNT2_NBUF) & 1u);
+                const u32 n = lds32(bufn_a + cb * 4u), lo = warp * COUNT2_SHARE, hi = min(n, lo + (u32)COUNT2_SHARE);
+                const u32 recs_a = rbuf_a + cb * (COUNT2_CHUNK * 16u);
+                for (u32 idx = lo + lane; idx < hi; idx += 32u) {
+                    const u64 w0 = lds64(recs_a + idx * 16u), w1r = lds64(recs_a + idx * 16u + 8u);
+                    const u64 w1 = w1r & ~1ull;
+                    u64 key[2] = {w0, w1};
+                    const u64 ph = place_hash<2>(key);
+                    u32 addr = sl_addr + (u32)(((u64)(u32)ph * SL) >> 32) * 24u;
+                    u32 left = SL;
+                    const u64 first_val = VAL_READY | 1ull | ((w1r & 1ull) << 32);
+                    while (true) {
+                        u64 v = lds64(addr);
+                        bool mine = false;
+                        if (v == 0ull) {
+                            u64 old;
+                            asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr), "l"(0ull), "l"(VAL_LOCK) : "memory");
+                            if (old == 0ull) {
+                                asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr + 8u), "l"(w0) : "memory");
+                                asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr + 16u), "l"(w1) : "memory");
+                                __threadfence_block();
+                                asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(addr), "l"(first_val) : "memory");
+                                n_unique32++;
+                                mine = true;
+                            } else v = old;
+                        }
+                        if (mine) break;
+                        while (!(v & VAL_READY)) {                     // another thread of the CTA is publishing this slot
+                            __nanosleep(20);
+                            asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+                        }
+                        const u64 k0 = lds64(addr + 8u), k1 = lds64(addr + 16u);
+                        if (k0 == w0 && k1 == w1) {
+                            if ((u32)v < MAX_COUNT) {
+                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+                                if (w1r & 1ull) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr + 4u) : "memory");
+                            }
+                            break;
+                        }
+                        addr += 24u;
+                        if (addr == sl_end) addr = sl_addr;
+                        if (--left == 0u) { n_full32++; break; }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(empty_a + cb * 8u);
+            }
+            fence_async_smem();
+        }
+        ph_slice ^= 1u;
+        qn += n_chunks;
+    }
+    __syncthreads();
+    if (producer && lane == 0) {
+        if (prev_gsl) bulk_s2g(prev_gsl, smem_raw, sl_bytes);
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     n_unique = n_unique32; n_full = n_full32;
