@@ -81,6 +81,7 @@ struct kmn_ctx {
     uint32_t split_S = 4, split_cap2 = 0, split_R = 0, split_batches = 1, split_gpb = 0;
     int split_tpb = 1024, split_ctas = 1, count_ctas = 3;
     bool count_tma = true;            // k_count_slices_tma (bulk-copy engine) instead of k_count_slices (KMN_COUNT_TMA=0)
+    bool smem_k32 = false;            // shared-memory slices for k = 32 on one GPU (k_slice_split2<true> + k_count_slices_k32)
     bool smem_w2 = false;             // shared-memory slices for two-word keys on one GPU (k_slice_split2 + k_count_slices_w2; KMN_SMEM_COUNT_W2=0: off)
     int count_db = 0;                 // KMN_COUNT_DB=1: k_count_slices_db (one CTA per SM, two slice buffers) instead of k_count_slices_tma
     int count_ws = 2;                 // k_count_slices_ws: 2 = producer warp + plain consumers (default), 1 = lane-persistent consumers, 0 = k_count_slices_tma
@@ -301,7 +302,10 @@ static int alloc_stage_sets(kmn_ctx *c)
     //  orders phase 1 behind the drains, see kmn_count_batch)
     c->smem_count = c->W == 1 && !c->hasx && ((c->nranks == 1 && !c->pipeline) || c->p2p) && c->table.part_slots * 16 <= 64 * 1024;
     if (c->smem_w2 && c->nranks == 1 && !c->pipeline && c->table.part_slots * 24 <= 48 * 1024) c->smem_count = true;
-    const bool w2 = c->smem_count && c->W == 2;
+    // k = 32: single-word slots, but the strand flag needs a second record word (KMN_SMEM_COUNT_K32=0: L2-resident path)
+    c->smem_k32 = c->W == 1 && c->hasx && !c->ext && !c->weights && !(getenv("KMN_SMEM_COUNT_K32") && atoi(getenv("KMN_SMEM_COUNT_K32")) == 0);
+    if (c->smem_k32 && c->nranks == 1 && !c->pipeline && c->table.part_slots * 16 <= 64 * 1024) c->smem_count = true; else c->smem_k32 = false;
+    const bool w2 = c->smem_count && (c->W == 2 || c->smem_k32);       // 16-byte records
     if (const char *e = getenv("KMN_SMEM_COUNT")) c->smem_count = c->smem_count && atoi(e) != 0;
     if (c->smem_count) {
         int dev_smem = 0;
@@ -341,7 +345,9 @@ static int alloc_stage_sets(kmn_ctx *c)
             CK(c, cudaMalloc((void **)&c->cnt2, n_sub2 * 4));
             if (!c->tickets) CK(c, cudaMalloc((void **)&c->tickets, 64));
             if (w2) {
-                CK(c, cudaFuncSetAttribute(k_slice_split2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
+                CK(c, cudaFuncSetAttribute(k_slice_split2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
+                CK(c, cudaFuncSetAttribute(k_slice_split2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
+                CK(c, cudaFuncSetAttribute(k_count_slices_k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(c->table.part_slots * 16 + COUNT32_NBUF * COUNT2_CHUNK * 16)));
                 CK(c, cudaFuncSetAttribute(k_count_slices_w2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((c->table.part_slots * 24 + 127) & ~(size_t)127) + COUNT2_NBUF * COUNT2_CHUNK * 16)));
             }
             CK(c, cudaFuncSetAttribute(k_slice_split<SPLIT_TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->split_smem));
@@ -646,14 +652,17 @@ static int launch_insert(kmn_ctx *c, const StageView &v, int rb, uint64_t units,
             CK(c, cudaMemsetAsync(c->tickets, 0, 8, si));
             {
                 ProfScope ps(c, KMN_PROF_SUBPART, g0 == 0 ? units : 0, si);
-                if (c->W == 2) k_slice_split2<<<c->n_sms, SPLIT_TPB, c->split_smem, si>>>(sa);
+                if (c->W == 2) k_slice_split2<false><<<c->n_sms, SPLIT_TPB, c->split_smem, si>>>(sa);
+                else if (c->smem_k32) k_slice_split2<true><<<c->n_sms, SPLIT_TPB, c->split_smem, si>>>(sa);
                 else if (c->split_tpb == SPLIT_TPB2) k_slice_split<SPLIT_TPB2><<<c->n_sms * c->split_ctas, SPLIT_TPB2, c->split_smem, si>>>(sa);
                 else k_slice_split<SPLIT_TPB><<<c->n_sms * c->split_ctas, SPLIT_TPB, c->split_smem, si>>>(sa);
             }
             {
                 ProfScope ps(c, KMN_PROF_INSERT, g0 == 0 ? units : 0, si);
                 const size_t sm_w = c->table.part_slots * 16 + COUNTW_NBUF * COUNTW_CHUNK * 8;
-                if (c->W == 2)
+                if (c->smem_k32)
+                    k_count_slices_k32<<<c->n_sms * 2, COUNTW_TPB, c->table.part_slots * 16 + COUNT32_NBUF * COUNT2_CHUNK * 16, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
+                else if (c->W == 2)
                     k_count_slices_w2<<<c->n_sms * 2, COUNTW_TPB, ((c->table.part_slots * 24 + 127) & ~(size_t)127) + COUNT2_NBUF * COUNT2_CHUNK * 16, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);
                 else if (c->count_tma && c->count_db)
                     k_count_slices_db<<<c->n_sms, COUNTD_TPB, c->table.part_slots * 32 + (size_t)COUNTD_NBUF * COUNTD_CHUNK * 8, si>>>(c->table, c->l2buf, c->cnt2, sa.S, sa.cap2, c->ctr, slice0, n_sl);

@@ -1635,6 +1635,8 @@ __global__ void __launch_bounds__(TPB, 2048 / TPB / 2) k_slice_split(SplitArgs a
 // bit 0 of the second); counted by k_count_slices_w2.  One GPU (KMN_SMEM_COUNT_W2=0 turns both off).
 // ------------------------------------------------------------------------------------------------
 static constexpr int SPLIT2_RPT = 2;       // records per thread and round: 2048 records = 32 KB per bulk copy
+// K32: k = 32 -- one key word that leaves no room for the strand flag, which travels in a second record word
+template <bool K32>
 __global__ void __launch_bounds__(SPLIT_TPB, 1) k_slice_split2(SplitArgs a)
 {
     constexpr int TPB = SPLIT_TPB, CHUNK = TPB * SPLIT2_RPT;
@@ -1724,15 +1726,15 @@ __global__ void __launch_bounds__(SPLIT_TPB, 1) k_slice_split2(SplitArgs a)
                 if (idx >= n) continue;
                 const ulonglong2 rec = in[idx];
                 u64 key[2] = {rec.x, rec.y & ~1ull};
-                const u64 ph = place_hash<2>(key);
+                const u64 ph = K32 ? mix64(rec.x) : place_hash<2>(key);
                 const u32 b = part_of(ph, a.table.n_parts) & (nb - 1u);
                 const u32 p = atomicAdd(&cnt[b], 1u);
                 if (p < cap2) {
                     u64 *d = (p - fl[b] < R) ? ring + ((size_t)b * R + (p & (R - 1u))) * 2 : obase + ((size_t)b * cap2 + p) * 2;
                     d[0] = rec.x; d[1] = rec.y;
                 } else {                                               // sub-run full (skewed input): straight into the table
-                    Rec<2, false> r; r.w[0] = rec.x; r.w[1] = rec.y;
-                    insert_record<2, false>(a.table, r, lc.unique, lc.full, lc.probes);
+                    if (K32) { Rec<1, true> r; r.w[0] = rec.x; r.w[1] = rec.y; insert_record<1, true>(a.table, r, lc.unique, lc.full, lc.probes); }
+                    else { Rec<2, false> r; r.w[0] = rec.x; r.w[1] = rec.y; insert_record<2, false>(a.table, r, lc.unique, lc.full, lc.probes); }
                     lc.direct++;
                 }
             }
@@ -2409,6 +2411,139 @@ __global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_w2(TableView t, 
                             break;
                         }
                         addr += 24u;
+                        if (addr == sl_end) addr = sl_addr;
+                        if (--left == 0u) { n_full32++; break; }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(empty_a + cb * 8u);
+            }
+            fence_async_smem();
+        }
+        ph_slice ^= 1u;
+        qn += n_chunks;
+    }
+    __syncthreads();
+    if (producer && lane == 0) {
+        if (prev_gsl) bulk_s2g(prev_gsl, smem_raw, sl_bytes);
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    n_unique = n_unique32; n_full = n_full32;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_unique += __shfl_xor_sync(0xffffffffu, n_unique, o);
+        n_full += __shfl_xor_sync(0xffffffffu, n_full, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_unique) atomicAdd(&ctr->unique, n_unique);
+        if (n_full) atomicAdd(&ctr->table_full, n_full);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_count_slices_k32: k_count_slices_ws<0> for k = 32 -- 16-byte slots as for k <= 31, but 16-byte records (the key fills
+// its word, the strand flag sits in bit 0 of the second word).  Two record buffers, so that two CTAs still share an SM.
+// ------------------------------------------------------------------------------------------------
+static constexpr int COUNT32_NBUF = 2;
+
+__global__ void __launch_bounds__(COUNTW_TPB, 2) k_count_slices_k32(TableView t, const u64 *buf, const u32 *cnt2, u32 S, u32 cap2, Counters *ctr, u32 slice0, u32 n_sl)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const u32 SL = (u32)t.part_slots;
+    const u32 sl_bytes = SL * 16u;
+    u64 *rbuf = reinterpret_cast<u64 *>(smem_raw + (size_t)((sl_bytes + 127u) & ~127u));
+    __shared__ __align__(8) u64 bar_slice, bar_full[COUNT32_NBUF], bar_empty[COUNT32_NBUF];
+    __shared__ u32 s_pre[2][32];
+    __shared__ u32 buf_n[COUNT32_NBUF];
+    const u32 nb = 1u << t.group_shift;
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const bool producer = warp == COUNTW_CONSUMERS;
+    u64 n_unique = 0, n_full = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_slice, 1);
+        for (int b = 0; b < COUNT32_NBUF; ++b) { mbar_init(&bar_full[b], 1); mbar_init(&bar_empty[b], COUNTW_CONSUMERS); }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    auto load_pre = [&](u32 pi, u32 *dst) {                            // warp 0
+        u32 c = (lane < S && pi < n_sl) ? cnt2[((size_t)(pi >> t.group_shift) * S + lane) * nb + (pi & (nb - 1u))] : 0u;
+        u32 v = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(0xffffffffu, v, d); if ((int)lane >= d) v += x; }
+        if (lane < COUNT_MAX_S + 1u) dst[lane] = v - c;
+    };
+    if (warp == 0) load_pre(blockIdx.x, s_pre[0]);
+    u32 it = 0, ph_slice = 0, qn = 0;
+    auto opaque = [](u32 x) { u32 y; asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x)); return y; };
+    const u32 sl_addr = opaque(smem_u32(smem_raw)), sl_end = opaque(sl_addr + sl_bytes);
+    const u32 rbuf_a = opaque(smem_u32(rbuf)), full_a = opaque(smem_u32(&bar_full[0])), empty_a = opaque(smem_u32(&bar_empty[0])),
+              bufn_a = opaque(smem_u32(&buf_n[0])), slice_bar_a = opaque(smem_u32(&bar_slice));
+    u32 n_unique32 = 0, n_full32 = 0;
+    unsigned char *prev_gsl = nullptr;
+    for (u32 pi = blockIdx.x; pi < n_sl; pi += gridDim.x, ++it) {
+        __syncthreads();
+        if (warp == 0) load_pre(pi + gridDim.x, s_pre[(it + 1u) & 1u]);
+        const u32 *pre = s_pre[it & 1u];
+        const u32 total = pre[S];
+        if (total == 0) continue;
+        u32 n_chunks = 0;
+        for (u32 p = 0; p < S; ++p) n_chunks += (pre[p + 1] - pre[p] + COUNT2_CHUNK - 1u) / COUNT2_CHUNK;
+        unsigned char *gsl = reinterpret_cast<unsigned char *>(t.slots) + (size_t)(slice0 + pi) * sl_bytes;
+        if (producer) {
+            if (lane == 0) {
+                const u32 g = pi >> t.group_shift, j = pi & (nb - 1u);
+                const u64 *run0 = buf + (((size_t)g * S) * nb + j) * cap2 * 2;
+                const size_t run_stride = (size_t)nb * cap2 * 2;
+                if (prev_gsl) bulk_s2g(prev_gsl, smem_raw, sl_bytes);
+                prev_gsl = gsl;
+                u32 pp = 0, po = 0, q = qn;
+                auto issue = [&]() {
+                    while (pp < S && po >= pre[pp + 1] - pre[pp]) { ++pp; po = 0; }
+                    const u32 b = q % COUNT32_NBUF;
+                    if (q >= COUNT32_NBUF) mbar_wait(&bar_empty[b], ((q / COUNT32_NBUF) - 1u) & 1u);
+                    const u32 n = min((u32)COUNT2_CHUNK, pre[pp + 1] - pre[pp] - po);
+                    buf_n[b] = n;
+                    mbar_expect_tx(&bar_full[b], n * 16u);
+                    bulk_g2s(rbuf + (size_t)b * COUNT2_CHUNK * 2, run0 + (size_t)pp * run_stride + (size_t)po * 2, n * 16u, &bar_full[b]);
+                    po += n; ++q;
+                };
+                const u32 first = min(n_chunks, (u32)COUNT32_NBUF);
+                for (u32 i = 0; i < first; ++i) issue();
+                bulk_wait_read();
+                mbar_expect_tx(&bar_slice, sl_bytes);
+                bulk_g2s(smem_raw, gsl, sl_bytes, &bar_slice);
+                for (u32 i = first; i < n_chunks; ++i) issue();
+            }
+        } else {
+            mbar_wait_a(slice_bar_a, ph_slice);
+            for (u32 c = 0; c < n_chunks; ++c) {
+                const u32 q = qn + c, cb = q % COUNT32_NBUF;
+                mbar_wait_a(full_a + cb * 8u, (q / COUNT32_NBUF) & 1u);
+                const u32 n = lds32(bufn_a + cb * 4u), lo = warp * COUNT2_SHARE, hi = min(n, lo + (u32)COUNT2_SHARE);
+                const u32 recs_a = rbuf_a + cb * (COUNT2_CHUNK * 16u);
+                for (u32 idx = lo + lane; idx < hi; idx += 32u) {
+                    const u64 key = lds64(recs_a + idx * 16u), fwd = lds64(recs_a + idx * 16u + 8u) & 1ull;
+                    const u64 want = ~key;
+                    u32 addr = sl_addr + (((u32)(((u64)(u32)mix64(key) * SL) >> 32)) & ~1u) * 16u;
+                    u32 left = SL;
+                    while (true) {
+                        u64 v, k;
+                        asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(v), "=l"(k) : "r"(addr));      // {val, key}
+                        bool hit = k == want;
+                        if (!hit && k == 0ull) {
+                            u64 old;
+                            asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr + 8u), "l"(0ull), "l"(want) : "memory");
+                            if (old == 0ull) n_unique32++;
+                            hit = old == 0ull || old == want;
+                            v = 0;
+                        }
+                        if (hit) {
+                            if ((u32)v < MAX_COUNT) {
+                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+                                if (fwd) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr + 4u) : "memory");
+                            }
+                            break;
+                        }
+                        addr += 16u;
                         if (addr == sl_end) addr = sl_addr;
                         if (--left == 0u) { n_full32++; break; }
                     }

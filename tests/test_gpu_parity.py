@@ -488,7 +488,7 @@ def test_hot_kmers_saturate_with_extensions(K):
     ctx.close()
 
 
-@pytest.mark.parametrize("k,mkq,mq", [(31, 0.10, 3), (21, 0.0, 2), (31, 0.5, 3), (31, 0.9, 3), (63, 0.10, 3), (31, 0.05, 10)])
+@pytest.mark.parametrize("k,mkq,mq", [(31, 0.10, 3), (21, 0.0, 2), (31, 0.5, 3), (31, 0.9, 3), (63, 0.10, 3), (31, 0.05, 10), (32, 0.10, 3), (47, 0.10, 3)])
 def test_weight_bound_mixed_qualities(K, k, mkq, mq):
     """phase 1a's bounded reads (a3): reads whose product of all non-zero base probabilities stays above
     min-kmer-quality get their "counted" bits without the recurrence, every other read walks it -- the table and the
