@@ -226,18 +226,31 @@ public:
     void writePicks(OFM &ofm, ReadSetSizeType offset = 0, bool byInputFile = ReadSelectorOptions::getOptions().getSeparateOutputs())
     {
         const int fmt = Options::getOptions().getFormatOutput();
+        // records are formatted into one buffer per output stream and written in blocks of ~1 MB; the key of a read's stream
+        // is looked up once per input file, not once per read
+        std::map<unsigned int, std::pair<std::ostream *, std::string> > out;        // input file number (0: one output) -> stream, pending bytes
         for (ReadSetSizeType p = offset; p < _picks.size(); ++p) {
             const ReadSetSizeType ids[2] = {_picks[p].read1, _picks[p].read2};
             for (int q = 0; q < 2; ++q) {
                 if (ids[q] == ReadSet::MAX_READ_IDX) continue;
                 const ReadTrimType &t = _trims[ids[q]];
-                std::string key;
-                if (byInputFile) key = "-" + _reads.getReadFileNamePrefix(ids[q]);
-                std::ostream &os = ofm.getOfstream(key);
+                const unsigned int fileKey = byInputFile ? _reads.getReadFileNum(ids[q]) : 0u;
+                std::map<unsigned int, std::pair<std::ostream *, std::string> >::iterator it = out.find(fileKey);
+                if (it == out.end()) {
+                    std::string key;
+                    if (byInputFile) key = "-" + _reads.getReadFileNamePrefix(ids[q]);
+                    it = out.insert(std::make_pair(fileKey, std::make_pair(&ofm.getOfstream(key), std::string()))).first;
+                    it->second.second.reserve((1u << 20) + 4096);
+                }
                 const Read &r = _reads.getRead(ids[q]);
-                os << ((fmt & 1) ? r.toFasta(t.trimOffset, t.trimLength, t.label) : r.toFastq(t.trimOffset, t.trimLength, t.label));
+                std::string &buf = it->second.second;
+                if (fmt & 1) buf += r.toFasta(t.trimOffset, t.trimLength, t.label);
+                else r.appendFastq(buf, t.trimOffset, t.trimLength, t.label);
+                if (buf.size() >= (1u << 20)) { it->second.first->write(buf.data(), (std::streamsize)buf.size()); buf.clear(); }
             }
         }
+        for (std::map<unsigned int, std::pair<std::ostream *, std::string> >::iterator it = out.begin(); it != out.end(); ++it)
+            if (!it->second.second.empty()) it->second.first->write(it->second.second.data(), (std::streamsize)it->second.second.size());
     }
 
 private:

@@ -14,6 +14,7 @@
 #ifndef KMERNATOR_HOST_READSET_H
 #define KMERNATOR_HOST_READSET_H
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
@@ -54,6 +55,21 @@ public:
         std::string q = quals.substr(trimOffset, trimLength);
         if (!q.empty() && (unsigned char)q[0] == REF_QUAL) q.assign(trimLength, (char)PRINT_REF_QUAL);   // quality-less reads, src/Sequence.cpp:744-747
         return hdr + "\n" + seq.substr(trimOffset, trimLength) + "\n+\n" + q + "\n";
+    }
+    // the same record appended to a buffer without temporaries (the writer formats millions of them)
+    void appendFastq(std::string &out, unsigned int trimOffset, unsigned int trimLength, const std::string &label) const
+    {
+        out += '@'; out += name;
+        if (Options::getOptions().getKeepReadComment() && !comment.empty()) { out += ' '; out += comment; }
+        if (!label.empty()) { out += ' '; out += label; }
+        if (discarded || trimLength <= 1) { out += "\nN\n+\n"; out += (char)(FASTQ_START_CHAR() + 1); out += '\n'; return; }
+        out += '\n';
+        out.append(seq, trimOffset, trimLength);
+        out += "\n+\n";
+        const size_t avail = trimOffset < quals.size() ? std::min<size_t>(trimLength, quals.size() - trimOffset) : 0;
+        if (avail && (unsigned char)quals[trimOffset] == REF_QUAL) out.append(trimLength, (char)PRINT_REF_QUAL);
+        else out.append(quals, trimOffset, trimLength);
+        out += '\n';
     }
     std::string toFasta(unsigned int trimOffset, unsigned int trimLength, const std::string &label) const
     {
