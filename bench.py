@@ -6,9 +6,14 @@ Contract (one JSON line on rank 0):
              post-build min-depth purge) with the reads already resident in HBM, CUDA events on the library's stream,
              max over ranks.
   e2e      = same metric through the C ABI with HOST (pinned) buffers: H2D of every batch and a D2H read of the
-             spectrum counters inside the timed region.
-  roofline = dominant kernel (k_insert_staged): 64 algorithmic bytes per staged instance (32-B sector read + 32-B
-             write-back of a 16-B slot RMW) / its measured launch time vs MEASURED_PEAKS.json hbm_gbs.
+             spectrum counters inside the timed region (kmn_count_batch_2na on TwoBitSequence-packed reads; the ASCII
+             entry beside it).  One GPU: on its own context with eight drains per step.
+  roofline = the dominant kernel (largest share of the step) with ITS algorithmic bytes per launch over its
+             measured launch time vs MEASURED_PEAKS.json hbm_gbs, `traffic` from profiles/r02_traffic.json (ncu);
+             `per_kernel` lists the three record passes; `whole_pass` is SURVEY.md 8d's figure for the pass as a whole
+             (66.5 B per presented instance) -- the one north_star's ">= 0.50" refers to.
+  checks   = full-size invariants + an exact comparison with the CPU oracle at the run's rank count (untimed).
+  lookup_pass / exchange = kmn_trim_batch on 20 M reads / bytes pushed between GPUs per step.
   cpu_baseline = the oracle port (reference binary is not buildable: no MPI/Boost) on a bounded sample, all host threads.
 
 `--impl reference` times only that CPU port (the one other place oracle/ may be executed).
