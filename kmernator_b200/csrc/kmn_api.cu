@@ -1,8 +1,10 @@
 // kmn_api.cu -- host side of the C ABI declared in include/kmernator_b200.h.
-// Owns the device memory plan (count table, staging sets cut by owner and table group, input staging, receive buffers),
-// launches the kernels of kmn_kernels.cuh (phase 1 on the main stream, phase 2 on the insert stream, pushes and round
-// barriers on the comm stream, H2D staging on the copy stream) and runs the multi-GPU build: records pushed into their
-// owners' receive buffers over NVLink through CUDA-IPC peer memory, or the NCCL all-to-all when peers cannot be mapped.
+// Owns the device memory plan (count table cut into slices and groups, staging set(s) cut by owner and table group, the
+// slice-sorted copy of one batch of groups, input staging slots, multi-GPU receive buffers) and launches the kernels of
+// kmn_kernels.cuh: phase 1 (k_weight_mask, k_kmer_scatter) and phase 2 (k_build_entries, k_slice_split*, k_count_slices_*
+// or k_insert_staged) on the main stream, H2D staging on two copy streams, and on several GPUs the rounds of the push
+// path -- records pushed into their owners' receive buffers over NVLink through CUDA-IPC peer memory by the copy engines
+// (comm stream, between two small NCCL all-reduces), or ncclSend / ncclRecv of the same parts when peers cannot be mapped.
 #include "../../include/kmernator_b200.h"
 #include "kmn_kernels.cuh"
 
